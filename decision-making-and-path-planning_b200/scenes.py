@@ -1,0 +1,361 @@
+"""Deterministic synthetic HD map + scripted scene episodes.
+
+Neutral input generation: the same arrays feed the unmodified reference (oracle/_ref), the CPU
+restatement (oracle/) and the CUDA path, so nothing here is part of either side of a parity check.
+Randomness is a stateless SplitMix64 hash of (scene seed, stream, index): scene s of any batch is
+always the same scene, whatever the batch size or the rank that generates it.
+
+Map (all lanes 2000 points, ~0.5 m spacing; lane 1 is the LEFTMOST lane, as in the reference where
+the left neighbour of lane n is lane n-1, Decision.cpp:602-604):
+  road 1  straight, heading 0 deg,   3 lanes, lanechg_attribute {2,3,1}   (lane changes allowed)
+  road 2  straight, heading 30 deg,  3 lanes, attribute 0                 (in-lane avoid sweep)
+  road 3  arc R=400 m (left turn),   3 lanes, attribute {2,3,1}
+  road 4  S-curve,                   3 lanes, attribute 0 up to id 700, {2,3,1} to 1500, 0 after
+  road 5  straight, heading 200 deg, 2 lanes, attribute {3,2}: both neighbours are virtual
+                                     (CreateNewPath(+-W), Decision.cpp:629-631,667-669)
+  road 6  approach,  heading 90 deg, 2 lanes, 400 points, attribute 0     (junction scenes)
+  road 7  departure, heading 180 deg,2 lanes, 400 points, attribute 0
+  connectors 6->7: lane 1->1 and lane 2->2, quarter circle left turn
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import abi
+
+LANE_W = 3.75
+SPACING = 0.5
+N_PTS = 2000
+MASK = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def rnd(seed, stream, k=0):
+    """uniform [0,1) double, stateless in (seed, stream, k); all arguments broadcast."""
+    with np.errstate(over="ignore"):
+        s = (np.asarray(seed, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+             + np.asarray(stream, dtype=np.uint64) * np.uint64(0xD1B54A32D192ED03)
+             + np.asarray(k, dtype=np.uint64) * np.uint64(0x8CB92BA72F3D8DD7))
+    return (splitmix64(splitmix64(s)) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+class Map:
+    """SoA map tables + the dp_map_desc view of them."""
+
+    def __init__(self):
+        xs, ys, dirs, widths, attrs = [], [], [], [], []
+        self.road_lane_base = [0]
+        self.lane_pt_off = [0]
+        self.lane_road = []
+        conns = []
+
+        def add_lane(cx, cy, hd, d_left, attr):
+            # offset the centre line by d_left metres to the LEFT of travel
+            h = np.radians(hd)
+            x = cx - d_left * np.sin(h)
+            y = cy + d_left * np.cos(h)
+            xs.append(x); ys.append(y); dirs.append(np.mod(hd, 360.0))
+            widths.append(np.full(x.shape, int(round(LANE_W * 100)), np.uint16))
+            attrs.append(np.broadcast_to(np.asarray(attr, np.uint16), x.shape).copy())
+            self.lane_pt_off.append(self.lane_pt_off[-1] + x.size)
+
+        def add_road(cx, cy, hd, lane_attrs):
+            n = len(lane_attrs)
+            for l in range(n):                      # lane 1 leftmost
+                d_left = (0.5 * (n - 1) - l) * LANE_W
+                add_lane(cx, cy, hd, d_left, lane_attrs[l])
+                self.lane_road.append(len(self.road_lane_base))
+            self.road_lane_base.append(self.road_lane_base[-1] + n)
+
+        s = np.arange(N_PTS) * SPACING
+        # road 1: straight east
+        add_road(100.0 + s, 50.0 + 0 * s, np.zeros(N_PTS), [2, 3, 1])
+        # road 2: straight, heading 30 deg
+        c30, s30 = math.cos(math.radians(30.0)), math.sin(math.radians(30.0))
+        add_road(-500.0 + s * c30, 200.0 + s * s30, np.full(N_PTS, 30.0), [0, 0, 0])
+        # road 3: arc, radius 400 m, turning left, starting heading 10 deg
+        R = 400.0
+        th = np.radians(10.0) + s / R
+        add_road(2000.0 + R * (np.sin(th) - math.sin(math.radians(10.0))),
+                 -300.0 - R * (np.cos(th) - math.cos(math.radians(10.0))), np.degrees(th), [2, 3, 1])
+        # road 4: S-curve y = A sin(2 pi x / Lw)
+        A, Lw = 12.0, 400.0
+        x4 = s
+        y4 = A * np.sin(2 * np.pi * x4 / Lw)
+        hd4 = np.degrees(np.arctan2(A * 2 * np.pi / Lw * np.cos(2 * np.pi * x4 / Lw), 1.0))
+        ids = np.arange(N_PTS)
+        seg = lambda a: np.where(ids < 700, 0, np.where(ids < 1500, a, 0))
+        add_road(-1500.0 + x4, -800.0 + y4, hd4, [seg(2), seg(3), seg(1)])
+        # road 5: straight heading 200 deg, 2 lanes with virtual neighbours
+        c2, s2 = math.cos(math.radians(200.0)), math.sin(math.radians(200.0))
+        add_road(800.0 + s * c2, 1500.0 + s * s2, np.full(N_PTS, 200.0), [3, 2])
+        # roads 6/7 + connectors (junction)
+        n_j = 400
+        sj = np.arange(n_j) * SPACING
+        jx, jy = 3000.0, 1000.0                      # stop line of the approach (north-bound)
+        add_road(jx + 0 * sj, jy - (n_j - 1) * SPACING + sj, np.full(n_j, 90.0), [0, 0])
+        Rc = 14.0                                    # left turn: north -> west
+        add_road(jx - Rc - 0.5 - sj, jy + Rc + 0.5 + 0 * sj, np.full(n_j, 180.0), [0, 0])
+        self.n_road_lanes = self.road_lane_base[-1]
+        for l in (0, 1):                             # connector lane l+1 -> lane l+1
+            r_l = Rc + (0.5 - l) * LANE_W            # left lane (l=0) has the smaller radius
+            n_c = int(r_l * (math.pi / 2) / SPACING) + 2
+            a = np.linspace(0.0, math.pi / 2, n_c)
+            # centre of the turn is (jx - Rc - 0.5, jy + 0.5); start heading north at angle 0
+            ccx, ccy = jx - Rc - 0.5, jy + 0.5
+            px = ccx + r_l * np.cos(a)
+            py = ccy + r_l * np.sin(a)
+            xs.append(px); ys.append(py); dirs.append(np.mod(90.0 + np.degrees(a), 360.0))
+            widths.append(np.full(px.shape, int(round(LANE_W * 100)), np.uint16))
+            attrs.append(np.zeros(px.shape, np.uint16))
+            self.lane_pt_off.append(self.lane_pt_off[-1] + px.size)
+            conns.append((6, 7, l + 1, l + 1, len(self.lane_pt_off) - 2))
+
+        self.x = np.ascontiguousarray(np.concatenate(xs), np.float64)
+        self.y = np.ascontiguousarray(np.concatenate(ys), np.float64)
+        self.dir = np.ascontiguousarray(np.concatenate(dirs), np.float64)
+        self.lane_width = np.ascontiguousarray(np.concatenate(widths), np.uint16)
+        self.lanechg_attr = np.ascontiguousarray(np.concatenate(attrs), np.uint16)
+        self.road_lane_base = np.asarray(self.road_lane_base, np.int32)
+        self.lane_pt_off = np.asarray(self.lane_pt_off, np.int32)
+        self.conn = np.array(conns, dtype=abi.connector)
+        self.n_roads = len(self.road_lane_base) - 1
+        self.n_lanes = len(self.lane_pt_off) - 1
+
+    def lanes_of(self, road):
+        return int(self.road_lane_base[road] - self.road_lane_base[road - 1])
+
+    def lane_index(self, road, lane):
+        return int(self.road_lane_base[road - 1]) + lane - 1
+
+    def desc(self):
+        d = abi.MapDesc()
+        d.n_roads = self.n_roads
+        d.road_lane_base = self.road_lane_base.ctypes.data
+        d.n_lanes = self.n_lanes
+        d.lane_pt_off = self.lane_pt_off.ctypes.data
+        d.n_conn = len(self.conn)
+        d.conn = self.conn.ctypes.data
+        d.n_points = self.x.size
+        d.x = self.x.ctypes.data
+        d.y = self.y.ctypes.data
+        d.dir = self.dir.ctypes.data
+        d.lane_width = self.lane_width.ctypes.data
+        d.lanechg_attr = self.lanechg_attr.ctypes.data
+        return d
+
+
+# streams of the per-scene hash
+(S_ROAD, S_LANE, S_ID0, S_SPEED, S_WOB_A, S_WOB_W, S_NAV, S_NAVL, S_CHG, S_CHG_T, S_CHG_D, S_YAW,
+ S_PERIOD, S_OB_LANE, S_OB_S, S_OB_V, S_OB_LAT, S_KIND, S_OB_NEAR) = range(19)
+
+
+class Episodes:
+    """Scripted (open-loop) episodes: `hdr(c)`, `obstacles(c)` give the inputs of cycle c for all scenes.
+
+    kind: 'highway' (roads 1-5, pos 0) or 'junction' (roads 6/7 + connector, pos 0 -> 1 -> 2 -> 0).
+    """
+
+    def __init__(self, m: Map, seeds, n_obs=10, kind="highway", cycles=25, roads=None):
+        self.m = m
+        self.seeds = np.asarray(seeds, dtype=np.uint64)
+        self.n = self.seeds.size
+        self.n_obs = int(n_obs)
+        self.kind = kind
+        self.cycles = cycles
+        sd = self.seeds
+        if kind == "highway":
+            roads = np.asarray(roads if roads is not None else [1, 2, 3, 4, 5], np.int32)
+            self.road = roads[(rnd(sd, S_ROAD) * len(roads)).astype(np.int64)]
+            nl = (m.road_lane_base[self.road] - m.road_lane_base[self.road - 1]).astype(np.int64)
+            self.lane0 = 1 + (rnd(sd, S_LANE) * nl).astype(np.int64)
+            self.nl = nl
+            self.s0 = 60.0 + rnd(sd, S_ID0) * 820.0           # metres along the lane
+            # a few scenes start close to the lane end (shortened front path, Decision.cpp:581)
+            near_end = rnd(sd, S_KIND) < 0.04
+            self.s0 = np.where(near_end, 925.0 + rnd(sd, S_ID0) * 30.0, self.s0)
+            self.v = 15.0 + rnd(sd, S_SPEED) * 60.0           # km/h
+        else:
+            self.road = np.full(self.n, 6, np.int32)
+            self.nl = np.full(self.n, 2, np.int64)
+            self.lane0 = 1 + (rnd(sd, S_LANE) * 2).astype(np.int64)
+            self.s0 = 150.0 + rnd(sd, S_ID0) * 35.0           # 14.5 .. 49.5 m before the stop line
+            self.v = 12.0 + rnd(sd, S_SPEED) * 25.0
+        self.wob_a = rnd(sd, S_WOB_A) * 0.3
+        self.wob_w = 0.2 + rnd(sd, S_WOB_W) * 0.6
+        # scripted ego lane change: direction +-1 at cycle t, only where a real neighbour exists
+        chg = rnd(sd, S_CHG) < (0.3 if kind == "highway" else 0.0)
+        d = np.where(rnd(sd, S_CHG_D) < 0.5, -1, 1)
+        ok = (self.lane0 + d >= 1) & (self.lane0 + d <= self.nl)
+        self.chg_dir = np.where(chg & ok, d, 0)
+        self.chg_t = 3 + (rnd(sd, S_CHG_T) * max(1, cycles - 6)).astype(np.int64)
+        # navigation: 0.55 no demand (all lanes exit), else a single exit lane
+        nav_all = rnd(sd, S_NAV) < 0.55
+        self.nav_lane = np.where(nav_all, 0, 1 + (rnd(sd, S_NAVL) * self.nl).astype(np.int64))
+        # obstacles: lane, start offset relative to ego (m), speed (m/s), lateral jitter (m)
+        k = np.arange(self.n_obs, dtype=np.uint64)[None, :]
+        s2 = sd[:, None]
+        self.ob_lane = 1 + (rnd(s2, S_OB_LANE, k) * self.nl[:, None]).astype(np.int64)
+        rel = -25.0 + rnd(s2, S_OB_S, k) * 125.0
+        # make the first obstacle a near in-lane blocker in 45 % of the scenes (arms avoid / lane change)
+        near = (rnd(sd, S_OB_NEAR) < 0.45)
+        rel[:, 0] = np.where(near, 6.0 + rnd(sd, S_OB_S, 1000) * 16.0, rel[:, 0])
+        self.ob_lane[:, 0] = np.where(near, self.lane0, self.ob_lane[:, 0])
+        self.ob_s0 = self.s0[:, None] + rel
+        self.ob_v = rnd(s2, S_OB_V, k) * 18.0
+        self.ob_v[:, 0] = np.where(near, self.v / 3.6 * (0.5 + 0.5 * rnd(sd, S_OB_V, 1000)), self.ob_v[:, 0])
+        self.ob_lat = (rnd(s2, S_OB_LAT, k) - 0.5) * 1.2
+        self.t = np.zeros(self.n)                               # elapsed ms, advanced by hdr()
+        self._t_cache = {}
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def period_ticks(self, c):
+        return 80 + (rnd(self.seeds, S_PERIOD, c) * 41.0).astype(np.int64)
+
+    def elapsed_s(self, c):
+        """scripted time at the START of cycle c (sum of the periods of cycles < c), seconds."""
+        if c not in self._t_cache:
+            t = np.zeros(self.n)
+            for i in range(c):
+                t = t + self.period_ticks(i) / 1000.0
+            self._t_cache[c] = t
+        return self._t_cache[c]
+
+    def _lane_xy(self, lane_idx, s):
+        """point at arclength-parameter s (metres, index = s / SPACING) of global lane lane_idx."""
+        m = self.m
+        off = m.lane_pt_off[lane_idx].astype(np.int64)
+        cnt = (m.lane_pt_off[lane_idx + 1] - m.lane_pt_off[lane_idx]).astype(np.int64)
+        f = np.clip(s / SPACING, 0.0, (cnt - 1) - 1e-9)
+        i = np.floor(f).astype(np.int64)
+        t = f - i
+        x = m.x[off + i] * (1 - t) + m.x[off + i + 1] * t
+        y = m.y[off + i] * (1 - t) + m.y[off + i + 1] * t
+        hd = m.dir[off + i]
+        idn = np.rint(f).astype(np.int64)
+        return x, y, hd, idn
+
+    def hdr(self, c):
+        m = self.m
+        h = np.zeros(self.n, dtype=abi.scene_hdr)
+        ticks = self.period_ticks(c)
+        h["period_ms"] = ticks.astype(np.float64) / 1000.0 * 1000.0      # == what the reference computes
+        t = self.elapsed_s(c)
+        s = self.s0 + self.v / 3.6 * t
+        if self.kind == "highway":
+            s = np.minimum(s, 985.0)        # keep id + ID_MORE inside the lane (no OOB map reads, Decision.cpp:590-594)
+        h["velocity"] = self.v
+        h["n_obs"] = self.n_obs
+        h["conn"] = -1
+        h["last_roadnum"] = 1; h["next_roadnum"] = 1; h["last_lanenum"] = 1; h["next_lanenum"] = 1
+        wob = self.wob_a * np.sin(self.wob_w * c)
+        yaw = (rnd(self.seeds, S_YAW, c) - 0.5) * 4.0
+        if self.kind == "highway":
+            # scripted lane change: lateral blend over 8 cycles centred on chg_t
+            prog = np.clip((c - self.chg_t + 4) / 8.0, 0.0, 1.0) * (self.chg_dir != 0)
+            lane = np.where(prog >= 0.5, self.lane0 + self.chg_dir, self.lane0)
+            lat_from_lane0 = -prog * self.chg_dir * LANE_W      # metres to the LEFT (+) of lane0 centre
+            lat_left = np.where(prog >= 0.5, lat_from_lane0 + self.chg_dir * LANE_W, lat_from_lane0) + wob
+            gl = m.road_lane_base[self.road - 1].astype(np.int64) + lane - 1
+            x, y, hd, idn = self._lane_xy(gl, s)
+            hr = np.radians(hd)
+            h["x"] = x - lat_left * np.sin(hr)
+            h["y"] = y + lat_left * np.cos(hr)
+            h["dir"] = np.mod(hd + yaw + 360.0, 360.0)
+            h["road_num"] = self.road
+            h["lane_num"] = lane
+            h["pos"] = 0
+            h["path_num"] = 0
+            for l in range(abi.LANESUM):
+                h["id"][:, l] = np.where(l < self.nl, idn, 0)
+            out = np.zeros((self.n, abi.LANESUM), np.uint16)
+            allm = self.nav_lane == 0
+            for l in range(abi.LANESUM):
+                out[:, l] = np.where(allm & (l < self.nl), l + 1, 0)
+            out[:, 0] = np.where(allm, out[:, 0], self.nav_lane)
+            h["out_lane_no"] = out
+            h["stub_attribute"] = 0
+        else:
+            lane = self.lane0
+            app_len = 399 * SPACING
+            gl6 = m.road_lane_base[5].astype(np.int64) + lane - 1
+            gl7 = m.road_lane_base[6].astype(np.int64) + lane - 1
+            cidx = lane - 1                                         # connector index == lane-1
+            gc = m.conn["lane"][cidx].astype(np.int64)
+            clen = (m.lane_pt_off[gc + 1] - m.lane_pt_off[gc] - 1) * SPACING
+            in_app = s < app_len
+            in_con = (~in_app) & (s < app_len + clen)
+            in_dep = ~(in_app | in_con)
+            xa, ya, ha, ia = self._lane_xy(gl6, np.minimum(s, app_len))
+            xc, yc, hc, ic = self._lane_xy(gc, np.clip(s - app_len, 0.0, clen))
+            xd, yd, hdd, idd = self._lane_xy(gl7, np.maximum(s - app_len - clen, 0.0))
+            x = np.where(in_app, xa, np.where(in_con, xc, xd))
+            y = np.where(in_app, ya, np.where(in_con, yc, yd))
+            hd = np.where(in_app, ha, np.where(in_con, hc, hdd))
+            hr = np.radians(hd)
+            h["x"] = x - wob * np.sin(hr)
+            h["y"] = y + wob * np.cos(hr)
+            h["dir"] = np.mod(hd + yaw + 360.0, 360.0)
+            pre = in_app & (s > app_len - 30.0)                    # pre-junction zone: last 30 m
+            h["pos"] = np.where(in_con, 2, np.where(pre, 1, 0))
+            h["road_num"] = np.where(in_app, 6, 7)                 # in the junction: NEXT road (Decision.cpp:417)
+            h["lane_num"] = lane
+            h["path_num"] = np.where(in_dep, 1, 0)
+            h["last_roadnum"] = 6; h["next_roadnum"] = 7
+            h["last_lanenum"] = lane; h["next_lanenum"] = lane
+            h["conn"] = cidx
+            idv = np.where(in_app, ia, np.where(in_con, ic, idd))
+            for l in range(abi.LANESUM):
+                h["id"][:, l] = np.where(l < 2, idv, 0)
+            out = np.zeros((self.n, abi.LANESUM), np.uint16)
+            out[:, 0] = 1; out[:, 1] = 2
+            h["out_lane_no"] = out
+            h["stub_attribute"] = np.where(in_dep, 0, 1 + (self.seeds % np.uint64(3)).astype(np.int64))
+        return h
+
+    def obstacles(self, c):
+        """(obs_x, obs_y) of cycle c, each [n, n_obs] C-contiguous."""
+        m = self.m
+        t = self.elapsed_s(c)[:, None]
+        s = self.ob_s0 + self.ob_v * t
+        if self.kind == "highway":
+            gl = m.road_lane_base[self.road - 1].astype(np.int64)[:, None] + self.ob_lane - 1
+            x, y, hd, _ = self._lane_xy(gl, s)
+        else:
+            # agents spread over approach lanes, connector and departure lanes by arclength
+            app_len = 399 * SPACING
+            gl6 = m.road_lane_base[5].astype(np.int64) + self.ob_lane - 1
+            gl7 = m.road_lane_base[6].astype(np.int64) + self.ob_lane - 1
+            gc = m.conn["lane"][self.ob_lane - 1].astype(np.int64)
+            clen = (m.lane_pt_off[gc + 1] - m.lane_pt_off[gc] - 1) * SPACING
+            in_app = s < app_len
+            in_con = (~in_app) & (s < app_len + clen)
+            xa, ya, ha, _ = self._lane_xy(gl6, np.clip(s, 0.0, app_len))
+            xc, yc, hc, _ = self._lane_xy(gc, np.clip(s - app_len, 0.0, clen))
+            xd, yd, hdd, _ = self._lane_xy(gl7, np.maximum(s - app_len - clen, 0.0))
+            x = np.where(in_app, xa, np.where(in_con, xc, xd))
+            y = np.where(in_app, ya, np.where(in_con, yc, yd))
+            hd = np.where(in_app, ha, np.where(in_con, hc, hdd))
+        hr = np.radians(hd)
+        ox = x - self.ob_lat * np.sin(hr)
+        oy = y + self.ob_lat * np.cos(hr)
+        return np.ascontiguousarray(ox), np.ascontiguousarray(oy)
+
+    def all_cycles(self):
+        """[cycles][n] hdr and [cycles][n][n_obs] obstacle arrays (cycle-major)."""
+        H = np.zeros((self.cycles, self.n), dtype=abi.scene_hdr)
+        OX = np.zeros((self.cycles, self.n, self.n_obs))
+        OY = np.zeros((self.cycles, self.n, self.n_obs))
+        for c in range(self.cycles):
+            H[c] = self.hdr(c)
+            OX[c], OY[c] = self.obstacles(c)
+        return H, OX, OY

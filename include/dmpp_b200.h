@@ -1,0 +1,236 @@
+/* include/dmpp_b200.h -- C ABI of the B200-native Decision/Planning hot path.
+ *
+ * One shared library (libdmpp_b200.so, built from decision-making-and-path-planning_b200/csrc/)
+ * exports exactly the symbols declared here.  Plain C types, caller-owned buffers, int status
+ * (0 = ok, negative = error; there is NO CPU fallback: every compute entry point fails with
+ * DP_ERR_CUDA when no sm_100-class device is usable).  Each entry point cites the reference
+ * interface (file:line in 123456jack/decision-making-and-path-planning) it replaces.
+ *
+ * Conventions (reference: SURVEY.md section 8): coordinates are double metres in the local
+ * "global" frame; headings are degrees, 0 = east, CCW, [0,360) (Planning.cpp:712-750); speed is
+ * km/h (Planning.cpp:258); periods are ms (Planning.cpp:77); lateral offsets passed to
+ * search/create operators are RIGHT-of-travel positive (Decision.cpp:629,942).
+ */
+#ifndef DMPP_B200_H
+#define DMPP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_LANESUM 6          /* LANESUM      (Decision.h:79, Decision.cpp:498) */
+#define DP_PATH_POINTS 200    /* local path   (Planning.h:33-34, Planning.cpp:115) */
+#define DP_OUT_POINTS 100     /* PlanningOut  (Planning.cpp:180-183,205-212) */
+#define DP_MAX_SWEEP 8        /* cap on K = #{i : i < (W - Vw)/0.6} per side (Decision.cpp:940) */
+#define DP_NOT_FOUND 999.0    /* sentinel of SearchObstacle (Planning.cpp:161-162) */
+
+enum {
+    DP_OK = 0,
+    DP_ERR_ARG = -1,          /* null pointer, size out of range */
+    DP_ERR_CUDA = -2,         /* no device / CUDA runtime error (message via dp_last_error) */
+    DP_ERR_STATE = -3,        /* map not uploaded, capacity exceeded */
+    DP_ERR_NOMEM = -4
+};
+
+/* All constants the reference hides in the absent Share.h (SURVEY.md section 5 "config").
+ * dp_default_params() returns the frozen values used by the oracle (oracle/compat/Share.h). */
+typedef struct dp_params {
+    double vehicle_width;            /* Vehicle_Width            Decision.cpp:370,811; 1.8 */
+    double epsilon;                  /* EPSILON                  Planning.cpp:690;     1e-6 */
+    double pi;                       /* PI                       Planning.cpp:728 */
+    double road_faraim_max;          /* ROAD_FARAIM_MAX          Planning.cpp:260;     60 */
+    double road_faraim_min;          /* ROAD_FARAIM_MIN          Planning.cpp:264;     15 */
+    double pre_inter_faraim;         /* PRE_INTER_FARAIM         Planning.cpp:275;     20 */
+    double inter_faraim;             /* INTER_FARAIM             Planning.cpp:283;     15 */
+    double road_remain_distance;     /* ROAD_REMAIN_DISTANCE     Planning.cpp:821;     15 */
+    double inter_remain_distance;    /* INTER_REMAIN_DISTANCE    Planning.cpp:826;     5 */
+    double lat0, lng0, k_lat, k_lng; /* datum of GlobalToWGS84   Planning.cpp:209 */
+    int32_t id_more;                 /* ID_MORE                  Decision.cpp:581;     8 */
+    int32_t reserved;
+} dp_params;
+
+/* HD-map tables: app->decision_MapData[road][lane][id] / planning_MapData (Decision.cpp:562-578,
+ * Planning.cpp:331-356) flattened to SoA, and the junction connectors
+ * decision_InterMapData[last_road][next_road][last_lane][next_lane][id] (Decision.cpp:348,364). */
+typedef struct dp_connector {
+    uint16_t last_road, next_road, last_lane, next_lane; /* 1-based, as in LocationOut */
+    int32_t lane;                                        /* index into lane_pt_off of its polyline */
+} dp_connector;
+
+typedef struct dp_map_desc {
+    int32_t n_roads;
+    const int32_t* road_lane_base;   /* [n_roads+1]: lanes of road r (1-based r) are base[r-1]..base[r]-1 */
+    int32_t n_lanes;                 /* road lanes first, then one pseudo-lane per connector */
+    const int32_t* lane_pt_off;      /* [n_lanes+1] offsets into the point arrays */
+    int32_t n_conn;
+    const dp_connector* conn;        /* [n_conn] */
+    int64_t n_points;
+    const double* x;                 /* [n_points] global_point.x */
+    const double* y;
+    const double* dir;               /* degrees */
+    const uint16_t* lane_width;      /* cm  (Decision.cpp:578) */
+    const uint16_t* lanechg_attr;    /* 0 none, 1 left, 2 right, 3 both (Decision.cpp:566) */
+} dp_map_desc;
+
+/* Per-scene, per-cycle input: LocationOut + the slice of RoadNavi the cycle reads
+ * (Decision.cpp:155-169; Planning.cpp:95-112) + cycle period.  One 128-byte line per scene. */
+typedef struct dp_scene_hdr {
+    double x, y, dir;                /* LocationOut.globalpoint */
+    double velocity;                 /* km/h */
+    double period_ms;                /* z_period_last (Decision.cpp:137) */
+    int32_t id[DP_LANESUM];          /* LocationOut.id[lane-1]: nearest map point per lane */
+    uint16_t road_num, lane_num, pos, path_num;
+    uint16_t last_roadnum, next_roadnum, last_lanenum, next_lanenum;
+    uint16_t out_lane_no[DP_LANESUM];/* z_RoadNavi[path_num].out_lane_no (Decision.cpp:696) */
+    uint16_t stub_attribute;         /* z_RoadNavi[path_num].stub_attribute (Decision.cpp:385) */
+    uint16_t n_obs;                  /* obstacle points of this scene (<= ctx max_obs) */
+    int32_t conn;                    /* connector index for pos 1/2, -1 otherwise */
+    uint8_t pad[128 - 40 - 24 - 16 - 12 - 4 - 4];
+} dp_scene_hdr;
+
+/* Per-scene result of one Decision + Planning cycle: DecisionOut (Decision.cpp:187-196),
+ * the public CPlanning fields (Planning.h:41-51) and PlanningOut scalars (Planning.cpp:189-201). */
+typedef struct dp_plan_record {
+    double velocity_expect;          /* DecisionOut.velocity_expect */
+    double path_lat_dis, path_dir_err, remain_dis;   /* Planning.cpp:131 */
+    double mindist_lat, mindist_lon; /* Planning.cpp:161-168 (brakedis = mindist_lon) */
+    double brakespeed, des_acc;      /* Planning.cpp:171 */
+    double radius;                   /* Planning.cpp:199 */
+    double aim_x, aim_y, aim_dir;    /* aimpoint_far after Planning.cpp:121 */
+    int32_t aim_id;
+    uint16_t behavior, target_roadnum, target_lanenum, light, behavior_to_dlg;
+    uint16_t afresh_cause;
+    int16_t sweep_index;             /* avoid candidate picked this cycle: 0..K-1 = left i,
+                                        K..2K-1 = right i, -1 = sweep not run or none feasible */
+    int16_t path_near_id, path_front_near_id;
+    int16_t ob_index;                /* obstacle that bounds the local path, -1 none */
+    uint16_t ob_pathid;
+    uint16_t n_traj;                 /* trajectories scored this cycle (SearchObstacle evaluations) */
+    uint8_t afresh_planning, ob_flag, acc_flag, cnt;
+} dp_plan_record;
+
+/* Optional per-scene trace for parity tests: every SearchObstacle evaluation of the cycle. */
+typedef struct dp_search_slot {
+    double dis_lat, dis_lng;
+    int16_t ob_index;
+    uint16_t pathid;
+    uint8_t evaluated, found;
+    uint8_t pad[2];
+} dp_search_slot;
+typedef struct dp_trace_record {
+    dp_search_slot region[6];        /* F, R, LF, LR, RF, RR   (Decision.cpp:811-842) */
+    dp_search_slot sweep[2 * DP_MAX_SWEEP]; /* L0..L7, R0..R7 (Decision.cpp:940-974) */
+    dp_search_slot junction;         /* Decision.cpp:370,455 */
+    dp_search_slot local;            /* Planning.cpp:168 */
+    double width_curlane, faraim_dis;
+    uint32_t navi_lanechg, navi_lanechg_times; /* Decision.cpp:268 */
+    uint16_t refpath_len;
+    uint16_t ub_hits;                /* reference undefined-behaviour sites hit this cycle (clamped) */
+    uint8_t pad[4];
+} dp_trace_record;
+
+/* Cross-cycle state of one scene (SURVEY.md section 5 "checkpoint / resume"): the function
+ * statics of Decision.cpp:915-917, the CDecision members of Decision.h:28-44, CPlanning's
+ * his_behavior / count / aimpoint_far (Planning.h:22-23,49; Planning.cpp:51).  The last local
+ * path (Planning.cpp:6) lives in a separate [scene][2][200] array. */
+typedef struct dp_carry {
+    double leftlight_time, rightlight_time, velocity_expect;
+    double aim_x, aim_y, aim_dir;
+    int32_t aim_id;
+    uint32_t obsavoid_time, no_obsavoid_time, frontobs_time;
+    int32_t plan_his_behavior;
+    int32_t path_near_id;
+    uint16_t behavior, target_roadnum, target_lanenum, light_status, behavior_to_dlg;
+    uint16_t his_behavior, his_target_lanenum, his_light_status;
+    uint8_t lanechg_status, obsavoid_status, plan_count, pad0;
+    uint8_t pad[128 - 48 - 24 - 16 - 4];
+} dp_carry;
+
+typedef struct dp_ctx dp_ctx;
+
+const char* dp_last_error(void);
+void dp_default_params(dp_params* p);
+
+/* (1) context: replaces the singletons CDecision::Instance()/CPlanning::Instance()
+ * (Decision.cpp:36-40, Planning.cpp:18-22) by an explicit, re-entrant handle. */
+int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes, int max_obs);
+int dp_destroy(dp_ctx* ctx);
+
+/* (2) map upload: replaces the app-owned tables read at Decision.cpp:562-666, Planning.cpp:331-374.
+ * Precomputes per-point segment length and unit normal on the device. */
+int dp_map_upload(dp_ctx* ctx, const dp_map_desc* map);
+
+/* reset the carry of scenes [first, first+count) to the constructor state
+ * (Decision.cpp:8-29, Planning.cpp:8-11,62). */
+int dp_reset(dp_ctx* ctx, int first, int count);
+int dp_carry_download(dp_ctx* ctx, int first, int count, dp_carry* host_out, double* host_last_path);
+int dp_carry_upload(dp_ctx* ctx, int first, int count, const dp_carry* host_in, const double* host_last_path);
+
+/* (3)+(4) one fused Decision + Planning cycle for n_scenes scenes: replaces one iteration of
+ * CDecisionThread (Decision.cpp:119-206) followed by one of CPlanningThread (Planning.cpp:64-226).
+ * Device-pointer form: inputs/outputs already resident in HBM, launched on `stream`
+ * (a cudaStream_t passed as void*), asynchronous.
+ *   hdr[n_scenes]; obs_x/obs_y[n_scenes][max_obs];
+ *   rec[n_scenes]; trace (nullable) [n_scenes]; path_xy (nullable) [n_scenes][2][200] = road_points;
+ *   path_ll (nullable) [n_scenes][2][100] = PlanningOut.pnts (lat row, lng row).
+ * scene i uses carry slot first_scene + i. */
+int dp_cycle_batch_dev(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scene_hdr* hdr,
+                       const double* obs_x, const double* obs_y, dp_plan_record* rec,
+                       dp_trace_record* trace, double* path_xy, double* path_ll, void* stream);
+
+/* Host-pointer form (the drop-in call): copies inputs host->device, runs the cycle, copies the
+ * requested outputs device->host, and returns when they are valid.  Buffers may be pageable or
+ * pinned; dp_host_alloc returns pinned memory. */
+int dp_cycle_batch(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scene_hdr* hdr,
+                   const double* obs_x, const double* obs_y, dp_plan_record* rec,
+                   dp_trace_record* trace, double* path_xy, double* path_ll);
+int dp_host_alloc(void** p, size_t bytes);
+int dp_host_free(void* p);
+
+/* (5) dense candidate sweep for ONE scene (latency mode, BASELINE config 3): candidate c is the
+ * lateral-offset copy (offset[c], RIGHT positive) of the first n_pts[c] points of the base
+ * polyline base_x/base_y[n_base], scored by SearchObstacle against obstacle tracks
+ * obs = o0 + j * dv for path point j (dv = 0 reproduces Decision.cpp:940-974).  cost =
+ * feasibility {0, +inf} with threshold `clear_dis` (dis_lng > clear_dis, Decision.cpp:944);
+ * best = lowest index among feasible, -1 if none.  Host pointers; out_dis_lng nullable. */
+int dp_score_candidates(dp_ctx* ctx, const double* base_x, const double* base_y, int n_base,
+                        const double* offset, const int32_t* n_pts, int n_cand,
+                        const double* obs_x, const double* obs_y, const double* obs_dvx,
+                        const double* obs_dvy, int n_obs, double lat_min, double lat_max,
+                        double clear_dis, int32_t* best_index, double* best_dis_lng,
+                        double* out_dis_lng);
+
+/* (6) operator-level batch calls, the CShare seam.  Host pointers.
+ * paths are [n_paths] polylines concatenated; path_off[n_paths+1]. */
+/* CShare::SearchObstacle  (Planning.cpp:168; Decision.cpp:370,...,962) */
+int dp_search_obstacle(dp_ctx* ctx, int n_paths, const int32_t* path_off, const double* px,
+                       const double* py, const double* obs_x, const double* obs_y, int n_obs,
+                       const double* lat_min, const double* lat_max, dp_search_slot* out);
+/* CShare::CreateNewPath   (Decision.cpp:629,631,667,669,942,961) */
+int dp_create_new_path(dp_ctx* ctx, int n_paths, const int32_t* path_off, const double* px,
+                       const double* py, const double* offset, double* out_x, double* out_y);
+/* CShare::BezierPlanning  (Planning.cpp:606,863): poses[n][6] = start x,y,dir, aim x,y,dir;
+ * out[n][2][200] */
+int dp_bezier_planning(dp_ctx* ctx, int n, const double* poses, double* out_xy);
+/* CShare::MeanPoints      (Planning.cpp:872): out[n][2][200] */
+int dp_mean_points(dp_ctx* ctx, int n_paths, const int32_t* path_off, const double* px,
+                   const double* py, double* out_xy);
+
+/* device properties + FMA micro-benchmark used as roofline denominator:
+ * returns measured FP64 / FP32 FMA throughput in TFLOP/s on the context's device. */
+int dp_measure_fma_peak(dp_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
+/* number of kernels this library has launched since dp_create (bench.py "gpu_launches") */
+int64_t dp_launch_count(dp_ctx* ctx);
+/* device pointer helpers so a Python/C++ caller can stage inputs for dp_cycle_batch_dev */
+int dp_dev_alloc(dp_ctx* ctx, void** p, size_t bytes);
+int dp_dev_free(dp_ctx* ctx, void* p);
+int dp_memcpy_h2d(dp_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int dp_memcpy_d2h(dp_ctx* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int dp_stream_sync(dp_ctx* ctx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMPP_B200_H */

@@ -1,0 +1,158 @@
+"""oracle/binding.py -- TEST INFRASTRUCTURE. ctypes loaders for liboracle.so (the restated CPU
+oracle) and _ref/libref.so (the unmodified reference + shim).  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference leg may import this module."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_root = os.path.dirname(_here)
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+import dmpp_b200  # noqa: E402
+from dmpp_b200 import abi  # noqa: E402
+
+CALLS_CAP = 32
+
+
+def build(ref_dir="/root/reference"):
+    """compile liboracle.so and, when the reference sources are present, _ref/libref.so."""
+    subprocess.check_call(["make", "-s", "-C", _here, "REF=" + ref_dir, "all"])
+
+
+def _load(path):
+    if not os.path.exists(path):
+        return None
+    return C.CDLL(path)
+
+
+class _Runner:
+    def __init__(self):
+        self._keep = None
+
+    @staticmethod
+    def _alloc(n, cycles, want_paths, want_calls, want_trace):
+        out = {"rec": np.zeros((cycles, n), abi.plan_record)}
+        out["trace"] = np.zeros((cycles, n), abi.trace_record) if want_trace else None
+        out["path_xy"] = np.zeros((cycles, n, 2, abi.PATH_POINTS)) if want_paths else None
+        out["path_ll"] = np.zeros((cycles, n, 2, abi.OUT_POINTS)) if want_paths else None
+        out["calls"] = np.zeros((cycles, n, CALLS_CAP), abi.ref_call) if want_calls else None
+        out["n_calls"] = np.zeros((cycles, n), np.int32) if want_calls else None
+        out["carry"] = np.zeros(n, abi.carry)
+        out["last_path"] = np.zeros((n, 2, abi.PATH_POINTS))
+        return out
+
+
+class Oracle(_Runner):
+    """the restated oracle (liboracle.so): re-entrant, multi-threaded."""
+
+    def __init__(self):
+        super().__init__()
+        self.lib = _load(os.path.join(_here, "liboracle.so"))
+        if self.lib is None:
+            raise RuntimeError("oracle/liboracle.so missing: run __graft_entry__.build()")
+        self.lib.oracle_run_batch.restype = C.c_longlong
+        self.lib.oracle_atan.restype = C.c_double
+        self.lib.oracle_atan.argtypes = [C.c_double]
+        self.lib.oracle_calc_global_dir.restype = C.c_double
+        self.lib.oracle_calc_global_dir.argtypes = [C.c_double] * 4
+        self.lib.oracle_lat_dis.restype = C.c_double
+        self.lib.oracle_lat_dis.argtypes = [C.c_double] * 6
+        self.lib.oracle_calc_distance.restype = C.c_double
+        self.lib.oracle_calc_distance.argtypes = [C.c_double] * 4
+        self.params = abi.Params()
+        self.lib.oracle_default_params(C.byref(self.params))
+
+    def set_map(self, m):
+        self._keep = m
+        self._desc = m.desc()
+        assert self.lib.oracle_set_map(C.byref(self._desc)) == 0
+
+    def run(self, H, OX, OY, paths=True, calls=True, trace=True, exhaustive=True, threads=1):
+        cycles, n = H.shape
+        max_obs = OX.shape[2]
+        o = self._alloc(n, cycles, paths, calls, trace)
+        sec = C.c_double(0)
+        traj = C.c_longlong(0)
+        ub = self.lib.oracle_run_batch(
+            C.byref(self.params), C.c_int(n), C.c_int(cycles), C.c_int(max_obs), abi.ptr(H), abi.ptr(OX), abi.ptr(OY),
+            abi.ptr(o["rec"]), abi.ptr(o["trace"]), abi.ptr(o["path_xy"]), abi.ptr(o["path_ll"]), abi.ptr(o["calls"]),
+            abi.ptr(o["n_calls"]), C.c_int(CALLS_CAP), abi.ptr(o["carry"]), abi.ptr(o["last_path"]),
+            C.c_int(1 if exhaustive else 0), C.c_int(threads), C.byref(sec), C.byref(traj))
+        if ub < 0:
+            raise RuntimeError("oracle_run_batch failed: %d" % ub)
+        o["ub_hits"] = ub
+        o["seconds"] = sec.value
+        o["traj"] = traj.value
+        return o
+
+    # operator-level
+    def search_obstacle(self, px, py, ox, oy, lo, hi):
+        px, py, ox, oy = (np.ascontiguousarray(a, np.float64) for a in (px, py, ox, oy))
+        out = np.zeros(1, abi.search_slot)
+        self.lib.oracle_search_obstacle(abi.ptr(px), abi.ptr(py), C.c_int(px.size), abi.ptr(ox), abi.ptr(oy),
+                                        C.c_int(ox.size), C.c_double(lo), C.c_double(hi), abi.ptr(out))
+        return out[0]
+
+    def create_new_path(self, px, py, d):
+        px, py = (np.ascontiguousarray(a, np.float64) for a in (px, py))
+        ox, oy = np.zeros_like(px), np.zeros_like(py)
+        self.lib.oracle_create_new_path(abi.ptr(px), abi.ptr(py), C.c_int(px.size), C.c_double(d), abi.ptr(ox), abi.ptr(oy))
+        return ox, oy
+
+    def bezier(self, poses6, n=abi.PATH_POINTS):
+        poses6 = np.ascontiguousarray(poses6, np.float64)
+        out = np.zeros((2, n))
+        self.lib.oracle_bezier(abi.ptr(poses6), abi.ptr(out), C.c_int(n))
+        return out
+
+    def mean_points(self, px, py, n_out=abi.PATH_POINTS):
+        px, py = (np.ascontiguousarray(a, np.float64) for a in (px, py))
+        out = np.zeros((2, n_out))
+        self.lib.oracle_mean_points(abi.ptr(px), abi.ptr(py), C.c_int(px.size), abi.ptr(out), C.c_int(n_out))
+        return out
+
+    def sincos_deg(self, a):
+        c, s = C.c_double(0), C.c_double(0)
+        self.lib.oracle_sincos_deg(C.c_double(a), C.byref(c), C.byref(s))
+        return c.value, s.value
+
+
+class Reference(_Runner):
+    """the UNMODIFIED reference (oracle/_ref/libref.so); single-threaded by construction."""
+
+    def __init__(self):
+        super().__init__()
+        self.lib = _load(os.path.join(_here, "_ref", "libref.so"))
+        if self.lib is None:
+            raise RuntimeError("oracle/_ref/libref.so missing (built by __graft_entry__.build() where /root/reference exists)")
+        self.lib.ref_run_batch.restype = C.c_longlong
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(_here, "_ref", "libref.so"))
+
+    def set_map(self, m):
+        self._keep = m
+        d = m.desc()
+        assert self.lib.ref_set_map(C.byref(d)) == 0
+
+    def run(self, H, OX, OY, paths=True, calls=True):
+        cycles, n = H.shape
+        max_obs = OX.shape[2]
+        o = self._alloc(n, cycles, paths, calls, False)
+        sec = C.c_double(0)
+        traj = C.c_longlong(0)
+        rc = self.lib.ref_run_batch(
+            C.c_int(n), C.c_int(cycles), C.c_int(max_obs), abi.ptr(H), abi.ptr(OX), abi.ptr(OY), abi.ptr(o["rec"]),
+            abi.ptr(o["path_xy"]), abi.ptr(o["path_ll"]), abi.ptr(o["calls"]), abi.ptr(o["n_calls"]), C.c_int(CALLS_CAP),
+            abi.ptr(o["carry"]), abi.ptr(o["last_path"]), C.byref(sec), C.byref(traj))
+        if rc < 0:
+            raise RuntimeError("ref_run_batch failed: %d" % rc)
+        o["msgbox"] = rc
+        o["seconds"] = sec.value
+        o["traj"] = traj.value
+        return o

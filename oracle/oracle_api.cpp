@@ -1,0 +1,128 @@
+// oracle/oracle_api.cpp -- TEST INFRASTRUCTURE. C API of liboracle.so: batch runner of the
+// restated oracle (planner_oracle.cpp) over independent scenes on T host threads, with the same
+// [cycle][scene] array layout the CUDA path and oracle/_ref/libref.so use, plus thin entry points
+// to the operator specification (cshare_spec.cpp) for known-answer tests.
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include "planner_oracle.h"
+
+namespace { oracle::MapView g_map; bool g_have_map = false; }
+
+extern "C" {
+
+int oracle_set_map(const dp_map_desc* m) { g_map.d = *m; g_have_map = true; return 0; }   // caller keeps arrays alive
+
+void oracle_default_params(dp_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->vehicle_width = 1.8; p->epsilon = 1e-6; p->pi = 3.14159265358979323846;
+    p->road_faraim_max = 60; p->road_faraim_min = 15; p->pre_inter_faraim = 20; p->inter_faraim = 15;
+    p->road_remain_distance = 15; p->inter_remain_distance = 5;
+    p->lat0 = 23.0; p->lng0 = 113.0; p->k_lat = 1.0 / 110574.0; p->k_lng = 1.0 / 102470.0;
+    p->id_more = 8;
+}
+
+// hdr[cycles][n], obs_[xy][cycles][n][max_obs], rec[cycles][n], trace[cycles][n] (nullable),
+// path_xy[cycles][n][2][200] (nullable), path_ll[cycles][n][2][100] (nullable),
+// calls[cycles][n][calls_cap] + n_calls[cycles][n] (nullable), carry_out[n] / last_path_out[n][2][200] (nullable).
+// Returns total ub_hits (>= 0) or a negative error.  *seconds = wall time of the compute loop.
+long long oracle_run_batch(const dp_params* p, int n, int cycles, int max_obs, const dp_scene_hdr* hdr,
+                           const double* ox, const double* oy, dp_plan_record* rec, dp_trace_record* trace,
+                           double* path_xy, double* path_ll, ref_call* calls, int32_t* n_calls, int calls_cap,
+                           dp_carry* carry_out, double* last_path_out, int exhaustive, int threads,
+                           double* seconds, long long* traj_scored) {
+    if (!g_have_map) return -1;
+    if (threads < 1) threads = 1;
+    std::atomic<long long> ub(0), traj(0);
+    auto work = [&](int s0, int s1) {
+        long long lub = 0, ltraj = 0;
+        for (int s = s0; s < s1; ++s) {
+            oracle::SceneState st;
+            oracle::reset_state(st);
+            for (int c = 0; c < cycles; ++c) {
+                size_t e = (size_t)c * n + s;
+                oracle::CycleOut o{};
+                o.rec = rec + e;
+                o.trace = trace ? trace + e : nullptr;
+                o.path_xy = path_xy ? path_xy + e * 400 : nullptr;
+                o.path_ll = path_ll ? path_ll + e * 200 : nullptr;
+                o.calls = calls ? calls + e * calls_cap : nullptr;
+                o.calls_cap = calls_cap;
+                oracle::cycle(g_map, *p, hdr[e], ox + e * max_obs, oy + e * max_obs, st, o, exhaustive != 0);
+                if (n_calls) n_calls[e] = o.n_calls;
+                lub += o.ub_hits;
+                ltraj += o.n_calls;
+            }
+            if (carry_out) carry_out[s] = st.c;
+            if (last_path_out) {
+                std::memcpy(last_path_out + (size_t)s * 400, st.last_x, sizeof(st.last_x));
+                std::memcpy(last_path_out + (size_t)s * 400 + 200, st.last_y, sizeof(st.last_y));
+            }
+        }
+        ub += lub; traj += ltraj;
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    if (threads == 1) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; ++t) th.emplace_back(work, (int)((long long)n * t / threads), (int)((long long)n * (t + 1) / threads));
+        for (auto& x : th) x.join();
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (traj_scored) *traj_scored = traj.load();
+    return ub.load();
+}
+
+// ---- operator-level entry points (known-answer tests, GPU operator parity) ----
+void oracle_search_obstacle(const double* px, const double* py, int P, const double* ox, const double* oy, int N,
+                            double lo, double hi, dp_search_slot* out) {
+    std::vector<spec::P2> p(P), o(N);
+    for (int i = 0; i < P; ++i) p[i] = spec::P2{px[i], py[i]};
+    for (int i = 0; i < N; ++i) o[i] = spec::P2{ox[i], oy[i]};
+    spec::SearchResult r = spec::search_obstacle(p.data(), P, o.data(), N, lo, hi);
+    std::memset(out, 0, sizeof(*out));
+    out->dis_lat = r.dis_lat; out->dis_lng = r.dis_lng; out->ob_index = (int16_t)r.ob_index;
+    out->pathid = (uint16_t)r.pathid; out->evaluated = 1; out->found = r.found;
+}
+void oracle_create_new_path(const double* px, const double* py, int P, double d, double* ox, double* oy) {
+    std::vector<spec::P2> p(P), o(P);
+    for (int i = 0; i < P; ++i) p[i] = spec::P2{px[i], py[i]};
+    spec::create_new_path(p.data(), P, d, o.data());
+    for (int i = 0; i < P; ++i) { ox[i] = o[i].x; oy[i] = o[i].y; }
+}
+void oracle_bezier(const double* poses6, double* out_xy /*[2][n]*/, int n) {
+    std::vector<spec::P2> o(n);
+    spec::bezier_planning(spec::P3{poses6[0], poses6[1], poses6[2]}, spec::P3{poses6[3], poses6[4], poses6[5]}, o.data(), n);
+    for (int i = 0; i < n; ++i) { out_xy[i] = o[i].x; out_xy[n + i] = o[i].y; }
+}
+void oracle_mean_points(const double* px, const double* py, int n_in, double* out_xy /*[2][n_out]*/, int n_out) {
+    std::vector<spec::P2> p(n_in > 0 ? n_in : 1), o(n_out);
+    for (int i = 0; i < n_in; ++i) p[i] = spec::P2{px[i], py[i]};
+    spec::mean_points(p.data(), n_in, o.data(), n_out);
+    for (int i = 0; i < n_out; ++i) { out_xy[i] = o[i].x; out_xy[n_out + i] = o[i].y; }
+}
+void oracle_sincos_deg(double a, double* c, double* s) { spec::spec_sincos_deg(a, c, s); }
+double oracle_atan(double z) { return spec::spec_atan(z); }
+double oracle_calc_global_dir(double ax, double ay, double bx, double by) {
+    return spec::calc_global_dir({ax, ay}, {bx, by}, 1e-6, 3.14159265358979323846);
+}
+double oracle_lat_dis(double qx, double qy, double ax, double ay, double bx, double by) {
+    return spec::lat_dis({qx, qy}, {ax, ay}, {bx, by}, 1e-6);
+}
+double oracle_calc_distance(double ax, double ay, double bx, double by) { return spec::calc_distance({ax, ay}, {bx, by}); }
+int oracle_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(dp_scene_hdr);
+        case 1: return (int)sizeof(dp_plan_record);
+        case 2: return (int)sizeof(dp_carry);
+        case 3: return (int)sizeof(ref_call);
+        case 4: return (int)sizeof(dp_trace_record);
+        case 5: return (int)sizeof(dp_params);
+        case 6: return (int)sizeof(dp_map_desc);
+    }
+    return -1;
+}
+}  // extern "C"
