@@ -54,7 +54,7 @@ trace_record = np.dtype(
         ("junction", search_slot), ("local", search_slot),
         ("width_curlane", "<f8"), ("faraim_dis", "<f8"),
         ("navi_lanechg", "<u4"), ("navi_lanechg_times", "<u4"),
-        ("refpath_len", "<u2"), ("ub_hits", "<u2"), ("pad", "u1", (4,)),
+        ("refpath_len", "<u2"), ("ub_hits", "<u2"), ("pts_scored", "<u4"),
     ]
 )
 assert trace_record.itemsize == 608

@@ -1,0 +1,445 @@
+// csrc/dp_api.cu -- host side of the C ABI declared in include/dmpp_b200.h.
+// Owns the device context: map tables (+ precomputed segment lengths / normals), per-scene
+// carry and last-path arrays, pinned staging for the host-pointer entry points, two streams so
+// that chunks of a large batch overlap H2D / kernel / D2H.  No CPU compute path exists here:
+// every entry point either launches the CUDA kernels or returns an error.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "dp_kernels.h"
+
+static_assert(sizeof(dp_scene_hdr) == 128, "dp_scene_hdr layout");
+static_assert(sizeof(dp_plan_record) == 128, "dp_plan_record layout");
+static_assert(sizeof(dp_carry) == 128, "dp_carry layout");
+static_assert(sizeof(dp_search_slot) == 24, "dp_search_slot layout");
+static_assert(sizeof(dp_trace_record) == 608, "dp_trace_record layout");
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(DP_ERR_CUDA, #call, e_); } while (0)
+
+const int kChunk = 32768;   // scenes per staged chunk of the host-pointer path
+}  // namespace
+
+struct dp_ctx {
+    int device = 0;
+    dp_params p;
+    int max_scenes = 0, max_obs = 0;
+    bool have_map = false;
+    DevMap map;
+    std::vector<void*> map_allocs;
+    dp_carry* d_carry = nullptr;
+    double* d_last = nullptr;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    // staging, two sets
+    int chunk = 0;
+    dp_scene_hdr* d_hdr[2] = {nullptr, nullptr};  dp_scene_hdr* h_hdr[2] = {nullptr, nullptr};
+    double* d_ox[2] = {nullptr, nullptr};         double* h_ox[2] = {nullptr, nullptr};
+    double* d_oy[2] = {nullptr, nullptr};         double* h_oy[2] = {nullptr, nullptr};
+    dp_plan_record* d_rec[2] = {nullptr, nullptr}; dp_plan_record* h_rec[2] = {nullptr, nullptr};
+    dp_trace_record* d_trace[2] = {nullptr, nullptr};
+    double* d_pxy[2] = {nullptr, nullptr};
+    double* d_pll[2] = {nullptr, nullptr};
+    long long launches = 0;
+};
+
+namespace {
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+template <class T> int dev_alloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(DP_ERR_NOMEM, "cudaMalloc", e);
+    return DP_OK;
+}
+int ensure_optional(dp_ctx* c, int which) {   // 0 trace, 1 path_xy, 2 path_ll: allocated on first use
+    for (int s = 0; s < 2; ++s) {
+        if (which == 0 && !c->d_trace[s]) { int r = dev_alloc(&c->d_trace[s], (size_t)c->chunk); if (r) return r; }
+        if (which == 1 && !c->d_pxy[s]) { int r = dev_alloc(&c->d_pxy[s], (size_t)c->chunk * 400); if (r) return r; }
+        if (which == 2 && !c->d_pll[s]) { int r = dev_alloc(&c->d_pll[s], (size_t)c->chunk * 200); if (r) return r; }
+    }
+    return DP_OK;
+}
+}  // namespace
+
+namespace {
+struct Tmp {
+    std::vector<void*> v;
+    ~Tmp() { for (void* p : v) cudaFree(p); }
+    template <class T> T* put(const T* src, size_t n, cudaError_t& e) {
+        T* d = nullptr;
+        e = cudaMalloc((void**)&d, (n ? n : 1) * sizeof(T));
+        if (e != cudaSuccess) return nullptr;
+        v.push_back(d);
+        if (src && n) e = cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice);
+        return d;
+    }
+};
+#define PUT(var, T, src, n) T* var = tmp.put<T>(src, n, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "operator staging", e)
+}  // namespace
+
+extern "C" {
+
+const char* dp_last_error(void) { return g_err.c_str(); }
+
+void dp_default_params(dp_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->vehicle_width = 1.8; p->epsilon = 1e-6; p->pi = 3.14159265358979323846;
+    p->road_faraim_max = 60; p->road_faraim_min = 15; p->pre_inter_faraim = 20; p->inter_faraim = 15;
+    p->road_remain_distance = 15; p->inter_remain_distance = 5;
+    p->lat0 = 23.0; p->lng0 = 113.0; p->k_lat = 1.0 / 110574.0; p->k_lng = 1.0 / 102470.0;
+    p->id_more = 8;
+}
+
+int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes, int max_obs) {
+    if (!out || max_scenes <= 0 || max_obs <= 0 || max_obs > 65535) return fail(DP_ERR_ARG, "dp_create: bad argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(DP_ERR_CUDA, "dp_create: no CUDA device (this library has no CPU path)", e);
+    if (device < 0 || device >= ndev) return fail(DP_ERR_ARG, "dp_create: device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(DP_ERR_CUDA, "dp_create: device is not sm_100-class (kernels are built for sm_100a only)");
+    dp_ctx* c = new dp_ctx();
+    c->device = device;
+    if (params) c->p = *params; else dp_default_params(&c->p);
+    c->max_scenes = max_scenes; c->max_obs = max_obs;
+    c->chunk = max_scenes < kChunk ? max_scenes : kChunk;
+    int r;
+    if ((r = dev_alloc(&c->d_carry, (size_t)max_scenes))) { delete c; return r; }
+    if ((r = dev_alloc(&c->d_last, (size_t)max_scenes * 400))) { delete c; return r; }
+    for (int s = 0; s < 2; ++s) {
+        CK(cudaStreamCreateWithFlags(&c->st[s], cudaStreamNonBlocking));
+        if ((r = dev_alloc(&c->d_hdr[s], (size_t)c->chunk))) return r;
+        if ((r = dev_alloc(&c->d_ox[s], (size_t)c->chunk * max_obs))) return r;
+        if ((r = dev_alloc(&c->d_oy[s], (size_t)c->chunk * max_obs))) return r;
+        if ((r = dev_alloc(&c->d_rec[s], (size_t)c->chunk))) return r;
+        CK(cudaMallocHost((void**)&c->h_hdr[s], (size_t)c->chunk * sizeof(dp_scene_hdr)));
+        CK(cudaMallocHost((void**)&c->h_ox[s], (size_t)c->chunk * max_obs * sizeof(double)));
+        CK(cudaMallocHost((void**)&c->h_oy[s], (size_t)c->chunk * max_obs * sizeof(double)));
+        CK(cudaMallocHost((void**)&c->h_rec[s], (size_t)c->chunk * sizeof(dp_plan_record)));
+    }
+    *out = c;
+    return dp_reset(c, 0, max_scenes);
+}
+
+int dp_destroy(dp_ctx* c) {
+    if (!c) return DP_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->map_allocs) cudaFree(p);
+    cudaFree(c->d_carry); cudaFree(c->d_last);
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(c->d_hdr[s]); cudaFree(c->d_ox[s]); cudaFree(c->d_oy[s]); cudaFree(c->d_rec[s]);
+        cudaFree(c->d_trace[s]); cudaFree(c->d_pxy[s]); cudaFree(c->d_pll[s]);
+        cudaFreeHost(c->h_hdr[s]); cudaFreeHost(c->h_ox[s]); cudaFreeHost(c->h_oy[s]); cudaFreeHost(c->h_rec[s]);
+        if (c->st[s]) cudaStreamDestroy(c->st[s]);
+    }
+    delete c;
+    return DP_OK;
+}
+
+int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
+    if (!c || !m || m->n_roads <= 0 || m->n_lanes <= 0 || m->n_points <= 0) return fail(DP_ERR_ARG, "dp_map_upload: bad argument");
+    CK(cudaSetDevice(c->device));
+    for (void* p : c->map_allocs) cudaFree(p);
+    c->map_allocs.clear();
+    auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 8);
+        if (e != cudaSuccess) return fail(DP_ERR_NOMEM, "cudaMalloc(map)", e);
+        c->map_allocs.push_back(*dst);
+        if (src && bytes) { e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "cudaMemcpy(map)", e); }
+        return DP_OK;
+    };
+    const size_t np = (size_t)m->n_points;
+    DevMap d;
+    int r;
+    if ((r = up(m->x, np * 8, (void**)&d.x))) return r;
+    if ((r = up(m->y, np * 8, (void**)&d.y))) return r;
+    if ((r = up(m->dir, np * 8, (void**)&d.dir))) return r;
+    if ((r = up(nullptr, np * 8, (void**)&d.nx))) return r;
+    if ((r = up(nullptr, np * 8, (void**)&d.ny))) return r;
+    if ((r = up(nullptr, np * 8, (void**)&d.lenp))) return r;
+    if ((r = up(m->lane_width, np * 2, (void**)&d.width))) return r;
+    if ((r = up(m->lanechg_attr, np * 2, (void**)&d.attr))) return r;
+    if ((r = up(m->road_lane_base, (size_t)(m->n_roads + 1) * 4, (void**)&d.road_lane_base))) return r;
+    if ((r = up(m->lane_pt_off, (size_t)(m->n_lanes + 1) * 4, (void**)&d.lane_pt_off))) return r;
+    if ((r = up(m->conn, (size_t)m->n_conn * sizeof(dp_connector), (void**)&d.conn))) return r;
+    d.n_roads = m->n_roads; d.n_lanes = m->n_lanes; d.n_conn = m->n_conn;
+    CK(dp_launch_map_prep(d.x, d.y, d.lane_pt_off, d.n_lanes, (double*)d.nx, (double*)d.ny, (double*)d.lenp, c->st[0]));
+    ++c->launches;
+    CK(cudaStreamSynchronize(c->st[0]));
+    c->map = d;
+    c->have_map = true;
+    return DP_OK;
+}
+
+int dp_reset(dp_ctx* c, int first, int count) {
+    if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_reset: range");
+    CK(cudaSetDevice(c->device));
+    CK(dp_launch_reset(c->d_carry, c->d_last, first, count, c->st[0]));
+    ++c->launches;
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+
+int dp_carry_download(dp_ctx* c, int first, int count, dp_carry* hc, double* hl) {
+    if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_carry_download: range");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    if (hc) CK(cudaMemcpy(hc, c->d_carry + first, (size_t)count * sizeof(dp_carry), cudaMemcpyDeviceToHost));
+    if (hl) CK(cudaMemcpy(hl, c->d_last + (size_t)first * 400, (size_t)count * 400 * 8, cudaMemcpyDeviceToHost));
+    return DP_OK;
+}
+int dp_carry_upload(dp_ctx* c, int first, int count, const dp_carry* hc, const double* hl) {
+    if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_carry_upload: range");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    if (hc) CK(cudaMemcpy(c->d_carry + first, hc, (size_t)count * sizeof(dp_carry), cudaMemcpyHostToDevice));
+    if (hl) CK(cudaMemcpy(c->d_last + (size_t)first * 400, hl, (size_t)count * 400 * 8, cudaMemcpyHostToDevice));
+    return DP_OK;
+}
+
+int dp_cycle_batch_dev(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec,
+                       dp_trace_record* trace, double* path_xy, double* path_ll, void* stream) {
+    if (!c || !hdr || !ox || !oy || !rec || n < 0 || first < 0 || first + n > c->max_scenes) return fail(DP_ERR_ARG, "dp_cycle_batch_dev: bad argument");
+    if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_batch_dev: map not uploaded");
+    CK(cudaSetDevice(c->device));
+    CK(dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * 400, rec, trace, path_xy,
+                       path_ll, (cudaStream_t)stream));
+    ++c->launches;
+    return DP_OK;
+}
+
+int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec,
+                   dp_trace_record* trace, double* path_xy, double* path_ll) {
+    if (!c || !hdr || !ox || !oy || !rec || n < 0 || first < 0 || first + n > c->max_scenes) return fail(DP_ERR_ARG, "dp_cycle_batch: bad argument");
+    if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_batch: map not uploaded");
+    CK(cudaSetDevice(c->device));
+    int r;
+    if (trace && (r = ensure_optional(c, 0))) return r;
+    if (path_xy && (r = ensure_optional(c, 1))) return r;
+    if (path_ll && (r = ensure_optional(c, 2))) return r;
+    const size_t mo = (size_t)c->max_obs;
+    const bool pin_in = is_pinned(hdr) && is_pinned(ox) && is_pinned(oy);
+    const bool pin_rec = is_pinned(rec);
+    int nchunks = (n + c->chunk - 1) / c->chunk;
+    for (int k = 0; k < nchunks; ++k) {
+        const int s = k & 1;
+        const int i0 = k * c->chunk, cn = (n - i0 < c->chunk) ? n - i0 : c->chunk;
+        cudaStream_t st = c->st[s];
+        if (k >= 2) {                                       // staging set s is being reused: drain its previous chunk
+            CK(cudaStreamSynchronize(st));
+            if (!pin_rec) memcpy(rec + (size_t)(k - 2) * c->chunk, c->h_rec[s], (size_t)c->chunk * sizeof(dp_plan_record));
+        }
+        const dp_scene_hdr* sh = hdr + i0; const double* sx = ox + i0 * mo; const double* sy = oy + i0 * mo;
+        if (!pin_in) {
+            memcpy(c->h_hdr[s], sh, (size_t)cn * sizeof(dp_scene_hdr));
+            memcpy(c->h_ox[s], sx, (size_t)cn * mo * 8);
+            memcpy(c->h_oy[s], sy, (size_t)cn * mo * 8);
+            sh = c->h_hdr[s]; sx = c->h_ox[s]; sy = c->h_oy[s];
+        }
+        CK(cudaMemcpyAsync(c->d_hdr[s], sh, (size_t)cn * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_ox[s], sx, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(c->d_oy[s], sy, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
+        CK(dp_launch_cycle(c->map, c->p, cn, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first + i0,
+                           c->d_last + (size_t)(first + i0) * 400, c->d_rec[s], trace ? c->d_trace[s] : nullptr,
+                           path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st));
+        ++c->launches;
+        CK(cudaMemcpyAsync(pin_rec ? rec + i0 : c->h_rec[s], c->d_rec[s], (size_t)cn * sizeof(dp_plan_record), cudaMemcpyDeviceToHost, st));
+        if (trace) CK(cudaMemcpyAsync(trace + i0, c->d_trace[s], (size_t)cn * sizeof(dp_trace_record), cudaMemcpyDeviceToHost, st));
+        if (path_xy) CK(cudaMemcpyAsync(path_xy + (size_t)i0 * 400, c->d_pxy[s], (size_t)cn * 400 * 8, cudaMemcpyDeviceToHost, st));
+        if (path_ll) CK(cudaMemcpyAsync(path_ll + (size_t)i0 * 200, c->d_pll[s], (size_t)cn * 200 * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int k = (nchunks >= 2 ? nchunks - 2 : 0); k < nchunks; ++k) {
+        const int s = k & 1;
+        const int i0 = k * c->chunk, cn = (n - i0 < c->chunk) ? n - i0 : c->chunk;
+        CK(cudaStreamSynchronize(c->st[s]));
+        if (!pin_rec) memcpy(rec + i0, c->h_rec[s], (size_t)cn * sizeof(dp_plan_record));
+    }
+    return DP_OK;
+}
+
+int dp_host_alloc(void** p, size_t bytes) {
+    if (!p) return fail(DP_ERR_ARG, "dp_host_alloc");
+    cudaError_t e = cudaMallocHost(p, bytes ? bytes : 8);
+    if (e != cudaSuccess) return fail(DP_ERR_NOMEM, "cudaMallocHost", e);
+    return DP_OK;
+}
+int dp_host_free(void* p) { if (p) cudaFreeHost(p); return DP_OK; }
+
+// ---- operator-level entry points: host buffers in, host buffers out ----
+
+int dp_search_obstacle(dp_ctx* c, int n_paths, const int32_t* path_off, const double* px, const double* py, const double* ox,
+                       const double* oy, int n_obs, const double* lat_min, const double* lat_max, dp_search_slot* out) {
+    if (!c || n_paths < 0 || !path_off || !lat_min || !lat_max || !out || n_obs < 0 || n_obs > 65535) return fail(DP_ERR_ARG, "dp_search_obstacle: bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t np = (size_t)path_off[n_paths];
+    for (int i = 0; i < n_paths; ++i) if (path_off[i + 1] - path_off[i] > 65535) return fail(DP_ERR_ARG, "dp_search_obstacle: path longer than 65535 points");
+    Tmp tmp; cudaError_t e;
+    PUT(d_off, int32_t, path_off, (size_t)n_paths + 1);
+    PUT(d_px, double, px, np); PUT(d_py, double, py, np);
+    PUT(d_ox, double, ox, (size_t)n_obs); PUT(d_oy, double, oy, (size_t)n_obs);
+    PUT(d_lo, double, lat_min, (size_t)n_paths); PUT(d_hi, double, lat_max, (size_t)n_paths);
+    PUT(d_out, dp_search_slot, (const dp_search_slot*)nullptr, (size_t)n_paths);
+    CK(dp_launch_search(n_paths, d_off, d_px, d_py, d_ox, d_oy, n_obs, d_lo, d_hi, d_out, c->st[0]));
+    ++c->launches;
+    CK(cudaMemcpyAsync(out, d_out, (size_t)n_paths * sizeof(dp_search_slot), cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+
+int dp_create_new_path(dp_ctx* c, int n_paths, const int32_t* path_off, const double* px, const double* py, const double* offset,
+                       double* out_x, double* out_y) {
+    if (!c || n_paths < 0 || !path_off || !offset || !out_x || !out_y) return fail(DP_ERR_ARG, "dp_create_new_path: bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t np = (size_t)path_off[n_paths];
+    Tmp tmp; cudaError_t e;
+    PUT(d_off, int32_t, path_off, (size_t)n_paths + 1);
+    PUT(d_px, double, px, np); PUT(d_py, double, py, np);
+    PUT(d_d, double, offset, (size_t)n_paths);
+    PUT(d_x, double, (const double*)nullptr, np); PUT(d_y, double, (const double*)nullptr, np);
+    CK(dp_launch_create(n_paths, d_off, d_px, d_py, d_d, d_x, d_y, c->st[0]));
+    ++c->launches;
+    CK(cudaMemcpyAsync(out_x, d_x, np * 8, cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaMemcpyAsync(out_y, d_y, np * 8, cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+
+int dp_bezier_planning(dp_ctx* c, int n, const double* poses, double* out_xy) {
+    if (!c || n < 0 || !poses || !out_xy) return fail(DP_ERR_ARG, "dp_bezier_planning: bad argument");
+    CK(cudaSetDevice(c->device));
+    Tmp tmp; cudaError_t e;
+    PUT(d_p, double, poses, (size_t)n * 6);
+    PUT(d_o, double, (const double*)nullptr, (size_t)n * 400);
+    CK(dp_launch_bezier(n, d_p, d_o, c->st[0]));
+    ++c->launches;
+    CK(cudaMemcpyAsync(out_xy, d_o, (size_t)n * 400 * 8, cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+
+int dp_mean_points(dp_ctx* c, int n_paths, const int32_t* path_off, const double* px, const double* py, double* out_xy) {
+    if (!c || n_paths < 0 || !path_off || !out_xy) return fail(DP_ERR_ARG, "dp_mean_points: bad argument");
+    for (int i = 0; i < n_paths; ++i) if (path_off[i + 1] - path_off[i] > DP_SCR) return fail(DP_ERR_ARG, "dp_mean_points: more than 256 input points (reference limit is 200, Planning.cpp:851)");
+    CK(cudaSetDevice(c->device));
+    const size_t np = (size_t)path_off[n_paths];
+    Tmp tmp; cudaError_t e;
+    PUT(d_off, int32_t, path_off, (size_t)n_paths + 1);
+    PUT(d_px, double, px, np); PUT(d_py, double, py, np);
+    PUT(d_o, double, (const double*)nullptr, (size_t)n_paths * 400);
+    CK(dp_launch_mean(n_paths, d_off, d_px, d_py, d_o, c->st[0]));
+    ++c->launches;
+    CK(cudaMemcpyAsync(out_xy, d_o, (size_t)n_paths * 400 * 8, cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+
+int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
+                        int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min,
+                        double lat_max, double clear_dis, int32_t* best_index, double* best_dis_lng, double* out_dis_lng) {
+    if (!c || !base_x || !base_y || n_base < 2 || n_base > 256 || !offset || !n_pts || n_cand <= 0 || n_obs < 0 || n_obs > 256 || !best_index)
+        return fail(DP_ERR_ARG, "dp_score_candidates: bad argument (n_base in [2,256], n_obs <= 256)");
+    CK(cudaSetDevice(c->device));
+    Tmp tmp; cudaError_t e;
+    PUT(d_bx, double, base_x, (size_t)n_base); PUT(d_by, double, base_y, (size_t)n_base);
+    PUT(d_off, double, offset, (size_t)n_cand); PUT(d_np, int32_t, n_pts, (size_t)n_cand);
+    PUT(d_ox, double, ox, (size_t)n_obs); PUT(d_oy, double, oy, (size_t)n_obs);
+    double* d_vx = nullptr; double* d_vy = nullptr;
+    if (dvx && dvy) { d_vx = tmp.put<double>(dvx, (size_t)n_obs, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "staging", e);
+                      d_vy = tmp.put<double>(dvy, (size_t)n_obs, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "staging", e); }
+    PUT(d_dis, double, (const double*)nullptr, (size_t)n_cand);
+    PUT(d_key, unsigned long long, (const unsigned long long*)nullptr, 1);
+    CK(cudaMemsetAsync(d_key, 0xff, 8, c->st[0]));
+    CK(dp_launch_sweep(d_bx, d_by, n_base, d_off, d_np, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs, lat_min, lat_max, clear_dis, d_dis, d_key, c->st[0]));
+    ++c->launches;
+    unsigned long long key = ~0ull;
+    CK(cudaMemcpyAsync(&key, d_key, 8, cudaMemcpyDeviceToHost, c->st[0]));
+    std::vector<double> dis;
+    if (out_dis_lng) CK(cudaMemcpyAsync(out_dis_lng, d_dis, (size_t)n_cand * 8, cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    const bool feasible = (key >> 32) == 0;
+    *best_index = feasible ? (int32_t)(key & 0xffffffffu) : -1;
+    if (best_dis_lng) {
+        *best_dis_lng = DP_NOT_FOUND;
+        if (feasible) CK(cudaMemcpy(best_dis_lng, d_dis + *best_index, 8, cudaMemcpyDeviceToHost));
+    }
+    return DP_OK;
+}
+
+int dp_measure_fma_peak(dp_ctx* c, double* fp64_tflops, double* fp32_tflops) {
+    if (!c) return fail(DP_ERR_ARG, "dp_measure_fma_peak");
+    CK(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    float* sink = nullptr;
+    CK(cudaMalloc((void**)&sink, 64));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    double out[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaEventRecord(a, c->st[0]));
+            CK(dp_launch_fma_peak(which, sink, iters, blocks, c->st[0]));
+            ++c->launches;
+            CK(cudaEventRecord(b, c->st[0]));
+            CK(cudaEventSynchronize(b));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, a, b));
+            const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;   // 64 fma per iteration per thread
+            const double tf = flops / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best) best = tf;
+        }
+        out[which] = best;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    if (fp64_tflops) *fp64_tflops = out[0];
+    if (fp32_tflops) *fp32_tflops = out[1];
+    return DP_OK;
+}
+
+int64_t dp_launch_count(dp_ctx* c) { return c ? c->launches : 0; }
+
+int dp_dev_alloc(dp_ctx* c, void** p, size_t bytes) {
+    if (!c || !p) return fail(DP_ERR_ARG, "dp_dev_alloc");
+    CK(cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);
+    if (e != cudaSuccess) return fail(DP_ERR_NOMEM, "cudaMalloc", e);
+    return DP_OK;
+}
+int dp_dev_free(dp_ctx* c, void* p) { if (c && p) { cudaSetDevice(c->device); cudaFree(p); } return DP_OK; }
+int dp_memcpy_h2d(dp_ctx* c, void* dst, const void* src, size_t bytes, void* stream) {
+    if (!c) return fail(DP_ERR_ARG, "dp_memcpy_h2d");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return DP_OK;
+}
+int dp_memcpy_d2h(dp_ctx* c, void* dst, const void* src, size_t bytes, void* stream) {
+    if (!c) return fail(DP_ERR_ARG, "dp_memcpy_d2h");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return DP_OK;
+}
+int dp_stream_sync(dp_ctx* c, void* stream) {
+    if (!c) return fail(DP_ERR_ARG, "dp_stream_sync");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return DP_OK;
+}
+
+}  // extern "C"

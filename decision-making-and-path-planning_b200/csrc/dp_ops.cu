@@ -1,0 +1,257 @@
+// csrc/dp_ops.cu -- operator-level kernels behind the CShare seam, the
+// dense candidate sweep of BASELINE config 3, and the FMA micro-benchmark that provides the
+// roofline denominator (MEASURED_PEAKS.json has no FP64/FP32 CUDA-core figure).
+#include "dp_device.cuh"
+#include "dp_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ DevMap null_map() {
+    DevMap m;
+    m.x = m.y = m.dir = m.nx = m.ny = m.lenp = nullptr; m.width = m.attr = nullptr;
+    m.road_lane_base = m.lane_pt_off = nullptr; m.conn = nullptr; m.n_roads = m.n_lanes = m.n_conn = 0;
+    return m;
+}
+__device__ __forceinline__ PathSrc global_path(const double* gx, const double* gy, int P, double d) {
+    PathSrc s;
+    s.kind = 2; s.P = P; s.base0 = s.n0 = s.base1 = s.s0 = 0; s.step0 = 1; s.d = d; s.gx = gx; s.gy = gy;
+    return s;
+}
+
+// CShare::SearchObstacle, one warp per path
+__global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32)
+op_search_kernel(int n_paths, const int32_t* __restrict__ path_off, const double* __restrict__ px, const double* __restrict__ py,
+                 const double* __restrict__ ox, const double* __restrict__ oy, int n_obs, const double* __restrict__ lat_min,
+                 const double* __restrict__ lat_max, dp_search_slot* __restrict__ out) {
+    __shared__ WarpSmem smem[DP_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pid = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
+    if (pid >= n_paths) return;
+    const int off = path_off[pid], P = path_off[pid + 1] - off;
+    const DevMap m = null_map();
+    const PathSrc s = global_path(px + off, py + off, P, 0.0);
+    const SearchRes r = dp_search_path(m, smem[wib], s, ox, oy, n_obs, lat_min[pid], lat_max[pid], lane);
+    if (lane == 0) {
+        dp_search_slot o;
+        o.dis_lat = r.dis_lat; o.dis_lng = r.dis_lng; o.ob_index = (int16_t)r.ob; o.pathid = (uint16_t)r.pathid;
+        o.evaluated = 1; o.found = r.found; o.pad[0] = o.pad[1] = 0;
+        out[pid] = o;
+    }
+}
+
+// CShare::CreateNewPath, one warp per path
+__global__ void op_create_kernel(int n_paths, const int32_t* __restrict__ path_off, const double* __restrict__ px,
+                                 const double* __restrict__ py, const double* __restrict__ offset, double* __restrict__ out_x,
+                                 double* __restrict__ out_y) {
+    const int lane = threadIdx.x & 31;
+    const int pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pid >= n_paths) return;
+    const int off = path_off[pid], P = path_off[pid + 1] - off;
+    const double d = offset[pid];
+    const double* gx = px + off; const double* gy = py + off;
+    for (int j = lane; j < P; j += 32) {
+        double x = gx[j], y = gy[j];
+        if (P >= 2) {                                       // unconditional fma, as the specification
+            const int k = (j == P - 1) ? P - 2 : j;
+            const double2 n = dp_normal(make_double2(gx[k], gy[k]), make_double2(gx[k + 1], gy[k + 1]));
+            x = fma(d, n.x, x); y = fma(d, n.y, y);
+        }
+        out_x[off + j] = x; out_y[off + j] = y;
+    }
+}
+
+// CShare::BezierPlanning, one warp per pose pair
+__global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32)
+op_bezier_kernel(int n, const double* __restrict__ poses, double* __restrict__ out_xy) {
+    __shared__ WarpSmem smem[DP_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pid = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
+    if (pid >= n) return;
+    const double* q = poses + (size_t)pid * 6;
+    dp_bezier_to_plan(smem[wib], q[0], q[1], q[2], q[3], q[4], q[5], lane);
+    for (int i = lane; i < DP_PATH_POINTS; i += 32) {
+        out_xy[(size_t)pid * 400 + i] = smem[wib].plan[i].x;
+        out_xy[(size_t)pid * 400 + DP_PATH_POINTS + i] = smem[wib].plan[i].y;
+    }
+}
+
+// CShare::MeanPoints, one warp per path (n_in <= DP_SCR checked by the host)
+__global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32)
+op_mean_kernel(int n_paths, const int32_t* __restrict__ path_off, const double* __restrict__ px, const double* __restrict__ py,
+               double* __restrict__ out_xy) {
+    __shared__ WarpSmem smem[DP_WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pid = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
+    if (pid >= n_paths) return;
+    const int off = path_off[pid], P = path_off[pid + 1] - off;
+    const DevMap m = null_map();
+    const PathSrc s = global_path(px + off, py + off, P, 0.0);
+    dp_mean_points_to_plan(m, smem[wib], s, P, lane);
+    for (int i = lane; i < DP_PATH_POINTS; i += 32) {
+        out_xy[(size_t)pid * 400 + i] = smem[wib].plan[i].x;
+        out_xy[(size_t)pid * 400 + DP_PATH_POINTS + i] = smem[wib].plan[i].y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense candidate sweep (BASELINE config 3): one warp per candidate, SWEEP_WARPS candidates per
+// block.  The base polyline and its segment normals are staged once per block in shared memory,
+// obstacle tracks (x, y, dvx, dvy) too; each warp materialises ITS candidate (offset copy of a
+// prefix of the base line) in its own shared-memory slab, then lanes = obstacles run the fused
+// rollout -> nearest-point -> corridor check; arclength is summed in index order.  Selection is
+// a packed (cost bits << 32 | candidate index) 64-bit atomicMin: feasible candidates have cost 0,
+// so the minimum is the LOWEST feasible index (the reference's first-feasible `break`,
+// Decision.cpp:944-953), deterministic whatever the launch geometry.
+// ------------------------------------------------------------------------------------------------
+#define SWEEP_WARPS 4
+#define SWEEP_MAX_BASE 256
+#define SWEEP_MAX_OBS 256
+
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, const double* __restrict__ offset,
+             const int32_t* __restrict__ n_pts, int n_cand, const double* __restrict__ ox, const double* __restrict__ oy,
+             const double* __restrict__ dvx, const double* __restrict__ dvy, int n_obs, double lat_min, double lat_max,
+             double clear_dis, double* __restrict__ cand_dis_lng, unsigned long long* __restrict__ best_key) {
+    __shared__ double2 s_base[SWEEP_MAX_BASE];
+    __shared__ double2 s_nrm[SWEEP_MAX_BASE];              // normal of segment j -> j+1
+    __shared__ double4 s_obs[SWEEP_MAX_OBS];
+    __shared__ double2 s_cand[SWEEP_WARPS][SWEEP_MAX_BASE];
+    __shared__ double s_len[SWEEP_WARPS][SWEEP_MAX_BASE];
+    __shared__ unsigned long long s_key[SWEEP_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int j = threadIdx.x; j < n_base; j += blockDim.x) s_base[j] = make_double2(base_x[j], base_y[j]);
+    for (int o = threadIdx.x; o < n_obs; o += blockDim.x) s_obs[o] = make_double4(ox[o], oy[o], dvx ? dvx[o] : 0.0, dvy ? dvy[o] : 0.0);
+    __syncthreads();
+    for (int j = threadIdx.x; j + 1 < n_base; j += blockDim.x) s_nrm[j] = dp_normal(s_base[j], s_base[j + 1]);
+    __syncthreads();
+
+    unsigned long long mykey = ~0ull;
+    for (int c = blockIdx.x * SWEEP_WARPS + wib; c < n_cand; c += gridDim.x * SWEEP_WARPS) {
+        const int P = min(n_pts[c], n_base);
+        const double off = offset[c];
+        double dis_lng = DP_NOT_FOUND;
+        if (P >= 2) {
+            double2* q = s_cand[wib];
+            for (int j = lane; j < P; j += 32) {           // rollout: offset copy, never leaves the SM
+                const double2 b = s_base[j], n = s_nrm[min(j, P - 2)];
+                q[j] = make_double2(fma(off, n.x, b.x), fma(off, n.y, b.y));
+            }
+            __syncwarp();
+            unsigned bestkey = 0xffffffffu;
+            for (int g = 0; g * 32 < n_obs; ++g) {
+                const int o = g * 32 + lane;
+                if (o < n_obs) {
+                    const double4 ob = s_obs[o];
+                    double bd = __longlong_as_double(0x7ff0000000000000LL);
+                    int bj = 0;
+                    double jd = 0.0;
+#pragma unroll 4
+                    for (int j = 0; j < P; ++j) {
+                        const double2 p = q[j];
+                        const double dx = fma(jd, ob.z, ob.x) - p.x, dy = fma(jd, ob.w, ob.y) - p.y;
+                        const double d2 = fma(dx, dx, dy * dy);
+                        if (d2 < bd) { bd = d2; bj = j; }
+                        jd += 1.0;
+                    }
+                    const double mx = fma((double)bj, ob.z, ob.x), my = fma((double)bj, ob.w, ob.y);
+                    const int k = (bj == P - 1) ? P - 2 : bj;
+                    const double2 pk = q[k], pk1 = q[k + 1];
+                    const double sx = pk1.x - pk.x, sy = pk1.y - pk.y;
+                    bool pass = true;
+                    if (bj == 0) pass = fma(mx - pk.x, sx, (my - pk.y) * sy) >= 0.0;
+                    else if (bj == P - 1) pass = fma(mx - pk1.x, sx, (my - pk1.y) * sy) <= 0.0;
+                    const double len = sqrt(dp_sq2(sx, sy));
+                    double d = 0.0;
+                    if (len > 0) d = fma(mx - pk.x, sy, -((my - pk.y) * sx)) / len;
+                    pass = pass && (d >= lat_min && d <= lat_max);
+                    const unsigned key = pass ? (((unsigned)bj << 16) | (unsigned)o) : 0xffffffffu;
+                    bestkey = min(bestkey, key);
+                }
+            }
+            const unsigned gmin = __reduce_min_sync(DP_FULL, bestkey);
+            if (gmin != 0xffffffffu) {
+                const int jstar = (int)(gmin >> 16);
+                for (int j = lane; j < jstar; j += 32) s_len[wib][j] = sqrt(dp_sq2(q[j + 1].x - q[j].x, q[j + 1].y - q[j].y));
+                __syncwarp();
+                double sum = 0.0;
+                for (int j = 0; j < jstar; ++j) sum += s_len[wib][j];
+                dis_lng = sum;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            cand_dis_lng[c] = dis_lng;
+            const float cost = (dis_lng > clear_dis) ? 0.0f : __int_as_float(0x7f800000);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)c;
+            mykey = min(mykey, key);
+        }
+    }
+    if (lane == 0) s_key[wib] = mykey;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long k = s_key[0];
+        for (int w = 1; w < SWEEP_WARPS; ++w) k = min(k, s_key[w]);
+        if (k != ~0ull) atomicMin(best_key, k);
+    }
+}
+
+// FMA micro-benchmark: 8 independent accumulator chains per thread
+template <typename T>
+__global__ void fma_peak_kernel(T* sink, int iters) {
+    T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3, a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6,
+      a7 = a0 + (T)7;
+    const T m = (T)0.999999, b = (T)1e-6;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    const T s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == (T)123456789) sink[0] = s;                    // never true: keeps the chains alive
+}
+
+}  // namespace
+
+cudaError_t dp_launch_search(int n_paths, const int32_t* path_off, const double* px, const double* py, const double* ox,
+                             const double* oy, int n_obs, const double* lat_min, const double* lat_max, dp_search_slot* out,
+                             cudaStream_t st) {
+    if (n_paths <= 0) return cudaSuccess;
+    op_search_kernel<<<(n_paths + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(
+        n_paths, path_off, px, py, ox, oy, n_obs, lat_min, lat_max, out);
+    return cudaGetLastError();
+}
+cudaError_t dp_launch_create(int n_paths, const int32_t* path_off, const double* px, const double* py, const double* offset,
+                             double* out_x, double* out_y, cudaStream_t st) {
+    if (n_paths <= 0) return cudaSuccess;
+    op_create_kernel<<<(n_paths * 32 + 127) / 128, 128, 0, st>>>(n_paths, path_off, px, py, offset, out_x, out_y);
+    return cudaGetLastError();
+}
+cudaError_t dp_launch_bezier(int n, const double* poses, double* out_xy, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    op_bezier_kernel<<<(n + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(n, poses, out_xy);
+    return cudaGetLastError();
+}
+cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double* px, const double* py, double* out_xy, cudaStream_t st) {
+    if (n_paths <= 0) return cudaSuccess;
+    op_mean_kernel<<<(n_paths + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(n_paths, path_off, px, py, out_xy);
+    return cudaGetLastError();
+}
+cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
+                            int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs,
+                            double lat_min, double lat_max, double clear_dis, double* cand_dis_lng, unsigned long long* best_key,
+                            cudaStream_t st) {
+    if (n_cand <= 0) return cudaSuccess;
+    int blocks = (n_cand + SWEEP_WARPS - 1) / SWEEP_WARPS;
+    const int cap = 148 * 4;                               // persistent-style: a few CTAs per SM, grid-stride over candidates
+    if (blocks > cap) blocks = cap;
+    sweep_kernel<<<blocks, SWEEP_WARPS * 32, 0, st>>>(base_x, base_y, n_base, offset, n_pts, n_cand, ox, oy, dvx, dvy, n_obs, lat_min,
+                                                      lat_max, clear_dis, cand_dis_lng, best_key);
+    return cudaGetLastError();
+}
+cudaError_t dp_launch_fma_peak(int which, float* sink, int iters, int blocks, cudaStream_t st) {
+    if (which == 0) fma_peak_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<double*>(sink), iters);
+    else fma_peak_kernel<float><<<blocks, 256, 0, st>>>(sink, iters);
+    return cudaGetLastError();
+}

@@ -1,0 +1,206 @@
+"""ctypes binding of libdmpp_b200.so (include/dmpp_b200.h) and the host-side mirror of the
+reference's Decision/Planning interface for batches of scenes.
+
+There is no CPU implementation behind this module: if the CUDA library is missing, or no
+sm_100-class device is usable, construction raises -- it never falls back.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_here = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_here, "libdmpp_b200.so")
+
+# every symbol include/dmpp_b200.h declares (tests/test_abi.py checks the export table against the header)
+SYMBOLS = [
+    "dp_last_error", "dp_default_params", "dp_create", "dp_destroy", "dp_map_upload", "dp_reset",
+    "dp_carry_download", "dp_carry_upload", "dp_cycle_batch_dev", "dp_cycle_batch", "dp_host_alloc",
+    "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
+    "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
+    "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync",
+]
+
+_lib = None
+
+
+def load():
+    """dlopen the product library (no CUDA call is made until dp_create)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.dp_last_error.restype = C.c_char_p
+        _lib.dp_launch_count.restype = C.c_int64
+        _lib.dp_launch_count.argtypes = [C.c_void_p]
+    return _lib
+
+
+class DpError(RuntimeError):
+    pass
+
+
+def _ck(rc, what):
+    if rc != 0:
+        raise DpError("%s failed (%d): %s" % (what, rc, load().dp_last_error().decode()))
+
+
+def default_params():
+    p = abi.Params()
+    load().dp_default_params(C.byref(p))
+    return p
+
+
+class Planner:
+    """Batched, explicit-state replacement for the CDecision + CPlanning singletons
+    (Decision.h:105-107, Planning.h:38-40): one `cycle()` call runs one iteration of
+    CDecisionThread followed by one of CPlanningThread for every scene of the batch."""
+
+    def __init__(self, max_scenes, max_obs, device=0, params=None):
+        self.lib = load()
+        self.max_scenes, self.max_obs, self.device = int(max_scenes), int(max_obs), int(device)
+        self.params = params if params is not None else default_params()
+        self.ctx = C.c_void_p()
+        _ck(self.lib.dp_create(C.byref(self.ctx), C.c_int(device), C.byref(self.params), C.c_int(self.max_scenes),
+                               C.c_int(self.max_obs)), "dp_create")
+        self._map = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.dp_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_map(self, m):
+        self._map = m
+        d = m.desc()
+        _ck(self.lib.dp_map_upload(self.ctx, C.byref(d)), "dp_map_upload")
+
+    def reset(self, first=0, count=None):
+        count = self.max_scenes - first if count is None else count
+        _ck(self.lib.dp_reset(self.ctx, C.c_int(first), C.c_int(count)), "dp_reset")
+
+    def launch_count(self):
+        return int(self.lib.dp_launch_count(self.ctx))
+
+    # ---- the drop-in call: host buffers in, host buffers out ---------------------------------
+    def cycle(self, hdr, ox, oy, first=0, trace=False, paths=False, out=None):
+        n = hdr.shape[0]
+        assert hdr.dtype == abi.scene_hdr and ox.shape == (n, self.max_obs) and oy.shape == (n, self.max_obs)
+        o = out if out is not None else {}
+        if "rec" not in o:
+            o["rec"] = np.zeros(n, abi.plan_record)
+        if trace and o.get("trace") is None:
+            o["trace"] = np.zeros(n, abi.trace_record)
+        if paths and o.get("path_xy") is None:
+            o["path_xy"] = np.zeros((n, 2, abi.PATH_POINTS))
+            o["path_ll"] = np.zeros((n, 2, abi.OUT_POINTS))
+        _ck(self.lib.dp_cycle_batch(self.ctx, C.c_int(first), C.c_int(n), abi.ptr(hdr), abi.ptr(ox), abi.ptr(oy),
+                                    abi.ptr(o["rec"]), abi.ptr(o.get("trace") if trace else None),
+                                    abi.ptr(o.get("path_xy") if paths else None),
+                                    abi.ptr(o.get("path_ll") if paths else None)), "dp_cycle_batch")
+        return o
+
+    def run_episodes(self, H, OX, OY, trace=True, paths=True):
+        """all cycles of [cycles][n] scripted episodes from a fresh carry; same layout as the oracle."""
+        cycles, n = H.shape
+        self.reset(0, n)
+        out = {"rec": np.zeros((cycles, n), abi.plan_record),
+               "trace": np.zeros((cycles, n), abi.trace_record) if trace else None,
+               "path_xy": np.zeros((cycles, n, 2, abi.PATH_POINTS)) if paths else None,
+               "path_ll": np.zeros((cycles, n, 2, abi.OUT_POINTS)) if paths else None}
+        for c in range(cycles):
+            o = {"rec": out["rec"][c], "trace": out["trace"][c] if trace else None,
+                 "path_xy": out["path_xy"][c] if paths else None, "path_ll": out["path_ll"][c] if paths else None}
+            self.cycle(np.ascontiguousarray(H[c]), np.ascontiguousarray(OX[c]), np.ascontiguousarray(OY[c]),
+                       trace=trace, paths=paths, out=o)
+        out["carry"], out["last_path"] = self.download_carry(0, n)
+        return out
+
+    def download_carry(self, first, count):
+        c = np.zeros(count, abi.carry)
+        lp = np.zeros((count, 2, abi.PATH_POINTS))
+        _ck(self.lib.dp_carry_download(self.ctx, C.c_int(first), C.c_int(count), abi.ptr(c), abi.ptr(lp)), "dp_carry_download")
+        return c, lp
+
+    def upload_carry(self, first, carry, last_path):
+        _ck(self.lib.dp_carry_upload(self.ctx, C.c_int(first), C.c_int(carry.shape[0]), abi.ptr(carry), abi.ptr(last_path)),
+            "dp_carry_upload")
+
+    # ---- device-pointer form (inputs resident in HBM; `stream` is a cudaStream_t value) ------
+    def cycle_dev(self, n, d_hdr, d_ox, d_oy, d_rec, first=0, d_trace=None, d_path_xy=None, d_path_ll=None, stream=0):
+        _ck(self.lib.dp_cycle_batch_dev(self.ctx, C.c_int(first), C.c_int(n), C.c_void_p(d_hdr), C.c_void_p(d_ox),
+                                        C.c_void_p(d_oy), C.c_void_p(d_rec), C.c_void_p(d_trace or 0),
+                                        C.c_void_p(d_path_xy or 0), C.c_void_p(d_path_ll or 0), C.c_void_p(stream)),
+            "dp_cycle_batch_dev")
+
+    # ---- operator level (the CShare seam) -----------------------------------------------------
+    def search_obstacle(self, paths, ox, oy, lat_min, lat_max):
+        """paths: list of (x[], y[]); one obstacle set; per-path windows."""
+        off = np.zeros(len(paths) + 1, np.int32)
+        off[1:] = np.cumsum([len(p[0]) for p in paths])
+        px = np.ascontiguousarray(np.concatenate([np.asarray(p[0], np.float64) for p in paths]) if paths else np.zeros(0))
+        py = np.ascontiguousarray(np.concatenate([np.asarray(p[1], np.float64) for p in paths]) if paths else np.zeros(0))
+        ox, oy = np.ascontiguousarray(ox, np.float64), np.ascontiguousarray(oy, np.float64)
+        lo = np.ascontiguousarray(np.broadcast_to(lat_min, len(paths)), np.float64)
+        hi = np.ascontiguousarray(np.broadcast_to(lat_max, len(paths)), np.float64)
+        out = np.zeros(len(paths), abi.search_slot)
+        _ck(self.lib.dp_search_obstacle(self.ctx, C.c_int(len(paths)), abi.ptr(off), abi.ptr(px), abi.ptr(py), abi.ptr(ox),
+                                        abi.ptr(oy), C.c_int(ox.size), abi.ptr(lo), abi.ptr(hi), abi.ptr(out)), "dp_search_obstacle")
+        return out
+
+    def create_new_path(self, paths, offsets):
+        off = np.zeros(len(paths) + 1, np.int32)
+        off[1:] = np.cumsum([len(p[0]) for p in paths])
+        px = np.ascontiguousarray(np.concatenate([np.asarray(p[0], np.float64) for p in paths]))
+        py = np.ascontiguousarray(np.concatenate([np.asarray(p[1], np.float64) for p in paths]))
+        d = np.ascontiguousarray(offsets, np.float64)
+        ox, oy = np.zeros_like(px), np.zeros_like(py)
+        _ck(self.lib.dp_create_new_path(self.ctx, C.c_int(len(paths)), abi.ptr(off), abi.ptr(px), abi.ptr(py), abi.ptr(d),
+                                        abi.ptr(ox), abi.ptr(oy)), "dp_create_new_path")
+        return [(ox[off[i]:off[i + 1]], oy[off[i]:off[i + 1]]) for i in range(len(paths))]
+
+    def bezier_planning(self, poses):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 6)
+        out = np.zeros((poses.shape[0], 2, abi.PATH_POINTS))
+        _ck(self.lib.dp_bezier_planning(self.ctx, C.c_int(poses.shape[0]), abi.ptr(poses), abi.ptr(out)), "dp_bezier_planning")
+        return out
+
+    def mean_points(self, paths):
+        off = np.zeros(len(paths) + 1, np.int32)
+        off[1:] = np.cumsum([len(p[0]) for p in paths])
+        px = np.ascontiguousarray(np.concatenate([np.asarray(p[0], np.float64) for p in paths]))
+        py = np.ascontiguousarray(np.concatenate([np.asarray(p[1], np.float64) for p in paths]))
+        out = np.zeros((len(paths), 2, abi.PATH_POINTS))
+        _ck(self.lib.dp_mean_points(self.ctx, C.c_int(len(paths)), abi.ptr(off), abi.ptr(px), abi.ptr(py), abi.ptr(out)), "dp_mean_points")
+        return out
+
+    def score_candidates(self, base_x, base_y, offset, n_pts, ox, oy, dvx=None, dvy=None, lat_min=-0.9, lat_max=0.9,
+                         clear_dis=25.0, want_all=True):
+        bx, by = np.ascontiguousarray(base_x, np.float64), np.ascontiguousarray(base_y, np.float64)
+        off = np.ascontiguousarray(offset, np.float64)
+        npt = np.ascontiguousarray(n_pts, np.int32)
+        ox, oy = np.ascontiguousarray(ox, np.float64), np.ascontiguousarray(oy, np.float64)
+        dvx = None if dvx is None else np.ascontiguousarray(dvx, np.float64)
+        dvy = None if dvy is None else np.ascontiguousarray(dvy, np.float64)
+        best = C.c_int32(-1)
+        best_d = C.c_double(0)
+        allv = np.zeros(off.size) if want_all else None
+        _ck(self.lib.dp_score_candidates(self.ctx, abi.ptr(bx), abi.ptr(by), C.c_int(bx.size), abi.ptr(off), abi.ptr(npt),
+                                         C.c_int(off.size), abi.ptr(ox), abi.ptr(oy), abi.ptr(dvx), abi.ptr(dvy), C.c_int(ox.size),
+                                         C.c_double(lat_min), C.c_double(lat_max), C.c_double(clear_dis), C.byref(best),
+                                         C.byref(best_d), abi.ptr(allv)), "dp_score_candidates")
+        return best.value, best_d.value, allv
+
+    def measure_fma_peak(self):
+        a, b = C.c_double(0), C.c_double(0)
+        _ck(self.lib.dp_measure_fma_peak(self.ctx, C.byref(a), C.byref(b)), "dp_measure_fma_peak")
+        return a.value, b.value

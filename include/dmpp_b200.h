@@ -128,7 +128,7 @@ typedef struct dp_trace_record {
     uint32_t navi_lanechg, navi_lanechg_times; /* Decision.cpp:268 */
     uint16_t refpath_len;
     uint16_t ub_hits;                /* reference undefined-behaviour sites hit this cycle (clamped) */
-    uint8_t pad[4];
+    uint32_t pts_scored;             /* sum of path points over the n_traj trajectories scored this cycle */
 } dp_trace_record;
 
 /* Cross-cycle state of one scene (SURVEY.md section 5 "checkpoint / resume"): the function

@@ -115,6 +115,21 @@ class Oracle(_Runner):
         self.lib.oracle_mean_points(abi.ptr(px), abi.ptr(py), C.c_int(px.size), abi.ptr(out), C.c_int(n_out))
         return out
 
+    def score_candidates(self, base_x, base_y, offset, n_pts, ox, oy, dvx=None, dvy=None, lat_min=-0.9, lat_max=0.9,
+                         clear_dis=25.0):
+        bx, by = np.ascontiguousarray(base_x, np.float64), np.ascontiguousarray(base_y, np.float64)
+        off = np.ascontiguousarray(offset, np.float64)
+        npt = np.ascontiguousarray(n_pts, np.int32)
+        ox, oy = np.ascontiguousarray(ox, np.float64), np.ascontiguousarray(oy, np.float64)
+        dvx = None if dvx is None else np.ascontiguousarray(dvx, np.float64)
+        dvy = None if dvy is None else np.ascontiguousarray(dvy, np.float64)
+        out = np.zeros(off.size)
+        best = self.lib.oracle_score_candidates(abi.ptr(bx), abi.ptr(by), C.c_int(bx.size), abi.ptr(off), abi.ptr(npt),
+                                                C.c_int(off.size), abi.ptr(ox), abi.ptr(oy), abi.ptr(dvx), abi.ptr(dvy),
+                                                C.c_int(ox.size), C.c_double(lat_min), C.c_double(lat_max),
+                                                C.c_double(clear_dis), abi.ptr(out))
+        return best, out
+
     def sincos_deg(self, a):
         c, s = C.c_double(0), C.c_double(0)
         self.lib.oracle_sincos_deg(C.c_double(a), C.byref(c), C.byref(s))

@@ -147,6 +147,42 @@ SearchResult search_obstacle(const P2* p, int P, const P2* obs, int N, double la
     return r;
 }
 
+SearchResult search_obstacle_tracks(const P2* p, int P, const P2* obs, const P2* dv, int N, double lat_min, double lat_max) {
+    SearchResult r{false, NOT_FOUND, NOT_FOUND, -1, 0};
+    if (P < 2) return r;
+    int best_j = P;
+    for (int o = 0; o < N; ++o) {
+        const double vx = dv ? dv[o].x : 0.0, vy = dv ? dv[o].y : 0.0;
+        double bd = 0; int bj = 0;
+        for (int j = 0; j < P; ++j) {
+            double ox = std::fma((double)j, vx, obs[o].x), oy = std::fma((double)j, vy, obs[o].y);
+            double d = sq2(ox - p[j].x, oy - p[j].y);
+            if (j == 0 || d < bd) { bd = d; bj = j; }
+        }
+        double ox = std::fma((double)bj, vx, obs[o].x), oy = std::fma((double)bj, vy, obs[o].y);
+        int k = (bj == P - 1) ? P - 2 : bj;
+        double sx = p[k + 1].x - p[k].x, sy = p[k + 1].y - p[k].y;
+        if (bj == 0) {
+            double dot = std::fma(ox - p[0].x, sx, (oy - p[0].y) * sy);
+            if (!(dot >= 0)) continue;
+        } else if (bj == P - 1) {
+            double dot = std::fma(ox - p[P - 1].x, sx, (oy - p[P - 1].y) * sy);
+            if (!(dot <= 0)) continue;
+        }
+        double len = std::sqrt(sq2(sx, sy));
+        double d = 0;
+        if (len > 0) d = std::fma(ox - p[k].x, sy, -((oy - p[k].y) * sx)) / len;
+        if (!(d >= lat_min && d <= lat_max)) continue;
+        if (bj < best_j) { best_j = bj; r.found = true; r.dis_lat = d; r.ob_index = o; r.pathid = bj; }
+    }
+    if (r.found) {
+        double s = 0;
+        for (int i = 0; i < r.pathid; ++i) s += std::sqrt(sq2(p[i + 1].x - p[i].x, p[i + 1].y - p[i].y));
+        r.dis_lng = s;
+    }
+    return r;
+}
+
 void create_new_path(const P2* p, int P, double d, P2* out) {
     if (P < 2) {
         for (int j = 0; j < P; ++j) out[j] = p[j];

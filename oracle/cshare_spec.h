@@ -84,6 +84,14 @@ double spec_atan(double z);
 SearchResult search_obstacle(const P2* path, int P, const P2* obs, int N,
                              double lat_min, double lat_max);
 
+// Generalisation of search_obstacle to predicted obstacle tracks (BASELINE config 3/5; the
+// reference itself has no prediction): obstacle o is at
+// ( fma(j, dv[o].x, obs[o].x), fma(j, dv[o].y, obs[o].y) ) when the ego reaches path point j.
+// Step 1 compares |o(j) - p_j|^2 over j; steps 2-5 use the obstacle position at j = j*.
+// dv == nullptr (or all zero) is exactly search_obstacle.
+SearchResult search_obstacle_tracks(const P2* path, int P, const P2* obs, const P2* dv, int N,
+                                    double lat_min, double lat_max);
+
 // CShare::CreateNewPath(path, d): lateral-offset copy, d > 0 shifts to the RIGHT of the direction
 // of travel (Decision.cpp:629 uses -W for the left lane, :942 -0.3*i for "left avoid").
 //   segment for point j: (j, j+1), last point reuses (P-2, P-1);

@@ -104,6 +104,26 @@ void oracle_mean_points(const double* px, const double* py, int n_in, double* ou
     spec::mean_points(p.data(), n_in, o.data(), n_out);
     for (int i = 0; i < n_out; ++i) { out_xy[i] = o[i].x; out_xy[n_out + i] = o[i].y; }
 }
+// dense candidate sweep (BASELINE config 3): CPU statement of dp_score_candidates
+int oracle_score_candidates(const double* bx, const double* by, int n_base, const double* offset, const int32_t* n_pts, int n_cand,
+                            const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs, double lo,
+                            double hi, double clear_dis, double* out_dis_lng) {
+    std::vector<spec::P2> base(n_base), cand(n_base), o(n_obs), dv(n_obs);
+    for (int i = 0; i < n_base; ++i) base[i] = spec::P2{bx[i], by[i]};
+    for (int i = 0; i < n_obs; ++i) { o[i] = spec::P2{ox[i], oy[i]}; dv[i] = spec::P2{dvx ? dvx[i] : 0.0, dvy ? dvy[i] : 0.0}; }
+    int best = -1;
+    for (int c = 0; c < n_cand; ++c) {
+        int P = n_pts[c] < n_base ? n_pts[c] : n_base;
+        double dis = spec::NOT_FOUND;
+        if (P >= 2) {
+            spec::create_new_path(base.data(), P, offset[c], cand.data());
+            dis = spec::search_obstacle_tracks(cand.data(), P, o.data(), dv.data(), n_obs, lo, hi).dis_lng;
+        }
+        if (out_dis_lng) out_dis_lng[c] = dis;
+        if (best < 0 && dis > clear_dis) best = c;      // first feasible == lowest feasible index
+    }
+    return best;
+}
 void oracle_sincos_deg(double a, double* c, double* s) { spec::spec_sincos_deg(a, c, s); }
 double oracle_atan(double z) { return spec::spec_atan(z); }
 double oracle_calc_global_dir(double ax, double ay, double bx, double by) {

@@ -31,6 +31,7 @@ struct Ctx {
     CycleOut& out;
     bool exhaustive;
     int n_traj = 0;
+    long pts = 0;
 };
 
 // one CShare::SearchObstacle evaluation + call log entry
@@ -45,6 +46,7 @@ spec::SearchResult search(Ctx& k, const Path& path, double lo, double hi, dp_sea
     }
     ++k.out.n_calls;
     ++k.n_traj;
+    k.pts += (long)path.size();
     if (slot) {
         slot->dis_lat = r.dis_lat; slot->dis_lng = r.dis_lng; slot->ob_index = (int16_t)r.ob_index;
         slot->pathid = (uint16_t)r.pathid; slot->evaluated = 1; slot->found = r.found;
@@ -73,7 +75,11 @@ void load_lane_paths(Ctx& k, int gl, int id, Path& fwd, Path& rear) {
     int a = std::min(n, id + more), b = std::min(n, id + 120 + more);
     for (int i = a; i < b; ++i) fwd.push_back(map_pt(k, gl, i));
     int lo = std::max(0, id + more - 40);
-    for (int i = a; i > lo; --i) rear.push_back(map_pt(k, gl, i));
+    // the reference starts this loop at index == size when id + ID_MORE >= size (out-of-range read,
+    // Decision.cpp:590-594); defined here as: start from the last valid point, same point count
+    int start = a;
+    if (start >= n) { start = n - 1; if (a > lo) ++k.out.ub_hits; }
+    for (int t = 0; t < a - lo; ++t) rear.push_back(map_pt(k, gl, start - t));
 }
 
 // Decision.cpp:1179-1187 and siblings: arclength from Id_CurLane while cond(attr[i+1])
@@ -655,7 +661,7 @@ void cycle(const MapView& m, const dp_params& p, const dp_scene_hdr& h, const do
     // ---- Planning thread iteration ----
     planning_cycle(k, st, refpath);
     r.n_traj = (uint16_t)k.n_traj;
-    if (out.trace) out.trace->ub_hits = (uint16_t)out.ub_hits;
+    if (out.trace) { out.trace->ub_hits = (uint16_t)out.ub_hits; out.trace->pts_scored = (uint32_t)k.pts; }
 }
 
 }  // namespace oracle
