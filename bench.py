@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Decision/Planning hot path (BASELINE.json metric:
+trajectories scored / s and plan cycles / s).
+
+Workload (BASELINE config 2): 4096 independent synthetic highway scenes per GPU, ego + 10
+vehicles, reference-derived default candidate set, 25-cycle scripted episodes.  One "step" = one
+fused Decision+Planning cycle for every scene of the batch (one launch of dp_cycle_kernel).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (one rank per GPU)
+  python bench.py --impl reference [...]                       the reference's own CPU code (oracle/_ref)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for how each number is obtained.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import dmpp_b200  # noqa: E402,F401
+from dmpp_b200 import abi, scenes  # noqa: E402
+
+SCENES = 4096
+N_OBS = 10
+EPISODE = 25
+METRIC = "trajectories_scored_per_s"
+UNIT = "trajectories/s"
+
+
+def workload_desc(world):
+    return {"workload": "config2: %d highway scenes/GPU x default candidate set (6 lane regions + 2K avoid offsets + 1 local path), "
+                        "ego + %d vehicles, %d-cycle scripted episodes" % (SCENES, N_OBS, EPISODE),
+            "scenes_per_gpu": SCENES, "obstacles": N_OBS, "episode_cycles": EPISODE,
+            "parallelism": "scenes sharded %d-way, no data-path collective; plan records all_gathered per step when N>1" % world,
+            "l2": "256 MiB buffer written between timed steps (L2 flush); inputs resident in HBM for `value`"}
+
+
+def alg_flops(pts, ntraj, n_obs):
+    """F(P,N) = 18 P + N (5 P + 12) summed over the trajectories actually scored."""
+    return 18.0 * pts + n_obs * (5.0 * pts + 12.0 * ntraj)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the UNMODIFIED reference (oracle/_ref/libref.so), one process per core
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _worker_init(seed0, n, cycles):
+    from oracle import binding
+    m = scenes.Map()
+    if binding.Reference.available():
+        r = binding.Reference(); kind = "reference"
+    else:
+        r = binding.Oracle(); kind = "port"
+    r.set_map(m)
+    ep = scenes.Episodes(m, np.arange(seed0, seed0 + n), cycles=cycles, n_obs=N_OBS)
+    _W.update(r=r, kind=kind, data=ep.all_cycles())
+    return kind
+
+
+def _worker_run(_):
+    H, OX, OY = _W["data"]
+    if _W["kind"] == "reference":
+        o = _W["r"].run(H, OX, OY, paths=False, calls=False)
+    else:
+        o = _W["r"].run(H, OX, OY, paths=False, calls=False, trace=False, exhaustive=False, threads=1)
+    return int(o["traj"]), float(o["seconds"]), int(H.size)
+
+
+class CpuArm:
+    """P worker processes, each owning a private copy of the (non re-entrant) reference and a scene slice."""
+
+    def __init__(self, total_scenes, cycles, procs):
+        import multiprocessing as mp
+        self.procs = procs
+        self.ctx = mp.get_context("spawn")
+        per = (total_scenes + procs - 1) // procs
+        self.pools = [self.ctx.Pool(1) for _ in range(procs)]
+        kinds = [p.apply_async(_worker_init, (10_000_000 + i * per, per, cycles)) for i, p in enumerate(self.pools)]
+        self.kind = kinds[0].get()
+        for k in kinds:
+            k.get()
+
+    def step(self):
+        t0 = time.perf_counter()
+        res = [p.apply_async(_worker_run, (0,)) for p in self.pools]
+        res = [r.get() for r in res]
+        dt = time.perf_counter() - t0
+        return sum(r[0] for r in res), dt, sum(r[2] for r in res)
+
+    def close(self):
+        for p in self.pools:
+            p.terminate()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = host_cores()
+    arm = CpuArm(SCENES, EPISODE, cores)
+    for _ in range(max(1, min(args.warmup, 2))):
+        arm.step()
+    traj = 0; secs = 0.0; cyc = 0
+    steps = max(1, min(args.steps, 20))
+    for _ in range(steps):
+        t, dt, c = arm.step()
+        traj += t; secs += dt; cyc += c
+    arm.close()
+    val = traj / secs
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": secs / cyc * SCENES * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_desc(1),
+            "plan_cycles_per_s": cyc / secs,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": arm.kind,
+                             "sample": "%d steps, each = %d scenes x %d cycles (whole episodes), one process per core running "
+                                       "the unmodified Decision.cpp/Planning.cpp objects" % (steps, SCENES, EPISODE)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "ms_per_step is normalised to one plan cycle of %d scenes" % SCENES}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.stop = False; self.sm = []; self.reasons = set(); self.max_sm = None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+            while not self.stop:
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.002)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add("sampler_error:%s" % type(e).__name__)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from dmpp_b200.planner import Planner
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, args.warmup
+    m = scenes.Map()
+    ep = scenes.Episodes(m, np.arange(rank * SCENES, (rank + 1) * SCENES), cycles=EPISODE, n_obs=N_OBS)
+    H, OX, OY = ep.all_cycles()
+    planner = Planner(max_scenes=SCENES, max_obs=N_OBS, device=local_rank)
+    planner.upload_map(m)
+
+    # ---- untimed replay with the trace on: trajectories and path points scored per cycle (deterministic) ----
+    rep = planner.run_episodes(H, OX, OY, trace=True, paths=False)
+    traj_c = rep["rec"]["n_traj"].astype(np.int64).sum(axis=1)
+    pts_c = rep["trace"]["pts_scored"].astype(np.int64).sum(axis=1)
+    flops_c = alg_flops(pts_c.astype(np.float64), traj_c.astype(np.float64), N_OBS)
+
+    # ---- inputs resident in HBM ----
+    d_hdr = torch.from_numpy(H.view(np.uint8).reshape(EPISODE, SCENES, 128)).to(dev)
+    d_ox = torch.from_numpy(OX).to(dev)
+    d_oy = torch.from_numpy(OY).to(dev)
+    d_rec = torch.empty((SCENES, 128), dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world * SCENES, 128), dtype=torch.uint8, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(W + K)]
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_loop(first, count):
+        for i in range(first, first + count):
+            c = i % EPISODE
+            if c == 0:
+                torch.cuda.synchronize()
+                planner.reset(0, SCENES)
+            flush.zero_()
+            ev[i][0].record(stream)
+            planner.cycle_dev(SCENES, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec.data_ptr(),
+                              stream=stream.cuda_stream)
+            ev[i][1].record(stream)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, d_rec)
+            ev[i][2].record(stream)
+
+    barrier()
+    dev_loop(0, W)
+    barrier()
+    l0 = planner.launch_count()
+    dev_loop(W, K)
+    barrier()
+    launches = planner.launch_count() - l0 - sum(1 for i in range(W, W + K) if i % EPISODE == 0)
+    kern_ms = np.array([ev[i][0].elapsed_time(ev[i][1]) for i in range(W, W + K)])
+    step_ms = np.array([ev[i][0].elapsed_time(ev[i][2]) for i in range(W, W + K)])
+    cyc_idx = np.array([i % EPISODE for i in range(W, W + K)])
+    total_ms = torch.tensor([step_ms.sum()], dtype=torch.float64, device=dev)
+    traj = torch.tensor([float(traj_c[cyc_idx].sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(traj, op=dist.ReduceOp.SUM)
+    total_s = float(total_ms.item()) * 1e-3
+    value = float(traj.item()) / total_s
+
+    # ---- end to end through the host-pointer C ABI: pinned host inputs, H2D + kernel + D2H every step ----
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
+    Hh = pin(H.view(np.uint8).reshape(EPISODE, SCENES, 128)).view(abi.scene_hdr).reshape(EPISODE, SCENES)
+    OXh, OYh = pin(OX), pin(OY)
+    rec_h = torch.empty((SCENES, 128), dtype=torch.uint8).pin_memory().numpy().view(abi.plan_record).reshape(SCENES)
+    out = {"rec": rec_h}
+    e2e_t = np.zeros(W + K)
+    barrier()
+    for i in range(W + K):
+        c = i % EPISODE
+        if c == 0:
+            planner.reset(0, SCENES)
+        if i == W:
+            barrier()
+        t0 = time.perf_counter()
+        planner.cycle(Hh[c], OXh[c], OYh[c], out=out)
+        e2e_t[i] = time.perf_counter() - t0
+    barrier()
+    e2e_s = torch.tensor([e2e_t[W:].sum()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = float(traj.item()) / float(e2e_s.item())
+    assert int(rec_h["n_traj"].astype(np.int64).sum()) == int(traj_c[(W + K - 1) % EPISODE]), "e2e result differs from replay"
+    sampler.stop = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fp64_tf, fp32_tf = planner.measure_fma_peak()
+    achieved = float(flops_c[cyc_idx].sum()) / (kern_ms.sum() * 1e-3) / 1e12
+    bytes_scene = 128 + N_OBS * 16 + 2 * 128 + 3200 + 128        # hdr + obstacles + carry r/w + last path read + record
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_desc(world),
+        "plan_cycles_per_s": world * SCENES * K / total_s,
+        "trajectories_per_step_per_gpu": float(traj_c[cyc_idx].mean()),
+        "e2e": {"value": e2e_val, "unit": UNIT,
+                "h2d_bytes_per_step": SCENES * (128 + 2 * N_OBS * 8), "d2h_bytes_per_step": SCENES * 128,
+                "ms_per_step": float(e2e_t[W:].mean() * 1e3), "plan_cycles_per_s": world * SCENES * K / float(e2e_s.item()),
+                "api": "dp_cycle_batch (host pointers, pinned)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "kernel": "dp_cycle_kernel", "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
+                     "frac": achieved / fp64_tf if fp64_tf else None, "traffic": None,
+                     "peak_source": "FP64 FMA micro-benchmark run in this process (dp_measure_fma_peak); MEASURED_PEAKS.json has no "
+                                    "CUDA-core FP64 figure. fp32 FMA peak measured the same way: %.1f TFLOP/s" % fp32_tf,
+                     "algorithmic_flops_per_launch": float(flops_c[cyc_idx].mean()),
+                     "kernel_ms": float(kern_ms.mean()),
+                     "hbm": {"achieved": SCENES * bytes_scene / (kern_ms.mean() * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "algorithmic_bytes_per_launch": SCENES * bytes_scene,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}},
+        "clocks": sampler.result(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cores = host_cores()
+            arm = CpuArm(SCENES, EPISODE, cores)
+            arm.step()
+            t_traj = 0; t_s = 0.0; n = 0
+            while t_s < 4.0 and n < 40:
+                t, dt, _ = arm.step()
+                t_traj += t; t_s += dt; n += 1
+            arm.close()
+            line["cpu_baseline"] = {"value": t_traj / t_s, "unit": UNIT, "cores": cores, "kind": arm.kind,
+                                    "sample": "%d passes over %d scenes x %d cycles, one process per core (unmodified reference "
+                                              "objects when kind=reference)" % (n, SCENES, EPISODE)}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    print(json.dumps(line))
+    planner.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

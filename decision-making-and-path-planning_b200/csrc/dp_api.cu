@@ -37,7 +37,7 @@ struct dp_ctx {
     DevMap map;
     std::vector<void*> map_allocs;
     dp_carry* d_carry = nullptr;
-    double* d_last = nullptr;
+    double2* d_last = nullptr;
     cudaStream_t st[2] = {nullptr, nullptr};
     // staging, two sets
     int chunk = 0;
@@ -85,6 +85,11 @@ struct Tmp {
         return d;
     }
 };
+std::vector<double2> interleave(const double* x, const double* y, size_t n) {
+    std::vector<double2> v(n ? n : 1);
+    for (size_t i = 0; i < n; ++i) v[i] = make_double2(x[i], y[i]);
+    return v;
+}
 #define PUT(var, T, src, n) T* var = tmp.put<T>(src, n, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "operator staging", e)
 }  // namespace
 
@@ -119,7 +124,7 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     c->chunk = max_scenes < kChunk ? max_scenes : kChunk;
     int r;
     if ((r = dev_alloc(&c->d_carry, (size_t)max_scenes))) { delete c; return r; }
-    if ((r = dev_alloc(&c->d_last, (size_t)max_scenes * 400))) { delete c; return r; }
+    if ((r = dev_alloc(&c->d_last, (size_t)max_scenes * DP_PATH_POINTS))) { delete c; return r; }
     for (int s = 0; s < 2; ++s) {
         CK(cudaStreamCreateWithFlags(&c->st[s], cudaStreamNonBlocking));
         if ((r = dev_alloc(&c->d_hdr[s], (size_t)c->chunk))) return r;
@@ -169,8 +174,8 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
     if ((r = up(m->x, np * 8, (void**)&d.x))) return r;
     if ((r = up(m->y, np * 8, (void**)&d.y))) return r;
     if ((r = up(m->dir, np * 8, (void**)&d.dir))) return r;
-    if ((r = up(nullptr, np * 8, (void**)&d.nx))) return r;
-    if ((r = up(nullptr, np * 8, (void**)&d.ny))) return r;
+    if ((r = up(nullptr, np * 16, (void**)&d.xy))) return r;
+    if ((r = up(nullptr, np * 16, (void**)&d.nrm))) return r;
     if ((r = up(nullptr, np * 8, (void**)&d.lenp))) return r;
     if ((r = up(m->lane_width, np * 2, (void**)&d.width))) return r;
     if ((r = up(m->lanechg_attr, np * 2, (void**)&d.attr))) return r;
@@ -178,7 +183,7 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
     if ((r = up(m->lane_pt_off, (size_t)(m->n_lanes + 1) * 4, (void**)&d.lane_pt_off))) return r;
     if ((r = up(m->conn, (size_t)m->n_conn * sizeof(dp_connector), (void**)&d.conn))) return r;
     d.n_roads = m->n_roads; d.n_lanes = m->n_lanes; d.n_conn = m->n_conn;
-    CK(dp_launch_map_prep(d.x, d.y, d.lane_pt_off, d.n_lanes, (double*)d.nx, (double*)d.ny, (double*)d.lenp, c->st[0]));
+    CK(dp_launch_map_prep(d.x, d.y, d.lane_pt_off, d.n_lanes, (double2*)d.xy, (double2*)d.nrm, (double*)d.lenp, c->st[0]));
     ++c->launches;
     CK(cudaStreamSynchronize(c->st[0]));
     c->map = d;
@@ -200,7 +205,15 @@ int dp_carry_download(dp_ctx* c, int first, int count, dp_carry* hc, double* hl)
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     if (hc) CK(cudaMemcpy(hc, c->d_carry + first, (size_t)count * sizeof(dp_carry), cudaMemcpyDeviceToHost));
-    if (hl) CK(cudaMemcpy(hl, c->d_last + (size_t)first * 400, (size_t)count * 400 * 8, cudaMemcpyDeviceToHost));
+    if (hl) {                                               // device keeps the path as [200] double2; the ABI layout is [2][200]
+        std::vector<double2> tmp((size_t)count * DP_PATH_POINTS);
+        CK(cudaMemcpy(tmp.data(), c->d_last + (size_t)first * DP_PATH_POINTS, tmp.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+        for (int s = 0; s < count; ++s)
+            for (int i = 0; i < DP_PATH_POINTS; ++i) {
+                hl[(size_t)s * 400 + i] = tmp[(size_t)s * DP_PATH_POINTS + i].x;
+                hl[(size_t)s * 400 + DP_PATH_POINTS + i] = tmp[(size_t)s * DP_PATH_POINTS + i].y;
+            }
+    }
     return DP_OK;
 }
 int dp_carry_upload(dp_ctx* c, int first, int count, const dp_carry* hc, const double* hl) {
@@ -208,7 +221,13 @@ int dp_carry_upload(dp_ctx* c, int first, int count, const dp_carry* hc, const d
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     if (hc) CK(cudaMemcpy(c->d_carry + first, hc, (size_t)count * sizeof(dp_carry), cudaMemcpyHostToDevice));
-    if (hl) CK(cudaMemcpy(c->d_last + (size_t)first * 400, hl, (size_t)count * 400 * 8, cudaMemcpyHostToDevice));
+    if (hl) {
+        std::vector<double2> tmp((size_t)count * DP_PATH_POINTS);
+        for (int s = 0; s < count; ++s)
+            for (int i = 0; i < DP_PATH_POINTS; ++i)
+                tmp[(size_t)s * DP_PATH_POINTS + i] = make_double2(hl[(size_t)s * 400 + i], hl[(size_t)s * 400 + DP_PATH_POINTS + i]);
+        CK(cudaMemcpy(c->d_last + (size_t)first * DP_PATH_POINTS, tmp.data(), tmp.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    }
     return DP_OK;
 }
 
@@ -217,7 +236,7 @@ int dp_cycle_batch_dev(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, con
     if (!c || !hdr || !ox || !oy || !rec || n < 0 || first < 0 || first + n > c->max_scenes) return fail(DP_ERR_ARG, "dp_cycle_batch_dev: bad argument");
     if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_batch_dev: map not uploaded");
     CK(cudaSetDevice(c->device));
-    CK(dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * 400, rec, trace, path_xy,
+    CK(dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace, path_xy,
                        path_ll, (cudaStream_t)stream));
     ++c->launches;
     return DP_OK;
@@ -255,7 +274,7 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         CK(cudaMemcpyAsync(c->d_ox[s], sx, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(c->d_oy[s], sy, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
         CK(dp_launch_cycle(c->map, c->p, cn, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first + i0,
-                           c->d_last + (size_t)(first + i0) * 400, c->d_rec[s], trace ? c->d_trace[s] : nullptr,
+                           c->d_last + (size_t)(first + i0) * DP_PATH_POINTS, c->d_rec[s], trace ? c->d_trace[s] : nullptr,
                            path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st));
         ++c->launches;
         CK(cudaMemcpyAsync(pin_rec ? rec + i0 : c->h_rec[s], c->d_rec[s], (size_t)cn * sizeof(dp_plan_record), cudaMemcpyDeviceToHost, st));
@@ -289,12 +308,13 @@ int dp_search_obstacle(dp_ctx* c, int n_paths, const int32_t* path_off, const do
     const size_t np = (size_t)path_off[n_paths];
     for (int i = 0; i < n_paths; ++i) if (path_off[i + 1] - path_off[i] > 65535) return fail(DP_ERR_ARG, "dp_search_obstacle: path longer than 65535 points");
     Tmp tmp; cudaError_t e;
+    std::vector<double2> hxy = interleave(px, py, np);
     PUT(d_off, int32_t, path_off, (size_t)n_paths + 1);
-    PUT(d_px, double, px, np); PUT(d_py, double, py, np);
+    PUT(d_pxy, double2, hxy.data(), np);
     PUT(d_ox, double, ox, (size_t)n_obs); PUT(d_oy, double, oy, (size_t)n_obs);
     PUT(d_lo, double, lat_min, (size_t)n_paths); PUT(d_hi, double, lat_max, (size_t)n_paths);
     PUT(d_out, dp_search_slot, (const dp_search_slot*)nullptr, (size_t)n_paths);
-    CK(dp_launch_search(n_paths, d_off, d_px, d_py, d_ox, d_oy, n_obs, d_lo, d_hi, d_out, c->st[0]));
+    CK(dp_launch_search(n_paths, d_off, d_pxy, d_ox, d_oy, n_obs, d_lo, d_hi, d_out, c->st[0]));
     ++c->launches;
     CK(cudaMemcpyAsync(out, d_out, (size_t)n_paths * sizeof(dp_search_slot), cudaMemcpyDeviceToHost, c->st[0]));
     CK(cudaStreamSynchronize(c->st[0]));
@@ -307,15 +327,16 @@ int dp_create_new_path(dp_ctx* c, int n_paths, const int32_t* path_off, const do
     CK(cudaSetDevice(c->device));
     const size_t np = (size_t)path_off[n_paths];
     Tmp tmp; cudaError_t e;
+    std::vector<double2> hxy = interleave(px, py, np);
     PUT(d_off, int32_t, path_off, (size_t)n_paths + 1);
-    PUT(d_px, double, px, np); PUT(d_py, double, py, np);
+    PUT(d_pxy, double2, hxy.data(), np);
     PUT(d_d, double, offset, (size_t)n_paths);
-    PUT(d_x, double, (const double*)nullptr, np); PUT(d_y, double, (const double*)nullptr, np);
-    CK(dp_launch_create(n_paths, d_off, d_px, d_py, d_d, d_x, d_y, c->st[0]));
+    PUT(d_o, double2, (const double2*)nullptr, np);
+    CK(dp_launch_create(n_paths, d_off, d_pxy, d_d, d_o, c->st[0]));
     ++c->launches;
-    CK(cudaMemcpyAsync(out_x, d_x, np * 8, cudaMemcpyDeviceToHost, c->st[0]));
-    CK(cudaMemcpyAsync(out_y, d_y, np * 8, cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaMemcpyAsync(hxy.data(), d_o, np * sizeof(double2), cudaMemcpyDeviceToHost, c->st[0]));
     CK(cudaStreamSynchronize(c->st[0]));
+    for (size_t i = 0; i < np; ++i) { out_x[i] = hxy[i].x; out_y[i] = hxy[i].y; }
     return DP_OK;
 }
 
@@ -334,14 +355,15 @@ int dp_bezier_planning(dp_ctx* c, int n, const double* poses, double* out_xy) {
 
 int dp_mean_points(dp_ctx* c, int n_paths, const int32_t* path_off, const double* px, const double* py, double* out_xy) {
     if (!c || n_paths < 0 || !path_off || !out_xy) return fail(DP_ERR_ARG, "dp_mean_points: bad argument");
-    for (int i = 0; i < n_paths; ++i) if (path_off[i + 1] - path_off[i] > DP_SCR) return fail(DP_ERR_ARG, "dp_mean_points: more than 256 input points (reference limit is 200, Planning.cpp:851)");
+    for (int i = 0; i < n_paths; ++i) if (path_off[i + 1] - path_off[i] > 2 * DP_TILE) return fail(DP_ERR_ARG, "dp_mean_points: more than 240 input points (reference limit is 200, Planning.cpp:851)");
     CK(cudaSetDevice(c->device));
     const size_t np = (size_t)path_off[n_paths];
     Tmp tmp; cudaError_t e;
+    std::vector<double2> hxy = interleave(px, py, np);
     PUT(d_off, int32_t, path_off, (size_t)n_paths + 1);
-    PUT(d_px, double, px, np); PUT(d_py, double, py, np);
+    PUT(d_pxy, double2, hxy.data(), np);
     PUT(d_o, double, (const double*)nullptr, (size_t)n_paths * 400);
-    CK(dp_launch_mean(n_paths, d_off, d_px, d_py, d_o, c->st[0]));
+    CK(dp_launch_mean(n_paths, d_off, d_pxy, d_o, c->st[0]));
     ++c->launches;
     CK(cudaMemcpyAsync(out_xy, d_o, (size_t)n_paths * 400 * 8, cudaMemcpyDeviceToHost, c->st[0]));
     CK(cudaStreamSynchronize(c->st[0]));

@@ -2,14 +2,15 @@
 // SURVEY.md 8a rows A1-A5) for sm_100a.  One WARP cooperates on one path/trajectory:
 //   * lanes are (obstacle, point-chunk) work items for the nearest-point search, so that
 //     N = 10 obstacles still fill 30 of 32 lanes; N >= 32 runs in groups of 32 obstacles;
-//   * path points are staged per warp in shared memory in tiles of DP_TILE points (gathered from
-//     the L2-resident map with coalesced loads, lateral offset fused into the gather), then read
-//     as 16-byte broadcast loads in the inner loop -- candidate paths never touch HBM;
+//   * a path is a RECIPE (map slice forward/reversed, optional lateral offset, junction
+//     concatenation, or a window of the local path): its points are staged per warp in a
+//     shared-memory tile by one coalesced gather from the L2-resident AoS map with the offset
+//     fused in, then read as 16-byte broadcast loads -- candidate paths never touch HBM;
 //   * selection is a packed (path index << 16 | obstacle index) warp min-reduction (redux.sync),
 //     i.e. nearest-along-path first, lowest obstacle index on ties;
 //   * sums the reference evaluates sequentially (arclength) stay sequential: terms are produced
-//     in parallel into shared memory, then added in index order, so results are bit-identical
-//     to a scalar CPU evaluation.
+//     in parallel into shared memory, then added in index order in blocks of 8 (loads and exit
+//     tests off the dependency chain), so results are bit-identical to a scalar CPU evaluation.
 // Arithmetic: IEEE binary64, compiled with -fmad=false; fma() appears exactly where the
 // operator specification says so.
 #pragma once
@@ -18,45 +19,54 @@
 #include "../../include/dmpp_b200.h"
 
 #define DP_FULL 0xffffffffu
-#define DP_TILE 128            // path points staged per warp per tile
-#define DP_SCR 256             // per-warp scratch doubles
+#define DP_TILE 120            // path points staged per warp per tile (= the reference's 120-point lane slice)
+#define DP_SCR 192             // sequential-sum terms per pass (multiple of 8)
 #define DP_WARPS_PER_BLOCK 4
 
 struct DevMap {
+    const double2* xy;                         // AoS copy of (x, y), built at upload
     const double* x; const double* y; const double* dir;
-    const double* nx; const double* ny;       // unit RIGHT normal of segment i -> i+1 (0 at a lane's last point)
-    const double* lenp;                        // |p[i+1]-p[i]| as sqrt(dx*dx+dy*dy)       (CalcDistance idiom)
+    const double2* nrm;                        // unit RIGHT normal of segment i -> i+1 (0 at a lane's last point)
+    const double* lenp;                        // |p[i+1]-p[i]| as sqrt(dx*dx+dy*dy)        (CalcDistance idiom)
     const uint16_t* width; const uint16_t* attr;
     const int32_t* road_lane_base; const int32_t* lane_pt_off;
     const dp_connector* conn;
     int n_roads, n_lanes, n_conn;
 };
 
-struct WarpSmem {
-    double2 tile[DP_TILE + 1];                 // current path tile (+1 so segments can be formed)
-    double scr[DP_SCR];                        // sequential-sum terms / cum[] of MeanPoints
-    double2 plan[DP_PATH_POINTS];              // road_points of this cycle (Planning.cpp:115)
+// 6728 bytes per warp: 7 CTAs of 4 warps fit the 196 KB shared-memory configuration and leave
+// 60 KB of L1 for the map gathers.
+struct __align__(16) WarpSmem {
+    double2 plan[DP_PATH_POINTS];              // last_Bpoints on entry (TMA bulk copy), road_points on exit
+    double2 tile[DP_TILE];                     // one staged path tile (also cum[] of MeanPoints, 240 doubles)
+    double scr[DP_SCR + 8];                    // sequential-sum terms, zero padded to a multiple of 8
+    unsigned long long mbar;                   // mbarrier of the bulk copy
 };
 
-// A path is never materialised in global memory: it is a recipe evaluated into the tile.
-struct PathSrc {
-    int kind;          // 0: up to two map segments, 1: window of sm.plan, 2: caller polyline in global memory
-    int P;             // number of points
-    int base0, step0, n0;   // kind 0: map point index base0 + step0*j for j < n0 (step0 = +1 / -1)
-    int base1;              // kind 0: second (forward) segment, points j >= n0
-    int s0;                 // kind 1: first plan index
-    double d;               // lateral offset, RIGHT positive; kind 0 single segment or kind 2
-    const double* gx; const double* gy;   // kind 2
+// A path is a recipe, never an array in HBM: up to two runs of map (or caller) points read with a
+// stride of +1/-1, an optional lateral offset applied with the precomputed unit normals while the
+// tile is staged, or a window of the local path already resident in sm.plan.
+struct Src {
+    const double2* p0; int stride0; int n0;    // run 0: p0[stride0 * j], j < n0
+    const double2* p1; int n1;                 // run 1 (forward): p1[j - n0]
+    const double2* nrm0;                       // normals aligned with p0 (only when d != 0, single run)
+    double d;                                  // lateral offset, RIGHT positive
+    int plan_off;                              // >= 0: the path is the window sm.plan[plan_off ...] (no staging needed)
 };
-
+struct LaneMap { int nchunk, o, c; };          // nearest-search work item of this lane for N < 32
 struct SearchRes { bool found; double dis_lat, dis_lng; int ob, pathid; };
 
+__device__ __forceinline__ LaneMap dp_lane_map(int N, int lane) {
+    LaneMap lm;
+    if (N >= 32 || N <= 0) { lm.nchunk = 1; lm.o = lane; lm.c = 0; }
+    else { lm.nchunk = 32 / N; lm.o = lane % N; lm.c = lane / N; }
+    return lm;
+}
 __device__ __forceinline__ double dp_sq2(double dx, double dy) { return fma(dx, dx, dy * dy); }
 __device__ __forceinline__ double dp_dist_plain(double ax, double ay, double bx, double by) {
     double dx = ax - bx, dy = ay - by;
     return sqrt(dx * dx + dy * dy);
 }
-
 // unit right normal of segment a->b per the CreateNewPath specification
 __device__ __forceinline__ double2 dp_normal(double2 a, double2 b) {
     double sx = b.x - a.x, sy = b.y - a.y;
@@ -64,89 +74,151 @@ __device__ __forceinline__ double2 dp_normal(double2 a, double2 b) {
     if (len > 0) return make_double2(sy / len, -sx / len);
     return make_double2(0.0, 0.0);
 }
-
-__device__ __forceinline__ double2 dp_path_point(const DevMap& m, const WarpSmem& sm, const PathSrc& s, int j) {
-    if (s.kind == 1) return sm.plan[s.s0 + j];
-    if (s.kind == 2) {
-        double x = s.gx[j], y = s.gy[j];
-        if (s.d != 0.0 && s.P >= 2) {
-            int k = (j == s.P - 1) ? s.P - 2 : j;
-            double2 n = dp_normal(make_double2(s.gx[k], s.gy[k]), make_double2(s.gx[k + 1], s.gy[k + 1]));
-            x = fma(s.d, n.x, x); y = fma(s.d, n.y, y);
-        }
-        return make_double2(x, y);
+__device__ __forceinline__ Src dp_src_run(const double2* p, int stride, int n) {
+    Src s;
+    s.p0 = p; s.stride0 = stride; s.n0 = n; s.p1 = p; s.n1 = 0; s.nrm0 = nullptr; s.d = 0.0; s.plan_off = -1;
+    return s;
+}
+// point j of the path (CreateNewPath fused in: p_j + d * n_j; fwd normal index min(j,P-2),
+// reversed: -(nrm[-min(j,P-2)-1]))
+__device__ __forceinline__ double2 dp_src_point(const Src& s, int j) {
+    if (j >= s.n0) return s.p1[j - s.n0];
+    double2 q = s.p0[s.stride0 * j];
+    if (s.d != 0.0 && s.n0 >= 2) {
+        const int jj = min(j, s.n0 - 2);
+        double2 n = (s.stride0 > 0) ? s.nrm0[jj] : s.nrm0[-jj - 1];
+        if (s.stride0 < 0) { n.x = -n.x; n.y = -n.y; }
+        q.x = fma(s.d, n.x, q.x); q.y = fma(s.d, n.y, q.y);
     }
-    if (j < s.n0) {
-        int idx = s.base0 + s.step0 * j;
-        double x = m.x[idx], y = m.y[idx];
-        if (s.d != 0.0 && s.P >= 2) {
-            int jj = min(j, s.P - 2);
-            int ni = (s.step0 > 0) ? s.base0 + jj : s.base0 - jj - 1;
-            double nx = m.nx[ni], ny = m.ny[ni];
-            if (s.step0 < 0) { nx = -nx; ny = -ny; }
-            x = fma(s.d, nx, x); y = fma(s.d, ny, y);
-        }
-        return make_double2(x, y);
-    }
-    int idx = s.base1 + (j - s.n0);
-    return make_double2(m.x[idx], m.y[idx]);
+    return q;
 }
 
-// sequential (index-order) sum of sm.scr[0..n): every lane runs the same chain, so the result is
-// warp-uniform without a shuffle and costs one issue slot per term.
+// ---- sequential sums over sm.scr[0..n) in index order, 8 terms per block ------------------------
+__device__ __forceinline__ void dp_pad_scr(WarpSmem& sm, int n, int lane) {   // zero terms up to the next multiple of 8
+    if (lane < 8) sm.scr[n + lane] = 0.0;
+}
 __device__ __forceinline__ double dp_seq_sum(const WarpSmem& sm, int n, double acc) {
-    int j = 0;
-    for (; j + 4 <= n; j += 4) {
-        double a = sm.scr[j], b = sm.scr[j + 1], c = sm.scr[j + 2], d = sm.scr[j + 3];
-        acc += a; acc += b; acc += c; acc += d;
+#pragma unroll 1
+    for (int j = 0; j < n; j += 8) {
+        const double t0 = sm.scr[j], t1 = sm.scr[j + 1], t2 = sm.scr[j + 2], t3 = sm.scr[j + 3];
+        const double t4 = sm.scr[j + 4], t5 = sm.scr[j + 5], t6 = sm.scr[j + 6], t7 = sm.scr[j + 7];
+        acc += t0; acc += t1; acc += t2; acc += t3; acc += t4; acc += t5; acc += t6; acc += t7;   // x + 0.0 == x for the padding
     }
-    for (; j < n; ++j) acc += sm.scr[j];
     return acc;
 }
+// first index j < n whose running sum s_j = acc + t_0 + ... + t_j satisfies (s_j - sub > thr), else -1;
+// acc is advanced by all n terms when nothing is found.
+struct SeqHit { int k; double acc; };
+__device__ __forceinline__ SeqHit dp_seq_first(const WarpSmem& sm, int n, double acc, double sub, double thr) {
+    SeqHit r;
+#pragma unroll 1
+    for (int j = 0; j < n; j += 8) {
+        const double t0 = sm.scr[j], t1 = sm.scr[j + 1], t2 = sm.scr[j + 2], t3 = sm.scr[j + 3];
+        const double t4 = sm.scr[j + 4], t5 = sm.scr[j + 5], t6 = sm.scr[j + 6], t7 = sm.scr[j + 7];
+        const double s0 = acc + t0, s1 = s0 + t1, s2 = s1 + t2, s3 = s2 + t3, s4 = s3 + t4, s5 = s4 + t5, s6 = s5 + t6, s7 = s6 + t7;
+        unsigned m = 0;
+        m |= ((s0 - sub) > thr) ? 1u : 0u;   m |= ((s1 - sub) > thr) ? 2u : 0u;
+        m |= ((s2 - sub) > thr) ? 4u : 0u;   m |= ((s3 - sub) > thr) ? 8u : 0u;
+        m |= ((s4 - sub) > thr) ? 16u : 0u;  m |= ((s5 - sub) > thr) ? 32u : 0u;
+        m |= ((s6 - sub) > thr) ? 64u : 0u;  m |= ((s7 - sub) > thr) ? 128u : 0u;
+        if (m) {
+            const int k = j + __ffs(m) - 1;
+            if (k < n) { r.k = k; r.acc = acc; return r; } // (padding terms are zero: cannot create a first hit)
+        }
+        acc = s7;
+    }
+    r.k = -1; r.acc = acc;
+    return r;
+}
 
-// CShare::SearchObstacle (Planning.cpp:168; Decision.cpp:370,455,811-842,943,962), one warp.
-// ox/oy: the scene's obstacle arrays in global memory.  Returns a warp-uniform result.
-static __device__ SearchRes dp_search_path(const DevMap& m, WarpSmem& sm, const PathSrc& s, const double* __restrict__ ox,
-                                    const double* __restrict__ oy, int N, double lo, double hi, int lane) {
+// ---- TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) with an mbarrier --------------
+__device__ __forceinline__ uint32_t dp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dp_bulk_prefetch(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* mbar, int lane) {
+    if (lane == 0) {
+        const uint32_t mb = dp_smem_u32(mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dp_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(mb) : "memory");
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void dp_bulk_wait(unsigned long long* mbar) {
+    const uint32_t mb = dp_smem_u32(mbar);
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 24) && !done; ++spin) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(mb) : "memory");
+    }
+    if (!done) __trap();                                    // never spin forever on a broken copy
+}
+
+// ---- CShare::SearchObstacle (Planning.cpp:168; Decision.cpp:370,455,811-842,943,962), one warp ----
+// One copy of this code serves every trajectory of the cycle (noinline keeps the kernel inside the
+// instruction cache).  (mx, my): this lane's obstacle when N < 32 (kept in registers for the whole
+// cycle); ox/oy: the scene's obstacle rows in global memory for the grouped N >= 32 case.
+__device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my, const double* __restrict__ ox,
+                                                   const double* __restrict__ oy, int N, const LaneMap lm, double lo, double hi,
+                                                   WarpSmem& sm, int lane) {
     SearchRes r;
     r.found = false; r.dis_lat = DP_NOT_FOUND; r.dis_lng = DP_NOT_FOUND; r.ob = -1; r.pathid = 0;
-    const int P = s.P;
+    const int P = s.n0 + s.n1;
     if (P < 2 || N <= 0) return r;
-    const int nchunk = (N >= 32) ? 1 : 32 / N;
-    const int CS = (P + nchunk - 1) / nchunk;
-    const int ngroups = (nchunk == 1) ? (N + 31) / 32 : 1;
-    const int tile_n = (s.kind == 1) ? P : DP_TILE;
+    const int nchunk = lm.nchunk;
+    const int CS = (nchunk == 1) ? P : (P + nchunk - 1) / nchunk;
+    const int ngroups = (nchunk == 1) ? (N + 31) >> 5 : 1;
+    const bool in_plan = s.plan_off >= 0;
+    const bool one_tile = in_plan || P <= DP_TILE;          // every point stays addressable in shared memory
+    const double2* pts = in_plan ? &sm.plan[s.plan_off] : &sm.tile[0];   // both shared: LDS in the hot loop
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
     unsigned bestkey = 0xffffffffu;
     double bestd = 0.0;
     for (int g = 0; g < ngroups; ++g) {
-        const int o = (nchunk == 1) ? g * 32 + lane : lane % N;
-        const int c = (nchunk == 1) ? 0 : lane / N;
+        const int o = (nchunk == 1) ? g * 32 + lane : lm.o;
         const bool active = (nchunk == 1) ? (o < N) : (lane < N * nchunk);
-        const double mx = active ? ox[o] : 0.0, my = active ? oy[o] : 0.0;
-        const int jlo = c * CS, jhi = min(P, jlo + CS);
-        double bd = __longlong_as_double(0x7ff0000000000000LL);
-        int bj = jlo;
-        for (int t0 = 0; t0 < P; t0 += tile_n) {
-            const int tn = min(tile_n, P - t0);
-            const double2* pts;
-            if (s.kind == 1) pts = sm.plan + s.s0;
-            else {
-                for (int j = lane; j < tn; j += 32) sm.tile[j] = dp_path_point(m, sm, s, t0 + j);
+        if (nchunk == 1) { mx = active ? ox[o] : 0.0; my = active ? oy[o] : 0.0; }
+        const int jlo = lm.c * CS, jhi = active ? min(P, jlo + CS) : 0;
+        // four independent running minima (j mod 4 classes) break the compare/select dependency chain;
+        // their lexicographic (d2, j) minimum is the sequential strict-'<' result (lowest index on ties)
+        double b0 = INF, b1 = INF, b2 = INF, b3 = INF;
+        int i0 = jlo, i1 = jlo, i2 = jlo, i3 = jlo;
+        const int tstep = in_plan ? P : DP_TILE;
+        for (int t0 = 0; t0 < P; t0 += tstep) {
+            const int tn = min(tstep, P - t0);
+            if (!in_plan && (g == 0 || !one_tile)) {        // stage the tile: coalesced gather, offset fused
                 __syncwarp();
-                pts = sm.tile;
+                for (int j = lane; j < tn; j += 32) sm.tile[j] = dp_src_point(s, t0 + j);
+                __syncwarp();
             }
-            const int a = max(jlo, t0), b = active ? min(jhi, t0 + tn) : 0;
-#pragma unroll 4
-            for (int j = a; j < b; ++j) {
-                const double2 p = pts[j - t0];
-                const double dx = mx - p.x, dy = my - p.y;
-                const double d2 = fma(dx, dx, dy * dy);
-                if (d2 < bd) { bd = d2; bj = j; }
+            int j = max(jlo, t0);
+            const int e = min(jhi, t0 + tn);
+            const double2* q = pts + (j - t0);
+            for (; j + 4 <= e; j += 4, q += 4) {
+                const double2 p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3];
+                const double x0 = mx - p0.x, y0 = my - p0.y, x1 = mx - p1.x, y1 = my - p1.y;
+                const double x2 = mx - p2.x, y2 = my - p2.y, x3 = mx - p3.x, y3 = my - p3.y;
+                const double d0 = fma(x0, x0, y0 * y0), d1 = fma(x1, x1, y1 * y1);
+                const double d2 = fma(x2, x2, y2 * y2), d3 = fma(x3, x3, y3 * y3);
+                if (d0 < b0) { b0 = d0; i0 = j; }
+                if (d1 < b1) { b1 = d1; i1 = j + 1; }
+                if (d2 < b2) { b2 = d2; i2 = j + 2; }
+                if (d3 < b3) { b3 = d3; i3 = j + 3; }
             }
-            __syncwarp();
+            for (; j < e; ++j, ++q) {
+                const double2 p0 = q[0];
+                const double x0 = mx - p0.x, y0 = my - p0.y;
+                const double d0 = fma(x0, x0, y0 * y0);
+                if (d0 < b0) { b0 = d0; i0 = j; }
+            }
         }
-        for (int cc = 1; cc < nchunk; ++cc) {            // chunks are index-ordered: strict '<' keeps the lowest j
-            const int src = (lane % N + cc * N) & 31;
+        if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+        if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
+        if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
+        double bd = b0;
+        int bj = i0;
+        for (int cc = 1; cc < nchunk; ++cc) {               // chunks are index-ordered: strict '<' keeps the lowest j
+            const int src = (lm.o + cc * N) & 31;
             const double od = __shfl_sync(DP_FULL, bd, src);
             const int oj = __shfl_sync(DP_FULL, bj, src);
             if (lane < N && od < bd) { bd = od; bj = oj; }
@@ -154,7 +226,7 @@ static __device__ SearchRes dp_search_path(const DevMap& m, WarpSmem& sm, const 
         const bool owner = (nchunk == 1) ? active : (lane < N);
         if (owner) {
             const int k = (bj == P - 1) ? P - 2 : bj;
-            const double2 pk = dp_path_point(m, sm, s, k), pk1 = dp_path_point(m, sm, s, k + 1);
+            const double2 pk = one_tile ? pts[k] : dp_src_point(s, k), pk1 = one_tile ? pts[k + 1] : dp_src_point(s, k + 1);
             const double sx = pk1.x - pk.x, sy = pk1.y - pk.y;
             bool pass = true;
             if (bj == 0) pass = fma(mx - pk.x, sx, (my - pk.y) * sy) >= 0.0;
@@ -173,15 +245,16 @@ static __device__ SearchRes dp_search_path(const DevMap& m, WarpSmem& sm, const 
     r.found = true; r.pathid = jstar; r.ob = ostar;
     r.dis_lat = __shfl_sync(DP_FULL, bestd, (nchunk == 1) ? (ostar & 31) : ostar);
     double sum = 0.0;
-    for (int t0 = 0; t0 < jstar; t0 += DP_SCR) {
+    for (int t0 = 0; t0 < jstar; t0 += DP_SCR) {            // arclength to the selected point, index order
         const int tn = min(DP_SCR, jstar - t0);
+        __syncwarp();
         for (int j = lane; j < tn; j += 32) {
-            const double2 a = dp_path_point(m, sm, s, t0 + j), b = dp_path_point(m, sm, s, t0 + j + 1);
+            const double2 a = one_tile ? pts[t0 + j] : dp_src_point(s, t0 + j), b = one_tile ? pts[t0 + j + 1] : dp_src_point(s, t0 + j + 1);
             sm.scr[j] = sqrt(dp_sq2(b.x - a.x, b.y - a.y));
         }
+        dp_pad_scr(sm, tn, lane);
         __syncwarp();
         sum = dp_seq_sum(sm, tn, sum);
-        __syncwarp();
     }
     r.dis_lng = sum;
     return r;
@@ -219,7 +292,7 @@ __device__ __forceinline__ void dp_sincos_deg(double a, double* c, double* s) {
     else { *c = sn; *s = -cs; }
 }
 
-__device__ __forceinline__ double dp_atan(double z) {
+static __device__ __noinline__ double dp_atan(double z) {
     const double PI_2 = 1.57079632679489661923, PI_4 = 0.78539816339744830962;
     const bool neg = z < 0;
     double a = neg ? -z : z;
@@ -274,8 +347,8 @@ __device__ __forceinline__ double dp_angle_err(double d1, double d2) {
 }
 
 // CShare::BezierPlanning (Planning.cpp:606,863) into sm.plan, one warp
-__device__ __forceinline__ void dp_bezier_to_plan(WarpSmem& sm, double x0, double y0, double dir0, double x3, double y3,
-                                                  double dir3, int lane) {
+static __device__ __noinline__ void dp_bezier_to_plan(WarpSmem& sm, double x0, double y0, double dir0, double x3, double y3,
+                                                      double dir3, int lane) {
     const double ex = x3 - x0, ey = y3 - y0;
     const double L = sqrt(dp_sq2(ex, ey)) / 3.0;
     double c0, s0, c3, s3;
@@ -283,6 +356,7 @@ __device__ __forceinline__ void dp_bezier_to_plan(WarpSmem& sm, double x0, doubl
     dp_sincos_deg(dir3, &c3, &s3);
     const double x1 = fma(L, c0, x0), y1 = fma(L, s0, y0);
     const double x2 = fma(-L, c3, x3), y2 = fma(-L, s3, y3);
+    __syncwarp();
     for (int i = lane; i < DP_PATH_POINTS; i += 32) {
         const double t = (double)i / (double)(DP_PATH_POINTS - 1);
         const double u = 1.0 - t;
@@ -296,46 +370,47 @@ __device__ __forceinline__ void dp_bezier_to_plan(WarpSmem& sm, double x0, doubl
     __syncwarp();
 }
 
-// CShare::MeanPoints (Planning.cpp:872): resample the first n_in points of `s` into sm.plan.
-// n_in <= DP_SCR.  cum[] lives in sm.scr.
-__device__ __forceinline__ void dp_mean_points_to_plan(const DevMap& m, WarpSmem& sm, const PathSrc& s, int n_in, int lane) {
+// CShare::MeanPoints (Planning.cpp:872): resample the first n_in (<= 240) points of `s` into sm.plan.
+// cum[] lives in the (idle) tile area.
+static __device__ __noinline__ void dp_mean_points_to_plan(WarpSmem& sm, const Src s, int n_in, int lane) {
+    double* cum = reinterpret_cast<double*>(sm.tile);
+    __syncwarp();
     if (n_in <= 0) {
         for (int i = lane; i < DP_PATH_POINTS; i += 32) sm.plan[i] = make_double2(0.0, 0.0);
         __syncwarp();
         return;
     }
     if (n_in == 1) {
-        const double2 p = dp_path_point(m, sm, s, 0);
+        const double2 p = dp_src_point(s, 0);
         for (int i = lane; i < DP_PATH_POINTS; i += 32) sm.plan[i] = p;
         __syncwarp();
         return;
     }
-    // segment lengths in parallel into tile[].x (n_in - 1 <= 255 terms would not fit the tile: use scr in two passes)
     for (int j = lane; j < n_in - 1; j += 32) {
-        const double2 a = dp_path_point(m, sm, s, j), b = dp_path_point(m, sm, s, j + 1);
-        sm.scr[j + 1] = sqrt(dp_sq2(b.x - a.x, b.y - a.y));
+        const double2 a = dp_src_point(s, j), b = dp_src_point(s, j + 1);
+        cum[j + 1] = sqrt(dp_sq2(b.x - a.x, b.y - a.y));
     }
     __syncwarp();
     if (lane == 0) {                                         // in-place sequential prefix: cum[i+1] = cum[i] + len[i]
         double acc = 0.0;
-        sm.scr[0] = 0.0;
-        for (int j = 1; j < n_in; ++j) { acc += sm.scr[j]; sm.scr[j] = acc; }
+        cum[0] = 0.0;
+        for (int j = 1; j < n_in; ++j) { acc += cum[j]; cum[j] = acc; }
     }
     __syncwarp();
-    const double step = sm.scr[n_in - 1] / (double)(DP_PATH_POINTS - 1);
+    const double step = cum[n_in - 1] / (double)(DP_PATH_POINTS - 1);
     for (int kx = lane; kx < DP_PATH_POINTS; kx += 32) {
         const double sv = (double)kx * step;
         int lo_i = 0, hi_i = n_in - 2;                       // largest i <= n_in-2 with cum[i] <= sv
         while (lo_i < hi_i) {
             const int mid = (lo_i + hi_i + 1) >> 1;
-            if (sm.scr[mid] <= sv) lo_i = mid; else hi_i = mid - 1;
+            if (cum[mid] <= sv) lo_i = mid; else hi_i = mid - 1;
         }
         const int i = lo_i;
-        const double seg = sm.scr[i + 1] - sm.scr[i];
-        const double t = seg > 0 ? (sv - sm.scr[i]) / seg : 0.0;
-        const double2 a = dp_path_point(m, sm, s, i), b = dp_path_point(m, sm, s, i + 1);
+        const double seg = cum[i + 1] - cum[i];
+        const double t = seg > 0 ? (sv - cum[i]) / seg : 0.0;
+        const double2 a = dp_src_point(s, i), b = dp_src_point(s, i + 1);
         double2 q = make_double2(fma(t, b.x - a.x, a.x), fma(t, b.y - a.y, a.y));
-        if (kx == DP_PATH_POINTS - 1) q = dp_path_point(m, sm, s, n_in - 1);
+        if (kx == DP_PATH_POINTS - 1) q = dp_src_point(s, n_in - 1);
         sm.plan[kx] = q;
     }
     __syncwarp();

@@ -4,20 +4,21 @@
 #include "dp_device.cuh"
 
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
-                            int max_obs, dp_carry* carry, double* last_path, dp_plan_record* rec, dp_trace_record* trace,
+                            int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
                             double* path_xy, double* path_ll, cudaStream_t st);
-cudaError_t dp_launch_reset(dp_carry* carry, double* last_path, int first, int count, cudaStream_t st);
-cudaError_t dp_launch_map_prep(const double* x, const double* y, const int32_t* lane_pt_off, int n_lanes, double* nx, double* ny,
+cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st);
+cudaError_t dp_launch_map_prep(const double* x, const double* y, const int32_t* lane_pt_off, int n_lanes, double2* xy, double2* nrm,
                                double* lenp, cudaStream_t st);
 
 // operator-level kernels (dp_ops.cu)
-cudaError_t dp_launch_search(int n_paths, const int32_t* path_off, const double* px, const double* py, const double* ox,
+// operator kernels take polylines as AoS double2 (the host entry points interleave x/y)
+cudaError_t dp_launch_search(int n_paths, const int32_t* path_off, const double2* pxy, const double* ox,
                              const double* oy, int n_obs, const double* lat_min, const double* lat_max, dp_search_slot* out,
                              cudaStream_t st);
-cudaError_t dp_launch_create(int n_paths, const int32_t* path_off, const double* px, const double* py, const double* offset,
-                             double* out_x, double* out_y, cudaStream_t st);
+cudaError_t dp_launch_create(int n_paths, const int32_t* path_off, const double2* pxy, const double* offset,
+                             double2* out_xy, cudaStream_t st);
 cudaError_t dp_launch_bezier(int n, const double* poses, double* out_xy, cudaStream_t st);
-cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double* px, const double* py, double* out_xy, cudaStream_t st);
+cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double2* pxy, double* out_xy, cudaStream_t st);
 cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
                             int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs,
                             double lat_min, double lat_max, double clear_dis, double* cand_dis_lng, unsigned long long* best_key,

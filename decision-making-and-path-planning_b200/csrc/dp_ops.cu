@@ -6,31 +6,20 @@
 
 namespace {
 
-__device__ __forceinline__ DevMap null_map() {
-    DevMap m;
-    m.x = m.y = m.dir = m.nx = m.ny = m.lenp = nullptr; m.width = m.attr = nullptr;
-    m.road_lane_base = m.lane_pt_off = nullptr; m.conn = nullptr; m.n_roads = m.n_lanes = m.n_conn = 0;
-    return m;
-}
-__device__ __forceinline__ PathSrc global_path(const double* gx, const double* gy, int P, double d) {
-    PathSrc s;
-    s.kind = 2; s.P = P; s.base0 = s.n0 = s.base1 = s.s0 = 0; s.step0 = 1; s.d = d; s.gx = gx; s.gy = gy;
-    return s;
-}
-
 // CShare::SearchObstacle, one warp per path
 __global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32)
-op_search_kernel(int n_paths, const int32_t* __restrict__ path_off, const double* __restrict__ px, const double* __restrict__ py,
-                 const double* __restrict__ ox, const double* __restrict__ oy, int n_obs, const double* __restrict__ lat_min,
-                 const double* __restrict__ lat_max, dp_search_slot* __restrict__ out) {
+op_search_kernel(int n_paths, const int32_t* __restrict__ path_off, const double2* __restrict__ pxy, const double* __restrict__ ox,
+                 const double* __restrict__ oy, int n_obs, const double* __restrict__ lat_min, const double* __restrict__ lat_max,
+                 dp_search_slot* __restrict__ out) {
     __shared__ WarpSmem smem[DP_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pid = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
     if (pid >= n_paths) return;
     const int off = path_off[pid], P = path_off[pid + 1] - off;
-    const DevMap m = null_map();
-    const PathSrc s = global_path(px + off, py + off, P, 0.0);
-    const SearchRes r = dp_search_path(m, smem[wib], s, ox, oy, n_obs, lat_min[pid], lat_max[pid], lane);
+    const LaneMap lm = dp_lane_map(n_obs, lane);
+    const bool act = (lm.nchunk > 1) && (lane < n_obs * lm.nchunk);
+    const SearchRes r = dp_search(dp_src_run(pxy + off, 1, P), act ? ox[lm.o] : 0.0, act ? oy[lm.o] : 0.0, ox, oy, n_obs, lm, lat_min[pid],
+                                  lat_max[pid], smem[wib], lane);
     if (lane == 0) {
         dp_search_slot o;
         o.dis_lat = r.dis_lat; o.dis_lng = r.dis_lng; o.ob_index = (int16_t)r.ob; o.pathid = (uint16_t)r.pathid;
@@ -40,23 +29,22 @@ op_search_kernel(int n_paths, const int32_t* __restrict__ path_off, const double
 }
 
 // CShare::CreateNewPath, one warp per path
-__global__ void op_create_kernel(int n_paths, const int32_t* __restrict__ path_off, const double* __restrict__ px,
-                                 const double* __restrict__ py, const double* __restrict__ offset, double* __restrict__ out_x,
-                                 double* __restrict__ out_y) {
+__global__ void op_create_kernel(int n_paths, const int32_t* __restrict__ path_off, const double2* __restrict__ pxy,
+                                 const double* __restrict__ offset, double2* __restrict__ out_xy) {
     const int lane = threadIdx.x & 31;
     const int pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (pid >= n_paths) return;
     const int off = path_off[pid], P = path_off[pid + 1] - off;
     const double d = offset[pid];
-    const double* gx = px + off; const double* gy = py + off;
+    const double2* g = pxy + off;
     for (int j = lane; j < P; j += 32) {
-        double x = gx[j], y = gy[j];
-        if (P >= 2) {                                       // unconditional fma, as the specification
+        double2 q = g[j];
+        if (P >= 2) {
             const int k = (j == P - 1) ? P - 2 : j;
-            const double2 n = dp_normal(make_double2(gx[k], gy[k]), make_double2(gx[k + 1], gy[k + 1]));
-            x = fma(d, n.x, x); y = fma(d, n.y, y);
+            const double2 n = dp_normal(g[k], g[k + 1]);
+            q.x = fma(d, n.x, q.x); q.y = fma(d, n.y, q.y);
         }
-        out_x[off + j] = x; out_y[off + j] = y;
+        out_xy[off + j] = q;
     }
 }
 
@@ -77,16 +65,13 @@ op_bezier_kernel(int n, const double* __restrict__ poses, double* __restrict__ o
 
 // CShare::MeanPoints, one warp per path (n_in <= DP_SCR checked by the host)
 __global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32)
-op_mean_kernel(int n_paths, const int32_t* __restrict__ path_off, const double* __restrict__ px, const double* __restrict__ py,
-               double* __restrict__ out_xy) {
+op_mean_kernel(int n_paths, const int32_t* __restrict__ path_off, const double2* __restrict__ pxy, double* __restrict__ out_xy) {
     __shared__ WarpSmem smem[DP_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pid = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
     if (pid >= n_paths) return;
     const int off = path_off[pid], P = path_off[pid + 1] - off;
-    const DevMap m = null_map();
-    const PathSrc s = global_path(px + off, py + off, P, 0.0);
-    dp_mean_points_to_plan(m, smem[wib], s, P, lane);
+    dp_mean_points_to_plan(smem[wib], dp_src_run(pxy + off, 1, P), P, lane);
     for (int i = lane; i < DP_PATH_POINTS; i += 32) {
         out_xy[(size_t)pid * 400 + i] = smem[wib].plan[i].x;
         out_xy[(size_t)pid * 400 + DP_PATH_POINTS + i] = smem[wib].plan[i].y;
@@ -214,18 +199,18 @@ __global__ void fma_peak_kernel(T* sink, int iters) {
 
 }  // namespace
 
-cudaError_t dp_launch_search(int n_paths, const int32_t* path_off, const double* px, const double* py, const double* ox,
+cudaError_t dp_launch_search(int n_paths, const int32_t* path_off, const double2* pxy, const double* ox,
                              const double* oy, int n_obs, const double* lat_min, const double* lat_max, dp_search_slot* out,
                              cudaStream_t st) {
     if (n_paths <= 0) return cudaSuccess;
     op_search_kernel<<<(n_paths + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(
-        n_paths, path_off, px, py, ox, oy, n_obs, lat_min, lat_max, out);
+        n_paths, path_off, pxy, ox, oy, n_obs, lat_min, lat_max, out);
     return cudaGetLastError();
 }
-cudaError_t dp_launch_create(int n_paths, const int32_t* path_off, const double* px, const double* py, const double* offset,
-                             double* out_x, double* out_y, cudaStream_t st) {
+cudaError_t dp_launch_create(int n_paths, const int32_t* path_off, const double2* pxy, const double* offset,
+                             double2* out_xy, cudaStream_t st) {
     if (n_paths <= 0) return cudaSuccess;
-    op_create_kernel<<<(n_paths * 32 + 127) / 128, 128, 0, st>>>(n_paths, path_off, px, py, offset, out_x, out_y);
+    op_create_kernel<<<(n_paths * 32 + 127) / 128, 128, 0, st>>>(n_paths, path_off, pxy, offset, out_xy);
     return cudaGetLastError();
 }
 cudaError_t dp_launch_bezier(int n, const double* poses, double* out_xy, cudaStream_t st) {
@@ -233,9 +218,9 @@ cudaError_t dp_launch_bezier(int n, const double* poses, double* out_xy, cudaStr
     op_bezier_kernel<<<(n + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(n, poses, out_xy);
     return cudaGetLastError();
 }
-cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double* px, const double* py, double* out_xy, cudaStream_t st) {
+cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double2* pxy, double* out_xy, cudaStream_t st) {
     if (n_paths <= 0) return cudaSuccess;
-    op_mean_kernel<<<(n_paths + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(n_paths, path_off, px, py, out_xy);
+    op_mean_kernel<<<(n_paths + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(n_paths, path_off, pxy, out_xy);
     return cudaGetLastError();
 }
 cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
