@@ -1,0 +1,44 @@
+// host/PlannerBatch.h -- batched host mirror of the two reference classes: what `CDecision::Instance()` +
+// `CPlanning::Instance()` (Decision.h:105-107, Planning.h:38-40) become when N independent scenes are planned at
+// once.  One `Cycle()` = one iteration of CDecisionThread (Decision.cpp:119-206) + one of CPlanningThread
+// (Planning.cpp:64-226) for every scene, in ONE fused CUDA launch.  Thin, header-only wrapper of the C ABI.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/dmpp_b200.h"
+
+class CPlannerBatch {
+public:
+    CPlannerBatch(int max_scenes, int max_obs, int device = 0, const dp_params* params = nullptr)
+        : max_scenes_(max_scenes), max_obs_(max_obs) {
+        check(dp_create(&ctx_, device, params, max_scenes, max_obs), "dp_create");
+    }
+    ~CPlannerBatch() { dp_destroy(ctx_); }
+    CPlannerBatch(const CPlannerBatch&) = delete;
+    CPlannerBatch& operator=(const CPlannerBatch&) = delete;
+
+    void UploadMap(const dp_map_desc& map) { check(dp_map_upload(ctx_, &map), "dp_map_upload"); }
+    // constructor state of both singletons for scenes [first, first+count)  (Decision.cpp:8-29, Planning.cpp:8-11)
+    void Reset(int first, int count) { check(dp_reset(ctx_, first, count), "dp_reset"); }
+    // host buffers in, host buffers out; trace / paths may be null
+    void Cycle(int first, int n, const dp_scene_hdr* hdr, const double* obs_x, const double* obs_y, dp_plan_record* rec,
+               dp_trace_record* trace = nullptr, double* road_points = nullptr, double* latlng = nullptr) {
+        check(dp_cycle_batch(ctx_, first, n, hdr, obs_x, obs_y, rec, trace, road_points, latlng), "dp_cycle_batch");
+    }
+    // device buffers, asynchronous on `stream`
+    void CycleDevice(int first, int n, const dp_scene_hdr* hdr, const double* obs_x, const double* obs_y, dp_plan_record* rec,
+                     void* stream, dp_trace_record* trace = nullptr, double* road_points = nullptr, double* latlng = nullptr) {
+        check(dp_cycle_batch_dev(ctx_, first, n, hdr, obs_x, obs_y, rec, trace, road_points, latlng, stream), "dp_cycle_batch_dev");
+    }
+    dp_ctx* ctx() const { return ctx_; }
+    int max_scenes() const { return max_scenes_; }
+    int max_obs() const { return max_obs_; }
+
+private:
+    static void check(int rc, const char* what) {
+        if (rc != DP_OK) throw std::runtime_error(std::string(what) + ": " + dp_last_error());
+    }
+    dp_ctx* ctx_ = nullptr;
+    int max_scenes_, max_obs_;
+};

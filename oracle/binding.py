@@ -139,16 +139,19 @@ class Oracle(_Runner):
 class Reference(_Runner):
     """the UNMODIFIED reference (oracle/_ref/libref.so); single-threaded by construction."""
 
-    def __init__(self):
+    def __init__(self, gpu_share=False):
+        """gpu_share=True loads _ref/libref_gpu.so: the same unmodified reference objects linked against the PRODUCT's
+        drop-in Share.h (host/), i.e. every CShare operator call is a CUDA launch in libdmpp_b200.so."""
         super().__init__()
-        self.lib = _load(os.path.join(_here, "_ref", "libref.so"))
+        name = "libref_gpu.so" if gpu_share else "libref.so"
+        self.lib = _load(os.path.join(_here, "_ref", name))
         if self.lib is None:
-            raise RuntimeError("oracle/_ref/libref.so missing (built by __graft_entry__.build() where /root/reference exists)")
+            raise RuntimeError("oracle/_ref/%s missing (built by __graft_entry__.build() where /root/reference exists)" % name)
         self.lib.ref_run_batch.restype = C.c_longlong
 
     @staticmethod
-    def available():
-        return os.path.exists(os.path.join(_here, "_ref", "libref.so"))
+    def available(gpu_share=False):
+        return os.path.exists(os.path.join(_here, "_ref", "libref_gpu.so" if gpu_share else "libref.so"))
 
     def set_map(self, m):
         self._keep = m

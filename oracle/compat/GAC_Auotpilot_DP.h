@@ -3,7 +3,7 @@
 // 4 auto-reset events, 5 critical sections, the HD-map tables and the Get*/Set* accessors the two
 // threads call.  oracle/ref_harness.cpp fills it per cycle and captures what the threads publish.
 #pragma once
-#include "Share.h"
+#include <Share.h>   // angle form: the -I order picks oracle/compat/Share.h (CPU spec) or host/Share.h (GPU)
 
 typedef vector<MapPoint> LanePts;                       // [id]
 typedef vector<vector<LanePts>> RoadMap;                // [road-1][lane-1][id]

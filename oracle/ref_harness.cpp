@@ -93,10 +93,17 @@ extern "C" BOOL SetEvent(HANDLE h) { *(int*)h = 1; return 1; }
 extern "C" BOOL QueryPerformanceCounter(LARGE_INTEGER* t) { t->QuadPart = g_clock; return 1; }
 extern "C" void Sleep(DWORD) {}
 
-// ---- call log filled by share_impl.cpp ---------------------------------------------------------
+// ---- call log filled by share_impl.cpp (CPU spec build); the GPU-Share build counts calls only ----
+#ifdef REF_GPU_SHARE
+static ref_call* g_calllog = nullptr;
+static int g_calllog_n = 0, g_calllog_cap = 0;
+#define g_search_calls (CShare::SearchCalls())
+extern "C" void share_set_datum(double, double, double, double) {}
+#else
 extern "C" ref_call* g_calllog;
 extern "C" int g_calllog_n, g_calllog_cap;
 extern "C" long long g_search_calls;
+#endif
 
 // ---- map ------------------------------------------------------------------------------------------
 extern "C" int ref_set_map(const dp_map_desc* m) {
@@ -219,12 +226,16 @@ extern "C" int ref_run_episode(int cycles, const dp_scene_hdr* hdr, long hdr_str
         g_calllog_n = 0;
         g_calllog_cap = calls_cap;
         int nd = g_app.n_set_decision, np = g_app.n_set_planning;
+        const long long calls_before = g_search_calls; (void)calls_before;
         g_ev[0] = 1; g_ev[1] = 1;
         co_resume(0);                         // one Decision cycle; ends with SetEvent(x_DecisionEvent)
         if (g_app.n_set_decision != nd + 1) return -3;
         co_resume(1);                         // one Planning cycle
         if (g_app.n_set_planning != np + 1) return -4;
         g_ev[3] = 0;
+#ifdef REF_GPU_SHARE
+        g_calllog_n = (int)(g_search_calls - calls_before);
+#endif
         if (n_calls) n_calls[c * ncalls_stride] = g_calllog_n;
 
         CPlanning& p = CPlanning::Instance();
