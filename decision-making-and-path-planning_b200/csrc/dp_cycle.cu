@@ -10,6 +10,7 @@
 // obstacle SoA rows, the 128-byte carry, the previous local path (the reference's own cross-cycle
 // state, Planning.cpp:6) and the 128-byte plan record.
 #include "dp_device.cuh"
+#include "dp_fused.cuh"
 #include "dp_kernels.h"
 
 namespace {
@@ -110,16 +111,15 @@ __device__ __forceinline__ Src junction_src(const DevMap& m, int base0, int n0, 
     return s;
 }
 
+// out-of-line copy for the rare trajectories (junction reference path, sweep with more than 16 obstacles)
+static __device__ __noinline__ SearchRes dp_search_cold(const Src s, double mx, double my, const double* ox, const double* oy, int N,
+                                                        const LaneMap lm, double lo, double hi, WarpSmem& sm, int lane) {
+    return dp_search(s, mx, my, ox, oy, N, lm, lo, hi, sm, lane);
+}
+
 }  // namespace
 
 #define DP_MIN_BLOCKS 7
-
-// The cycle is a small stage machine around ONE inlined copy of the SearchObstacle operator: each
-// stage either prepares a trajectory (a Src recipe + corridor window) for the shared search code
-// below the switch, or runs scalar logic and moves on.  Compared with one call site per trajectory
-// this keeps the kernel a few thousand SASS instructions (instruction-cache resident) without paying
-// a call ABI (spills around every call).
-enum { ST_F = 0, ST_R, ST_NF, ST_NR, ST_SWEEP, ST_JUNC, ST_PRELUDE, ST_LOCAL };
 
 __global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32, DP_MIN_BLOCKS)
 dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restrict__ hdr, const double* __restrict__ obs_x,
@@ -132,7 +132,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     if (scene >= n_scenes) return;
 #ifdef DP_DEBUG_CLOCK
     const long long dbg_t0 = clock64();
-    long long dbg_t[8] = {0,0,0,0,0,0,0,0};
+    long long dbg_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define DBG_T(i) dbg_t[i] = clock64() - dbg_t0
 #else
 #define DBG_T(i)
@@ -143,9 +143,8 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     const double* oy = obs_y + (size_t)scene * max_obs;
     const int N = min((int)h.n_obs, max_obs);
     double2* lastp = last_path + (size_t)scene * DP_PATH_POINTS;
-    // last_Bpoints (Planning.cpp:6) -> sm.plan by one TMA bulk copy; it lands while the Decision half runs
-    dp_bulk_prefetch(sm.plan, lastp, DP_PATH_POINTS * (uint32_t)sizeof(double2), &sm.mbar, lane);
-    dp_carry c = carry[scene];
+    dp_carry* const cg = carry + scene;
+    dp_plan_record* const out = rec + scene;                // the record is assembled in place: fields are stored when final
     const LaneMap lm = dp_lane_map(N, lane);
     // this lane's obstacle stays in registers for the whole cycle when N < 32
     const bool lm_act = (lm.nchunk > 1) && (lane < N * lm.nchunk);
@@ -158,41 +157,23 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     }
     const double Vw = p.vehicle_width;
     const int pos = h.pos;
-    const double period = h.period_ms;
-    int ub = 0, n_traj = 0, sweep_pick = -1, pts = 0;
+    int ub = 0, n_traj = 0, pts = 0;
     int rp_base0 = 0, rp_n0 = 0, rp_base1 = 0, rp_n1 = 0;    // DecisionOut.refpath as a recipe (two forward map runs)
+    int gl = 0, lane_sum = 0;
+    const int lane_n = h.lane_num;
+    // decision outputs that the planning half consumes
+    int d_behavior = 1, d_target = 0;
+    double v_exp = 10.0;
 
-    // ---- scene-wide scalars of SegmentDecision ----
-    int gl = 0, lane_n = h.lane_num, lane_sum = 0, id = 0, lanechg = 0, side = 0, K = 0;
-    unsigned navi = 4, navi_t = 0;
-    double W = 0.0, gF = 0.0, gNF = 0.0, gNR = 0.0;
-    int nb_gl = -1, nb_id = 0;                               // neighbour lane of the cycle (-1: none or virtual)
-    double nb_d = 0.0;                                       // lateral offset of a virtual neighbour (+-W)
-    int F_base = 0, F_P = 0, NF_P = 0;
-    Beh cur;
-    cur.behavior = c.behavior; cur.target = c.target_lanenum; cur.light = c.light_status;
-    cur.lanechg = c.lanechg_status != 0; cur.obsavoid = c.obsavoid_status != 0; cur.dlg = c.behavior_to_dlg;
-    int lane_cur = lane_n, sw_sd = 0, sw_i = 0;
-    bool picked = false;
-    // ---- planning scalars that cross the local-path search ----
-    float faraim = 0.f;
-    double v_exp = 0.0;
-    int near_id = 0, d_behavior = 0;
-    bool plan_dirty = false;
-    // planning half of the carry, (re)read at ST_PRELUDE so that it occupies no registers during the decision half
-    double aim_x = 0.0, aim_y = 0.0, aim_dir = 0.0;
-    int aim_id = 0, plan_count = 0;
-    dp_plan_record* const out = rec + scene;                // the record is assembled in place: fields are stored when final
-
-    int stage;
     if (pos == 0) {
-        // =========================== SegmentDecision (Decision.cpp:216-315): set-up ===========================
+        // =========================== SegmentDecision (Decision.cpp:216-315) ===========================
         const int road = h.road_num;
         gl = m.road_lane_base[road - 1] + lane_n - 1;
         lane_sum = m.road_lane_base[road] - m.road_lane_base[road - 1];
         const int off = m.lane_pt_off[gl], id_sum = m.lane_pt_off[gl + 1] - off;
-        id = (int)(uint16_t)h.id[lane_n - 1];
+        const int id = (int)(uint16_t)h.id[lane_n - 1];
         // ---- Nav_LaneChange (Decision.cpp:685-738) ----
+        unsigned navi = 4, navi_t = 0;
         for (int i = 0; i < DP_LANESUM && h.out_lane_no[i] != 0; ++i)
             if (lane_n == h.out_lane_no[i]) { navi = 0; break; }
         int out_min = h.out_lane_no[0], out_max = 1;
@@ -213,31 +194,255 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         }
         // ---- LoadRefPath (Decision.cpp:553-673) ----
         const int idc = min(id, id_sum - 1);
-        lanechg = m.attr[off + idc];
-        W = m.width[off + idc] / 100.0;
+        const int lanechg = m.attr[off + idc];
+        const double W = m.width[off + idc] / 100.0;
         // F and R always; at most ONE neighbour pair exists per cycle: left for attribute 1/3, right only
         // for attribute 2 (the reference never loads the right lane for 3, Decision.cpp:636)
-        // (slices are rebuilt from (lane, id) at the stage that scores them: nothing but F stays live)
+        Slice F, R, NF, NR;
+        NF.base = NR.base = 0; NF.stride = 1; NR.stride = -1; NF.P = NR.P = 0; NF.d = NR.d = 0.0;
+        lane_slices(m, gl, id, p.id_more, F, R, ub);
+        int side = 0;
         if (lanechg == 1 || lanechg == 3) {
             side = 1;
             if (lane_n > 1) {
                 const int idl = (int)(uint16_t)h.id[lane_n - 2];
                 const int nl = m.lane_pt_off[gl] - m.lane_pt_off[gl - 1];
-                if (idl > 0 && idl < nl) { nb_gl = gl - 1; nb_id = idl; } else side = -1;   // no left slice: gaps stay 0
-            } else nb_d = -1 * W;
+                if (idl > 0 && idl < nl) lane_slices(m, gl - 1, idl, p.id_more, NF, NR, ub);
+            } else { NF = F; NF.d = -1 * W; NR = R; NR.d = -1 * W; }
         } else if (lanechg == 2) {
             side = 2;
             if (lane_n < lane_sum) {
                 const int idr = (int)(uint16_t)h.id[lane_n];
                 const int nr = m.lane_pt_off[gl + 2] - m.lane_pt_off[gl + 1];
-                if (idr > 0 && idr < nr) { nb_gl = gl + 1; nb_id = idr; } else side = -2;
-            } else nb_d = W;
+                if (idr > 0 && idr < nr) lane_slices(m, gl + 1, idr, p.id_more, NF, NR, ub);
+            } else { NF = F; NF.d = W; NR = R; NR.d = W; }
         }
-        while (K < DP_MAX_SWEEP && (double)K < (W - Vw) / 0.6) ++K;
+        // ---- AroundObstacle (Decision.cpp:759-881): the four trajectories in ONE fused pass ----
+        const int nslot = (side == 2) ? 4 : 2;
+        double gF = 0.0, gNF = 0.0, gNR = 0.0;              // gaps stay 0 (memset state) for paths that are not evaluated
+        {
+            const int rb[4] = {F.base, R.base, NF.base, NR.base}, rs[4] = {F.stride, R.stride, NF.stride, NR.stride};
+            const int rP[4] = {F.P, R.P, NF.P, NR.P};
+            const double rd[4] = {0.0, 0.0, NF.d, NR.d};
+            dp_region_stage(m, sm, rb, rs, rP, rd, lane);
+            const double nlo = (side == 2) ? -0.5 * W : -0.5 * Vw, nhi = (side == 2) ? 0.5 * Vw : 0.5 * W;
+            int qoff = 0;
+#pragma unroll 1
+            for (int r = 0; r < 4; ++r) {                   // one copy of the search code, four staged trajectories
+                const int Pr = (r == 0) ? F.P : (r == 1) ? R.P : (r == 2) ? NF.P : NR.P;
+                if (Pr != 0) {
+                    Src sp = dp_src_run(m.xy, 1, Pr);
+                    sp.q_off = qoff;
+                    const SearchRes sr = dp_search(sp, mx, my, ox, oy, N, lm, r < 2 ? -0.5 * Vw : nlo, r < 2 ? 0.5 * Vw : nhi, sm, lane);
+                    ++n_traj; pts += Pr;
+                    put_slot(tr ? &tr->region[r < 2 ? r : nslot + r - 2] : nullptr, sr, 1, lane);
+                    if (r == 0) gF = sr.dis_lng; else if (r == 2) gNF = sr.dis_lng; else if (r == 3) gNR = sr.dis_lng;
+                }
+                qoff += Pr;
+            }
+        }
+        const double gLF = (side == 1) ? gNF : 0.0, gLR = (side == 1) ? gNR : 0.0;
+        const double gRF = (side == 2) ? gNF : 0.0, gRR = (side == 2) ? gNR : 0.0;
         if (tr && lane == 0) { tr->width_curlane = W; tr->navi_lanechg = navi; tr->navi_lanechg_times = navi_t; }
-        stage = ST_F;
+        DBG_T(5);
+
+        // ---- BehaviorDecision (Decision.cpp:898-1773) ----
+        dp_carry c = *cg;
+        Beh cur;
+        cur.behavior = c.behavior; cur.target = c.target_lanenum; cur.light = c.light_status;
+        cur.lanechg = c.lanechg_status != 0; cur.obsavoid = c.obsavoid_status != 0; cur.dlg = c.behavior_to_dlg;
+        const int his_behavior = c.his_behavior, his_target = c.his_target_lanenum, his_light = c.his_light_status;
+        int lane_cur = lane_n;
+        int z_light = c.light_status;
+        int sweep_pick = -1;
+        const double period = h.period_ms;
+        int K = 0;
+        while (K < DP_MAX_SWEEP && (double)K < (W - Vw) / 0.6) ++K;
+#define DP_KEEP(reset) do { cur.behavior = 1; cur.target = lane_cur; if (reset) cur.lanechg = false; } while (0)
+#define DP_TICK do { c.leftlight_time += period; if (c.leftlight_time > 2000) c.leftlight_time = 2000; } while (0)
+        if (lanechg == 0) {                                 // :920-1010
+            if (gF < 15) {
+                c.no_obsavoid_time = 0;
+                c.obsavoid_time++;
+                if (c.obsavoid_time > 2) {
+                    // in-lane avoid sweep: candidates L0..L(K-1), R0..R(K-1), first feasible wins (Decision.cpp:940-974).
+                    // With a trace buffer the remaining candidates are scored too (evaluated = 2) but neither counted nor used.
+                    const int total = 2 * K;
+                    if (total > 0 && N > 0 && N <= 16) {
+                        dp_sweep_stage(m, sm, F.base, F.P, lane);
+                        const int per = min(8, 32 / N);
+                        for (int g0 = 0; g0 < total && (sweep_pick < 0 || tr); g0 += per) {
+                            const int cnt = min(per, total - g0);
+                            const bool none_yet = sweep_pick < 0;
+                            const int FP = F.P;
+                            const int first = dp_sweep_pass(sm, FP, g0, cnt, K, mx, my, N, lm, -0.5 * Vw, 0.5 * Vw, 25.0, tr != nullptr, lane,
+                                [&](int ci, const SearchRes& r, bool before_first) {
+                                    const bool before = none_yet && before_first;          // scored by the reference too
+                                    if (before) { ++n_traj; pts += FP; }
+                                    if (tr) { const int g = g0 + ci; put_slot(&tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)], r, before ? 1 : 2, lane); }
+                                });
+                            if (sweep_pick < 0 && first >= 0) sweep_pick = g0 + first;
+                        }
+                    } else {
+                        for (int g = 0; g < total && (sweep_pick < 0 || tr); ++g) {   // one candidate at a time (N > 16, N == 0)
+                            const double cd = ((g / K) == 0 ? -0.3 : 0.3) * (g % K);
+                            const SearchRes s = dp_search_cold(slice_src(m, F.base, 1, F.P, cd), mx, my, ox, oy, N, lm, -0.5 * Vw, 0.5 * Vw, sm, lane);
+                            const bool before = sweep_pick < 0;
+                            if (before) { ++n_traj; pts += F.P; }
+                            put_slot(tr ? &tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)] : nullptr, s, before ? 1 : 2, lane);
+                            if (before && s.dis_lng > 25) sweep_pick = g;
+                        }
+                    }
+                    if (sweep_pick >= 0) {
+                        const int sd = sweep_pick / K;
+                        cur.behavior = sd == 0 ? 4 : 5; cur.target = lane_cur; cur.light = sd == 0 ? 1 : 2;
+                        cur.obsavoid = true; cur.dlg = sd == 0 ? 11 : 12;
+                    }
+                } else { cur.behavior = 1; cur.target = lane_cur; cur.light = 0; cur.dlg = 1; }
+            } else {
+                if (c.obsavoid_status == 0) { cur.behavior = 1; cur.target = lane_cur; cur.light = 0; cur.dlg = 1; }
+                else {
+                    c.no_obsavoid_time++;
+                    if (c.no_obsavoid_time > 3) { cur.behavior = 1; cur.target = lane_cur; cur.light = 0; cur.dlg = 1; cur.obsavoid = false; }
+                }
+                cur.dlg = 1;
+            }
+        } else {                                            // :1012-1772
+            c.no_obsavoid_time = 0;
+            c.obsavoid_time = 0;
+            if (!cur.lanechg) {
+                if (navi != 0) {                            // :1021-1144
+                    if (navi == 1) {
+                        if (lanechg == 1 || lanechg == 3) {
+                            cur.dlg = 2;
+                            if (cur.light != 1) { cur.light = 1; c.leftlight_time = 0; }
+                            c.leftlight_time += period;
+                            if (((gLF > gF + 10) || (gLF > 40)) && gLR > 15 && c.leftlight_time > 2000) {
+                                cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
+                            } else DP_KEEP(true);
+                        } else { DP_KEEP(true); cur.dlg = 4; }
+                    } else if (navi == 2) {
+                        if (lanechg == 2 || lanechg == 3) {
+                            cur.dlg = 3;
+                            if (cur.light != 2) { cur.lanechg = true; c.rightlight_time = 0; }   // sic: lanechg_status = 2 (:1094)
+                            c.rightlight_time += period;
+                            if (((gRF > gF + 10) || (gRF > 40)) && gRR > 15 && c.rightlight_time >= 2000) {
+                                cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
+                            } else DP_KEEP(true);
+                        } else { DP_KEEP(true); cur.dlg = 4; }
+                    }
+                } else {                                    // :1146-1757
+                    if (gF < (2 * 10 + 5)) {
+                        c.frontobs_time++;
+                        if (c.frontobs_time > 2) {
+                            c.frontobs_time = 3;
+                            bool has_m1 = false, has_p1 = false;    // exit-lane list contains lane-1 / lane+1
+                            for (int i = 0; i < DP_LANESUM && h.out_lane_no[i] != 0; ++i) {
+                                if (h.out_lane_no[i] == lane_cur - 1) has_m1 = true;
+                                if (h.out_lane_no[i] == lane_cur + 1) has_p1 = true;
+                            }
+                            if (lanechg == 1) {             // :1157-1294
+                                if (lane_cur > 1) {
+                                    cur.dlg = 5;
+                                    const bool no_back = !has_m1;
+                                    bool chg = false;
+                                    if (no_back) {
+                                        if (run_exceeds(m, sm, gl, id, 0, 60.0, lane)) {
+                                            chg = true;
+                                            if (z_light != 1) { z_light = 1; c.leftlight_time = 0; }
+                                            c.leftlight_time += period;
+                                            if (c.leftlight_time > 2000) c.leftlight_time = 2000;
+                                        } else z_light = 0;
+                                    } else {
+                                        if (run_exceeds(m, sm, gl, id, 1, 15.0, lane)) {
+                                            chg = true;
+                                            if (cur.light != 1) { cur.light = 1; c.leftlight_time = 0; }
+                                            c.leftlight_time += period;
+                                            if (c.leftlight_time > 2000) c.leftlight_time = 2100;
+                                        } else cur.light = 0;
+                                    }
+                                    if (chg && gLF > gF + 10 && gLR > 10 && c.leftlight_time > 1500) {
+                                        c.frontobs_time = 0; cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
+                                    } else DP_KEEP(true);
+                                } else DP_KEEP(true);
+                            } else if (lanechg == 2) {      // :1296-1424
+                                if (lane_cur < lane_sum) {
+                                    cur.dlg = 6;
+                                    const bool no_back = !has_m1;                     // sic (:1307)
+                                    bool chg = false;
+                                    if (run_exceeds(m, sm, gl, id, 1, no_back ? 50.0 : 10.0, lane)) {
+                                        chg = true;
+                                        const int want = no_back ? 2 : 1;
+                                        if (cur.light != want) { cur.light = want; c.leftlight_time = 0; }
+                                        c.leftlight_time += period;
+                                        if (c.leftlight_time > 2000) c.leftlight_time = 2000;
+                                    }
+                                    if (chg && gRF > gF + 10 && gRR > 10 && c.leftlight_time > 1500) {
+                                        c.frontobs_time = 0; cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
+                                    } else DP_KEEP(true);
+                                } else DP_KEEP(true);
+                            } else if (lanechg == 3) {      // :1426-1738
+                                const bool nb_left = !has_m1, nb_right = !has_p1;
+                                bool left_ok = false, right_ok = false;
+                                if (lane_cur > 1) left_ok = run_exceeds(m, sm, gl, id, nb_left ? 1 : 2, nb_left ? 50.0 : 10.0, lane);
+                                if (lane_cur < lane_sum) right_ok = run_exceeds(m, sm, gl, id, 1, nb_right ? 50.0 : 10.0, lane);
+                                if (left_ok && !nb_left) {                          // :1545-1594
+                                    if (!cur.lanechg) { cur.light = 1; c.leftlight_time = 0; }
+                                    DP_TICK;
+                                    if (gLF > gF + 10 && gLR > 10 && c.leftlight_time > 2000) {
+                                        c.frontobs_time = 0; cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
+                                    } else DP_KEEP(true);
+                                } else if (right_ok && !nb_right) {                 // :1596-1636
+                                    if (cur.light != 2) { cur.light = 2; c.leftlight_time = 0; }
+                                    DP_TICK;
+                                    if (gRF > gF + 10) {
+                                        if (gRR > 10 && c.leftlight_time > 2000) {
+                                            c.frontobs_time = 0; cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
+                                        } else DP_KEEP(false);
+                                    }
+                                } else if (left_ok) {                               // :1638-1686
+                                    if (cur.light != 1) { cur.lanechg = true; c.leftlight_time = 0; }   // sic (:1642)
+                                    DP_TICK;
+                                    if (gLF > gF + 10 && gLR > 10 && c.leftlight_time > 2000) {
+                                        c.frontobs_time = 0; cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
+                                    } else DP_KEEP(false);
+                                } else if (right_ok) {                              // :1688-1730
+                                    if (cur.light != 2) { cur.light = 2; c.leftlight_time = 0; }
+                                    DP_TICK;
+                                    if (gRF > gF + 10) {
+                                        if (gRR > 10 && c.leftlight_time > 2000) {
+                                            c.frontobs_time = 0; cur.behavior = 3; lane_cur = 1; cur.target = 1; cur.lanechg = true;   // sic (:1712)
+                                        } else DP_KEEP(false);
+                                    }
+                                } else DP_KEEP(true);
+                            }
+                        } else DP_KEEP(true);               // :1741-1746
+                    } else { c.frontobs_time = 0; cur.dlg = 8; DP_KEEP(true); }
+                }
+            } else {                                        // lane change in progress, :1760-1771
+                cur.dlg = 9;
+                if (cur.target == lane_cur) { cur.lanechg = false; cur.light = 0; }
+                cur.behavior = his_behavior; cur.target = his_target; cur.light = his_light;
+            }
+        }
+        (void)z_light;
+        // ---- SpeedDecision / RefPath / write-back (Decision.cpp:1781-1816, 307-313) + thread-loop tail (:187-201) ----
+        v_exp = (cur.behavior == 4 || cur.behavior == 5) ? 5 : 10;
+        rp_n0 = (cur.behavior == 2) ? (side == 1 ? NF.P : 0) : (cur.behavior == 3) ? (side == 2 ? NF.P : 0) : F.P;   // only its length is consumed at pos 0
+        d_behavior = cur.behavior; d_target = cur.target;
+        if (lane == 0) {                                    // decision half of the carry and of the record is final: store it now
+            cg->leftlight_time = c.leftlight_time; cg->rightlight_time = c.rightlight_time; cg->velocity_expect = v_exp;
+            cg->obsavoid_time = c.obsavoid_time; cg->no_obsavoid_time = c.no_obsavoid_time; cg->frontobs_time = c.frontobs_time;
+            cg->behavior = (uint16_t)cur.behavior; cg->target_roadnum = h.road_num; cg->target_lanenum = (uint16_t)cur.target;
+            cg->light_status = (uint16_t)cur.light; cg->behavior_to_dlg = (uint16_t)cur.dlg;
+            cg->his_behavior = (uint16_t)cur.behavior; cg->his_target_lanenum = (uint16_t)cur.target; cg->his_light_status = (uint16_t)cur.light;
+            cg->lanechg_status = cur.lanechg; cg->obsavoid_status = cur.obsavoid;
+            out->velocity_expect = v_exp;
+            out->behavior = (uint16_t)cur.behavior; out->target_roadnum = h.road_num; out->target_lanenum = (uint16_t)cur.target;
+            out->light = (uint16_t)cur.light; out->behavior_to_dlg = (uint16_t)cur.dlg; out->sweep_index = (int16_t)sweep_pick;
+        }
     } else if (pos == 1 || pos == 2) {
-        // =================== PreStubDecision / StubDecision (Decision.cpp:323-486): set-up ===================
+        // =================== PreStubDecision / StubDecision (Decision.cpp:323-486) ===================
         const int gc = (h.conn >= 0 && h.conn < m.n_conn) ? m.conn[h.conn].lane : -1;
         const int coff = gc >= 0 ? m.lane_pt_off[gc] : 0, n_inter = gc >= 0 ? m.lane_pt_off[gc + 1] - coff : 0;
         const int gj = m.road_lane_base[h.road_num - 1] + h.lane_num - 1;
@@ -251,128 +456,83 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             rp_base0 = coff + idj; rp_n0 = max(0, n_inter - idj);
             rp_base1 = off; rp_n1 = min(60, n);
         }
-        stage = ST_JUNC;
-    } else stage = ST_PRELUDE;
+        const SearchRes s = dp_search_cold(junction_src(m, rp_base0, rp_n0, rp_base1, rp_n1), mx, my, ox, oy, N, lm, -0.5 * Vw, 0.5 * Vw, sm, lane);
+        ++n_traj; pts += rp_n0 + rp_n1;
+        put_slot(tr ? &tr->junction : nullptr, s, 1, lane);
+        int dlg;
+        if (s.dis_lng < 13) {
+            const double v = s.dis_lng - 3;
+            v_exp = v > 0 ? v : 0;
+            dlg = 13;
+        } else { v_exp = 10; dlg = 1; }
+        const int light = (h.stub_attribute == 3) ? 1 : h.stub_attribute;
+        d_behavior = 1; d_target = h.lane_num;
+        if (lane == 0) {                                    // members the junction functions write (:394-399) + thread-loop tail
+            cg->velocity_expect = v_exp; cg->behavior_to_dlg = (uint16_t)dlg; cg->light_status = (uint16_t)light;
+            cg->behavior = 1; cg->target_roadnum = h.road_num; cg->target_lanenum = h.lane_num;
+            cg->his_behavior = 1; cg->his_light_status = (uint16_t)light; cg->his_target_lanenum = h.lane_num;
+            out->velocity_expect = v_exp; out->behavior = 1; out->target_roadnum = h.road_num; out->target_lanenum = h.lane_num;
+            out->light = (uint16_t)light; out->behavior_to_dlg = (uint16_t)dlg; out->sweep_index = -1;
+        }
+    } else {
+        // no decision function runs for other pos values (Decision.cpp:183): members keep their values
+        d_behavior = cg->behavior; d_target = cg->target_lanenum; v_exp = cg->velocity_expect;
+        if (lane == 0) {
+            cg->his_behavior = cg->behavior; cg->his_light_status = cg->light_status; cg->his_target_lanenum = cg->target_lanenum;
+            out->velocity_expect = v_exp; out->behavior = cg->behavior; out->target_roadnum = cg->target_roadnum;
+            out->target_lanenum = cg->target_lanenum; out->light = cg->light_status; out->behavior_to_dlg = cg->behavior_to_dlg;
+            out->sweep_index = -1;
+        }
+    }
+    DBG_T(0);
+    if (tr && lane == 0) tr->refpath_len = (uint16_t)(rp_n0 + rp_n1);
 
-#define DP_KEEP(reset) do { cur.behavior = 1; cur.target = lane_cur; if (reset) cur.lanechg = false; } while (0)
-#define DP_TICK do { c.leftlight_time += period; if (c.leftlight_time > 2000) c.leftlight_time = 2000; } while (0)
-
-    for (;;) {
-        // ------------------------------------------------------------------ prepare the stage's trajectory
-        Src src = dp_src_run(m.xy, 1, 0);
-        double lo = -0.5 * Vw, hi = 0.5 * Vw;
-        dp_search_slot* slot = nullptr;
-        int slot_eval = 1;
-        if (stage <= ST_NR) {                               // lane-region paths (Decision.cpp:811-842)
-            const bool nb = (stage >= ST_NF), rear = (stage == ST_R || stage == ST_NR);
-            Slice fw, rr;
-            fw.base = rr.base = 0; fw.stride = rr.stride = 1; fw.P = rr.P = 0; fw.d = rr.d = 0.0;
-            int ubl = 0;
-            if (!nb || side > 0) lane_slices(m, (nb && nb_gl >= 0) ? nb_gl : gl, (nb && nb_gl >= 0) ? nb_id : id, p.id_more, fw, rr, ubl);
-            if (stage == ST_F || stage == ST_NF) ub += ubl;  // count the clamp once per lane
-            const Slice& sl = rear ? rr : fw;
-            src = slice_src(m, sl.base, sl.stride, sl.P, nb ? nb_d : 0.0);
-            if (stage == ST_F) { F_base = fw.base; F_P = fw.P; }
-            if (stage == ST_NF) NF_P = fw.P;
-            if (nb) { if (side == 2 || side == -2) lo = -0.5 * W; else hi = 0.5 * W; }
-            const int sidx = !nb ? (rear ? 1 : 0) : ((side == 2 || side == -2) ? 4 : 2) + (rear ? 1 : 0);
-            slot = tr ? &tr->region[sidx] : nullptr;
-        } else if (stage == ST_SWEEP) {                     // avoid candidate (sw_sd, sw_i): offset copy of F (Decision.cpp:942,961)
-            src = slice_src(m, F_base, 1, F_P, (sw_sd == 0 ? -0.3 : 0.3) * sw_i);
-            slot = tr ? &tr->sweep[sw_sd * DP_MAX_SWEEP + sw_i] : nullptr;
-            slot_eval = picked ? 2 : 1;
-        } else if (stage == ST_JUNC) {
-            src = junction_src(m, rp_base0, rp_n0, rp_base1, rp_n1);
-            slot = tr ? &tr->junction : nullptr;
-        } else if (stage == ST_PRELUDE) {
-            DBG_T(0);
-            // ---- tail of the Decision thread iteration (Decision.cpp:187-201) ----
-            d_behavior = c.behavior;
-            const int d_target = c.target_lanenum;
-            v_exp = c.velocity_expect;
-            c.his_behavior = c.behavior; c.his_light_status = c.light_status; c.his_target_lanenum = c.target_lanenum;
-            if (tr && lane == 0) tr->refpath_len = (uint16_t)(rp_n0 + rp_n1);
-            dp_carry* const cg = carry + scene;
-            const int plan_his_behavior = cg->plan_his_behavior, carried_near_id = cg->path_near_id;
-            aim_x = cg->aim_x; aim_y = cg->aim_y; aim_dir = cg->aim_dir; aim_id = cg->aim_id; plan_count = cg->plan_count;
-            if (lane == 0) {                                // decision half of the carry and of the record is final: store it now
-                cg->leftlight_time = c.leftlight_time; cg->rightlight_time = c.rightlight_time; cg->velocity_expect = c.velocity_expect;
-                cg->obsavoid_time = c.obsavoid_time; cg->no_obsavoid_time = c.no_obsavoid_time; cg->frontobs_time = c.frontobs_time;
-                cg->behavior = c.behavior; cg->target_roadnum = c.target_roadnum; cg->target_lanenum = c.target_lanenum;
-                cg->light_status = c.light_status; cg->behavior_to_dlg = c.behavior_to_dlg;
-                cg->his_behavior = c.his_behavior; cg->his_target_lanenum = c.his_target_lanenum; cg->his_light_status = c.his_light_status;
-                cg->lanechg_status = c.lanechg_status; cg->obsavoid_status = c.obsavoid_status;
-                cg->plan_his_behavior = d_behavior;         // history update of Planning.cpp:216 (read above)
-                out->velocity_expect = v_exp;
-                out->behavior = c.behavior; out->target_roadnum = c.target_roadnum; out->target_lanenum = c.target_lanenum;
-                out->light = c.light_status; out->behavior_to_dlg = c.behavior_to_dlg; out->sweep_index = (int16_t)sweep_pick;
+    // ================================ Planning thread iteration ================================
+    // last_Bpoints (Planning.cpp:6) -> sm.plan by one TMA bulk copy; the staging area of the decision half is free now and
+    // the copy lands while the aim point is searched
+    __syncwarp();
+    dp_bulk_prefetch(sm.plan, lastp, DP_PATH_POINTS * (uint32_t)sizeof(double2), &sm.mbar, lane);
+    const int plan_his_behavior = cg->plan_his_behavior, carried_near_id = cg->path_near_id, plan_count = cg->plan_count;
+    double aim_x = cg->aim_x, aim_y = cg->aim_y, aim_dir = cg->aim_dir;
+    int aim_id = cg->aim_id;
+    // ---- Calculate_aim_dis (Planning.cpp:242-290), FLOAT faraim_dis ----
+    float faraim = 0.f;
+    if (pos == 0) {
+        faraim = (float)((h.velocity / 3.6) * 5 + 4);
+        if (faraim > p.road_faraim_max) faraim = (float)p.road_faraim_max;
+        else if (faraim < p.road_faraim_min) faraim = (float)p.road_faraim_min;
+    } else if (pos == 1) faraim = (float)p.pre_inter_faraim;
+    else if (pos == 2) faraim = (float)p.inter_faraim;
+    if (tr && lane == 0) tr->faraim_dis = faraim;
+    // ---- SearchAimPoint (Planning.cpp:303-583) ----
+    if (pos == 0) {
+        const int cur_id = h.id[lane_n - 1], cur_sum = m.lane_pt_off[gl + 1] - m.lane_pt_off[gl];
+        int left_id = 0, left_sum = 0, right_id = 0, right_sum = 0;
+        if (lane_n > 1) { left_id = h.id[lane_n - 2]; left_sum = m.lane_pt_off[gl] - m.lane_pt_off[gl - 1]; }
+        if (lane_n < lane_sum) { right_id = h.id[lane_n]; right_sum = m.lane_pt_off[gl + 2] - m.lane_pt_off[gl + 1]; }
+        int wl = -1, wfrom = 0, wto = 0, fb_gl = gl, fb_idx = 0, fb_id = 0;   // lane to walk, fallback point
+        if (d_target == lane_n) {
+            if (d_behavior == 1) { wl = gl; wfrom = cur_id; wto = cur_sum - 1; fb_gl = gl; fb_idx = cur_sum - 1; fb_id = cur_sum - 1; }
+        } else {
+            if (d_behavior == 2) {
+                if (lane_n > 1) { wl = gl - 1; wfrom = left_id; wto = left_sum - 1; fb_gl = gl; fb_idx = left_sum - 2; fb_id = left_sum - 1; }
+            } else if (d_behavior == 3) {
+                if (lane_n < lane_sum) { wl = gl + 1; wfrom = right_id; wto = left_sum - 1; fb_gl = gl + 1; fb_idx = right_sum - 1; fb_id = right_sum - 1; }
+                else if (right_id < left_sum - 1) ++ub;
             }
-            // ================================ Planning thread iteration ================================
-            // ---- Calculate_aim_dis (Planning.cpp:242-290), FLOAT faraim_dis ----
-            if (pos == 0) {
-                faraim = (float)((h.velocity / 3.6) * 5 + 4);
-                if (faraim > p.road_faraim_max) faraim = (float)p.road_faraim_max;
-                else if (faraim < p.road_faraim_min) faraim = (float)p.road_faraim_min;
-            } else if (pos == 1) faraim = (float)p.pre_inter_faraim;
-            else if (pos == 2) faraim = (float)p.inter_faraim;
-            if (tr && lane == 0) tr->faraim_dis = faraim;
-            // ---- SearchAimPoint (Planning.cpp:303-583) ----
-            if (pos == 0) {
-                const int cur_id = h.id[lane_n - 1], cur_sum = m.lane_pt_off[gl + 1] - m.lane_pt_off[gl];
-                int left_id = 0, left_sum = 0, right_id = 0, right_sum = 0;
-                if (lane_n > 1) { left_id = h.id[lane_n - 2]; left_sum = m.lane_pt_off[gl] - m.lane_pt_off[gl - 1]; }
-                if (lane_n < lane_sum) { right_id = h.id[lane_n]; right_sum = m.lane_pt_off[gl + 2] - m.lane_pt_off[gl + 1]; }
-                int wl = -1, wfrom = 0, wto = 0, fb_gl = gl, fb_idx = 0, fb_id = 0;   // lane to walk, fallback point
-                if (d_target == lane_n) {
-                    if (d_behavior == 1) { wl = gl; wfrom = cur_id; wto = cur_sum - 1; fb_gl = gl; fb_idx = cur_sum - 1; fb_id = cur_sum - 1; }
-                } else {
-                    if (d_behavior == 2) {
-                        if (lane_n > 1) { wl = gl - 1; wfrom = left_id; wto = left_sum - 1; fb_gl = gl; fb_idx = left_sum - 2; fb_id = left_sum - 1; }
-                    } else if (d_behavior == 3) {
-                        if (lane_n < lane_sum) { wl = gl + 1; wfrom = right_id; wto = left_sum - 1; fb_gl = gl + 1; fb_idx = right_sum - 1; fb_id = right_sum - 1; }
-                        else if (right_id < left_sum - 1) ++ub;
-                    }
-                }
-                if (wl >= 0 && wfrom < wto) {
-                    const int woff = m.lane_pt_off[wl], wn = m.lane_pt_off[wl + 1] - woff;
-                    int hit = -1;
-                    bool walk = true;
-                    if (wfrom < 0) { ++ub; walk = false; }
-                    if (wto > wn - 1) { ++ub; wto = wn - 1; if (wfrom >= wto) walk = false; }
-                    if (walk) {
-                        double sum = 0.0;
-                        for (int i0 = wfrom; i0 < wto && hit < 0; i0 += DP_SCR) {
-                            const int cnt = min(DP_SCR, wto - i0);
-                            __syncwarp();
-                            for (int j = lane; j < cnt; j += 32) sm.scr[j] = m.lenp[woff + i0 + j];
-                            dp_pad_scr(sm, cnt, lane);
-                            __syncwarp();
-                            const SeqHit hq = dp_seq_first(sm, cnt, sum, 4.0, (double)faraim);
-                            if (hq.k >= 0) hit = i0 + hq.k;
-                            sum = hq.acc;
-                        }
-                        if (hit >= 0) {
-                            aim_x = m.x[woff + hit]; aim_y = m.y[woff + hit]; aim_dir = m.dir[woff + hit]; aim_id = hit;
-                        } else {
-                            const int offb = m.lane_pt_off[fb_gl], nb = m.lane_pt_off[fb_gl + 1] - offb;
-                            int fi = fb_idx;
-                            if (fi < 0 || fi >= nb) { ++ub; fi = fi < 0 ? 0 : nb - 1; }
-                            aim_x = m.x[offb + fi]; aim_y = m.y[offb + fi]; aim_dir = m.dir[offb + fi]; aim_id = fb_id;
-                        }
-                    }
-                }
-            } else if (pos == 1 || pos == 2) {
-                const Src rv = junction_src(m, rp_base0, rp_n0, rp_base1, rp_n1);
-                const int n = rp_n0 + rp_n1;
+        }
+        if (wl >= 0 && wfrom < wto) {
+            const int woff = m.lane_pt_off[wl], wn = m.lane_pt_off[wl + 1] - woff;
+            int hit = -1;
+            bool walk = true;
+            if (wfrom < 0) { ++ub; walk = false; }
+            if (wto > wn - 1) { ++ub; wto = wn - 1; if (wfrom >= wto) walk = false; }
+            if (walk) {
                 double sum = 0.0;
-                int hit = -1;
-                for (int i0 = 0; i0 < n - 1 && hit < 0; i0 += DP_SCR) {
-                    const int cnt = min(DP_SCR, n - 1 - i0);
+                for (int i0 = wfrom; i0 < wto && hit < 0; i0 += DP_SCR) {
+                    const int cnt = min(DP_SCR, wto - i0);
                     __syncwarp();
-                    for (int j = lane; j < cnt; j += 32) {
-                        const double2 a = dp_src_point(rv, i0 + j), b = dp_src_point(rv, i0 + j + 1);
-                        sm.scr[j] = dp_dist_plain(a.x, a.y, b.x, b.y);
-                    }
+                    for (int j = lane; j < cnt; j += 32) sm.scr[j] = m.lenp[woff + i0 + j];
                     dp_pad_scr(sm, cnt, lane);
                     __syncwarp();
                     const SeqHit hq = dp_seq_first(sm, cnt, sum, 4.0, (double)faraim);
@@ -380,361 +540,194 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                     sum = hq.acc;
                 }
                 if (hit >= 0) {
-                    const double2 a = dp_src_point(rv, hit);
-                    aim_x = a.x; aim_y = a.y;
-                    if ((size_t)hit < (size_t)n - 4) {
-                        const double2 b = dp_src_point(rv, hit + 2);
-                        aim_dir = dp_heading(a.x, a.y, b.x, b.y, p.epsilon, p.pi);
-                    } else {
-                        int ia = hit - 2; if (ia < 0) { ++ub; ia = 0; }
-                        const double2 b = dp_src_point(rv, ia);
-                        aim_dir = dp_heading(b.x, b.y, a.x, a.y, p.epsilon, p.pi);
-                    }
-                    aim_id = hit;
-                } else if (n - 1 > 0) {
-                    int ia = n - 3; if (ia < 0) { ++ub; ia = 0; }
-                    const double2 e = dp_src_point(rv, n - 1), b = dp_src_point(rv, ia);
-                    aim_x = e.x; aim_y = e.y;
-                    aim_dir = dp_heading(b.x, b.y, e.x, e.y, p.epsilon, p.pi);
-                    aim_id = n - 1;
+                    aim_x = m.x[woff + hit]; aim_y = m.y[woff + hit]; aim_dir = m.dir[woff + hit]; aim_id = hit;
+                } else {
+                    const int offb = m.lane_pt_off[fb_gl], nb = m.lane_pt_off[fb_gl + 1] - offb;
+                    int fi = fb_idx;
+                    if (fi < 0 || fi >= nb) { ++ub; fi = fi < 0 ? 0 : nb - 1; }
+                    aim_x = m.x[offb + fi]; aim_y = m.y[offb + fi]; aim_dir = m.dir[offb + fi]; aim_id = fb_id;
                 }
             }
-            DBG_T(1);
-            // ---- last_Bpoints must have landed in sm.plan by now ----
-            dp_bulk_wait(&sm.mbar);
-            DBG_T(2);
-            // ---- InitialPlanning on the first cycle (Planning.cpp:124-128) ----
-            const bool first = (plan_count == 0);
-            if (first) {
-                dp_bezier_to_plan(sm, h.x, h.y, h.dir, aim_x, aim_y, aim_dir, lane);
-                plan_dirty = true;
+        }
+    } else if (pos == 1 || pos == 2) {
+        const Src rv = junction_src(m, rp_base0, rp_n0, rp_base1, rp_n1);
+        const int n = rp_n0 + rp_n1;
+        double sum = 0.0;
+        int hit = -1;
+        for (int i0 = 0; i0 < n - 1 && hit < 0; i0 += DP_SCR) {
+            const int cnt = min(DP_SCR, n - 1 - i0);
+            __syncwarp();
+            for (int j = lane; j < cnt; j += 32) {
+                const double2 a = dp_src_point(rv, i0 + j), b = dp_src_point(rv, i0 + j + 1);
+                sm.scr[j] = dp_dist_plain(a.x, a.y, b.x, b.y);
             }
-            // ---- GetVhclLocalState (Planning.cpp:623-676) on last_Bpoints ----
-            double md = 9999.0;
-            int mi = 0x7fffffff;
-            for (int i = lane; i < DP_PATH_POINTS; i += 32) {
-                const double2 q = sm.plan[i];
-                const double d = dp_dist_plain(h.x, h.y, q.x, q.y);
-                if (d < md) { md = d; mi = i; }
+            dp_pad_scr(sm, cnt, lane);
+            __syncwarp();
+            const SeqHit hq = dp_seq_first(sm, cnt, sum, 4.0, (double)faraim);
+            if (hq.k >= 0) hit = i0 + hq.k;
+            sum = hq.acc;
+        }
+        if (hit >= 0) {
+            const double2 a = dp_src_point(rv, hit);
+            aim_x = a.x; aim_y = a.y;
+            if ((size_t)hit < (size_t)n - 4) {
+                const double2 b = dp_src_point(rv, hit + 2);
+                aim_dir = dp_heading(a.x, a.y, b.x, b.y, p.epsilon, p.pi);
+            } else {
+                int ia = hit - 2; if (ia < 0) { ++ub; ia = 0; }
+                const double2 b = dp_src_point(rv, ia);
+                aim_dir = dp_heading(b.x, b.y, a.x, a.y, p.epsilon, p.pi);
             }
+            aim_id = hit;
+        } else if (n - 1 > 0) {
+            int ia = n - 3; if (ia < 0) { ++ub; ia = 0; }
+            const double2 e = dp_src_point(rv, n - 1), b = dp_src_point(rv, ia);
+            aim_x = e.x; aim_y = e.y;
+            aim_dir = dp_heading(b.x, b.y, e.x, e.y, p.epsilon, p.pi);
+            aim_id = n - 1;
+        }
+    }
+    DBG_T(1);
+    dp_bulk_wait(&sm.mbar);
+    DBG_T(2);
+    // ---- InitialPlanning on the first cycle (Planning.cpp:124-128) ----
+    bool plan_dirty = false;
+    const bool first = (plan_count == 0);
+    if (first) {
+        dp_bezier_to_plan(sm, h.x, h.y, h.dir, aim_x, aim_y, aim_dir, lane);
+        plan_dirty = true;
+    }
+    // ---- GetVhclLocalState (Planning.cpp:623-676) on last_Bpoints ----
+    double md = 9999.0;
+    int mi = 0x7fffffff;
+    for (int i = lane; i < DP_PATH_POINTS; i += 32) {
+        const double2 q = sm.plan[i];
+        const double d = dp_dist_plain(h.x, h.y, q.x, q.y);
+        if (d < md) { md = d; mi = i; }
+    }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double od = __shfl_xor_sync(DP_FULL, md, o);
-                const int oi = __shfl_xor_sync(DP_FULL, mi, o);
-                if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
-            }
-            near_id = (mi == 0x7fffffff) ? carried_near_id : mi;
-            const int front_id = near_id + 8;
-            int idx = (near_id == 199) ? near_id - 1 : near_id;
-            if (idx < 0 || idx > 198) { ++ub; idx = idx < 0 ? 0 : 198; }
-            const double2 pt = sm.plan[idx], pn = sm.plan[idx + 1];
-            const double lat = dp_lat_dis(h.x, h.y, pt.x, pt.y, pn.x, pn.y, p.epsilon);
-            double remain;
-            {
-                const int f0 = max(front_id, 0);
-                if (front_id < 0) ++ub;
-                const int cnt = max(0, 199 - f0);
-                __syncwarp();
-                for (int j = lane; j < cnt; j += 32) {
-                    const double2 a = sm.plan[f0 + j], b = sm.plan[f0 + j + 1];
-                    sm.scr[j] = dp_dist_plain(b.x, b.y, a.x, a.y);
-                }
-                dp_pad_scr(sm, cnt, lane);
-                __syncwarp();
-                remain = dp_seq_sum(sm, cnt, 0.0);
-            }
-            const double dir_err = dp_angle_err(dp_heading(pt.x, pt.y, pn.x, pn.y, p.epsilon, p.pi), h.dir);
-            DBG_T(3);
-            // ---- UpdatePlanJudge (Planning.cpp:797-832) ----
-            bool afresh = true;
-            int cause = 0;
-            if (plan_his_behavior != d_behavior) cause = 1;
-            else if (fabs(lat) > 0.2) cause = 2;
-            else if (fabs(dir_err) > 45) cause = 3;
-            else if (pos == 0 && remain < p.road_remain_distance) cause = 4;
-            else if (pos != 0 && remain < p.inter_remain_distance) cause = 4;
-            else afresh = false;
-            // ---- CalculateRadius reads the PREVIOUS path (Planning.cpp:199, 1000-1019): before overwriting ----
-            double radius;
-            {
-                int ia = near_id, ib = (near_id + front_id) / 2, ic = front_id;
-                if (ia < 0 || ia > 199) { ++ub; ia = ia < 0 ? 0 : 199; }
-                if (ib < 0 || ib > 199) { ++ub; ib = ib < 0 ? 0 : 199; }
-                if (ic < 0 || ic > 199) { ++ub; ic = ic < 0 ? 0 : 199; }
-                const double2 A = sm.plan[ia], B = sm.plan[ib], Fp = sm.plan[ic];
-                const double d1 = dp_dist_plain(A.x, A.y, B.x, B.y), d2 = dp_dist_plain(B.x, B.y, Fp.x, Fp.y), d3 = dp_dist_plain(A.x, A.y, Fp.x, Fp.y);
-                const double dd = d1 * d1 + d2 * d2 - d3 * d3;
-                const double cosA = dd / (2 * d1 * d2);
-                const double sinA = sqrt(1 - cosA * cosA);
-                radius = (sinA < 0.001) ? 1000 : 0.5 * d3 / sinA;
-            }
-            if (lane == 0) {                                // local-state half of the record is final
-                out->path_lat_dis = lat; out->path_dir_err = dir_err; out->remain_dis = remain; out->radius = radius;
-                out->aim_x = aim_x; out->aim_y = aim_y; out->aim_dir = aim_dir; out->aim_id = aim_id;
-                out->afresh_cause = (uint16_t)cause; out->afresh_planning = afresh;
-                out->path_near_id = (int16_t)near_id; out->path_front_near_id = (int16_t)front_id;
-                cg->aim_x = aim_x; cg->aim_y = aim_y; cg->aim_dir = aim_dir; cg->aim_id = aim_id; cg->path_near_id = near_id;
-            }
-            // ---- PathPlanning (Planning.cpp:845-877) or reuse (:142-146): road_points -> sm.plan ----
-            if (afresh) {
-                plan_dirty = true;
-                if (pos == 0) {
-                    // the first-cycle Bezier above used the same two poses: identical points, nothing to redo
-                    if (!first) dp_bezier_to_plan(sm, h.x, h.y, h.dir, aim_x, aim_y, aim_dir, lane);
-                } else if (pos == 1 || pos == 2) {
-                    int n = aim_id;
-                    if (n > DP_PATH_POINTS) { ++ub; n = DP_PATH_POINTS; }
-                    if (n > rp_n0 + rp_n1) { ++ub; n = rp_n0 + rp_n1; }
-                    dp_mean_points_to_plan(sm, junction_src(m, rp_base0, rp_n0, rp_base1, rp_n1), n, lane);
-                } else {
-                    __syncwarp();
-                    for (int i = lane; i < DP_PATH_POINTS; i += 32) sm.plan[i] = make_double2(0.0, 0.0);
-                    __syncwarp();
-                }
-            }                                               // else: road_points = last_Bpoints, already in sm.plan
-            DBG_T(4);
-            stage = ST_LOCAL;
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(DP_FULL, md, o);
+        const int oi = __shfl_xor_sync(DP_FULL, mi, o);
+        if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+    }
+    const int near_id = (mi == 0x7fffffff) ? carried_near_id : mi;
+    const int front_id = near_id + 8;
+    int idx = (near_id == 199) ? near_id - 1 : near_id;
+    if (idx < 0 || idx > 198) { ++ub; idx = idx < 0 ? 0 : 198; }
+    const double2 pt = sm.plan[idx], pn = sm.plan[idx + 1];
+    const double lat = dp_lat_dis(h.x, h.y, pt.x, pt.y, pn.x, pn.y, p.epsilon);
+    double remain;
+    {
+        const int f0 = max(front_id, 0);
+        if (front_id < 0) ++ub;
+        const int cnt = max(0, 199 - f0);
+        __syncwarp();
+        for (int j = lane; j < cnt; j += 32) {
+            const double2 a = sm.plan[f0 + j], b = sm.plan[f0 + j + 1];
+            sm.scr[j] = dp_dist_plain(b.x, b.y, a.x, a.y);
         }
-        if (stage == ST_LOCAL) {                            // local path collision (Planning.cpp:152-168): a window of sm.plan
-            const int s0 = max(near_id, 0);
-            src = dp_src_run(sm.plan + s0, 1, DP_PATH_POINTS - s0);
-            src.plan_off = s0;
-            lo = (double)(float)(-1.1); hi = (double)(float)(1.1);
-            slot = tr ? &tr->local : nullptr;
+        dp_pad_scr(sm, cnt, lane);
+        __syncwarp();
+        remain = dp_seq_sum(sm, cnt, 0.0);
+    }
+    const double dir_err = dp_angle_err(dp_heading(pt.x, pt.y, pn.x, pn.y, p.epsilon, p.pi), h.dir);
+    DBG_T(3);
+    // ---- UpdatePlanJudge (Planning.cpp:797-832) ----
+    bool afresh = true;
+    int cause = 0;
+    if (plan_his_behavior != d_behavior) cause = 1;
+    else if (fabs(lat) > 0.2) cause = 2;
+    else if (fabs(dir_err) > 45) cause = 3;
+    else if (pos == 0 && remain < p.road_remain_distance) cause = 4;
+    else if (pos != 0 && remain < p.inter_remain_distance) cause = 4;
+    else afresh = false;
+    // ---- CalculateRadius reads the PREVIOUS path (Planning.cpp:199, 1000-1019): before overwriting ----
+    double radius;
+    {
+        int ia = near_id, ib = (near_id + front_id) / 2, ic = front_id;
+        if (ia < 0 || ia > 199) { ++ub; ia = ia < 0 ? 0 : 199; }
+        if (ib < 0 || ib > 199) { ++ub; ib = ib < 0 ? 0 : 199; }
+        if (ic < 0 || ic > 199) { ++ub; ic = ic < 0 ? 0 : 199; }
+        const double2 A = sm.plan[ia], B = sm.plan[ib], Fp = sm.plan[ic];
+        const double d1 = dp_dist_plain(A.x, A.y, B.x, B.y), d2 = dp_dist_plain(B.x, B.y, Fp.x, Fp.y), d3 = dp_dist_plain(A.x, A.y, Fp.x, Fp.y);
+        const double dd = d1 * d1 + d2 * d2 - d3 * d3;
+        const double cosA = dd / (2 * d1 * d2);
+        const double sinA = sqrt(1 - cosA * cosA);
+        radius = (sinA < 0.001) ? 1000 : 0.5 * d3 / sinA;
+    }
+    if (lane == 0) {                                        // local-state half of the record and of the carry is final
+        out->path_lat_dis = lat; out->path_dir_err = dir_err; out->remain_dis = remain; out->radius = radius;
+        out->aim_x = aim_x; out->aim_y = aim_y; out->aim_dir = aim_dir; out->aim_id = aim_id;
+        out->afresh_cause = (uint16_t)cause; out->afresh_planning = afresh;
+        out->path_near_id = (int16_t)near_id; out->path_front_near_id = (int16_t)front_id;
+        cg->aim_x = aim_x; cg->aim_y = aim_y; cg->aim_dir = aim_dir; cg->aim_id = aim_id; cg->path_near_id = near_id;
+        cg->plan_his_behavior = d_behavior;                 // history update of Planning.cpp:216
+        uint8_t cnt = (uint8_t)(plan_count + 1);            // BYTE count of CPlanningThread (Planning.cpp:219-223)
+        if (cnt % 100 == 1) cnt = 1;
+        cg->plan_count = cnt;
+        out->cnt = (uint8_t)(plan_count % 100);
+    }
+    // ---- PathPlanning (Planning.cpp:845-877) or reuse (:142-146): road_points -> sm.plan ----
+    if (afresh) {
+        plan_dirty = true;
+        if (pos == 0) {
+            // the first-cycle Bezier above used the same two poses: identical points, nothing to redo
+            if (!first) dp_bezier_to_plan(sm, h.x, h.y, h.dir, aim_x, aim_y, aim_dir, lane);
+        } else if (pos == 1 || pos == 2) {
+            int n = aim_id;
+            if (n > DP_PATH_POINTS) { ++ub; n = DP_PATH_POINTS; }
+            if (n > rp_n0 + rp_n1) { ++ub; n = rp_n0 + rp_n1; }
+            dp_mean_points_to_plan(sm, junction_src(m, rp_base0, rp_n0, rp_base1, rp_n1), n, lane);
+        } else {
+            __syncwarp();
+            for (int i = lane; i < DP_PATH_POINTS; i += 32) sm.plan[i] = make_double2(0.0, 0.0);
+            __syncwarp();
         }
-
-        // ------------------------------------------------------------------ the one SearchObstacle evaluation
-        SearchRes sr;
-        const int P = src.n0 + src.n1;
-        const bool counted = !(stage == ST_SWEEP && picked);
-        if (P != 0 || stage == ST_SWEEP || stage == ST_JUNC || stage == ST_LOCAL) {
-            sr = dp_search(src, mx, my, ox, oy, N, lm, lo, hi, sm, lane);
-            if (counted) { ++n_traj; pts += P; }
-            put_slot(slot, sr, slot_eval, lane);
-        } else { sr.found = false; sr.dis_lat = 0.0; sr.dis_lng = 0.0; sr.ob = -1; sr.pathid = 0; }   // empty path: memset state
-
-        // ------------------------------------------------------------------ consume the result
-        if (stage == ST_F) { DBG_T(5); gF = sr.dis_lng; stage = ST_R; continue; }
-        if (stage == ST_R) { stage = ST_NF; continue; }
-        if (stage == ST_NF) { gNF = sr.dis_lng; stage = ST_NR; continue; }
-        if (stage == ST_LOCAL) {
-            // ---- SpeedPlanning (Planning.cpp:888-990) ----
-            double brake = 0.0, des_acc = 0.0;
-            bool acc_flag = false;
-            if (pos <= 2) {
-                if (sr.found) {
-                    if (sr.dis_lng - 4 > 9) brake = 3 + (sr.dis_lng - 9) / (faraim - 9) * (v_exp - 3);
-                    else if (sr.dis_lng - 4 > 5) brake = 3;
-                    else { brake = 0; acc_flag = true; des_acc = -3; }
-                } else brake = v_exp;
-            }
-            // ---- outputs (Planning.cpp:173-214) and history (:216-223) ----
-            if (plan_dirty)                                 // the carried path only changes on (re)planning cycles
-                for (int i = lane; i < DP_PATH_POINTS; i += 32) lastp[i] = sm.plan[i];
-            if (path_xy)
-                for (int i = lane; i < DP_PATH_POINTS; i += 32) {
-                    const double2 q = sm.plan[i];
-                    path_xy[(size_t)scene * 400 + i] = q.x; path_xy[(size_t)scene * 400 + DP_PATH_POINTS + i] = q.y;
-                }
-            if (path_ll) {
-                for (int i = lane; i < DP_OUT_POINTS; i += 32) {
-                    const double2 q = sm.plan[2 * i];
-                    path_ll[(size_t)scene * 200 + i] = fma(q.y, p.k_lat, p.lat0);
-                    path_ll[(size_t)scene * 200 + DP_OUT_POINTS + i] = fma(q.x, p.k_lng, p.lng0);
-                }
-            }
-            if (lane == 0) {
-                uint8_t cnt = (uint8_t)(plan_count + 1);    // BYTE count of CPlanningThread (Planning.cpp:219-223)
-                if (cnt % 100 == 1) cnt = 1;
-                carry[scene].plan_count = cnt;
-                out->mindist_lat = sr.dis_lat; out->mindist_lon = sr.dis_lng; out->brakespeed = brake; out->des_acc = des_acc;
-                out->ob_index = (int16_t)sr.ob; out->ob_pathid = (uint16_t)sr.pathid; out->n_traj = (uint16_t)n_traj;
-                out->ob_flag = sr.found; out->acc_flag = acc_flag; out->cnt = (uint8_t)(plan_count % 100);
+    }                                                       // else: road_points = last_Bpoints, already in sm.plan
+    DBG_T(4);
+    // ---- local path collision (Planning.cpp:152-168): rem_path is a window of sm.plan ----
+    const int s0 = max(near_id, 0);
+    Src rem = dp_src_run(sm.plan + s0, 1, DP_PATH_POINTS - s0);
+    rem.q_off = s0;
+    const SearchRes ls = dp_search(rem, mx, my, ox, oy, N, lm, (double)(float)(-1.1), (double)(float)(1.1), sm, lane);
+    ++n_traj; pts += DP_PATH_POINTS - s0;
+    put_slot(tr ? &tr->local : nullptr, ls, 1, lane);
+    // ---- SpeedPlanning (Planning.cpp:888-990) ----
+    double brake = 0.0, des_acc = 0.0;
+    bool acc_flag = false;
+    if (pos <= 2) {
+        if (ls.found) {
+            if (ls.dis_lng - 4 > 9) brake = 3 + (ls.dis_lng - 9) / (faraim - 9) * (v_exp - 3);
+            else if (ls.dis_lng - 4 > 5) brake = 3;
+            else { brake = 0; acc_flag = true; des_acc = -3; }
+        } else brake = v_exp;
+    }
+    // ---- outputs (Planning.cpp:173-214) and history (:216-223) ----
+    if (plan_dirty)                                         // the carried path only changes on (re)planning cycles
+        for (int i = lane; i < DP_PATH_POINTS; i += 32) lastp[i] = sm.plan[i];
+    if (path_xy)
+        for (int i = lane; i < DP_PATH_POINTS; i += 32) {
+            const double2 q = sm.plan[i];
+            path_xy[(size_t)scene * 400 + i] = q.x; path_xy[(size_t)scene * 400 + DP_PATH_POINTS + i] = q.y;
+        }
+    if (path_ll) {
+        for (int i = lane; i < DP_OUT_POINTS; i += 32) {
+            const double2 q = sm.plan[2 * i];
+            path_ll[(size_t)scene * 200 + i] = fma(q.y, p.k_lat, p.lat0);
+            path_ll[(size_t)scene * 200 + DP_OUT_POINTS + i] = fma(q.x, p.k_lng, p.lng0);
+        }
+    }
+    if (lane == 0) {
+        out->mindist_lat = ls.dis_lat; out->mindist_lon = ls.dis_lng; out->brakespeed = brake; out->des_acc = des_acc;
+        out->ob_index = (int16_t)ls.ob; out->ob_pathid = (uint16_t)ls.pathid; out->n_traj = (uint16_t)n_traj;
+        out->ob_flag = ls.found; out->acc_flag = acc_flag;
 #ifdef DP_DEBUG_CLOCK
-                out->radius = (double)(clock64() - dbg_t0); out->des_acc = (double)dbg_t0;
-                out->path_lat_dis = (double)dbg_t[0]; out->path_dir_err = (double)dbg_t[1]; out->remain_dis = (double)dbg_t[2];
-                out->mindist_lat = (double)dbg_t[3]; out->mindist_lon = (double)dbg_t[4]; out->brakespeed = (double)dbg_t[5];
+        out->radius = (double)(clock64() - dbg_t0); out->des_acc = (double)dbg_t0;
+        out->path_lat_dis = (double)dbg_t[0]; out->path_dir_err = (double)dbg_t[1]; out->remain_dis = (double)dbg_t[2];
+        out->mindist_lat = (double)dbg_t[3]; out->mindist_lon = (double)dbg_t[4]; out->brakespeed = (double)dbg_t[5];
 #endif
-                if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
-            }
-            return;
-        }
-        if (stage == ST_JUNC) {                             // Decision.cpp:373-399, 458-484
-            if (sr.dis_lng < 13) {
-                const double v = sr.dis_lng - 3;
-                c.velocity_expect = v > 0 ? v : 0;
-                c.behavior_to_dlg = 13;
-            } else { c.velocity_expect = 10; c.behavior_to_dlg = 1; }
-            c.light_status = (h.stub_attribute == 3) ? 1 : h.stub_attribute;
-            c.behavior = 1;
-            c.target_roadnum = h.road_num;
-            c.target_lanenum = h.lane_num;
-            stage = ST_PRELUDE;
-            continue;
-        }
-        bool decided = false;                               // BehaviorDecision finished for this cycle?
-        if (stage == ST_SWEEP) {                            // Decision.cpp:940-974: first feasible candidate wins
-            if (!picked && sr.dis_lng > 25) {
-                cur.behavior = sw_sd == 0 ? 4 : 5; cur.target = lane_cur; cur.light = sw_sd == 0 ? 1 : 2;
-                cur.obsavoid = true; cur.dlg = sw_sd == 0 ? 11 : 12;
-                picked = true; sweep_pick = sw_sd * K + sw_i;
-            }
-            if (++sw_i >= K) { sw_i = 0; ++sw_sd; }
-            if (sw_sd < 2 && (!picked || tr)) continue;     // with a trace buffer the rest is scored too (evaluated = 2)
-            decided = true;
-        }
-        if (stage == ST_NR) {
-            gNR = sr.dis_lng;
-            const double gLF = (side == 1) ? gNF : 0.0, gLR = (side == 1) ? gNR : 0.0;   // side < 0: slice missing, gaps 0
-            const double gRF = (side == 2) ? gNF : 0.0, gRR = (side == 2) ? gNR : 0.0;
-            // ---- BehaviorDecision (Decision.cpp:898-1773) ----
-            const int his_behavior = c.his_behavior, his_target = c.his_target_lanenum, his_light = c.his_light_status;
-            int z_light = c.light_status;
-            decided = true;
-            if (lanechg == 0) {                             // :920-1010
-                if (gF < 15) {
-                    c.no_obsavoid_time = 0;
-                    c.obsavoid_time++;
-                    if (c.obsavoid_time > 2) {
-                        if (K > 0) { sw_sd = 0; sw_i = 0; picked = false; stage = ST_SWEEP; continue; }
-                    } else { cur.behavior = 1; cur.target = lane_cur; cur.light = 0; cur.dlg = 1; }
-                } else {
-                    if (c.obsavoid_status == 0) { cur.behavior = 1; cur.target = lane_cur; cur.light = 0; cur.dlg = 1; }
-                    else {
-                        c.no_obsavoid_time++;
-                        if (c.no_obsavoid_time > 3) { cur.behavior = 1; cur.target = lane_cur; cur.light = 0; cur.dlg = 1; cur.obsavoid = false; }
-                    }
-                    cur.dlg = 1;
-                }
-            } else {                                        // :1012-1772
-                c.no_obsavoid_time = 0;
-                c.obsavoid_time = 0;
-                if (!cur.lanechg) {
-                    if (navi != 0) {                        // :1021-1144
-                        if (navi == 1) {
-                            if (lanechg == 1 || lanechg == 3) {
-                                cur.dlg = 2;
-                                if (cur.light != 1) { cur.light = 1; c.leftlight_time = 0; }
-                                c.leftlight_time += period;
-                                if (((gLF > gF + 10) || (gLF > 40)) && gLR > 15 && c.leftlight_time > 2000) {
-                                    cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
-                                } else DP_KEEP(true);
-                            } else { DP_KEEP(true); cur.dlg = 4; }
-                        } else if (navi == 2) {
-                            if (lanechg == 2 || lanechg == 3) {
-                                cur.dlg = 3;
-                                if (cur.light != 2) { cur.lanechg = true; c.rightlight_time = 0; }   // sic: lanechg_status = 2 (:1094)
-                                c.rightlight_time += period;
-                                if (((gRF > gF + 10) || (gRF > 40)) && gRR > 15 && c.rightlight_time >= 2000) {
-                                    cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
-                                } else DP_KEEP(true);
-                            } else { DP_KEEP(true); cur.dlg = 4; }
-                        }
-                    } else {                                // :1146-1757
-                        if (gF < (2 * 10 + 5)) {
-                            c.frontobs_time++;
-                            if (c.frontobs_time > 2) {
-                                c.frontobs_time = 3;
-                                bool has_m1 = false, has_p1 = false;    // exit-lane list contains lane-1 / lane+1
-                                for (int i = 0; i < DP_LANESUM && h.out_lane_no[i] != 0; ++i) {
-                                    if (h.out_lane_no[i] == lane_cur - 1) has_m1 = true;
-                                    if (h.out_lane_no[i] == lane_cur + 1) has_p1 = true;
-                                }
-                                if (lanechg == 1) {         // :1157-1294
-                                    if (lane_cur > 1) {
-                                        cur.dlg = 5;
-                                        const bool no_back = !has_m1;
-                                        bool chg = false;
-                                        if (no_back) {
-                                            if (run_exceeds(m, sm, gl, id, 0, 60.0, lane)) {
-                                                chg = true;
-                                                if (z_light != 1) { z_light = 1; c.leftlight_time = 0; }
-                                                c.leftlight_time += period;
-                                                if (c.leftlight_time > 2000) c.leftlight_time = 2000;
-                                            } else z_light = 0;
-                                        } else {
-                                            if (run_exceeds(m, sm, gl, id, 1, 15.0, lane)) {
-                                                chg = true;
-                                                if (cur.light != 1) { cur.light = 1; c.leftlight_time = 0; }
-                                                c.leftlight_time += period;
-                                                if (c.leftlight_time > 2000) c.leftlight_time = 2100;
-                                            } else cur.light = 0;
-                                        }
-                                        if (chg && gLF > gF + 10 && gLR > 10 && c.leftlight_time > 1500) {
-                                            c.frontobs_time = 0; cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
-                                        } else DP_KEEP(true);
-                                    } else DP_KEEP(true);
-                                } else if (lanechg == 2) {  // :1296-1424
-                                    if (lane_cur < lane_sum) {
-                                        cur.dlg = 6;
-                                        const bool no_back = !has_m1;                 // sic (:1307)
-                                        bool chg = false;
-                                        if (run_exceeds(m, sm, gl, id, 1, no_back ? 50.0 : 10.0, lane)) {
-                                            chg = true;
-                                            const int want = no_back ? 2 : 1;
-                                            if (cur.light != want) { cur.light = want; c.leftlight_time = 0; }
-                                            c.leftlight_time += period;
-                                            if (c.leftlight_time > 2000) c.leftlight_time = 2000;
-                                        }
-                                        if (chg && gRF > gF + 10 && gRR > 10 && c.leftlight_time > 1500) {
-                                            c.frontobs_time = 0; cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
-                                        } else DP_KEEP(true);
-                                    } else DP_KEEP(true);
-                                } else if (lanechg == 3) {  // :1426-1738
-                                    const bool nb_left = !has_m1, nb_right = !has_p1;
-                                    bool left_ok = false, right_ok = false;
-                                    if (lane_cur > 1) left_ok = run_exceeds(m, sm, gl, id, nb_left ? 1 : 2, nb_left ? 50.0 : 10.0, lane);
-                                    if (lane_cur < lane_sum) right_ok = run_exceeds(m, sm, gl, id, 1, nb_right ? 50.0 : 10.0, lane);
-                                    if (left_ok && !nb_left) {                          // :1545-1594
-                                        if (!cur.lanechg) { cur.light = 1; c.leftlight_time = 0; }
-                                        DP_TICK;
-                                        if (gLF > gF + 10 && gLR > 10 && c.leftlight_time > 2000) {
-                                            c.frontobs_time = 0; cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
-                                        } else DP_KEEP(true);
-                                    } else if (right_ok && !nb_right) {                 // :1596-1636
-                                        if (cur.light != 2) { cur.light = 2; c.leftlight_time = 0; }
-                                        DP_TICK;
-                                        if (gRF > gF + 10) {
-                                            if (gRR > 10 && c.leftlight_time > 2000) {
-                                                c.frontobs_time = 0; cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
-                                            } else DP_KEEP(false);
-                                        }
-                                    } else if (left_ok) {                               // :1638-1686
-                                        if (cur.light != 1) { cur.lanechg = true; c.leftlight_time = 0; }   // sic (:1642)
-                                        DP_TICK;
-                                        if (gLF > gF + 10 && gLR > 10 && c.leftlight_time > 2000) {
-                                            c.frontobs_time = 0; cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
-                                        } else DP_KEEP(false);
-                                    } else if (right_ok) {                              // :1688-1730
-                                        if (cur.light != 2) { cur.light = 2; c.leftlight_time = 0; }
-                                        DP_TICK;
-                                        if (gRF > gF + 10) {
-                                            if (gRR > 10 && c.leftlight_time > 2000) {
-                                                c.frontobs_time = 0; cur.behavior = 3; lane_cur = 1; cur.target = 1; cur.lanechg = true;   // sic (:1712)
-                                            } else DP_KEEP(false);
-                                        }
-                                    } else DP_KEEP(true);
-                                }
-                            } else DP_KEEP(true);           // :1741-1746
-                        } else { c.frontobs_time = 0; cur.dlg = 8; DP_KEEP(true); }
-                    }
-                } else {                                    // lane change in progress, :1760-1771
-                    cur.dlg = 9;
-                    if (cur.target == lane_cur) { cur.lanechg = false; cur.light = 0; }
-                    cur.behavior = his_behavior; cur.target = his_target; cur.light = his_light;
-                }
-            }
-            (void)z_light;
-        }
-        if (decided) {
-            // ---- SpeedDecision / RefPath / write-back (Decision.cpp:1781-1816, 307-313) ----
-            c.velocity_expect = (cur.behavior == 4 || cur.behavior == 5) ? 5 : 10;
-            rp_n0 = (cur.behavior == 2) ? (side == 1 ? NF_P : 0) : (cur.behavior == 3) ? (side == 2 ? NF_P : 0) : F_P;   // only its length is consumed at pos 0
-            c.behavior = (uint16_t)cur.behavior; c.light_status = (uint16_t)cur.light; c.target_lanenum = (uint16_t)cur.target;
-            c.lanechg_status = cur.lanechg; c.obsavoid_status = cur.obsavoid; c.behavior_to_dlg = (uint16_t)cur.dlg;
-            c.target_roadnum = h.road_num;
-            stage = ST_PRELUDE;
-        }
+        if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
     }
 }
 

@@ -37,8 +37,13 @@ struct DevMap {
 // 6728 bytes per warp: 7 CTAs of 4 warps fit the 196 KB shared-memory configuration and leave
 // 60 KB of L1 for the map gathers.
 struct __align__(16) WarpSmem {
-    double2 plan[DP_PATH_POINTS];              // last_Bpoints on entry (TMA bulk copy), road_points on exit
-    double2 tile[DP_TILE];                     // one staged path tile (also cum[] of MeanPoints, 240 doubles)
+    union {
+        struct {
+            double2 plan[DP_PATH_POINTS];      // last_Bpoints (TMA bulk copy) during the planning half, road_points on exit
+            double2 tile[DP_TILE];             // one staged path tile (also cum[] of MeanPoints, 240 doubles)
+        };
+        double2 q[DP_PATH_POINTS + DP_TILE];   // decision half: the 4 lane-region paths (<= 320 points) staged back to back,
+    };                                         //                or F + its normals for the fused avoid sweep
     double scr[DP_SCR + 8];                    // sequential-sum terms, zero padded to a multiple of 8
     unsigned long long mbar;                   // mbarrier of the bulk copy
 };
@@ -51,7 +56,7 @@ struct Src {
     const double2* p1; int n1;                 // run 1 (forward): p1[j - n0]
     const double2* nrm0;                       // normals aligned with p0 (only when d != 0, single run)
     double d;                                  // lateral offset, RIGHT positive
-    int plan_off;                              // >= 0: the path is the window sm.plan[plan_off ...] (no staging needed)
+    int q_off;                                 // >= 0: the path is already staged at sm.q[q_off ...] (no staging needed)
 };
 struct LaneMap { int nchunk, o, c; };          // nearest-search work item of this lane for N < 32
 struct SearchRes { bool found; double dis_lat, dis_lng; int ob, pathid; };
@@ -76,7 +81,7 @@ __device__ __forceinline__ double2 dp_normal(double2 a, double2 b) {
 }
 __device__ __forceinline__ Src dp_src_run(const double2* p, int stride, int n) {
     Src s;
-    s.p0 = p; s.stride0 = stride; s.n0 = n; s.p1 = p; s.n1 = 0; s.nrm0 = nullptr; s.d = 0.0; s.plan_off = -1;
+    s.p0 = p; s.stride0 = stride; s.n0 = n; s.p1 = p; s.n1 = 0; s.nrm0 = nullptr; s.d = 0.0; s.q_off = -1;
     return s;
 }
 // point j of the path (CreateNewPath fused in: p_j + d * n_j; fwd normal index min(j,P-2),
@@ -168,9 +173,9 @@ __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my
     const int nchunk = lm.nchunk;
     const int CS = (nchunk == 1) ? P : (P + nchunk - 1) / nchunk;
     const int ngroups = (nchunk == 1) ? (N + 31) >> 5 : 1;
-    const bool in_plan = s.plan_off >= 0;
+    const bool in_plan = s.q_off >= 0;
     const bool one_tile = in_plan || P <= DP_TILE;          // every point stays addressable in shared memory
-    const double2* pts = in_plan ? &sm.plan[s.plan_off] : &sm.tile[0];   // both shared: LDS in the hot loop
+    const double2* pts = &sm.q[in_plan ? s.q_off : DP_PATH_POINTS];      // shared: LDS in the hot loop (tile = q[200..320))
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     unsigned bestkey = 0xffffffffu;
     double bestd = 0.0;

@@ -1,0 +1,174 @@
+// csrc/dp_fused.cuh -- fused multi-trajectory passes of the Decision half.
+//
+// The four lane-region trajectories of AroundObstacle (F, R and one neighbour pair, Decision.cpp:811-842)
+// are independent, and so are the lateral-offset candidates of the avoid sweep (Decision.cpp:940-974).
+// Scoring them one after the other makes a scene a chain of ~8.5 k-cycle searches; here they share ONE
+// staging round trip, ONE scan and ONE reduction phase:
+//   * dp_region_pass: the <= 320 points of the 4 paths are staged back to back in shared memory by a single
+//     coalesced gather; each lane scans one third of that array for its obstacle, keeping one running
+//     argmin per path; per-path results are combined across the chunk lanes with shuffles;
+//   * dp_sweep_pass: F and its unit normals are staged once; lanes are (candidate, obstacle) pairs, the
+//     candidate point p + d*n is rolled out in registers inside the scan (CreateNewPath fused), never stored.
+// Results are bit-identical to scoring each trajectory alone with dp_search (tests/test_gpu_parity.py).
+#pragma once
+#include "dp_device.cuh"
+
+// 4 independent running minima over q[a..b): lexicographic (d2, j) minimum = sequential strict-'<' argmin
+__device__ __forceinline__ void dp_scan(const double2* __restrict__ q, int a, int b, double mx, double my, double& bd, int& bj) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double b0 = INF, b1 = INF, b2 = INF, b3 = INF;
+    int i0 = a, i1 = a, i2 = a, i3 = a;
+    int j = a;
+    const double2* p = q + a;
+    for (; j + 4 <= b; j += 4, p += 4) {
+        const double2 p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
+        const double x0 = mx - p0.x, y0 = my - p0.y, x1 = mx - p1.x, y1 = my - p1.y;
+        const double x2 = mx - p2.x, y2 = my - p2.y, x3 = mx - p3.x, y3 = my - p3.y;
+        const double d0 = fma(x0, x0, y0 * y0), d1 = fma(x1, x1, y1 * y1);
+        const double d2 = fma(x2, x2, y2 * y2), d3 = fma(x3, x3, y3 * y3);
+        if (d0 < b0) { b0 = d0; i0 = j; }
+        if (d1 < b1) { b1 = d1; i1 = j + 1; }
+        if (d2 < b2) { b2 = d2; i2 = j + 2; }
+        if (d3 < b3) { b3 = d3; i3 = j + 3; }
+    }
+    for (; j < b; ++j, ++p) {
+        const double2 p0 = p[0];
+        const double x0 = mx - p0.x, y0 = my - p0.y;
+        const double d0 = fma(x0, x0, y0 * y0);
+        if (d0 < b0) { b0 = d0; i0 = j; }
+    }
+    if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+    if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
+    if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
+    bd = b0; bj = i0;
+}
+
+// gate + signed lateral offset + corridor test of one obstacle against segment (pk, pk1) of a P-point path whose
+// nearest point is bj: returns the packed selection key, d in *dout
+__device__ __forceinline__ unsigned dp_owner_key(double2 pk, double2 pk1, int bj, int P, int o, double mx, double my, double lo,
+                                                 double hi, double* dout) {
+    const double sx = pk1.x - pk.x, sy = pk1.y - pk.y;
+    bool pass = true;
+    if (bj == 0) pass = fma(mx - pk.x, sx, (my - pk.y) * sy) >= 0.0;
+    else if (bj == P - 1) pass = fma(mx - pk1.x, sx, (my - pk1.y) * sy) <= 0.0;
+    const double len = sqrt(dp_sq2(sx, sy));
+    double d = 0.0;
+    if (len > 0) d = fma(mx - pk.x, sy, -((my - pk.y) * sx)) / len;
+    pass = pass && (d >= lo && d <= hi);
+    *dout = d;
+    return pass ? (((unsigned)bj << 16) | (unsigned)o) : 0xffffffffu;
+}
+
+// ---- the four lane-region trajectories share one staging round trip -------------------------------------------
+// path r: map points base[r] + stride[r]*j, j < P[r], lateral offset d[r] (virtual neighbour lane).  All (<= 320)
+// points are gathered back to back into sm.q by ONE coalesced pass (CreateNewPath fused for virtual lanes), so the
+// four SearchObstacle evaluations that follow read shared memory only.
+__device__ __forceinline__ void dp_region_stage(const DevMap& m, WarpSmem& sm, const int (&base)[4], const int (&stride)[4],
+                                                const int (&P)[4], const double (&d)[4], int lane) {
+    const int S1 = P[0], S2 = S1 + P[1], S3 = S2 + P[2], Ptot = S3 + P[3];
+    double2* Q = sm.q;
+    __syncwarp();
+#pragma unroll 5
+    for (int v = lane; v < Ptot; v += 32) {
+        const int r = (v >= S3) ? 3 : (v >= S2) ? 2 : (v >= S1) ? 1 : 0;
+        const int j = v - ((r == 3) ? S3 : (r == 2) ? S2 : (r == 1) ? S1 : 0);
+        const int bs = (r == 3) ? base[3] : (r == 2) ? base[2] : (r == 1) ? base[1] : base[0];
+        const int st = (r == 3) ? stride[3] : (r == 2) ? stride[2] : (r == 1) ? stride[1] : stride[0];
+        const int Pr = (r == 3) ? P[3] : (r == 2) ? P[2] : (r == 1) ? P[1] : P[0];
+        const double dr = (r == 3) ? d[3] : (r == 2) ? d[2] : (r == 1) ? d[1] : d[0];
+        double2 pt = m.xy[bs + st * j];
+        if (dr != 0.0 && Pr >= 2) {
+            const int jj = min(j, Pr - 2);
+            double2 n = m.nrm[(st > 0) ? bs + jj : bs - jj - 1];
+            if (st < 0) { n.x = -n.x; n.y = -n.y; }
+            pt.x = fma(dr, n.x, pt.x); pt.y = fma(dr, n.y, pt.y);
+        }
+        Q[v] = pt;
+    }
+    __syncwarp();
+}
+
+// ---- avoid sweep: several lateral-offset candidates of F per pass ---------------------------------------------------
+// stage F (P <= 120 points from map index base) at sm.q[0..P) and the unit normal used for point j at sm.q[128 + j]
+__device__ __forceinline__ void dp_sweep_stage(const DevMap& m, WarpSmem& sm, int base, int P, int lane) {
+    __syncwarp();
+    for (int j = lane; j < P; j += 32) {
+        sm.q[j] = m.xy[base + j];
+        sm.q[128 + j] = (P >= 2) ? m.nrm[base + min(j, P - 2)] : make_double2(0.0, 0.0);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ double2 dp_sweep_point(const WarpSmem& sm, int j, double dc) {
+    const double2 p = sm.q[j], n = sm.q[128 + j];
+    return make_double2(fma(dc, n.x, p.x), fma(dc, n.y, p.y));
+}
+// Scores candidates g0 .. g0+cnt-1 (reference order L0..L(K-1), R0..R(K-1); cnt * N <= 32) against the scene's
+// obstacles (this lane's obstacle = (mx, my), N < 32).  sink(ci, result, counted) receives the result of candidate g0+ci;
+// with need_all == false the arclength of a candidate is only resolved as far as the `> clear` decision needs and
+// candidates after the first feasible one are skipped.  Returns the index (0..cnt-1) of the first feasible candidate or -1.
+template <class Sink>
+__device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int g0, int cnt, int K, double mx, double my, int N, const LaneMap lm,
+                                             double lo, double hi, double clear, bool need_all, int lane, Sink sink) {
+    const int ci_me = lane / N, o = lane - ci_me * N;       // N <= 16 here
+    const bool active = ci_me < cnt;
+    const int g_me = g0 + ci_me;
+    const double dc = ((g_me / K) == 0 ? -0.3 : 0.3) * (g_me % K);   // Decision.cpp:942 (-0.3*i), :961 (0.3*i)
+    (void)lm;
+    unsigned key = 0xffffffffu;
+    double dlat = 0.0;
+    if (active && P >= 2) {
+        // scan all P points of MY candidate for MY obstacle; the candidate point is rolled out in registers
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        double b0 = INF, b1 = INF; int i0 = 0, i1 = 0;
+        int j = 0;
+        for (; j + 2 <= P; j += 2) {
+            const double2 q0 = dp_sweep_point(sm, j, dc), q1 = dp_sweep_point(sm, j + 1, dc);
+            const double x0 = mx - q0.x, y0 = my - q0.y, x1 = mx - q1.x, y1 = my - q1.y;
+            const double d0 = fma(x0, x0, y0 * y0), d1 = fma(x1, x1, y1 * y1);
+            if (d0 < b0) { b0 = d0; i0 = j; }
+            if (d1 < b1) { b1 = d1; i1 = j + 1; }
+        }
+        for (; j < P; ++j) {
+            const double2 q0 = dp_sweep_point(sm, j, dc);
+            const double x0 = mx - q0.x, y0 = my - q0.y;
+            const double d0 = fma(x0, x0, y0 * y0);
+            if (d0 < b0) { b0 = d0; i0 = j; }
+        }
+        if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+        const int bj = i0, k = (bj == P - 1) ? P - 2 : bj;
+        key = dp_owner_key(dp_sweep_point(sm, k, dc), dp_sweep_point(sm, k + 1, dc), bj, P, o, mx, my, lo, hi, &dlat);
+    }
+    // per-candidate selection: min of the packed key over the candidate's N lanes (xor butterfly restricted by compare)
+    // done with full-warp shuffles so that every lane takes part: lanes of other candidates are ignored by index
+    int first = -1;
+#pragma unroll 1
+    for (int ci = 0; ci < cnt; ++ci) {
+        if (first >= 0 && !need_all) break;
+        const unsigned mine = (ci_me == ci) ? key : 0xffffffffu;
+        const unsigned gmin = __reduce_min_sync(DP_FULL, mine);
+        SearchRes r;
+        r.found = false; r.dis_lat = DP_NOT_FOUND; r.dis_lng = DP_NOT_FOUND; r.ob = -1; r.pathid = 0;
+        if (P >= 2 && gmin != 0xffffffffu) {
+            const int jstar = (int)(gmin >> 16), ostar = (int)(gmin & 0xffffu);
+            r.found = true; r.pathid = jstar; r.ob = ostar;
+            r.dis_lat = __shfl_sync(DP_FULL, dlat, ci * N + ostar);
+            const int gc = g0 + ci;
+            const double dcc = ((gc / K) == 0 ? -0.3 : 0.3) * (gc % K);
+            __syncwarp();
+            for (int j = lane; j < jstar; j += 32) {
+                const double2 a = dp_sweep_point(sm, j, dcc), b = dp_sweep_point(sm, j + 1, dcc);
+                sm.scr[j] = sqrt(dp_sq2(b.x - a.x, b.y - a.y));
+            }
+            dp_pad_scr(sm, jstar, lane);
+            __syncwarp();
+            if (need_all) r.dis_lng = dp_seq_sum(sm, jstar, 0.0);
+            else {                                          // only the `dis_lng > clear` decision is needed: monotone partial sums
+                const SeqHit hq = dp_seq_first(sm, jstar, 0.0, 0.0, clear);
+                r.dis_lng = (hq.k >= 0) ? DP_NOT_FOUND : hq.acc;   // (value beyond the threshold is not consumed)
+            }
+        }
+        sink(ci, r, first < 0);                              // (candidate, result, scored by the reference too?)
+        if (first < 0 && r.dis_lng > clear) first = ci;
+    }
+    return first;
+}
