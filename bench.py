@@ -281,19 +281,26 @@ def run_ours(args, rank, world, local_rank):
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:   # DRAM bytes per launch of dp_cycle_kernel from the committed `ncu --set full` capture of tools/profile_cycle.py
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_r1.json")))["dp_cycle_kernel"]["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_desc(world),
         "plan_cycles_per_s": world * SCENES * K / total_s,
         "trajectories_per_step_per_gpu": float(traj_c[cyc_idx].mean()),
+        "cycle_latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),
+                             "max": float(step_ms.max()), "what": "device time of one fused cycle of %d scenes (+ gather when N>1)" % SCENES},
         "e2e": {"value": e2e_val, "unit": UNIT,
                 "h2d_bytes_per_step": SCENES * (128 + 2 * N_OBS * 8), "d2h_bytes_per_step": SCENES * 128,
                 "ms_per_step": float(e2e_t[W:].mean() * 1e3), "plan_cycles_per_s": world * SCENES * K / float(e2e_s.item()),
                 "api": "dp_cycle_batch (host pointers, pinned)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp64", "kernel": "dp_cycle_kernel", "achieved": achieved, "peak": fp64_tf, "unit": "TFLOP/s",
-                     "frac": achieved / fp64_tf if fp64_tf else None, "traffic": None,
+                     "frac": achieved / fp64_tf if fp64_tf else None, "traffic": traffic,
                      "peak_source": "FP64 FMA micro-benchmark run in this process (dp_measure_fma_peak); MEASURED_PEAKS.json has no "
                                     "CUDA-core FP64 figure. fp32 FMA peak measured the same way: %.1f TFLOP/s" % fp32_tf,
                      "algorithmic_flops_per_launch": float(flops_c[cyc_idx].mean()),
