@@ -49,6 +49,7 @@ struct dp_ctx {
     double* d_pxy[2] = {nullptr, nullptr};
     double* d_pll[2] = {nullptr, nullptr};
     long long launches = 0;
+    int split = 1;                                          // Decision / Planning halves as two launches (DP_SPLIT=0: one fused launch)
 };
 
 namespace {
@@ -121,6 +122,7 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     c->device = device;
     if (params) c->p = *params; else dp_default_params(&c->p);
     c->max_scenes = max_scenes; c->max_obs = max_obs;
+    if (const char* e = getenv("DP_SPLIT")) c->split = atoi(e) != 0;
     c->chunk = max_scenes < kChunk ? max_scenes : kChunk;
     int r;
     if ((r = dev_alloc(&c->d_carry, (size_t)max_scenes))) { delete c; return r; }
@@ -237,8 +239,8 @@ int dp_cycle_batch_dev(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, con
     if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_batch_dev: map not uploaded");
     CK(cudaSetDevice(c->device));
     CK(dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace, path_xy,
-                       path_ll, (cudaStream_t)stream));
-    ++c->launches;
+                       path_ll, (cudaStream_t)stream, c->split));
+    c->launches += c->split ? 2 : 1;
     return DP_OK;
 }
 
@@ -275,8 +277,8 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         CK(cudaMemcpyAsync(c->d_oy[s], sy, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
         CK(dp_launch_cycle(c->map, c->p, cn, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first + i0,
                            c->d_last + (size_t)(first + i0) * DP_PATH_POINTS, c->d_rec[s], trace ? c->d_trace[s] : nullptr,
-                           path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st));
-        ++c->launches;
+                           path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st, c->split));
+        c->launches += c->split ? 2 : 1;
         CK(cudaMemcpyAsync(pin_rec ? rec + i0 : c->h_rec[s], c->d_rec[s], (size_t)cn * sizeof(dp_plan_record), cudaMemcpyDeviceToHost, st));
         if (trace) CK(cudaMemcpyAsync(trace + i0, c->d_trace[s], (size_t)cn * sizeof(dp_trace_record), cudaMemcpyDeviceToHost, st));
         if (path_xy) CK(cudaMemcpyAsync(path_xy + (size_t)i0 * 400, c->d_pxy[s], (size_t)cn * 400 * 8, cudaMemcpyDeviceToHost, st));

@@ -111,6 +111,24 @@ __device__ __forceinline__ Src junction_src(const DevMap& m, int base0, int n0, 
     return s;
 }
 
+// junction reference path as two forward map runs: remaining approach lane + connector (PreStubDecision,
+// Decision.cpp:352-367) or remaining connector + first 60 points of the next lane (StubDecision, :438-452)
+__device__ __forceinline__ void junction_recipe(const DevMap& m, const dp_scene_hdr& h, int& base0, int& n0, int& base1, int& n1) {
+    const int gc = (h.conn >= 0 && h.conn < m.n_conn) ? m.conn[h.conn].lane : -1;
+    const int coff = gc >= 0 ? m.lane_pt_off[gc] : 0, n_inter = gc >= 0 ? m.lane_pt_off[gc + 1] - coff : 0;
+    const int gj = m.road_lane_base[h.road_num - 1] + h.lane_num - 1;
+    const int off = m.lane_pt_off[gj], n = m.lane_pt_off[gj + 1] - off;
+    if (h.pos == 1) {
+        const int idj = (int)(uint16_t)h.id[h.lane_num - 1];
+        base0 = off + idj; n0 = max(0, n - idj);
+        base1 = coff; n1 = n_inter;
+    } else {
+        const int idj = (int)(uint16_t)h.id[h.last_lanenum - 1];
+        base0 = coff + idj; n0 = max(0, n_inter - idj);
+        base1 = off; n1 = min(60, n);
+    }
+}
+
 // out-of-line copy for the rare trajectories (junction reference path, sweep with more than 16 obstacles)
 static __device__ __noinline__ SearchRes dp_search_cold(const Src s, double mx, double my, const double* ox, const double* oy, int N,
                                                         const LaneMap lm, double lo, double hi, WarpSmem& sm, int lane) {
@@ -121,6 +139,12 @@ static __device__ __noinline__ SearchRes dp_search_cold(const Src s, double mx, 
 
 #define DP_MIN_BLOCKS 7
 
+// PHASE 0: whole cycle in one launch.  PHASE 1 / 2: Decision half / Planning half as two back-to-back launches -- the
+// same work with half the code per kernel: with 28 warps per SM in different places of a ~11 k-instruction kernel the
+// instruction cache thrashes (ncu: 25 % `no_instruction` stalls); each half alone fits.  The hand-off between the two
+// halves is what the reference hands from CDecisionThread to CPlanningThread (DecisionOut, Decision.cpp:187-205),
+// already stored in dp_carry / dp_plan_record.
+template <int PHASE>
 __global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32, DP_MIN_BLOCKS)
 dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restrict__ hdr, const double* __restrict__ obs_x,
                 const double* __restrict__ obs_y, int max_obs, dp_carry* __restrict__ carry, double2* __restrict__ last_path,
@@ -150,7 +174,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     const bool lm_act = (lm.nchunk > 1) && (lane < N * lm.nchunk);
     const double mx = lm_act ? ox[lm.o] : 0.0, my = lm_act ? oy[lm.o] : 0.0;
     dp_trace_record* tr = trace ? trace + scene : nullptr;
-    if (tr) {                                               // zero the trace record cooperatively
+    if (tr && PHASE != 2) {                                 // zero the trace record cooperatively
         uint32_t* w = reinterpret_cast<uint32_t*>(tr);
         for (int i = lane; i < (int)(sizeof(dp_trace_record) / 4); i += 32) w[i] = 0;
         __syncwarp();
@@ -165,7 +189,16 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     int d_behavior = 1, d_target = 0;
     double v_exp = 10.0;
 
-    if (pos == 0) {
+    if (PHASE == 2) {
+        // ---- hand-off from the Decision launch ----
+        d_behavior = cg->behavior; d_target = cg->target_lanenum; v_exp = cg->velocity_expect;
+        n_traj = out->n_traj;
+        if (tr) { ub = tr->ub_hits; pts = (int)tr->pts_scored; }
+        if (pos == 0) {
+            gl = m.road_lane_base[h.road_num - 1] + lane_n - 1;
+            lane_sum = m.road_lane_base[h.road_num] - m.road_lane_base[h.road_num - 1];
+        } else if (pos == 1 || pos == 2) junction_recipe(m, h, rp_base0, rp_n0, rp_base1, rp_n1);
+    } else if (pos == 0) {
         // =========================== SegmentDecision (Decision.cpp:216-315) ===========================
         const int road = h.road_num;
         gl = m.road_lane_base[road - 1] + lane_n - 1;
@@ -443,19 +476,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         }
     } else if (pos == 1 || pos == 2) {
         // =================== PreStubDecision / StubDecision (Decision.cpp:323-486) ===================
-        const int gc = (h.conn >= 0 && h.conn < m.n_conn) ? m.conn[h.conn].lane : -1;
-        const int coff = gc >= 0 ? m.lane_pt_off[gc] : 0, n_inter = gc >= 0 ? m.lane_pt_off[gc + 1] - coff : 0;
-        const int gj = m.road_lane_base[h.road_num - 1] + h.lane_num - 1;
-        const int off = m.lane_pt_off[gj], n = m.lane_pt_off[gj + 1] - off;
-        if (pos == 1) {
-            const int idj = (int)(uint16_t)h.id[h.lane_num - 1];
-            rp_base0 = off + idj; rp_n0 = max(0, n - idj);
-            rp_base1 = coff; rp_n1 = n_inter;
-        } else {
-            const int idj = (int)(uint16_t)h.id[h.last_lanenum - 1];
-            rp_base0 = coff + idj; rp_n0 = max(0, n_inter - idj);
-            rp_base1 = off; rp_n1 = min(60, n);
-        }
+        junction_recipe(m, h, rp_base0, rp_n0, rp_base1, rp_n1);
         const SearchRes s = dp_search_cold(junction_src(m, rp_base0, rp_n0, rp_base1, rp_n1), mx, my, ox, oy, N, lm, -0.5 * Vw, 0.5 * Vw, sm, lane);
         ++n_traj; pts += rp_n0 + rp_n1;
         put_slot(tr ? &tr->junction : nullptr, s, 1, lane);
@@ -485,7 +506,14 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         }
     }
     DBG_T(0);
-    if (tr && lane == 0) tr->refpath_len = (uint16_t)(rp_n0 + rp_n1);
+    if (PHASE != 2 && tr && lane == 0) tr->refpath_len = (uint16_t)(rp_n0 + rp_n1);
+    if (PHASE == 1) {                                       // hand the counters over and stop: the Planning launch follows
+        if (lane == 0) {
+            out->n_traj = (uint16_t)n_traj;
+            if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
+        }
+        return;
+    }
 
     // ================================ Planning thread iteration ================================
     // last_Bpoints (Planning.cpp:6) -> sm.plan by one TMA bulk copy; the staging area of the decision half is free now and
@@ -765,15 +793,22 @@ __global__ void dp_map_prep_kernel(const double* x, const double* y, const int32
 // ---- launchers (called from dp_api.cu) ----
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                            double* path_xy, double* path_ll, cudaStream_t st) {
+                            double* path_xy, double* path_ll, cudaStream_t st, int split) {
     if (n <= 0) return cudaSuccess;
     static bool configured = false;
-    if (!configured) {                                      // let 7 CTAs x 29 KB of static shared memory fit on one SM
-        cudaFuncSetAttribute(dp_cycle_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 77);   // 196 of 256 KB: 7 CTAs, rest stays L1
+    if (!configured) {                                      // 196 of 256 KB as shared memory: 7 CTAs per SM, the rest stays L1
+        cudaFuncSetAttribute(dp_cycle_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 77);
+        cudaFuncSetAttribute(dp_cycle_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 77);
+        cudaFuncSetAttribute(dp_cycle_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 77);
         configured = true;
     }
-    const int blocks = (n + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK;
-    dp_cycle_kernel<<<blocks, DP_WARPS_PER_BLOCK * 32, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll);
+    const int blocks = (n + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, threads = DP_WARPS_PER_BLOCK * 32;
+    if (!split) {
+        dp_cycle_kernel<0><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll);
+    } else {
+        dp_cycle_kernel<1><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll);
+        dp_cycle_kernel<2><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll);
+    }
     return cudaGetLastError();
 }
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st) {

@@ -31,3 +31,13 @@ for c in range(K):
     ev[c][1].record(st)
 torch.cuda.synchronize()
 print("kernel ms per cycle:", ["%.3f" % e[0].elapsed_time(e[1]) for e in ev])
+if len(sys.argv) > 3:
+    from dmpp_b200 import abi
+    p.reset(0, n)
+    for c in range(K):
+        p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec.data_ptr(), stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        r = d_rec.cpu().numpy().view(abi.plan_record).reshape(n)
+        nt = r["n_traj"]
+        print("cycle", c, "traj", int(nt.sum()), "hist", dict(zip(*[x.tolist() for x in np.unique(nt, return_counts=True)])),
+              "afresh", int(r["afresh_planning"].sum()), "dlg", dict(zip(*[x.tolist() for x in np.unique(r["behavior_to_dlg"], return_counts=True)])))
