@@ -50,12 +50,14 @@ struct dp_ctx {
     double* d_pll[2] = {nullptr, nullptr};
     long long launches = 0;
     int split = 1;                                          // Decision / Planning halves as two launches (DP_SPLIT=0: one fused launch)
+    int zero_copy = 1;                                      // pinned host buffers are read / written by the kernels directly (DP_ZERO_COPY=0: staged copies)
 };
 
 namespace {
-bool is_pinned(const void* p) {
+bool is_pinned(const void* p, void** dev = nullptr) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (dev) *dev = a.devicePointer;                        // device-side alias of the pinned allocation (== p under UVA)
     return a.type == cudaMemoryTypeHost;
 }
 template <class T> int dev_alloc(T** p, size_t n) {
@@ -123,6 +125,7 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     if (params) c->p = *params; else dp_default_params(&c->p);
     c->max_scenes = max_scenes; c->max_obs = max_obs;
     if (const char* e = getenv("DP_SPLIT")) c->split = atoi(e) != 0;
+    if (const char* e = getenv("DP_ZERO_COPY")) c->zero_copy = atoi(e) != 0;
     c->chunk = max_scenes < kChunk ? max_scenes : kChunk;
     int r;
     if ((r = dev_alloc(&c->d_carry, (size_t)max_scenes))) { delete c; return r; }
@@ -239,7 +242,7 @@ int dp_cycle_batch_dev(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, con
     if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_batch_dev: map not uploaded");
     CK(cudaSetDevice(c->device));
     CK(dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace, path_xy,
-                       path_ll, (cudaStream_t)stream, c->split));
+                       path_ll, (cudaStream_t)stream, c->split, DpIo{nullptr, nullptr, nullptr, nullptr}));
     c->launches += c->split ? 2 : 1;
     return DP_OK;
 }
@@ -254,8 +257,21 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
     if (path_xy && (r = ensure_optional(c, 1))) return r;
     if (path_ll && (r = ensure_optional(c, 2))) return r;
     const size_t mo = (size_t)c->max_obs;
-    const bool pin_in = is_pinned(hdr) && is_pinned(ox) && is_pinned(oy);
-    const bool pin_rec = is_pinned(rec);
+    void *dv_hdr = nullptr, *dv_ox = nullptr, *dv_oy = nullptr, *dv_rec = nullptr;
+    const bool pin_in = is_pinned(hdr, &dv_hdr) && is_pinned(ox, &dv_ox) && is_pinned(oy, &dv_oy);
+    const bool pin_rec = is_pinned(rec, &dv_rec);
+    if (c->zero_copy && c->split && pin_in && pin_rec && dv_hdr && dv_ox && dv_oy && dv_rec && n <= c->chunk && !trace && !path_xy && !path_ll) {
+        // Zero-copy drop-in call: the Decision launch pulls the 128-byte headers and the obstacle rows straight out of the
+        // caller's pinned buffers over PCIe (one coalesced load per scene), the Planning launch pushes each finished
+        // 128-byte record straight into the caller's pinned result buffer.  No staging copies, no copy engines.
+        cudaStream_t st = c->st[0];
+        DpIo io{c->d_hdr[0], c->d_ox[0], c->d_oy[0], (dp_plan_record*)dv_rec};
+        CK(dp_launch_cycle(c->map, c->p, n, (const dp_scene_hdr*)dv_hdr, (const double*)dv_ox, (const double*)dv_oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
+                           c->d_rec[0], nullptr, nullptr, nullptr, st, 1, io));
+        c->launches += 2;
+        CK(cudaStreamSynchronize(st));
+        return DP_OK;
+    }
     int nchunks = (n + c->chunk - 1) / c->chunk;
     for (int k = 0; k < nchunks; ++k) {
         const int s = k & 1;
@@ -277,7 +293,7 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         CK(cudaMemcpyAsync(c->d_oy[s], sy, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
         CK(dp_launch_cycle(c->map, c->p, cn, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first + i0,
                            c->d_last + (size_t)(first + i0) * DP_PATH_POINTS, c->d_rec[s], trace ? c->d_trace[s] : nullptr,
-                           path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st, c->split));
+                           path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st, c->split, DpIo{nullptr, nullptr, nullptr, nullptr}));
         c->launches += c->split ? 2 : 1;
         CK(cudaMemcpyAsync(pin_rec ? rec + i0 : c->h_rec[s], c->d_rec[s], (size_t)cn * sizeof(dp_plan_record), cudaMemcpyDeviceToHost, st));
         if (trace) CK(cudaMemcpyAsync(trace + i0, c->d_trace[s], (size_t)cn * sizeof(dp_trace_record), cudaMemcpyDeviceToHost, st));

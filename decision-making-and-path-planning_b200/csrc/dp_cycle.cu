@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32, DP_MIN_BLOCKS)
 dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restrict__ hdr, const double* __restrict__ obs_x,
                 const double* __restrict__ obs_y, int max_obs, dp_carry* __restrict__ carry, double2* __restrict__ last_path,
                 dp_plan_record* __restrict__ rec, dp_trace_record* __restrict__ trace, double* __restrict__ path_xy,
-                double* __restrict__ path_ll) {
+                double* __restrict__ path_ll, DpIo io) {
     __shared__ WarpSmem smem[DP_WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int scene = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
@@ -162,10 +162,21 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
 #define DBG_T(i)
 #endif
     WarpSmem& sm = smem[wib];
-    const dp_scene_hdr& h = hdr[scene];
+    // the 128-byte scene header comes in with one coalesced warp load (from HBM, or straight from pinned host memory
+    // over PCIe in the zero-copy mode of dp_cycle_batch) and is read from shared memory afterwards
+    sm.hdr[lane] = reinterpret_cast<const uint32_t*>(hdr + scene)[lane];
+    __syncwarp();
+    const dp_scene_hdr& h = *reinterpret_cast<const dp_scene_hdr*>(sm.hdr);
     const double* ox = obs_x + (size_t)scene * max_obs;
     const double* oy = obs_y + (size_t)scene * max_obs;
     const int N = min((int)h.n_obs, max_obs);
+    if (PHASE != 2 && io.hdr_stage) {                       // zero-copy ingest: keep a device copy for the Planning launch
+        reinterpret_cast<uint32_t*>(io.hdr_stage + scene)[lane] = sm.hdr[lane];
+        for (int k = lane; k < N; k += 32) {
+            io.ox_stage[(size_t)scene * max_obs + k] = ox[k];
+            io.oy_stage[(size_t)scene * max_obs + k] = oy[k];
+        }
+    }
     double2* lastp = last_path + (size_t)scene * DP_PATH_POINTS;
     dp_carry* const cg = carry + scene;
     dp_plan_record* const out = rec + scene;                // the record is assembled in place: fields are stored when final
@@ -757,6 +768,11 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
 #endif
         if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
     }
+    if (io.rec_host) {                                      // zero-copy result: one coalesced 128-byte store to pinned host memory
+        __syncwarp();
+        __threadfence_block();
+        reinterpret_cast<uint32_t*>(io.rec_host + scene)[lane] = reinterpret_cast<const volatile uint32_t*>(out)[lane];
+    }
 }
 
 // ---- reset carry to constructor state (Decision.cpp:8-29, Planning.cpp:8-11,62) ----
@@ -793,7 +809,7 @@ __global__ void dp_map_prep_kernel(const double* x, const double* y, const int32
 // ---- launchers (called from dp_api.cu) ----
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                            double* path_xy, double* path_ll, cudaStream_t st, int split) {
+                            double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io) {
     if (n <= 0) return cudaSuccess;
     static bool configured = false;
     if (!configured) {                                      // 196 of 256 KB as shared memory: 7 CTAs per SM, the rest stays L1
@@ -804,10 +820,14 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
     }
     const int blocks = (n + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, threads = DP_WARPS_PER_BLOCK * 32;
     if (!split) {
-        dp_cycle_kernel<0><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll);
+        dp_cycle_kernel<0><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io);
     } else {
-        dp_cycle_kernel<1><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll);
-        dp_cycle_kernel<2><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll);
+        // Decision launch ingests (hdr/ox/oy may be pinned host memory); Planning launch reads the staged device copies
+        DpIo io1 = io; io1.rec_host = nullptr;
+        DpIo io2 = io; io2.hdr_stage = nullptr; io2.ox_stage = nullptr; io2.oy_stage = nullptr;
+        dp_cycle_kernel<1><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
+        dp_cycle_kernel<2><<<blocks, threads, 0, st>>>(m, p, n, io.hdr_stage ? io.hdr_stage : hdr, io.ox_stage ? io.ox_stage : ox,
+                                                       io.oy_stage ? io.oy_stage : oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2);
     }
     return cudaGetLastError();
 }

@@ -34,7 +34,7 @@ struct DevMap {
     int n_roads, n_lanes, n_conn;
 };
 
-// 6728 bytes per warp: 7 CTAs of 4 warps fit the 196 KB shared-memory configuration and leave
+// 6864 bytes per warp: 7 CTAs of 4 warps fit the 196 KB shared-memory configuration and leave
 // 60 KB of L1 for the map gathers.
 struct __align__(16) WarpSmem {
     union {
@@ -46,6 +46,8 @@ struct __align__(16) WarpSmem {
     };                                         //                or F + its normals for the fused avoid sweep
     double scr[DP_SCR + 8];                    // sequential-sum terms, zero padded to a multiple of 8
     unsigned long long mbar;                   // mbarrier of the bulk copy
+    unsigned long long pad_;
+    uint32_t hdr[32];                          // the scene's dp_scene_hdr, fetched by ONE coalesced 128-byte warp load
 };
 
 // A path is a recipe, never an array in HBM: up to two runs of map (or caller) points read with a

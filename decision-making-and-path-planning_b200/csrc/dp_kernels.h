@@ -3,9 +3,13 @@
 #include <cuda_runtime.h>
 #include "dp_device.cuh"
 
+// optional zero-copy plumbing of the host-pointer entry point: the Decision launch reads hdr/obstacles from pinned host
+// memory and leaves device copies in *_stage for the Planning launch; the finished record is also stored to rec_host
+struct DpIo { dp_scene_hdr* hdr_stage; double* ox_stage; double* oy_stage; dp_plan_record* rec_host; };
+
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                            double* path_xy, double* path_ll, cudaStream_t st, int split);
+                            double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io);
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st);
 cudaError_t dp_launch_map_prep(const double* x, const double* y, const int32_t* lane_pt_off, int n_lanes, double2* xy, double2* nrm,
                                double* lenp, cudaStream_t st);

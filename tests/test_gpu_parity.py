@@ -176,3 +176,29 @@ def test_library_is_the_cuda_path(planner):
     assert planner.launch_count() > 100
     fp64, fp32 = planner.measure_fma_peak()
     assert fp64 > 5 and fp32 > 20, (fp64, fp32)
+
+
+def test_zero_copy_host_path(planner, oracle, the_map):
+    """dp_cycle_batch with PINNED host buffers takes the zero-copy route (kernels read the inputs from host memory and
+    store the records there); it must give byte-identical records to the staged-copy route used with pageable buffers."""
+    import torch
+    from dmpp_b200 import abi, scenes
+    n, cycles = 512, 12
+    ep = scenes.Episodes(the_map, np.arange(4242, 4242 + n), cycles=cycles, n_obs=10)
+    H, OX, OY = ep.all_cycles()
+    PX, PY = pad_obs(OX, OY, planner.max_obs)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    Hp = pin(H.view(np.uint8).reshape(cycles, n, 128)).view(abi.scene_hdr).reshape(cycles, n)
+    PXp, PYp = pin(PX), pin(PY)
+    rec_p = torch.empty((n, 128), dtype=torch.uint8).pin_memory().numpy().view(abi.plan_record).reshape(n)
+    planner.reset(0, n)
+    got = []
+    for c in range(cycles):
+        planner.cycle(Hp[c], PXp[c], PYp[c], out={"rec": rec_p})
+        got.append(rec_p.copy())
+    planner.reset(0, n)
+    for c in range(cycles):
+        o = planner.cycle(np.ascontiguousarray(H[c]), PX[c], PY[c])
+        assert o["rec"].tobytes() == got[c].tobytes(), "cycle %d" % c
+    want = oracle.run(H, OX, OY, paths=False, calls=False, trace=False, exhaustive=False)
+    assert_records_equal(np.stack(got), want["rec"], REC_EXACT, close=DIR_ERR_TOL, what="zero-copy")
