@@ -201,6 +201,7 @@ __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my
             int j = max(jlo, t0);
             const int e = min(jhi, t0 + tn);
             const double2* q = pts + (j - t0);
+#pragma unroll 2
             for (; j + 4 <= e; j += 4, q += 4) {
                 const double2 p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3];
                 const double x0 = mx - p0.x, y0 = my - p0.y, x1 = mx - p1.x, y1 = my - p1.y;

@@ -119,14 +119,21 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int g0, int cn
     if (active && P >= 2) {
         // scan all P points of MY candidate for MY obstacle; the candidate point is rolled out in registers
         const double INF = __longlong_as_double(0x7ff0000000000000LL);
-        double b0 = INF, b1 = INF; int i0 = 0, i1 = 0;
+        double b0 = INF, b1 = INF, b2 = INF, b3 = INF;
+        int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
         int j = 0;
-        for (; j + 2 <= P; j += 2) {
+#pragma unroll 2
+        for (; j + 4 <= P; j += 4) {                        // 4 independent running minima, 8 points in flight
             const double2 q0 = dp_sweep_point(sm, j, dc), q1 = dp_sweep_point(sm, j + 1, dc);
+            const double2 q2 = dp_sweep_point(sm, j + 2, dc), q3 = dp_sweep_point(sm, j + 3, dc);
             const double x0 = mx - q0.x, y0 = my - q0.y, x1 = mx - q1.x, y1 = my - q1.y;
+            const double x2 = mx - q2.x, y2 = my - q2.y, x3 = mx - q3.x, y3 = my - q3.y;
             const double d0 = fma(x0, x0, y0 * y0), d1 = fma(x1, x1, y1 * y1);
+            const double d2 = fma(x2, x2, y2 * y2), d3 = fma(x3, x3, y3 * y3);
             if (d0 < b0) { b0 = d0; i0 = j; }
             if (d1 < b1) { b1 = d1; i1 = j + 1; }
+            if (d2 < b2) { b2 = d2; i2 = j + 2; }
+            if (d3 < b3) { b3 = d3; i3 = j + 3; }
         }
         for (; j < P; ++j) {
             const double2 q0 = dp_sweep_point(sm, j, dc);
@@ -135,6 +142,8 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int g0, int cn
             if (d0 < b0) { b0 = d0; i0 = j; }
         }
         if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+        if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
+        if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
         const int bj = i0, k = (bj == P - 1) ? P - 2 : bj;
         key = dp_owner_key(dp_sweep_point(sm, k, dc), dp_sweep_point(sm, k + 1, dc), bj, P, o, mx, my, lo, hi, &dlat);
     }
