@@ -420,6 +420,97 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
     return DP_OK;
 }
 
+// ---- latency-mode sweep session: device-resident candidate set + one captured CUDA graph per scoring call ----
+struct dp_sweep {
+    dp_ctx* c = nullptr;
+    int n_base = 0, n_cand = 0, max_obs = 0;
+    double *d_bx = nullptr, *d_by = nullptr, *d_off = nullptr, *d_obs = nullptr, *d_dis = nullptr;   // d_obs: [4][max_obs]
+    int32_t* d_np = nullptr;
+    unsigned long long* d_key = nullptr;
+    double* h_obs = nullptr;                                // pinned [4][max_obs]
+    unsigned long long* h_key = nullptr;                    // pinned
+    double* h_args = nullptr;                               // pinned {lat_min, lat_max, clear}
+    cudaGraphExec_t exec = nullptr;
+    int graph_n_obs = -1;
+    double g_lo = 0, g_hi = 0, g_clear = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const double* base_y, int n_base, const double* offset,
+                    const int32_t* n_pts, int n_cand, int max_obs) {
+    if (!c || !out || !base_x || !base_y || n_base < 2 || n_base > 256 || !offset || !n_pts || n_cand <= 0 || max_obs <= 0 || max_obs > 256)
+        return fail(DP_ERR_ARG, "dp_sweep_create: bad argument (n_base in [2,256], max_obs <= 256)");
+    CK(cudaSetDevice(c->device));
+    dp_sweep* s = new dp_sweep();
+    s->c = c; s->n_base = n_base; s->n_cand = n_cand; s->max_obs = max_obs;
+    CK(cudaMalloc((void**)&s->d_bx, n_base * 8)); CK(cudaMalloc((void**)&s->d_by, n_base * 8));
+    CK(cudaMalloc((void**)&s->d_off, (size_t)n_cand * 8)); CK(cudaMalloc((void**)&s->d_np, (size_t)n_cand * 4));
+    CK(cudaMalloc((void**)&s->d_obs, (size_t)4 * max_obs * 8)); CK(cudaMalloc((void**)&s->d_dis, (size_t)n_cand * 8));
+    CK(cudaMalloc((void**)&s->d_key, 8));
+    CK(cudaMallocHost((void**)&s->h_obs, (size_t)4 * max_obs * 8)); CK(cudaMallocHost((void**)&s->h_key, 8));
+    CK(cudaMemcpy(s->d_bx, base_x, n_base * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->d_by, base_y, n_base * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_off, offset, (size_t)n_cand * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_np, n_pts, (size_t)n_cand * 4, cudaMemcpyHostToDevice));
+    CK(cudaEventCreate(&s->e0)); CK(cudaEventCreate(&s->e1));
+    *out = s;
+    return DP_OK;
+}
+
+int dp_sweep_score(dp_sweep* s, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min,
+                   double lat_max, double clear_dis, int32_t* best_index, double* best_dis_lng, float* device_ms) {
+    if (!s || !best_index || n_obs < 0 || n_obs > s->max_obs || (n_obs > 0 && (!ox || !oy))) return fail(DP_ERR_ARG, "dp_sweep_score: bad argument");
+    dp_ctx* c = s->c;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->st[0];
+    const int mo = s->max_obs;
+    for (int i = 0; i < n_obs; ++i) {
+        s->h_obs[i] = ox[i]; s->h_obs[mo + i] = oy[i];
+        s->h_obs[2 * mo + i] = dvx ? dvx[i] : 0.0; s->h_obs[3 * mo + i] = dvy ? dvy[i] : 0.0;
+    }
+    if (!s->exec || s->graph_n_obs != n_obs || s->g_lo != lat_min || s->g_hi != lat_max || s->g_clear != clear_dis) {
+        // (re)capture: the graph bakes in the scalar arguments; in the steady state of a planning loop they do not change
+        if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        cudaMemcpyAsync(s->d_obs, s->h_obs, (size_t)4 * mo * 8, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(s->d_key, 0xff, 8, st);
+        dp_launch_sweep(s->d_bx, s->d_by, s->n_base, s->d_off, s->d_np, s->n_cand, s->d_obs, s->d_obs + mo, s->d_obs + 2 * mo, s->d_obs + 3 * mo,
+                        n_obs, lat_min, lat_max, clear_dis, s->d_dis, s->d_key, st);
+        cudaMemcpyAsync(s->h_key, s->d_key, 8, cudaMemcpyDeviceToHost, st);
+        CK(cudaStreamEndCapture(st, &g));
+        CK(cudaGraphInstantiate(&s->exec, g, 0));
+        cudaGraphDestroy(g);
+        s->graph_n_obs = n_obs; s->g_lo = lat_min; s->g_hi = lat_max; s->g_clear = clear_dis;
+    }
+    if (device_ms) CK(cudaEventRecord(s->e0, st));
+    CK(cudaGraphLaunch(s->exec, st));
+    c->launches += 1;
+    if (device_ms) CK(cudaEventRecord(s->e1, st));
+    CK(cudaStreamSynchronize(st));
+    if (device_ms) CK(cudaEventElapsedTime(device_ms, s->e0, s->e1));
+    const unsigned long long key = *s->h_key;
+    const bool feasible = (key >> 32) == 0;
+    *best_index = feasible ? (int32_t)(key & 0xffffffffu) : -1;
+    if (best_dis_lng) {
+        *best_dis_lng = DP_NOT_FOUND;
+        if (feasible) CK(cudaMemcpy(best_dis_lng, s->d_dis + *best_index, 8, cudaMemcpyDeviceToHost));
+    }
+    return DP_OK;
+}
+
+int dp_sweep_destroy(dp_sweep* s) {
+    if (!s) return DP_OK;
+    cudaSetDevice(s->c->device);
+    cudaStreamSynchronize(s->c->st[0]);
+    if (s->exec) cudaGraphExecDestroy(s->exec);
+    cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_off); cudaFree(s->d_np); cudaFree(s->d_obs); cudaFree(s->d_dis); cudaFree(s->d_key);
+    cudaFreeHost(s->h_obs); cudaFreeHost(s->h_key);
+    if (s->e0) cudaEventDestroy(s->e0);
+    if (s->e1) cudaEventDestroy(s->e1);
+    delete s;
+    return DP_OK;
+}
+
 int dp_measure_fma_peak(dp_ctx* c, double* fp64_tflops, double* fp32_tflops) {
     if (!c) return fail(DP_ERR_ARG, "dp_measure_fma_peak");
     CK(cudaSetDevice(c->device));

@@ -20,7 +20,7 @@ SYMBOLS = [
     "dp_carry_download", "dp_carry_upload", "dp_cycle_batch_dev", "dp_cycle_batch", "dp_host_alloc",
     "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
-    "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync",
+    "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
 ]
 
 _lib = None
@@ -200,7 +200,40 @@ class Planner:
                                          C.byref(best_d), abi.ptr(allv)), "dp_score_candidates")
         return best.value, best_d.value, allv
 
+    def sweep_session(self, base_x, base_y, offset, n_pts, max_obs):
+        return SweepSession(self, base_x, base_y, offset, n_pts, max_obs)
+
     def measure_fma_peak(self):
         a, b = C.c_double(0), C.c_double(0)
         _ck(self.lib.dp_measure_fma_peak(self.ctx, C.byref(a), C.byref(b)), "dp_measure_fma_peak")
         return a.value, b.value
+
+
+class SweepSession:
+    """latency-mode dense candidate sweep (BASELINE config 3): candidate set resident on the device, one CUDA-graph
+    replay per call"""
+
+    def __init__(self, planner, base_x, base_y, offset, n_pts, max_obs):
+        self.lib = planner.lib
+        bx, by = np.ascontiguousarray(base_x, np.float64), np.ascontiguousarray(base_y, np.float64)
+        off, npt = np.ascontiguousarray(offset, np.float64), np.ascontiguousarray(n_pts, np.int32)
+        self.h = C.c_void_p()
+        _ck(self.lib.dp_sweep_create(planner.ctx, C.byref(self.h), abi.ptr(bx), abi.ptr(by), C.c_int(bx.size), abi.ptr(off), abi.ptr(npt),
+                                     C.c_int(off.size), C.c_int(max_obs)), "dp_sweep_create")
+        self._ms = C.c_float(0)
+        self._best = C.c_int32(-1)
+        self._dis = C.c_double(0)
+
+    def score(self, ox, oy, dvx=None, dvy=None, lat_min=-0.9, lat_max=0.9, clear_dis=25.0, want_dis=True):
+        ox, oy = np.ascontiguousarray(ox, np.float64), np.ascontiguousarray(oy, np.float64)
+        dvx = None if dvx is None else np.ascontiguousarray(dvx, np.float64)
+        dvy = None if dvy is None else np.ascontiguousarray(dvy, np.float64)
+        _ck(self.lib.dp_sweep_score(self.h, abi.ptr(ox), abi.ptr(oy), abi.ptr(dvx), abi.ptr(dvy), C.c_int(ox.size), C.c_double(lat_min),
+                                    C.c_double(lat_max), C.c_double(clear_dis), C.byref(self._best),
+                                    C.byref(self._dis) if want_dis else None, C.byref(self._ms)), "dp_sweep_score")
+        return self._best.value, self._dis.value, self._ms.value
+
+    def close(self):
+        if self.h:
+            self.lib.dp_sweep_destroy(self.h)
+            self.h = C.c_void_p()

@@ -202,6 +202,17 @@ int dp_score_candidates(dp_ctx* ctx, const double* base_x, const double* base_y,
                         double clear_dis, int32_t* best_index, double* best_dis_lng,
                         double* out_dis_lng);
 
+/* Latency-mode session of (5): the candidate set (base line, offsets, point counts) is uploaded once; each
+ * dp_sweep_score call stages the obstacle tracks, replays ONE captured CUDA graph (H2D of the obstacles, key reset,
+ * sweep kernel, D2H of the winner) and returns when the winner is on the host.  n_obs <= max_obs <= 256. */
+typedef struct dp_sweep dp_sweep;
+int dp_sweep_create(dp_ctx* ctx, dp_sweep** out, const double* base_x, const double* base_y, int n_base,
+                    const double* offset, const int32_t* n_pts, int n_cand, int max_obs);
+int dp_sweep_score(dp_sweep* s, const double* obs_x, const double* obs_y, const double* obs_dvx,
+                   const double* obs_dvy, int n_obs, double lat_min, double lat_max, double clear_dis,
+                   int32_t* best_index, double* best_dis_lng, float* device_ms);
+int dp_sweep_destroy(dp_sweep* s);
+
 /* (6) operator-level batch calls, the CShare seam.  Host pointers.
  * paths are [n_paths] polylines concatenated; path_off[n_paths+1]. */
 /* CShare::SearchObstacle  (Planning.cpp:168; Decision.cpp:370,...,962) */

@@ -88,6 +88,21 @@ def test_obstacle_counts(planner, oracle, the_map, n_obs):
     check(got, want, "n_obs=%d" % n_obs)
 
 
+def test_urban_junction_200_agents(oracle, the_map):
+    """BASELINE config 5 shape: junction episodes (pos 0 -> 1 -> 2 -> 0), 200 agents per scene"""
+    from dmpp_b200 import scenes
+    from dmpp_b200.planner import Planner
+    ep = scenes.Episodes(the_map, np.arange(880000, 880000 + 96), cycles=70, kind="junction", n_obs=200)
+    H, OX, OY = ep.all_cycles()
+    want = oracle.run(H, OX, OY, exhaustive=True, threads=8)
+    p = Planner(max_scenes=96, max_obs=200)
+    p.upload_map(the_map)
+    got = p.run_episodes(H, OX, OY)
+    p.close()
+    check(got, want, "junction-200")
+    assert set(np.unique(H["pos"]).tolist()) == {0, 1, 2}
+
+
 def test_zero_obstacles_and_ragged(planner, oracle, the_map):
     from dmpp_b200 import scenes
     ep = scenes.Episodes(the_map, np.arange(300, 300 + 256), cycles=8, n_obs=12)
@@ -150,6 +165,35 @@ def test_dense_sweep(planner, oracle, the_map):
         assert np.array_equal(allv, wall)
         if best >= 0:
             assert best_d == wall[best]
+
+
+def test_dense_sweep_session_full_grid(planner, oracle, the_map):
+    """BASELINE config 3 at full size through the latency-mode session: 64 lateral offsets x 32 aim distances x 32
+    horizons = 65 536 candidates, 50 obstacle tracks.  The CPU oracle scores the full grid once (a few seconds);
+    repeated graph replays with moved obstacles are checked on the winner only."""
+    rng = np.random.default_rng(2024)
+    gl = the_map.lane_index(3, 2)
+    o = the_map.lane_pt_off[gl] + 900
+    bx, by = the_map.x[o:o + 256], the_map.y[o:o + 256]
+    lat = -3.15 + 0.1 * np.arange(64)
+    aim = 10.0 + 2.5 * np.arange(32)
+    hor = 8 * (1 + np.arange(32))
+    # enumeration order lateral-major; the candidate's point count is min(horizon, points within the aim distance)
+    L, A, Hh = np.meshgrid(lat, aim, hor, indexing="ij")
+    n_pts = np.minimum(Hh, np.maximum(2, (A / 0.5).astype(np.int64))).astype(np.int32).ravel()
+    offset = L.ravel()
+    assert offset.size == 65536
+    ox = bx[rng.integers(5, 250, 50)] + rng.normal(0, 1.5, 50); oy = by[rng.integers(5, 250, 50)] + rng.normal(0, 1.5, 50)
+    dvx, dvy = rng.normal(0, 0.04, 50), rng.normal(0, 0.04, 50)
+    sess = planner.sweep_session(bx, by, offset, n_pts, 64)
+    best, dis, ms = sess.score(ox, oy, dvx, dvy)
+    wbest, wall = oracle.score_candidates(bx, by, offset, n_pts, ox, oy, dvx, dvy)
+    assert best == wbest and (best < 0 or dis == wall[best])
+    b2, d2, all2 = planner.score_candidates(bx, by, offset, n_pts, ox, oy, dvx, dvy)
+    assert b2 == wbest and np.array_equal(all2, wall)
+    for it in range(20):                                     # graph replays: idempotent for equal inputs
+        assert sess.score(ox, oy, dvx, dvy)[:2] == (best, dis)
+    sess.close()
 
 
 def test_reset_and_carry_roundtrip(planner, oracle, the_map):

@@ -1,0 +1,56 @@
+"""BASELINE config 3, latency mode: 65 536 candidates (64 lateral offsets x 32 aim distances x 32 horizons) x 50
+obstacle tracks, ONE scene, scored by one CUDA-graph replay per call.  Prints a JSON line with p50/p99 latency."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dmpp_b200  # noqa: E402,F401
+from dmpp_b200 import scenes  # noqa: E402
+from dmpp_b200.planner import Planner  # noqa: E402
+
+calls = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+m = scenes.Map()
+rng = np.random.default_rng(2024)
+gl = m.lane_index(3, 2)
+o = m.lane_pt_off[gl] + 900
+bx, by = m.x[o:o + 256], m.y[o:o + 256]
+lat = -3.15 + 0.1 * np.arange(64)
+aim = 10.0 + 2.5 * np.arange(32)
+hor = 8 * (1 + np.arange(32))
+L, A, Hh = np.meshgrid(lat, aim, hor, indexing="ij")
+n_pts = np.minimum(Hh, np.maximum(2, (A / 0.5).astype(np.int64))).astype(np.int32).ravel()
+offset = L.ravel()
+N = 50
+p = Planner(16, 64)
+p.upload_map(m)
+sess = p.sweep_session(bx, by, offset, n_pts, 64)
+idx = rng.integers(5, 250, N)
+ox0, oy0 = bx[idx] + rng.normal(0, 1.5, N), by[idx] + rng.normal(0, 1.5, N)
+dvx, dvy = rng.normal(0, 0.04, N), rng.normal(0, 0.04, N)
+wall, dev = np.zeros(calls), np.zeros(calls)
+for i in range(50):
+    sess.score(ox0, oy0, dvx, dvy, want_dis=False)
+for i in range(calls):
+    ox = ox0 + 0.01 * (i % 97)                      # obstacles move between calls
+    t0 = time.perf_counter()
+    best, _, ms = sess.score(ox, oy0, dvx, dvy, want_dis=False)
+    wall[i] = time.perf_counter() - t0
+    dev[i] = ms
+pts = float(n_pts.astype(np.int64).sum())
+flops = 18.0 * pts + N * (5.0 * pts + 12.0 * offset.size)
+fp64, fp32 = p.measure_fma_peak()
+print(json.dumps({
+    "workload": "config3: 1 scene, 65536 candidates, 50 obstacle tracks, graph-replayed", "calls": calls,
+    "latency_ms_wall": {"p50": float(np.percentile(wall, 50) * 1e3), "p99": float(np.percentile(wall, 99) * 1e3), "max": float(wall.max() * 1e3)},
+    "latency_ms_device": {"p50": float(np.percentile(dev, 50)), "p99": float(np.percentile(dev, 99))},
+    "candidates_per_s": offset.size / float(np.median(wall)),
+    "roofline": {"bound": "fp64", "achieved_tflops": flops / (np.median(dev) * 1e-3) / 1e12, "peak_tflops": fp64,
+                 "frac": flops / (np.median(dev) * 1e-3) / 1e12 / fp64, "algorithmic_flops_per_call": flops},
+    "last_best": best}))
+sess.close()
+p.close()
