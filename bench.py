@@ -35,7 +35,7 @@ UNIT = "trajectories/s"
 
 
 def workload_desc(world):
-    return {"workload": "config2: %d highway scenes/GPU x default candidate set (6 lane regions + 2K avoid offsets + 1 local path), "
+    return {"workload": ("config2" if SCENES == 4096 else "config4 shard") + ": %d highway scenes/GPU x default candidate set (6 lane regions + 2K avoid offsets + 1 local path), "
                         "ego + %d vehicles, %d-cycle scripted episodes" % (SCENES, N_OBS, EPISODE),
             "scenes_per_gpu": SCENES, "obstacles": N_OBS, "episode_cycles": EPISODE,
             "parallelism": "scenes sharded %d-way, no data-path collective; plan records all_gathered per step when N>1" % world,
@@ -112,7 +112,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = host_cores()
-    arm = CpuArm(SCENES, EPISODE, cores)
+    arm = CpuArm(min(SCENES, 4096), EPISODE, cores)
     for _ in range(max(1, min(args.warmup, 2))):
         arm.step()
     traj = 0; secs = 0.0; cyc = 0
@@ -123,14 +123,14 @@ def run_reference(args, rank, world):
     arm.close()
     val = traj / secs
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": args.warmup, "ms_per_step": secs / cyc * SCENES * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": secs / cyc * min(SCENES, 4096) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_desc(1),
             "plan_cycles_per_s": cyc / secs,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": arm.kind,
                              "sample": "%d steps, each = %d scenes x %d cycles (whole episodes), one process per core running "
-                                       "the unmodified Decision.cpp/Planning.cpp objects" % (steps, SCENES, EPISODE)},
+                                       "the unmodified Decision.cpp/Planning.cpp objects" % (steps, min(SCENES, 4096), EPISODE)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "ms_per_step is normalised to one plan cycle of %d scenes" % SCENES}
+            "note": "ms_per_step is normalised to one plan cycle of %d scenes" % min(SCENES, 4096)}
     print(json.dumps(line))
 
 
@@ -313,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         try:
             cores = host_cores()
-            arm = CpuArm(SCENES, EPISODE, cores)
+            arm = CpuArm(min(SCENES, 4096), EPISODE, cores)
             arm.step()
             t_traj = 0; t_s = 0.0; n = 0
             while t_s < 4.0 and n < 40:
@@ -322,7 +322,7 @@ def run_ours(args, rank, world, local_rank):
             arm.close()
             line["cpu_baseline"] = {"value": t_traj / t_s, "unit": UNIT, "cores": cores, "kind": arm.kind,
                                     "sample": "%d passes over %d scenes x %d cycles, one process per core (unmodified reference "
-                                              "objects when kind=reference)" % (n, SCENES, EPISODE)}
+                                              "objects when kind=reference)" % (n, min(SCENES, 4096), EPISODE)}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     print(json.dumps(line))
@@ -338,12 +338,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scenes", type=int, default=SCENES,
+                    help="scenes per GPU (default = BASELINE config 2; 131072 x 8 GPUs = config 4, the 1M-scene sweep)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    globals()["SCENES"] = args.scenes
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
