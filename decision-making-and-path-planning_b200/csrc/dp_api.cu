@@ -391,8 +391,8 @@ int dp_mean_points(dp_ctx* c, int n_paths, const int32_t* path_off, const double
 int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
                         int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min,
                         double lat_max, double clear_dis, int32_t* best_index, double* best_dis_lng, double* out_dis_lng) {
-    if (!c || !base_x || !base_y || n_base < 2 || n_base > 256 || !offset || !n_pts || n_cand <= 0 || n_obs < 0 || n_obs > 256 || !best_index)
-        return fail(DP_ERR_ARG, "dp_score_candidates: bad argument (n_base in [2,256], n_obs <= 256)");
+    if (!c || !base_x || !base_y || n_base < 2 || n_base > 256 || !offset || !n_pts || n_cand <= 0 || n_obs < 0 || n_obs > 192 || !best_index)
+        return fail(DP_ERR_ARG, "dp_score_candidates: bad argument (n_base in [2,256], n_obs <= 192)");
     CK(cudaSetDevice(c->device));
     Tmp tmp; cudaError_t e;
     PUT(d_bx, double, base_x, (size_t)n_base); PUT(d_by, double, base_y, (size_t)n_base);
@@ -438,8 +438,8 @@ struct dp_sweep {
 
 int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const double* base_y, int n_base, const double* offset,
                     const int32_t* n_pts, int n_cand, int max_obs) {
-    if (!c || !out || !base_x || !base_y || n_base < 2 || n_base > 256 || !offset || !n_pts || n_cand <= 0 || max_obs <= 0 || max_obs > 256)
-        return fail(DP_ERR_ARG, "dp_sweep_create: bad argument (n_base in [2,256], max_obs <= 256)");
+    if (!c || !out || !base_x || !base_y || n_base < 2 || n_base > 256 || !offset || !n_pts || n_cand <= 0 || max_obs <= 0 || max_obs > 192)
+        return fail(DP_ERR_ARG, "dp_sweep_create: bad argument (n_base in [2,256], max_obs <= 192)");
     CK(cudaSetDevice(c->device));
     dp_sweep* s = new dp_sweep();
     s->c = c; s->n_base = n_base; s->n_cand = n_cand; s->max_obs = max_obs;

@@ -2,6 +2,7 @@
 // dense candidate sweep of BASELINE config 3, and the FMA micro-benchmark that provides the
 // roofline denominator (MEASURED_PEAKS.json has no FP64/FP32 CUDA-core figure).
 #include "dp_device.cuh"
+#include "dp_fused.cuh"
 #include "dp_kernels.h"
 
 namespace {
@@ -88,11 +89,17 @@ op_mean_kernel(int n_paths, const int32_t* __restrict__ path_off, const double2*
 // so the minimum is the LOWEST feasible index (the reference's first-feasible `break`,
 // Decision.cpp:944-953), deterministic whatever the launch geometry.
 // ------------------------------------------------------------------------------------------------
-#define SWEEP_WARPS 4
+#define SWEEP_WARPS 8
 #define SWEEP_MAX_BASE 256
-#define SWEEP_MAX_OBS 256
+#define SWEEP_MAX_OBS 192
 
-__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+// argmin update (a 64-bit integer compare on the bit patterns was tried to unload the FP64 pipe: 2 ISETP + 3 SEL cost more
+// issue slots than DSETP + 3 SEL, and this kernel is issue-bound -- profiles/README.md)
+__device__ __forceinline__ void sweep_upd(double d2, int j, double& bb, int& bj) {
+    if (d2 < bb) { bb = d2; bj = j; }
+}
+
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, 3)
 sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, const double* __restrict__ offset,
              const int32_t* __restrict__ n_pts, int n_cand, const double* __restrict__ ox, const double* __restrict__ oy,
              const double* __restrict__ dvx, const double* __restrict__ dvy, int n_obs, double lat_min, double lat_max,
@@ -100,8 +107,7 @@ sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_
     __shared__ double2 s_base[SWEEP_MAX_BASE];
     __shared__ double2 s_nrm[SWEEP_MAX_BASE];              // normal of segment j -> j+1
     __shared__ double4 s_obs[SWEEP_MAX_OBS];
-    __shared__ double2 s_cand[SWEEP_WARPS][SWEEP_MAX_BASE];
-    __shared__ double s_len[SWEEP_WARPS][SWEEP_MAX_BASE];
+    __shared__ double2 s_cand[SWEEP_WARPS][SWEEP_MAX_BASE]; // the warp's candidate; reused for the arclength terms afterwards
     __shared__ unsigned long long s_key[SWEEP_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     for (int j = threadIdx.x; j < n_base; j += blockDim.x) s_base[j] = make_double2(base_x[j], base_y[j]);
@@ -117,6 +123,7 @@ sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_
         double dis_lng = DP_NOT_FOUND;
         if (P >= 2) {
             double2* q = s_cand[wib];
+            __syncwarp();
             for (int j = lane; j < P; j += 32) {           // rollout: offset copy, never leaves the SM
                 const double2 b = s_base[j], n = s_nrm[min(j, P - 2)];
                 q[j] = make_double2(fma(off, n.x, b.x), fma(off, n.y, b.y));
@@ -127,42 +134,62 @@ sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_
                 const int o = g * 32 + lane;
                 if (o < n_obs) {
                     const double4 ob = s_obs[o];
-                    double bd = __longlong_as_double(0x7ff0000000000000LL);
-                    int bj = 0;
-                    double jd = 0.0;
-#pragma unroll 4
-                    for (int j = 0; j < P; ++j) {
-                        const double2 p = q[j];
-                        const double dx = fma(jd, ob.z, ob.x) - p.x, dy = fma(jd, ob.w, ob.y) - p.y;
-                        const double d2 = fma(dx, dx, dy * dy);
-                        if (d2 < bd) { bd = d2; bj = j; }
-                        jd += 1.0;
+                    // 4 independent running minima (j mod 4): lexicographic (d2, j) min == sequential strict-'<' argmin
+                    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+                    double b0 = INF, b1 = INF, b2 = INF, b3 = INF;
+                    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+                    int j = 0;
+                    double jd = 0.0;                        // (double)j, kept as a running exact integer
+                    for (; j + 4 <= P; j += 4, jd += 4.0) {
+                        const double2 p0 = q[j], p1 = q[j + 1], p2 = q[j + 2], p3 = q[j + 3];
+                        const double t0 = jd, t1 = jd + 1.0, t2 = jd + 2.0, t3 = jd + 3.0;
+                        const double x0 = fma(t0, ob.z, ob.x) - p0.x, y0 = fma(t0, ob.w, ob.y) - p0.y;
+                        const double x1 = fma(t1, ob.z, ob.x) - p1.x, y1 = fma(t1, ob.w, ob.y) - p1.y;
+                        const double x2 = fma(t2, ob.z, ob.x) - p2.x, y2 = fma(t2, ob.w, ob.y) - p2.y;
+                        const double x3 = fma(t3, ob.z, ob.x) - p3.x, y3 = fma(t3, ob.w, ob.y) - p3.y;
+                        sweep_upd(fma(x0, x0, y0 * y0), j, b0, i0);
+                        sweep_upd(fma(x1, x1, y1 * y1), j + 1, b1, i1);
+                        sweep_upd(fma(x2, x2, y2 * y2), j + 2, b2, i2);
+                        sweep_upd(fma(x3, x3, y3 * y3), j + 3, b3, i3);
                     }
+                    for (; j < P; ++j, jd += 1.0) {
+                        const double2 p0 = q[j];
+                        const double t0 = jd;
+                        const double x0 = fma(t0, ob.z, ob.x) - p0.x, y0 = fma(t0, ob.w, ob.y) - p0.y;
+                        sweep_upd(fma(x0, x0, y0 * y0), j, b0, i0);
+                    }
+                    if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+                    if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
+                    if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
+                    const int bj = i0;
                     const double mx = fma((double)bj, ob.z, ob.x), my = fma((double)bj, ob.w, ob.y);
                     const int k = (bj == P - 1) ? P - 2 : bj;
-                    const double2 pk = q[k], pk1 = q[k + 1];
-                    const double sx = pk1.x - pk.x, sy = pk1.y - pk.y;
-                    bool pass = true;
-                    if (bj == 0) pass = fma(mx - pk.x, sx, (my - pk.y) * sy) >= 0.0;
-                    else if (bj == P - 1) pass = fma(mx - pk1.x, sx, (my - pk1.y) * sy) <= 0.0;
-                    const double len = sqrt(dp_sq2(sx, sy));
-                    double d = 0.0;
-                    if (len > 0) d = fma(mx - pk.x, sy, -((my - pk.y) * sx)) / len;
-                    pass = pass && (d >= lat_min && d <= lat_max);
-                    const unsigned key = pass ? (((unsigned)bj << 16) | (unsigned)o) : 0xffffffffu;
-                    bestkey = min(bestkey, key);
+                    double dd;
+                    bestkey = min(bestkey, dp_owner_key(q[k], q[k + 1], bj, P, o, mx, my, lat_min, lat_max, &dd));
                 }
             }
             const unsigned gmin = __reduce_min_sync(DP_FULL, bestkey);
             if (gmin != 0xffffffffu) {
                 const int jstar = (int)(gmin >> 16);
-                for (int j = lane; j < jstar; j += 32) s_len[wib][j] = sqrt(dp_sq2(q[j + 1].x - q[j].x, q[j + 1].y - q[j].y));
+                double t[(SWEEP_MAX_BASE + 31) / 32];
+#pragma unroll
+                for (int u = 0; u < (SWEEP_MAX_BASE + 31) / 32; ++u) {
+                    const int j = lane + 32 * u;
+                    t[u] = (j < jstar) ? sqrt(dp_sq2(q[j + 1].x - q[j].x, q[j + 1].y - q[j].y)) : 0.0;
+                }
+                __syncwarp();                               // every lane is done with q: reuse it for the terms
+                double* len = reinterpret_cast<double*>(q);
+#pragma unroll
+                for (int u = 0; u < (SWEEP_MAX_BASE + 31) / 32; ++u) len[lane + 32 * u] = t[u];   // zero padded to 256
                 __syncwarp();
                 double sum = 0.0;
-                for (int j = 0; j < jstar; ++j) sum += s_len[wib][j];
+                for (int j = 0; j < jstar; j += 8) {        // index order; the zero padding does not change the sum
+                    const double a0 = len[j], a1 = len[j + 1], a2 = len[j + 2], a3 = len[j + 3];
+                    const double a4 = len[j + 4], a5 = len[j + 5], a6 = len[j + 6], a7 = len[j + 7];
+                    sum += a0; sum += a1; sum += a2; sum += a3; sum += a4; sum += a5; sum += a6; sum += a7;
+                }
                 dis_lng = sum;
             }
-            __syncwarp();
         }
         if (lane == 0) {
             cand_dis_lng[c] = dis_lng;
@@ -229,7 +256,7 @@ cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_ba
                             cudaStream_t st) {
     if (n_cand <= 0) return cudaSuccess;
     int blocks = (n_cand + SWEEP_WARPS - 1) / SWEEP_WARPS;
-    const int cap = 148 * 4;                               // persistent-style: a few CTAs per SM, grid-stride over candidates
+    const int cap = 148 * 3;                               // persistent-style: 3 CTAs x 8 warps per SM, grid-stride over candidates
     if (blocks > cap) blocks = cap;
     sweep_kernel<<<blocks, SWEEP_WARPS * 32, 0, st>>>(base_x, base_y, n_base, offset, n_pts, n_cand, ox, oy, dvx, dvy, n_obs, lat_min,
                                                       lat_max, clear_dis, cand_dis_lng, best_key);

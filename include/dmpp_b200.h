@@ -204,7 +204,7 @@ int dp_score_candidates(dp_ctx* ctx, const double* base_x, const double* base_y,
 
 /* Latency-mode session of (5): the candidate set (base line, offsets, point counts) is uploaded once; each
  * dp_sweep_score call stages the obstacle tracks, replays ONE captured CUDA graph (H2D of the obstacles, key reset,
- * sweep kernel, D2H of the winner) and returns when the winner is on the host.  n_obs <= max_obs <= 256. */
+ * sweep kernel, D2H of the winner) and returns when the winner is on the host.  n_obs <= max_obs <= 192. */
 typedef struct dp_sweep dp_sweep;
 int dp_sweep_create(dp_ctx* ctx, dp_sweep** out, const double* base_x, const double* base_y, int n_base,
                     const double* offset, const int32_t* n_pts, int n_cand, int max_obs);
