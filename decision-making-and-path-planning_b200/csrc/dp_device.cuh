@@ -113,8 +113,9 @@ __device__ __forceinline__ double dp_seq_sum(const WarpSmem& sm, int n, double a
     }
     return acc;
 }
-// first index j < n whose running sum s_j = acc + t_0 + ... + t_j satisfies (s_j - sub > thr), else -1;
-// acc is advanced by all n terms when nothing is found.
+// first index j < n whose running sum s_j = acc + t_0 + ... + t_j satisfies (s_j - sub > thr), else -1 (acc advanced by
+// all n terms).  Terms are >= 0, so the test is monotone in j: a block of 8 terms is only searched when its LAST partial
+// sum passes the test -- one compare per block instead of eight.
 struct SeqHit { int k; double acc; };
 __device__ __forceinline__ SeqHit dp_seq_first(const WarpSmem& sm, int n, double acc, double sub, double thr) {
     SeqHit r;
@@ -123,14 +124,16 @@ __device__ __forceinline__ SeqHit dp_seq_first(const WarpSmem& sm, int n, double
         const double t0 = sm.scr[j], t1 = sm.scr[j + 1], t2 = sm.scr[j + 2], t3 = sm.scr[j + 3];
         const double t4 = sm.scr[j + 4], t5 = sm.scr[j + 5], t6 = sm.scr[j + 6], t7 = sm.scr[j + 7];
         const double s0 = acc + t0, s1 = s0 + t1, s2 = s1 + t2, s3 = s2 + t3, s4 = s3 + t4, s5 = s4 + t5, s6 = s5 + t6, s7 = s6 + t7;
-        unsigned m = 0;
-        m |= ((s0 - sub) > thr) ? 1u : 0u;   m |= ((s1 - sub) > thr) ? 2u : 0u;
-        m |= ((s2 - sub) > thr) ? 4u : 0u;   m |= ((s3 - sub) > thr) ? 8u : 0u;
-        m |= ((s4 - sub) > thr) ? 16u : 0u;  m |= ((s5 - sub) > thr) ? 32u : 0u;
-        m |= ((s6 - sub) > thr) ? 64u : 0u;  m |= ((s7 - sub) > thr) ? 128u : 0u;
-        if (m) {
-            const int k = j + __ffs(m) - 1;
-            if (k < n) { r.k = k; r.acc = acc; return r; } // (padding terms are zero: cannot create a first hit)
+        if ((s7 - sub) > thr) {
+            int k = j + 7;
+            if ((s6 - sub) > thr) k = j + 6;
+            if ((s5 - sub) > thr) k = j + 5;
+            if ((s4 - sub) > thr) k = j + 4;
+            if ((s3 - sub) > thr) k = j + 3;
+            if ((s2 - sub) > thr) k = j + 2;
+            if ((s1 - sub) > thr) k = j + 1;
+            if ((s0 - sub) > thr) k = j;
+            if (k < n) { r.k = k; r.acc = acc; return r; }   // (padding terms are zero: they cannot create a first hit)
         }
         acc = s7;
     }
