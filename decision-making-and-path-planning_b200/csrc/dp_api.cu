@@ -51,6 +51,10 @@ struct dp_ctx {
     long long launches = 0;
     int split = 1;                                          // Decision / Planning halves as two launches (DP_SPLIT=0: one fused launch)
     int zero_copy = 1;                                      // pinned host buffers are read / written by the kernels directly (DP_ZERO_COPY=0: staged copies)
+    // pipelined submit / wait: inputs of cycle k+1 cross PCIe on the copy stream while cycle k computes
+    cudaStream_t cp = nullptr;
+    cudaEvent_t in_ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    unsigned long long submitted = 0, waited = 0;
 };
 
 namespace {
@@ -140,7 +144,10 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
         CK(cudaMallocHost((void**)&c->h_ox[s], (size_t)c->chunk * max_obs * sizeof(double)));
         CK(cudaMallocHost((void**)&c->h_oy[s], (size_t)c->chunk * max_obs * sizeof(double)));
         CK(cudaMallocHost((void**)&c->h_rec[s], (size_t)c->chunk * sizeof(dp_plan_record)));
+        CK(cudaEventCreateWithFlags(&c->in_ready[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->done[s], cudaEventDisableTiming));
     }
+    CK(cudaStreamCreateWithFlags(&c->cp, cudaStreamNonBlocking));
     *out = c;
     return dp_reset(c, 0, max_scenes);
 }
@@ -156,7 +163,10 @@ int dp_destroy(dp_ctx* c) {
         cudaFree(c->d_trace[s]); cudaFree(c->d_pxy[s]); cudaFree(c->d_pll[s]);
         cudaFreeHost(c->h_hdr[s]); cudaFreeHost(c->h_ox[s]); cudaFreeHost(c->h_oy[s]); cudaFreeHost(c->h_rec[s]);
         if (c->st[s]) cudaStreamDestroy(c->st[s]);
+        if (c->in_ready[s]) cudaEventDestroy(c->in_ready[s]);
+        if (c->done[s]) cudaEventDestroy(c->done[s]);
     }
+    if (c->cp) cudaStreamDestroy(c->cp);
     delete c;
     return DP_OK;
 }
@@ -198,6 +208,7 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
 
 int dp_reset(dp_ctx* c, int first, int count) {
     if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_reset: range");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_reset: submitted cycles in flight, call dp_cycle_wait first");
     CK(cudaSetDevice(c->device));
     CK(dp_launch_reset(c->d_carry, c->d_last, first, count, c->st[0]));
     ++c->launches;
@@ -207,6 +218,7 @@ int dp_reset(dp_ctx* c, int first, int count) {
 
 int dp_carry_download(dp_ctx* c, int first, int count, dp_carry* hc, double* hl) {
     if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_carry_download: range");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_carry_download: submitted cycles in flight, call dp_cycle_wait first");
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     if (hc) CK(cudaMemcpy(hc, c->d_carry + first, (size_t)count * sizeof(dp_carry), cudaMemcpyDeviceToHost));
@@ -223,6 +235,7 @@ int dp_carry_download(dp_ctx* c, int first, int count, dp_carry* hc, double* hl)
 }
 int dp_carry_upload(dp_ctx* c, int first, int count, const dp_carry* hc, const double* hl) {
     if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_carry_upload: range");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_carry_upload: submitted cycles in flight, call dp_cycle_wait first");
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     if (hc) CK(cudaMemcpy(c->d_carry + first, hc, (size_t)count * sizeof(dp_carry), cudaMemcpyHostToDevice));
@@ -251,6 +264,7 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
                    dp_trace_record* trace, double* path_xy, double* path_ll) {
     if (!c || !hdr || !ox || !oy || !rec || n < 0 || first < 0 || first + n > c->max_scenes) return fail(DP_ERR_ARG, "dp_cycle_batch: bad argument");
     if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_batch: map not uploaded");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_cycle_batch: submitted cycles in flight, call dp_cycle_wait first");
     CK(cudaSetDevice(c->device));
     int r;
     if (trace && (r = ensure_optional(c, 0))) return r;
@@ -306,6 +320,41 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         CK(cudaStreamSynchronize(c->st[s]));
         if (!pin_rec) memcpy(rec + i0, c->h_rec[s], (size_t)cn * sizeof(dp_plan_record));
     }
+    return DP_OK;
+}
+
+int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec) {
+    if (!c || !hdr || !ox || !oy || !rec || n < 0 || first < 0 || first + n > c->max_scenes || n > c->chunk)
+        return fail(DP_ERR_ARG, "dp_cycle_submit: bad argument");
+    if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_submit: map not uploaded");
+    if (c->submitted - c->waited >= 2) return fail(DP_ERR_STATE, "dp_cycle_submit: two cycles already in flight, call dp_cycle_wait");
+    void* dv_rec = nullptr;
+    if (!is_pinned(hdr) || !is_pinned(ox) || !is_pinned(oy) || !is_pinned(rec, &dv_rec) || !dv_rec)
+        return fail(DP_ERR_ARG, "dp_cycle_submit: buffers must be page-locked (dp_host_alloc)");
+    CK(cudaSetDevice(c->device));
+    // staging set s was last read by cycle (submitted - 2), which has been waited for: it is free.
+    const int s = (int)(c->submitted & 1);
+    const size_t mo = (size_t)c->max_obs;
+    CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp));
+    CK(cudaMemcpyAsync(c->d_ox[s], ox, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp));
+    CK(cudaMemcpyAsync(c->d_oy[s], oy, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp));
+    CK(cudaEventRecord(c->in_ready[s], c->cp));
+    cudaStream_t st = c->st[0];                             // one compute stream: cycle k+1 reads the carry cycle k wrote
+    CK(cudaStreamWaitEvent(st, c->in_ready[s], 0));
+    CK(dp_launch_cycle(c->map, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
+                       c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, DpIo{nullptr, nullptr, nullptr, (dp_plan_record*)dv_rec}));
+    c->launches += c->split ? 2 : 1;
+    CK(cudaEventRecord(c->done[s], st));
+    ++c->submitted;
+    return DP_OK;
+}
+
+int dp_cycle_wait(dp_ctx* c) {
+    if (!c) return fail(DP_ERR_ARG, "dp_cycle_wait: null context");
+    if (c->submitted == c->waited) return fail(DP_ERR_STATE, "dp_cycle_wait: nothing in flight");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->done[c->waited & 1]));
+    ++c->waited;
     return DP_OK;
 }
 

@@ -21,6 +21,7 @@ SYMBOLS = [
     "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
     "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
+    "dp_cycle_submit", "dp_cycle_wait",
 ]
 
 _lib = None
@@ -108,6 +109,16 @@ class Planner:
                                     abi.ptr(o.get("path_xy") if paths else None),
                                     abi.ptr(o.get("path_ll") if paths else None)), "dp_cycle_batch")
         return o
+
+    # ---- pipelined form: at most two cycles in flight, buffers page-locked (see include/dmpp_b200.h) ----
+    def submit(self, hdr, ox, oy, rec, first=0):
+        n = hdr.shape[0]
+        assert hdr.dtype == abi.scene_hdr and ox.shape == (n, self.max_obs) and oy.shape == (n, self.max_obs) and rec.shape == (n,)
+        _ck(self.lib.dp_cycle_submit(self.ctx, C.c_int(first), C.c_int(n), abi.ptr(hdr), abi.ptr(ox), abi.ptr(oy), abi.ptr(rec)),
+            "dp_cycle_submit")
+
+    def wait(self):
+        _ck(self.lib.dp_cycle_wait(self.ctx), "dp_cycle_wait")
 
     def run_episodes(self, H, OX, OY, trace=True, paths=True):
         """all cycles of [cycles][n] scripted episodes from a fresh carry; same layout as the oracle."""

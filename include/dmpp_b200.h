@@ -186,6 +186,18 @@ int dp_cycle_batch_dev(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scen
 int dp_cycle_batch(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scene_hdr* hdr,
                    const double* obs_x, const double* obs_y, dp_plan_record* rec,
                    dp_trace_record* trace, double* path_xy, double* path_ll);
+
+/* Pipelined form of dp_cycle_batch for replay / Monte-Carlo hosts whose inputs of cycle k+1 do not depend on the
+ * outputs of cycle k (the reference's two thread loops are already one cycle apart: CPlanningThread consumes the
+ * DecisionOut of the previous wake-up, Planning.cpp:117-131).  dp_cycle_submit queues the host->device copies of one
+ * cycle on a copy stream and its kernels on the compute stream and returns at once; dp_cycle_wait blocks until the
+ * OLDEST submitted cycle has written its records into `rec`.  At most two cycles may be in flight; all four buffers
+ * must be page-locked (dp_host_alloc) and must not be touched between submit and the matching wait; n_scenes is
+ * limited to 32768 per call.  Cycles execute in submission order (each reads the carry the previous one wrote).
+ * dp_cycle_batch / dp_reset / dp_carry_* return DP_ERR_STATE while cycles are in flight. */
+int dp_cycle_submit(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scene_hdr* hdr,
+                    const double* obs_x, const double* obs_y, dp_plan_record* rec);
+int dp_cycle_wait(dp_ctx* ctx);
 int dp_host_alloc(void** p, size_t bytes);
 int dp_host_free(void* p);
 

@@ -246,3 +246,43 @@ def test_zero_copy_host_path(planner, oracle, the_map):
         assert o["rec"].tobytes() == got[c].tobytes(), "cycle %d" % c
     want = oracle.run(H, OX, OY, paths=False, calls=False, trace=False, exhaustive=False)
     assert_records_equal(np.stack(got), want["rec"], REC_EXACT, close=DIR_ERR_TOL, what="zero-copy")
+
+
+def test_pipelined_submit_wait(planner, oracle, the_map):
+    """dp_cycle_submit / dp_cycle_wait with two cycles in flight: records byte-identical to the synchronous call, in
+    submission order; the state errors the header promises."""
+    import torch
+    from dmpp_b200 import abi, scenes
+    from dmpp_b200.planner import DpError
+    n, cycles = 512, 12
+    ep = scenes.Episodes(the_map, np.arange(777, 777 + n), cycles=cycles, n_obs=10)
+    H, OX, OY = ep.all_cycles()
+    PX, PY = pad_obs(OX, OY, planner.max_obs)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    Hp = pin(H.view(np.uint8).reshape(cycles, n, 128)).view(abi.scene_hdr).reshape(cycles, n)
+    PXp, PYp = pin(PX), pin(PY)
+    recs = [torch.empty((n, 128), dtype=torch.uint8).pin_memory().numpy().view(abi.plan_record).reshape(n) for _ in range(2)]
+    planner.reset(0, n)
+    with pytest.raises(DpError):
+        planner.wait()                                           # nothing in flight
+    got = []
+    planner.submit(Hp[0], PXp[0], PYp[0], recs[0])
+    for c in range(1, cycles):
+        planner.submit(Hp[c], PXp[c], PYp[c], recs[c & 1])
+        if c == 1:
+            with pytest.raises(DpError):
+                planner.submit(Hp[c], PXp[c], PYp[c], recs[0])   # a third cycle in flight is refused
+            with pytest.raises(DpError):
+                planner.reset(0, n)                              # state calls are refused while cycles are in flight
+        planner.wait()
+        got.append(recs[(c - 1) & 1].copy())
+    planner.wait()
+    got.append(recs[(cycles - 1) & 1].copy())
+    with pytest.raises(DpError):
+        planner.submit(np.ascontiguousarray(H[0]), PX[0], PY[0], recs[0])   # pageable inputs are refused
+    want = oracle.run(H, OX, OY, paths=False, calls=False, trace=False, exhaustive=False)
+    assert_records_equal(np.stack(got), want["rec"], REC_EXACT, close=DIR_ERR_TOL, what="pipelined")
+    planner.reset(0, n)
+    for c in range(cycles):
+        o = planner.cycle(np.ascontiguousarray(H[c]), PX[c], PY[c])
+        assert o["rec"].tobytes() == got[c].tobytes(), "cycle %d" % c
