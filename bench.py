@@ -177,6 +177,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version banner off stdout (one JSON line there)
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, args.warmup
     m = scenes.Map()
