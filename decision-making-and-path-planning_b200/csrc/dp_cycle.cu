@@ -144,6 +144,21 @@ static __device__ __noinline__ SearchRes dp_search_cold(const Src s, double mx, 
 // instruction cache thrashes (ncu: 25 % `no_instruction` stalls); each half alone fits.  The hand-off between the two
 // halves is what the reference hands from CDecisionThread to CPlanningThread (DecisionOut, Decision.cpp:187-205),
 // already stored in dp_carry / dp_plan_record.
+#ifdef DP_DEBUG_CLOCK
+// instrumented build only (make debug, tools/scene_timeline.py): per scene and launch {start ns, end ns, SM id, n_traj,
+// regions done ns, sweep start ns, sweep end ns, -}
+__device__ long long g_dbg_timeline[65536 * 2 * 8];
+__device__ __forceinline__ long long dbg_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (long long)t; }
+#define DBG_MARK(ph, slot) if (lane == 0) g_dbg_timeline[((size_t)scene * 2 + (ph)) * 8 + (slot)] = dbg_now()
+#define DBG_END(ph, nt) if (lane == 0) { long long* g = g_dbg_timeline + ((size_t)scene * 2 + (ph)) * 8; g[1] = dbg_now(); g[3] = (nt); }
+extern "C" int dp_debug_timeline(long long* dst, int n_scenes) {
+    return (int)cudaMemcpyFromSymbol(dst, g_dbg_timeline, (size_t)n_scenes * 16 * sizeof(long long));
+}
+#else
+#define DBG_MARK(ph, slot)
+#define DBG_END(ph, nt)
+#endif
+
 template <int PHASE>
 __global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32, DP_MIN_BLOCKS)
 dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restrict__ hdr, const double* __restrict__ obs_x,
@@ -155,6 +170,12 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     const int scene = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
     if (scene >= n_scenes) return;
 #ifdef DP_DEBUG_CLOCK
+    if (lane == 0) {
+        unsigned sid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(sid));
+        long long* g = g_dbg_timeline + ((size_t)scene * 2 + (PHASE == 2 ? 1 : 0)) * 8;
+        g[0] = dbg_now(); g[2] = sid; g[4] = g[5] = g[6] = 0;
+    }
     const long long dbg_t0 = clock64();
     long long dbg_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define DBG_T(i) dbg_t[i] = clock64() - dbg_t0
@@ -289,6 +310,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         const double gRF = (side == 2) ? gNF : 0.0, gRR = (side == 2) ? gNR : 0.0;
         if (tr && lane == 0) { tr->width_curlane = W; tr->navi_lanechg = navi; tr->navi_lanechg_times = navi_t; }
         DBG_T(5);
+        DBG_MARK(0, 4);
 
         // ---- BehaviorDecision (Decision.cpp:898-1773) ----
         dp_carry c = *cg;
@@ -311,32 +333,47 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                 if (c.obsavoid_time > 2) {
                     // in-lane avoid sweep: candidates L0..L(K-1), R0..R(K-1), first feasible wins (Decision.cpp:940-974).
                     // With a trace buffer the remaining candidates are scored too (evaluated = 2) but neither counted nor used.
-                    const int total = 2 * K;
-                    if (total > 0 && N > 0 && N <= 16) {
+                    // Candidate 0 of either side is F itself under the F region's window: result known (the F slot) and, with
+                    // gF < 15, never feasible -- only the 2(K-1) shifted candidates are scored (dp_fused.cuh, dp_sweep_g).
+                    const int total = 2 * K, shifted = 2 * (K - 1);
+                    DBG_MARK(0, 5);
+                    if (shifted > 0 && N > 0 && N <= 16) {
                         dp_sweep_stage(m, sm, F.base, F.P, lane);
                         const int per = min(8, 32 / N);
-                        for (int g0 = 0; g0 < total && (sweep_pick < 0 || tr); g0 += per) {
-                            const int cnt = min(per, total - g0);
+                        for (int u0 = 0; u0 < shifted && (sweep_pick < 0 || tr); u0 += per) {
+                            const int cnt = min(per, shifted - u0);
                             const bool none_yet = sweep_pick < 0;
-                            const int FP = F.P;
-                            const int first = dp_sweep_pass(sm, FP, g0, cnt, K, mx, my, N, lm, -0.5 * Vw, 0.5 * Vw, 25.0, tr != nullptr, lane,
-                                [&](int ci, const SearchRes& r, bool before_first) {
-                                    const bool before = none_yet && before_first;          // scored by the reference too
-                                    if (before) { ++n_traj; pts += FP; }
-                                    if (tr) { const int g = g0 + ci; put_slot(&tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)], r, before ? 1 : 2, lane); }
+                            int first_g = -1;
+                            const int first = dp_sweep_pass(sm, F.P, u0, cnt, K, mx, my, N, lm, -0.5 * Vw, 0.5 * Vw, 25.0, tr != nullptr, lane,
+                                [&](int g, const SearchRes& r, bool before_first) {
+                                    if (before_first && r.dis_lng > 25) first_g = g;
+                                    if (tr) put_slot(&tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)], r, (none_yet && before_first) ? 1 : 2, lane);
                                 });
-                            if (sweep_pick < 0 && first >= 0) sweep_pick = g0 + first;
+                            if (sweep_pick < 0 && first >= 0) sweep_pick = first_g;
                         }
                     } else {
-                        for (int g = 0; g < total && (sweep_pick < 0 || tr); ++g) {   // one candidate at a time (N > 16, N == 0)
+                        for (int u = 0; u < shifted && (sweep_pick < 0 || tr); ++u) {   // one candidate at a time (N > 16)
+                            const int g = dp_sweep_g(u, K);
                             const double cd = ((g / K) == 0 ? -0.3 : 0.3) * (g % K);
                             const SearchRes s = dp_search_cold(slice_src(m, F.base, 1, F.P, cd), mx, my, ox, oy, N, lm, -0.5 * Vw, 0.5 * Vw, sm, lane);
                             const bool before = sweep_pick < 0;
-                            if (before) { ++n_traj; pts += F.P; }
                             put_slot(tr ? &tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)] : nullptr, s, before ? 1 : 2, lane);
                             if (before && s.dis_lng > 25) sweep_pick = g;
                         }
                     }
+                    {
+                        const int scored = sweep_pick < 0 ? total : sweep_pick + 1;        // what the reference evaluates
+                        n_traj += scored; pts += scored * F.P;
+                        if (tr && total > 0) {                                          // L0 and R0: copies of the F region slot
+                            __syncwarp();
+                            if (lane == 0) {
+                                dp_search_slot s0 = tr->region[0];
+                                s0.evaluated = 1; tr->sweep[0] = s0;
+                                s0.evaluated = (uint8_t)(K < scored ? 1 : 2); tr->sweep[DP_MAX_SWEEP] = s0;
+                            }
+                        }
+                    }
+                    DBG_MARK(0, 6);
                     if (sweep_pick >= 0) {
                         const int sd = sweep_pick / K;
                         cur.behavior = sd == 0 ? 4 : 5; cur.target = lane_cur; cur.light = sd == 0 ? 1 : 2;
@@ -523,6 +560,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             out->n_traj = (uint16_t)n_traj;
             if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
         }
+        DBG_END(0, n_traj);
         return;
     }
 
@@ -768,6 +806,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
 #endif
         if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
     }
+    DBG_END(1, n_traj);
     if (io.rec_host) {                                      // zero-copy result: one coalesced 128-byte store to pinned host memory
         __syncwarp();
         __threadfence_block();

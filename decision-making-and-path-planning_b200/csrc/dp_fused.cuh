@@ -102,16 +102,21 @@ __device__ __forceinline__ double2 dp_sweep_point(const WarpSmem& sm, int j, dou
     const double2 p = sm.q[j], n = sm.q[128 + j];
     return make_double2(fma(dc, n.x, p.x), fma(dc, n.y, p.y));
 }
-// Scores candidates g0 .. g0+cnt-1 (reference order L0..L(K-1), R0..R(K-1); cnt * N <= 32) against the scene's
-// obstacles (this lane's obstacle = (mx, my), N < 32).  sink(ci, result, counted) receives the result of candidate g0+ci;
+// Candidate 0 of either side is F itself (offsets -0.3*0 and 0.3*0, Decision.cpp:942,961) under the window of the F region
+// search: its result is the F region's, already known, and -- the sweep only runs when that gap is < 15 -- never feasible.
+// So only the 2(K-1) shifted candidates are scored; they are numbered u = 0 .. 2(K-1)-1 in reference order
+// (L1..L(K-1), R1..R(K-1)); dp_sweep_g maps u to the reference's candidate index g (L0..L(K-1), R0..R(K-1)).
+__device__ __forceinline__ int dp_sweep_g(int u, int K) { return (u / (K - 1)) * K + 1 + (u % (K - 1)); }
+// Scores shifted candidates u0 .. u0+cnt-1 (cnt * N <= 32) against the scene's obstacles (this lane's obstacle =
+// (mx, my), N < 32).  sink(g, result, before_first) receives the result of candidate g;
 // with need_all == false the arclength of a candidate is only resolved as far as the `> clear` decision needs and
 // candidates after the first feasible one are skipped.  Returns the index (0..cnt-1) of the first feasible candidate or -1.
 template <class Sink>
-__device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int g0, int cnt, int K, double mx, double my, int N, const LaneMap lm,
+__device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int u0, int cnt, int K, double mx, double my, int N, const LaneMap lm,
                                              double lo, double hi, double clear, bool need_all, int lane, Sink sink) {
     const int ci_me = lane / N, o = lane - ci_me * N;       // N <= 16 here
     const bool active = ci_me < cnt;
-    const int g_me = g0 + ci_me;
+    const int g_me = dp_sweep_g(u0 + ci_me, K);
     const double dc = ((g_me / K) == 0 ? -0.3 : 0.3) * (g_me % K);   // Decision.cpp:942 (-0.3*i), :961 (0.3*i)
     (void)lm;
     unsigned key = 0xffffffffu;
@@ -161,7 +166,7 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int g0, int cn
             const int jstar = (int)(gmin >> 16), ostar = (int)(gmin & 0xffffu);
             r.found = true; r.pathid = jstar; r.ob = ostar;
             r.dis_lat = __shfl_sync(DP_FULL, dlat, ci * N + ostar);
-            const int gc = g0 + ci;
+            const int gc = dp_sweep_g(u0 + ci, K);
             const double dcc = ((gc / K) == 0 ? -0.3 : 0.3) * (gc % K);
             __syncwarp();
             for (int j = lane; j < jstar; j += 32) {
@@ -176,7 +181,7 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int g0, int cn
                 r.dis_lng = (hq.k >= 0) ? DP_NOT_FOUND : hq.acc;   // (value beyond the threshold is not consumed)
             }
         }
-        sink(ci, r, first < 0);                              // (candidate, result, scored by the reference too?)
+        sink(dp_sweep_g(u0 + ci, K), r, first < 0);          // (candidate, result, scored by the reference too?)
         if (first < 0 && r.dis_lng > clear) first = ci;
     }
     return first;

@@ -33,7 +33,7 @@ def load():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(os.environ.get("DP_DEBUG_LIB") or LIB_PATH)   # DP_DEBUG_LIB: instrumented build for tools/ only
         _lib.dp_last_error.restype = C.c_char_p
         _lib.dp_launch_count.restype = C.c_int64
         _lib.dp_launch_count.argtypes = [C.c_void_p]
