@@ -65,25 +65,30 @@ __device__ __forceinline__ unsigned dp_owner_key(double2 pk, double2 pk1, int bj
 // four SearchObstacle evaluations that follow read shared memory only.
 __device__ __forceinline__ void dp_region_stage(const DevMap& m, WarpSmem& sm, const int (&base)[4], const int (&stride)[4],
                                                 const int (&P)[4], const double (&d)[4], int lane) {
-    const int S1 = P[0], S2 = S1 + P[1], S3 = S2 + P[2], Ptot = S3 + P[3];
     double2* Q = sm.q;
     __syncwarp();
-#pragma unroll 5
-    for (int v = lane; v < Ptot; v += 32) {
-        const int r = (v >= S3) ? 3 : (v >= S2) ? 2 : (v >= S1) ? 1 : 0;
-        const int j = v - ((r == 3) ? S3 : (r == 2) ? S2 : (r == 1) ? S1 : 0);
-        const int bs = (r == 3) ? base[3] : (r == 2) ? base[2] : (r == 1) ? base[1] : base[0];
-        const int st = (r == 3) ? stride[3] : (r == 2) ? stride[2] : (r == 1) ? stride[1] : stride[0];
-        const int Pr = (r == 3) ? P[3] : (r == 2) ? P[2] : (r == 1) ? P[1] : P[0];
-        const double dr = (r == 3) ? d[3] : (r == 2) ? d[2] : (r == 1) ? d[1] : d[0];
-        double2 pt = m.xy[bs + st * j];
-        if (dr != 0.0 && Pr >= 2) {
-            const int jj = min(j, Pr - 2);
-            double2 n = m.nrm[(st > 0) ? bs + jj : bs - jj - 1];
-            if (st < 0) { n.x = -n.x; n.y = -n.y; }
-            pt.x = fma(dr, n.x, pt.x); pt.y = fma(dr, n.y, pt.y);
+    int S = 0;
+    // paths 0/2 are forward slices of <= 120 points (4 rounds of 32 lanes), paths 1/3 rear slices of <= 40 (2 rounds): twelve
+    // independent predicated gathers with compile-time path parameters (no per-element path lookup)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int Pr = P[r], bs = base[r], st = stride[r];
+        const double dr = d[r];
+#pragma unroll
+        for (int k = 0; k < ((r & 1) ? 2 : 4); ++k) {
+            const int j = lane + 32 * k;
+            if (j < Pr) {
+                double2 pt = m.xy[bs + st * j];
+                if (dr != 0.0 && Pr >= 2) {
+                    const int jj = min(j, Pr - 2);
+                    double2 n = m.nrm[(st > 0) ? bs + jj : bs - jj - 1];
+                    if (st < 0) { n.x = -n.x; n.y = -n.y; }
+                    pt.x = fma(dr, n.x, pt.x); pt.y = fma(dr, n.y, pt.y);
+                }
+                Q[S + j] = pt;
+            }
         }
-        Q[v] = pt;
+        S += Pr;
     }
     __syncwarp();
 }
