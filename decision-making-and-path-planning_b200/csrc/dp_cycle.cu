@@ -354,7 +354,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                     } else {
                         for (int u = 0; u < shifted && (sweep_pick < 0 || tr); ++u) {   // one candidate at a time (N > 16)
                             const int g = dp_sweep_g(u, K);
-                            const double cd = ((g / K) == 0 ? -0.3 : 0.3) * (g % K);
+                            const double cd = dp_sweep_offset(g, K);
                             const SearchRes s = dp_search_cold(slice_src(m, F.base, 1, F.P, cd), mx, my, ox, oy, N, lm, -0.5 * Vw, 0.5 * Vw, sm, lane);
                             const bool before = sweep_pick < 0;
                             put_slot(tr ? &tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)] : nullptr, s, before ? 1 : 2, lane);

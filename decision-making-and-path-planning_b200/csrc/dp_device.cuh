@@ -60,13 +60,16 @@ struct Src {
     double d;                                  // lateral offset, RIGHT positive
     int q_off;                                 // >= 0: the path is already staged at sm.q[q_off ...] (no staging needed)
 };
-struct LaneMap { int nchunk, o, c; };          // nearest-search work item of this lane for N < 32
+struct LaneMap { int nchunk, o, c; unsigned magic; };   // nearest-search work item of this lane for N < 32; magic: x / nchunk
+// x / lm.nchunk for 0 <= x < 8192 without an integer division (nchunk <= 32; checked exhaustively on the host)
+__device__ __forceinline__ int dp_div_chunks(int x, const LaneMap& lm) { return (int)(((unsigned)x * lm.magic) >> 20); }
 struct SearchRes { bool found; double dis_lat, dis_lng; int ob, pathid; };
 
 __device__ __forceinline__ LaneMap dp_lane_map(int N, int lane) {
     LaneMap lm;
     if (N >= 32 || N <= 0) { lm.nchunk = 1; lm.o = lane; lm.c = 0; }
-    else { lm.nchunk = 32 / N; lm.o = lane % N; lm.c = lane / N; }
+    else { lm.nchunk = 32 / N; lm.c = lane / N; lm.o = lane - lm.c * N; }
+    lm.magic = (1u << 20) / (unsigned)lm.nchunk + 1u;
     return lm;
 }
 __device__ __forceinline__ double dp_sq2(double dx, double dy) { return fma(dx, dx, dy * dy); }
@@ -176,7 +179,7 @@ __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my
     const int P = s.n0 + s.n1;
     if (P < 2 || N <= 0) return r;
     const int nchunk = lm.nchunk;
-    const int CS = (nchunk == 1) ? P : (P + nchunk - 1) / nchunk;
+    const int CS = (nchunk == 1 || P >= 8192) ? ((nchunk == 1) ? P : (P + nchunk - 1) / nchunk) : dp_div_chunks(P + nchunk - 1, lm);
     const int ngroups = (nchunk == 1) ? (N + 31) >> 5 : 1;
     const bool in_plan = s.q_off >= 0;
     const bool one_tile = in_plan || P <= DP_TILE;          // every point stays addressable in shared memory

@@ -111,7 +111,9 @@ __device__ __forceinline__ double2 dp_sweep_point(const WarpSmem& sm, int j, dou
 // search: its result is the F region's, already known, and -- the sweep only runs when that gap is < 15 -- never feasible.
 // So only the 2(K-1) shifted candidates are scored; they are numbered u = 0 .. 2(K-1)-1 in reference order
 // (L1..L(K-1), R1..R(K-1)); dp_sweep_g maps u to the reference's candidate index g (L0..L(K-1), R0..R(K-1)).
-__device__ __forceinline__ int dp_sweep_g(int u, int K) { return (u / (K - 1)) * K + 1 + (u % (K - 1)); }
+__device__ __forceinline__ int dp_sweep_g(int u, int K) { return (u >= K - 1) ? u + 2 : u + 1; }
+// lateral offset of candidate g: -0.3*i on the left (g = i < K, Decision.cpp:942), 0.3*i on the right (g = K + i, :961)
+__device__ __forceinline__ double dp_sweep_offset(int g, int K) { return (g < K) ? -0.3 * g : 0.3 * (g - K); }
 // Scores shifted candidates u0 .. u0+cnt-1 (cnt * N <= 32) against the scene's obstacles (this lane's obstacle =
 // (mx, my), N < 32).  sink(g, result, before_first) receives the result of candidate g;
 // with need_all == false the arclength of a candidate is only resolved as far as the `> clear` decision needs and
@@ -122,7 +124,7 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int u0, int cn
     const int ci_me = lane / N, o = lane - ci_me * N;       // N <= 16 here
     const bool active = ci_me < cnt;
     const int g_me = dp_sweep_g(u0 + ci_me, K);
-    const double dc = ((g_me / K) == 0 ? -0.3 : 0.3) * (g_me % K);   // Decision.cpp:942 (-0.3*i), :961 (0.3*i)
+    const double dc = dp_sweep_offset(g_me, K);
     (void)lm;
     unsigned key = 0xffffffffu;
     double dlat = 0.0;
@@ -172,7 +174,7 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int u0, int cn
             r.found = true; r.pathid = jstar; r.ob = ostar;
             r.dis_lat = __shfl_sync(DP_FULL, dlat, ci * N + ostar);
             const int gc = dp_sweep_g(u0 + ci, K);
-            const double dcc = ((gc / K) == 0 ? -0.3 : 0.3) * (gc % K);
+            const double dcc = dp_sweep_offset(gc, K);
             __syncwarp();
             for (int j = lane; j < jstar; j += 32) {
                 const double2 a = dp_sweep_point(sm, j, dcc), b = dp_sweep_point(sm, j + 1, dcc);
