@@ -135,6 +135,30 @@ static __device__ __noinline__ SearchRes dp_search_cold(const Src s, double mx, 
     return dp_search(s, mx, my, ox, oy, N, lm, lo, hi, sm, lane);
 }
 
+// ---- per-scene hand-off between the two overlapped launches ----------------------------------------------------------
+// The Planning launch is a programmatic dependent launch: its CTAs become eligible as soon as every Decision CTA has
+// STARTED (they trigger at entry), and take the SM slots the Decision launch frees as its short scenes retire, instead of
+// waiting for the slowest scene of the batch (the ~16 % that run the avoid sweep).  A scene's Planning warp therefore
+// waits for THAT scene's Decision warp only: release/acquire on done[scene] at GPU scope.  No deadlock: when the first
+// Planning CTA is scheduled every Decision CTA is already resident, so every awaited flag has a running producer.
+__device__ __forceinline__ void dp_publish(unsigned* flag, unsigned epoch, int lane) {
+    __threadfence();                                        // every lane: its stores of this scene before the flag
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void dp_await(const unsigned* flag, unsigned epoch) {
+    unsigned v = 0;
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == epoch) break;
+        __nanosleep(spin < 64 ? 100 : 1000);
+    }
+    if (v != epoch) __trap();                               // never spin forever on a producer that is not there
+    __syncwarp();
+}
+// reads of what the Decision launch of THIS cycle wrote go to L2 (the SM's L1 may hold an older copy of the line)
+template <class T> __device__ __forceinline__ T dp_l2(const T* p) { return __ldcg(p); }
+
 }  // namespace
 
 #define DP_MIN_BLOCKS 7
@@ -183,9 +207,12 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
 #define DBG_T(i)
 #endif
     WarpSmem& sm = smem[wib];
+    if (PHASE == 1 && io.done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // Planning CTAs may start filling in
+    if (PHASE == 2 && io.done) dp_await(io.done + scene, io.epoch);
     // the 128-byte scene header comes in with one coalesced warp load (from HBM, or straight from pinned host memory
     // over PCIe in the zero-copy mode of dp_cycle_batch) and is read from shared memory afterwards
-    sm.hdr[lane] = reinterpret_cast<const uint32_t*>(hdr + scene)[lane];
+    sm.hdr[lane] = (PHASE == 2) ? dp_l2(reinterpret_cast<const uint32_t*>(hdr + scene) + lane)
+                                : reinterpret_cast<const uint32_t*>(hdr + scene)[lane];
     __syncwarp();
     const dp_scene_hdr& h = *reinterpret_cast<const dp_scene_hdr*>(sm.hdr);
     const double* ox = obs_x + (size_t)scene * max_obs;
@@ -204,7 +231,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     const LaneMap lm = dp_lane_map(N, lane);
     // this lane's obstacle stays in registers for the whole cycle when N < 32
     const bool lm_act = (lm.nchunk > 1) && (lane < N * lm.nchunk);
-    const double mx = lm_act ? ox[lm.o] : 0.0, my = lm_act ? oy[lm.o] : 0.0;
+    const double mx = lm_act ? (PHASE == 2 ? dp_l2(ox + lm.o) : ox[lm.o]) : 0.0, my = lm_act ? (PHASE == 2 ? dp_l2(oy + lm.o) : oy[lm.o]) : 0.0;
     dp_trace_record* tr = trace ? trace + scene : nullptr;
     if (tr && PHASE != 2) {                                 // zero the trace record cooperatively
         uint32_t* w = reinterpret_cast<uint32_t*>(tr);
@@ -223,9 +250,9 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
 
     if (PHASE == 2) {
         // ---- hand-off from the Decision launch ----
-        d_behavior = cg->behavior; d_target = cg->target_lanenum; v_exp = cg->velocity_expect;
-        n_traj = out->n_traj;
-        if (tr) { ub = tr->ub_hits; pts = (int)tr->pts_scored; }
+        d_behavior = dp_l2(&cg->behavior); d_target = dp_l2(&cg->target_lanenum); v_exp = dp_l2(&cg->velocity_expect);
+        n_traj = dp_l2(&out->n_traj);
+        if (tr) { ub = dp_l2(&tr->ub_hits); pts = (int)dp_l2(&tr->pts_scored); }
         if (pos == 0) {
             gl = m.road_lane_base[h.road_num - 1] + lane_n - 1;
             lane_sum = m.road_lane_base[h.road_num] - m.road_lane_base[h.road_num - 1];
@@ -561,6 +588,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
         }
         DBG_END(0, n_traj);
+        if (io.done) dp_publish(io.done + scene, io.epoch, lane);
         return;
     }
 
@@ -569,9 +597,9 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     // the copy lands while the aim point is searched
     __syncwarp();
     dp_bulk_prefetch(sm.plan, lastp, DP_PATH_POINTS * (uint32_t)sizeof(double2), &sm.mbar, lane);
-    const int plan_his_behavior = cg->plan_his_behavior, carried_near_id = cg->path_near_id, plan_count = cg->plan_count;
-    double aim_x = cg->aim_x, aim_y = cg->aim_y, aim_dir = cg->aim_dir;
-    int aim_id = cg->aim_id;
+    const int plan_his_behavior = dp_l2(&cg->plan_his_behavior), carried_near_id = dp_l2(&cg->path_near_id), plan_count = dp_l2(&cg->plan_count);
+    double aim_x = dp_l2(&cg->aim_x), aim_y = dp_l2(&cg->aim_y), aim_dir = dp_l2(&cg->aim_dir);
+    int aim_id = dp_l2(&cg->aim_id);
     // ---- Calculate_aim_dis (Planning.cpp:242-290), FLOAT faraim_dis ----
     float faraim = 0.f;
     if (pos == 0) {
@@ -859,14 +887,31 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
     }
     const int blocks = (n + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, threads = DP_WARPS_PER_BLOCK * 32;
     if (!split) {
-        dp_cycle_kernel<0><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io);
+        DpIo io0 = io; io0.done = nullptr;
+        dp_cycle_kernel<0><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io0);
     } else {
         // Decision launch ingests (hdr/ox/oy may be pinned host memory); Planning launch reads the staged device copies
         DpIo io1 = io; io1.rec_host = nullptr;
         DpIo io2 = io; io2.hdr_stage = nullptr; io2.ox_stage = nullptr; io2.oy_stage = nullptr;
+        if (split != 2) io1.done = io2.done = nullptr;
         dp_cycle_kernel<1><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
-        dp_cycle_kernel<2><<<blocks, threads, 0, st>>>(m, p, n, io.hdr_stage ? io.hdr_stage : hdr, io.ox_stage ? io.ox_stage : ox,
-                                                       io.oy_stage ? io.oy_stage : oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2);
+        const dp_scene_hdr* hdr2 = io.hdr_stage ? io.hdr_stage : hdr;
+        const double* ox2 = io.ox_stage ? io.ox_stage : ox; const double* oy2 = io.oy_stage ? io.oy_stage : oy;
+        if (io2.done) {
+            // programmatic dependent launch WITHOUT a grid-wide dependency wait in the kernel: scenes hand over one by one
+            // (dp_publish / dp_await), so Planning CTAs run in the slots the Decision launch frees while its tail finishes
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, dp_cycle_kernel<2>, m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy,
+                                               path_ll, io2);
+            if (e != cudaSuccess) return e;
+        } else {
+            dp_cycle_kernel<2><<<blocks, threads, 0, st>>>(m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2);
+        }
     }
     return cudaGetLastError();
 }

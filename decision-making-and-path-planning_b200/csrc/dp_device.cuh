@@ -190,7 +190,7 @@ __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my
     for (int g = 0; g < ngroups; ++g) {
         const int o = (nchunk == 1) ? g * 32 + lane : lm.o;
         const bool active = (nchunk == 1) ? (o < N) : (lane < N * nchunk);
-        if (nchunk == 1) { mx = active ? ox[o] : 0.0; my = active ? oy[o] : 0.0; }
+        if (nchunk == 1) { mx = active ? __ldcg(ox + o) : 0.0; my = active ? __ldcg(oy + o) : 0.0; }   // (L2: rows may have been staged by the overlapped Decision launch)
         const int jlo = lm.c * CS, jhi = active ? min(P, jlo + CS) : 0;
         // four independent running minima (j mod 4 classes) break the compare/select dependency chain;
         // their lexicographic (d2, j) minimum is the sequential strict-'<' result (lowest index on ties)

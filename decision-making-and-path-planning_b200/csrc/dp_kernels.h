@@ -5,11 +5,13 @@
 
 // optional zero-copy plumbing of the host-pointer entry point: the Decision launch reads hdr/obstacles from pinned host
 // memory and leaves device copies in *_stage for the Planning launch; the finished record is also stored to rec_host
-struct DpIo { dp_scene_hdr* hdr_stage; double* ox_stage; double* oy_stage; dp_plan_record* rec_host; };
+// done / epoch: per-scene hand-off flags of the overlapped split launch (dp_cycle.cu): the Decision warp of a scene
+// publishes `epoch` in done[scene] when its outputs are in memory, the Planning warp of that scene waits for it
+struct DpIo { dp_scene_hdr* hdr_stage; double* ox_stage; double* oy_stage; dp_plan_record* rec_host; unsigned* done; unsigned epoch; };
 
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                            double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io);
+                            double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io);   // split: 0 fused, 1 two launches, 2 overlapped
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st);
 cudaError_t dp_launch_map_prep(const double* x, const double* y, const int32_t* lane_pt_off, int n_lanes, double2* xy, double2* nrm,
                                double* lenp, cudaStream_t st);

@@ -222,11 +222,13 @@ def test_library_is_the_cuda_path(planner):
     assert fp64 > 5 and fp32 > 20, (fp64, fp32)
 
 
-def test_zero_copy_host_path(planner, oracle, the_map):
-    """dp_cycle_batch with PINNED host buffers takes the zero-copy route (kernels read the inputs from host memory and
-    store the records there); it must give byte-identical records to the staged-copy route used with pageable buffers."""
+def test_pinned_host_paths(planner, oracle, the_map, monkeypatch):
+    """dp_cycle_batch with PINNED host buffers: the default route (three input DMAs, records stored straight into the
+    caller's buffer) and the DP_ZERO_COPY=1 route (kernels read the inputs from host memory over PCIe) must both give
+    byte-identical records to the staged-copy route used with pageable buffers."""
     import torch
     from dmpp_b200 import abi, scenes
+    from dmpp_b200.planner import Planner
     n, cycles = 512, 12
     ep = scenes.Episodes(the_map, np.arange(4242, 4242 + n), cycles=cycles, n_obs=10)
     H, OX, OY = ep.all_cycles()
@@ -245,7 +247,14 @@ def test_zero_copy_host_path(planner, oracle, the_map):
         o = planner.cycle(np.ascontiguousarray(H[c]), PX[c], PY[c])
         assert o["rec"].tobytes() == got[c].tobytes(), "cycle %d" % c
     want = oracle.run(H, OX, OY, paths=False, calls=False, trace=False, exhaustive=False)
-    assert_records_equal(np.stack(got), want["rec"], REC_EXACT, close=DIR_ERR_TOL, what="zero-copy")
+    assert_records_equal(np.stack(got), want["rec"], REC_EXACT, close=DIR_ERR_TOL, what="pinned")
+    monkeypatch.setenv("DP_ZERO_COPY", "1")                     # read by dp_create
+    zc = Planner(max_scenes=n, max_obs=planner.max_obs)
+    zc.upload_map(the_map)
+    for c in range(cycles):
+        zc.cycle(Hp[c], PXp[c], PYp[c], out={"rec": rec_p})
+        assert rec_p.tobytes() == got[c].tobytes(), "zero-copy cycle %d" % c
+    zc.close()
 
 
 def test_pipelined_submit_wait(planner, oracle, the_map):
