@@ -291,19 +291,24 @@ def run_ours(args, rank, world, local_rank):
     #      inputs host->device and its records device->host inside the timed region; the region ends after the last wait. ----
     recs2 = [rec_h, torch.empty((SCENES, 128), dtype=torch.uint8).pin_memory().numpy().view(abi.plan_record).reshape(SCENES)]
 
+    CH = 32768                                               # dp_cycle_submit takes at most 32768 scenes per call
+
     def pipe_loop(first, count):
-        got = 0; pend = None
+        got = 0; pend = []                                   # record slices in flight (at most two)
         for i in range(first, first + count):
             c = i % EPISODE
             if c == 0:
-                if pend is not None:
-                    planner.wait(); got += int(recs2[pend & 1]["n_traj"].sum(dtype=np.int64)); pend = None
+                while pend:
+                    planner.wait(); got += int(pend.pop(0)["n_traj"].sum(dtype=np.int64))
                 planner.reset(0, SCENES)
-            planner.submit(Hh[c], OXh[c], OYh[c], recs2[i & 1])
-            if pend is not None:
-                planner.wait(); got += int(recs2[pend & 1]["n_traj"].sum(dtype=np.int64))
-            pend = i
-        planner.wait(); got += int(recs2[pend & 1]["n_traj"].sum(dtype=np.int64))
+            for s0 in range(0, SCENES, CH):
+                s1 = min(SCENES, s0 + CH)
+                if len(pend) == 2:
+                    planner.wait(); got += int(pend.pop(0)["n_traj"].sum(dtype=np.int64))
+                planner.submit(Hh[c, s0:s1], OXh[c, s0:s1], OYh[c, s0:s1], recs2[i & 1][s0:s1], first=s0)
+                pend.append(recs2[i & 1][s0:s1])
+        while pend:
+            planner.wait(); got += int(pend.pop(0)["n_traj"].sum(dtype=np.int64))
         return got
 
     barrier()
