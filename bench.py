@@ -38,8 +38,9 @@ def workload_desc(world):
     return {"workload": ("config2" if SCENES == 4096 else "config4 shard") + ": %d highway scenes/GPU x default candidate set (6 lane regions + 2K avoid offsets + 1 local path), "
                         "ego + %d vehicles, %d-cycle scripted episodes" % (SCENES, N_OBS, EPISODE),
             "scenes_per_gpu": SCENES, "obstacles": N_OBS, "episode_cycles": EPISODE,
-            "parallelism": "scenes sharded %d-way, no data-path collective; when N>1 the plan records of step i are all_gathered on a side "
-                           "stream while step i+1 computes (double-buffered), last gather exposed and counted" % world,
+            "parallelism": "scenes sharded %d-way, no data-path collective in the compute phase; when N>1 every rank's plan records are "
+                           "gathered on every rank each step: GATHER_KIND; the gather of step i is finished beside the kernels of "
+                           "step i+1 (triple-buffered), the last one is exposed and counted" % world,
             "l2": "256 MiB buffer written between timed steps (L2 flush); inputs resident in HBM for `value`"}
 
 
@@ -132,7 +133,7 @@ def run_reference(args, rank, world):
                                        "the unmodified Decision.cpp/Planning.cpp objects" % (steps, min(SCENES, 4096), EPISODE)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "ms_per_step is normalised to one plan cycle of %d scenes" % min(SCENES, 4096)}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -177,7 +178,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version banner off stdout (one JSON line there)
+        # the record gather runs beside the next step's kernels: keep its footprint to a few CTAs so that the one-wave
+        # Decision launch (1024 CTAs on 1036 slots) still fits
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, args.warmup
     m = scenes.Map()
@@ -196,12 +199,31 @@ def run_ours(args, rank, world, local_rank):
     d_hdr = torch.from_numpy(H.view(np.uint8).reshape(EPISODE, SCENES, 128)).to(dev)
     d_ox = torch.from_numpy(OX).to(dev)
     d_oy = torch.from_numpy(OY).to(dev)
-    d_recs = [torch.empty((SCENES, 128), dtype=torch.uint8, device=dev) for _ in range(2)]   # double-buffered plan records
-    gathered = torch.empty((world * SCENES, 128), dtype=torch.uint8, device=dev) if world > 1 else None
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    d_recs = [torch.empty((SCENES, 128), dtype=torch.uint8, device=dev) for _ in range(3)]   # plan records, rotated per step
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(W + K)]
+    # N > 1: the records of every rank are gathered on every rank each step.  The gather is fused into the Planning launch:
+    # each rank's kernel stores its finished records straight into its slice of every peer's gathered buffer over NVLink
+    # (torch symmetric memory gives the peer mappings, dp_set_record_mirrors hands them to the kernel); what is left of the
+    # collective is a barrier, run on a side stream beside the next step's kernels.  Three gathered buffers rotate so that a
+    # step never overwrites records a peer may still be reading.
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    gath = hdl = None
+    gather_kind = "none"
+    if world > 1:
+        try:
+            import torch.distributed._symmetric_memory as symm
+            gath = [symm.empty((world * SCENES, 128), dtype=torch.uint8, device=dev) for _ in range(3)]
+            hdl = [symm.rendezvous(g, dist.group.WORLD) for g in gath]
+            for g in gath:
+                g.zero_()
+            gather_kind = "peer stores from the Planning launch (NVLink, symmetric memory) + barrier on a side stream"
+        except Exception as e:  # noqa: BLE001 -- no peer mapping on this box: fall back to NCCL's all_gather
+            print("symmetric memory unavailable (%s): using all_gather_into_tensor" % e, file=sys.stderr)
+            gath = [torch.empty((world * SCENES, 128), dtype=torch.uint8, device=dev) for _ in range(3)]
+            hdl = None
+            gather_kind = "all_gather_into_tensor on a side stream"
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -213,23 +235,32 @@ def run_ours(args, rank, world, local_rank):
 
     tail_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
+    def finish_gather(i, rec_i):
+        """what is left of step i's gather after its kernels: a barrier (peer stores) or the whole all_gather (fallback)"""
+        if hdl is not None:
+            hdl[i % 3].barrier()
+        else:
+            dist.all_gather_into_tensor(gath[i % 3], rec_i)
+
     def dev_loop(first, count):
-        """N > 1: the all_gather of step i's records runs on a side stream concurrently with the kernels of step i+1
-        (it is released by the start event of step i+1, so it cannot hide inside the untimed L2 flush); a step is
-        complete when its kernels AND the previous step's gather are done; the last gather is timed on its own."""
-        pending = None                                       # records of the previous step, not yet gathered
+        """N > 1: the gather of step i is finished on a side stream concurrently with the kernels of step i+1 (it is
+        released by the start event of step i+1, so it cannot hide inside the untimed L2 flush); a step is complete when
+        its kernels AND the previous step's gather are done; the last one is timed on its own."""
+        pending = None                                       # (step, records) whose gather is not finished yet
         for i in range(first, first + count):
             c = i % EPISODE
             if c == 0:
                 torch.cuda.synchronize()
                 planner.reset(0, SCENES)
             flush.zero_()
-            rec_i = d_recs[i & 1]
+            rec_i = d_recs[i % 3]
+            if hdl is not None:                              # this step's records go to slice `rank` of every rank's buffer i % 3
+                planner.set_record_mirrors([p + rank * SCENES * 128 for p in hdl[i % 3].buffer_ptrs])
             ev[i][0].record(stream)
             if pending is not None:
                 comm.wait_event(ev[i][0])
                 with torch.cuda.stream(comm):
-                    dist.all_gather_into_tensor(gathered, pending)
+                    finish_gather(*pending)
                     gdone = torch.cuda.Event()
                     gdone.record(comm)
             planner.cycle_dev(SCENES, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), rec_i.data_ptr(),
@@ -238,18 +269,28 @@ def run_ours(args, rank, world, local_rank):
             if pending is not None:
                 stream.wait_event(gdone)
             ev[i][2].record(stream)
-            pending = rec_i if world > 1 else None
+            pending = (i, rec_i) if world > 1 else None
         if world > 1:
             tail_ev[0].record(stream)
-            dist.all_gather_into_tensor(gathered, pending)
+            finish_gather(*pending)
             tail_ev[1].record(stream)
+        return pending
 
     barrier()
     dev_loop(0, W)
     barrier()
     l0 = planner.launch_count()
-    dev_loop(W, K)
+    last = dev_loop(W, K)
     barrier()
+    if world > 1:                                            # the gathered buffer of the last step holds every rank's records
+        g = gath[last[0] % 3].view(world, SCENES, 128)
+        assert torch.equal(g[rank], last[1]), "own slice of the gathered records differs"
+        chk = torch.tensor([float(last[1][:, :].sum(dtype=torch.int64).item())], dtype=torch.float64, device=dev)
+        allchk = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        for r in range(world):
+            assert float(g[r].sum(dtype=torch.int64).item()) == float(allchk[r].item()), "gathered slice of rank %d differs" % r
+        planner.set_record_mirrors([])
     launches = planner.launch_count() - l0 - sum(1 for i in range(W, W + K) if i % EPISODE == 0)
     kern_ms = np.array([ev[i][0].elapsed_time(ev[i][1]) for i in range(W, W + K)])
     step_ms = np.array([ev[i][0].elapsed_time(ev[i][2]) for i in range(W, W + K)])
@@ -348,7 +389,8 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_desc(world),
+        "dtype": "f64", "data": "synthetic", "config": {k: (v.replace("GATHER_KIND", gather_kind) if isinstance(v, str) else v)
+                                                        for k, v in workload_desc(world).items()},
         "plan_cycles_per_s": world * SCENES * K / total_s,
         "trajectories_per_step_per_gpu": float(traj_c[cyc_idx].mean()),
         "cycle_latency_ms": {"p50": float(np.percentile(step_ms, 50)), "p99": float(np.percentile(step_ms, 99)),
@@ -388,13 +430,30 @@ def run_ours(args, rank, world, local_rank):
                                               "objects when kind=reference)" % (n, min(SCENES, 4096), EPISODE)}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
-    print(json.dumps(line))
+    emit(line)
     planner.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_OUT_FD = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner ...) was
+    redirected to stderr in main()"""
+    data = (json.dumps(line) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
+
+
 def main():
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)                                            # C-level and Python-level stdout -> stderr from here on
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -58,7 +58,21 @@ struct dp_ctx {
     // overlapped split launch (split == 2): per-scene hand-off flags and the epoch of the next cycle
     unsigned* d_done = nullptr;
     unsigned epoch = 0;
+    // record mirrors (dp_set_record_mirrors): device-accessible bases indexed by carry slot
+    dp_plan_record* mirror[DP_MAX_MIRRORS - 1] = {};
+    int n_mirror = 0;
 };
+
+namespace {
+// launch plumbing of one cycle call: hand-off flags, then the caller's pinned record buffer (if any) and the context's mirrors
+DpIo make_io(dp_ctx* c, int first, dp_plan_record* host_rec) {
+    DpIo io = dp_io_none();
+    io.done = c->d_done + first; io.epoch = ++c->epoch;
+    if (host_rec) io.mirror[io.n_mirror++] = host_rec;
+    for (int k = 0; k < c->n_mirror; ++k) io.mirror[io.n_mirror++] = c->mirror[k] + first;
+    return io;
+}
+}  // namespace
 
 namespace {
 bool is_pinned(const void* p, void** dev = nullptr) {
@@ -261,7 +275,7 @@ int dp_cycle_batch_dev(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, con
     if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_batch_dev: map not uploaded");
     CK(cudaSetDevice(c->device));
     CK(dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace, path_xy,
-                       path_ll, (cudaStream_t)stream, c->split, DpIo{nullptr, nullptr, nullptr, nullptr, c->d_done + first, ++c->epoch}));
+                       path_ll, (cudaStream_t)stream, c->split, make_io(c, first, nullptr)));
     c->launches += c->split ? 2 : 1;
     return DP_OK;
 }
@@ -294,7 +308,8 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         // pushes each finished record into the caller's pinned result buffer.  No copy engines -- but GPU-issued PCIe reads
         // are slower than the DMA route above (163 vs 120 us per 4096-scene call), so this is not the default.
         cudaStream_t st = c->st[0];
-        DpIo io{c->d_hdr[0], c->d_ox[0], c->d_oy[0], (dp_plan_record*)dv_rec, c->d_done + first, ++c->epoch};
+        DpIo io = make_io(c, first, (dp_plan_record*)dv_rec);
+        io.hdr_stage = c->d_hdr[0]; io.ox_stage = c->d_ox[0]; io.oy_stage = c->d_oy[0];
         CK(dp_launch_cycle(c->map, c->p, n, (const dp_scene_hdr*)dv_hdr, (const double*)dv_ox, (const double*)dv_oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
                            c->d_rec[0], nullptr, nullptr, nullptr, st, c->split, io));
         c->launches += 2;
@@ -322,7 +337,7 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         CK(cudaMemcpyAsync(c->d_oy[s], sy, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
         CK(dp_launch_cycle(c->map, c->p, cn, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first + i0,
                            c->d_last + (size_t)(first + i0) * DP_PATH_POINTS, c->d_rec[s], trace ? c->d_trace[s] : nullptr,
-                           path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st, c->split, DpIo{nullptr, nullptr, nullptr, nullptr, c->d_done + first + i0, ++c->epoch}));
+                           path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st, c->split, make_io(c, first + i0, nullptr)));
         c->launches += c->split ? 2 : 1;
         CK(cudaMemcpyAsync(pin_rec ? rec + i0 : c->h_rec[s], c->d_rec[s], (size_t)cn * sizeof(dp_plan_record), cudaMemcpyDeviceToHost, st));
         if (trace) CK(cudaMemcpyAsync(trace + i0, c->d_trace[s], (size_t)cn * sizeof(dp_trace_record), cudaMemcpyDeviceToHost, st));
@@ -359,7 +374,7 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
         CK(cudaStreamWaitEvent(st, c->in_ready[s][k], 0));
     }
     CK(dp_launch_cycle(c->map, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
-                       c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, DpIo{nullptr, nullptr, nullptr, (dp_plan_record*)dv_rec, c->d_done + first, ++c->epoch}));
+                       c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, make_io(c, first, (dp_plan_record*)dv_rec)));
     c->launches += c->split ? 2 : 1;
     CK(cudaEventRecord(c->done[s], st));
     ++c->submitted;
@@ -372,6 +387,17 @@ int dp_cycle_wait(dp_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaEventSynchronize(c->done[c->waited & 1]));
     ++c->waited;
+    return DP_OK;
+}
+
+int dp_set_record_mirrors(dp_ctx* c, int n, void* const* bases) {
+    if (!c || n < 0 || n > DP_MAX_MIRRORS - 1 || (n > 0 && !bases)) return fail(DP_ERR_ARG, "dp_set_record_mirrors: bad argument");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_set_record_mirrors: submitted cycles in flight, call dp_cycle_wait first");
+    for (int k = 0; k < n; ++k) {
+        if (!bases[k]) return fail(DP_ERR_ARG, "dp_set_record_mirrors: null base");
+        c->mirror[k] = (dp_plan_record*)bases[k];
+    }
+    c->n_mirror = n;
     return DP_OK;
 }
 

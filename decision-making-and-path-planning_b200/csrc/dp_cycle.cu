@@ -835,10 +835,13 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
     }
     DBG_END(1, n_traj);
-    if (io.rec_host) {                                      // zero-copy result: one coalesced 128-byte store to pinned host memory
+    if (io.n_mirror) {                                      // mirrors: one coalesced 128-byte store each (pinned host / peer GPUs)
         __syncwarp();
         __threadfence_block();
-        reinterpret_cast<uint32_t*>(io.rec_host + scene)[lane] = reinterpret_cast<const volatile uint32_t*>(out)[lane];
+        const uint32_t w = reinterpret_cast<const volatile uint32_t*>(out)[lane];
+#pragma unroll
+        for (int k = 0; k < DP_MAX_MIRRORS; ++k)             // (static indices: the parameter array stays in the constant bank)
+            if (k < io.n_mirror) reinterpret_cast<uint32_t*>(io.mirror[k] + scene)[lane] = w;
     }
 }
 
@@ -891,7 +894,7 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
         dp_cycle_kernel<0><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io0);
     } else {
         // Decision launch ingests (hdr/ox/oy may be pinned host memory); Planning launch reads the staged device copies
-        DpIo io1 = io; io1.rec_host = nullptr;
+        DpIo io1 = io; io1.n_mirror = 0;
         DpIo io2 = io; io2.hdr_stage = nullptr; io2.ox_stage = nullptr; io2.oy_stage = nullptr;
         if (split != 2) io1.done = io2.done = nullptr;
         dp_cycle_kernel<1><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);

@@ -3,11 +3,21 @@
 #include <cuda_runtime.h>
 #include "dp_device.cuh"
 
-// optional zero-copy plumbing of the host-pointer entry point: the Decision launch reads hdr/obstacles from pinned host
-// memory and leaves device copies in *_stage for the Planning launch; the finished record is also stored to rec_host
-// done / epoch: per-scene hand-off flags of the overlapped split launch (dp_cycle.cu): the Decision warp of a scene
-// publishes `epoch` in done[scene] when its outputs are in memory, the Planning warp of that scene waits for it
-struct DpIo { dp_scene_hdr* hdr_stage; double* ox_stage; double* oy_stage; dp_plan_record* rec_host; unsigned* done; unsigned epoch; };
+// optional plumbing of the cycle launches:
+//   *_stage   zero-copy ingest (DP_ZERO_COPY=1): the Decision launch reads hdr/obstacles from pinned host memory and leaves
+//             device copies here for the Planning launch;
+//   mirror    every finished 128-byte plan record is ALSO stored (one coalesced warp store each) at mirror[k][scene]:
+//             the caller's pinned result buffer (no D2H copy), and/or the gathered-records buffers of the peer GPUs
+//             mapped over NVLink -- the per-step record gather fused into the Planning launch (dp_set_record_mirrors);
+//   done / epoch  per-scene hand-off flags of the overlapped split launch (dp_cycle.cu): the Decision warp of a scene
+//             publishes `epoch` in done[scene] when its outputs are in memory, the Planning warp of that scene waits for it
+#define DP_MAX_MIRRORS 9
+struct DpIo {
+    dp_scene_hdr* hdr_stage; double* ox_stage; double* oy_stage;
+    dp_plan_record* mirror[DP_MAX_MIRRORS]; int n_mirror;
+    unsigned* done; unsigned epoch;
+};
+inline DpIo dp_io_none() { DpIo io = {}; return io; }
 
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,

@@ -21,7 +21,7 @@ SYMBOLS = [
     "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
     "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
-    "dp_cycle_submit", "dp_cycle_wait",
+    "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors",
 ]
 
 _lib = None
@@ -109,6 +109,11 @@ class Planner:
                                     abi.ptr(o.get("path_xy") if paths else None),
                                     abi.ptr(o.get("path_ll") if paths else None)), "dp_cycle_batch")
         return o
+
+    def set_record_mirrors(self, bases):
+        """bases: device-accessible addresses (ints); every finished record of slot s is also stored at base + 128 * s"""
+        arr = (C.c_void_p * max(1, len(bases)))(*[C.c_void_p(int(b)) for b in bases])
+        _ck(self.lib.dp_set_record_mirrors(self.ctx, C.c_int(len(bases)), arr), "dp_set_record_mirrors")
 
     # ---- pipelined form: at most two cycles in flight, buffers page-locked (see include/dmpp_b200.h) ----
     def submit(self, hdr, ox, oy, rec, first=0):

@@ -198,6 +198,13 @@ int dp_cycle_batch(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scene_hd
 int dp_cycle_submit(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scene_hdr* hdr,
                     const double* obs_x, const double* obs_y, dp_plan_record* rec);
 int dp_cycle_wait(dp_ctx* ctx);
+/* Record mirrors: from now on every finished plan record of scene slot s is ALSO stored at bases[k] + s for k < n
+ * (n <= 8; n = 0 switches it off).  The bases must be addresses the device of `ctx` can store to: device memory of this
+ * GPU, page-locked host memory, or -- the reason this exists -- the gathered-records buffers of the PEER GPUs mapped into
+ * this process over NVLink (CUDA IPC / VMM / torch symmetric memory).  With one base per peer, pointing at this rank's slice of
+ * the peer's buffer, the per-step all-gather of plan records happens inside the Planning launch as 128-byte
+ * peer stores instead of a separate collective; the caller only needs a barrier before it reads the gathered buffer. */
+int dp_set_record_mirrors(dp_ctx* ctx, int n, void* const* bases);
 int dp_host_alloc(void** p, size_t bytes);
 int dp_host_free(void* p);
 

@@ -295,3 +295,29 @@ def test_pipelined_submit_wait(planner, oracle, the_map):
     for c in range(cycles):
         o = planner.cycle(np.ascontiguousarray(H[c]), PX[c], PY[c])
         assert o["rec"].tobytes() == got[c].tobytes(), "cycle %d" % c
+
+
+def test_record_mirrors(planner, the_map):
+    """dp_set_record_mirrors: every finished record is also stored at base[k] + slot (the hook the multi-GPU gather uses
+    with peer-mapped buffers); here two device buffers on the same GPU and a non-zero first slot."""
+    import torch
+    from dmpp_b200 import abi, scenes
+    n, first, cycles = 300, 40, 6
+    ep = scenes.Episodes(the_map, np.arange(9000, 9000 + n), cycles=cycles, n_obs=10)
+    H, OX, OY = ep.all_cycles()
+    PX, PY = pad_obs(OX, OY, planner.max_obs)
+    dev = torch.device("cuda", 0)
+    m1 = torch.zeros((first + n + 8, 128), dtype=torch.uint8, device=dev)
+    m2 = torch.zeros((first + n + 8, 128), dtype=torch.uint8, device=dev)
+    planner.reset(first, n)
+    planner.set_record_mirrors([m1.data_ptr(), m2.data_ptr()])
+    try:
+        for c in range(cycles):
+            o = planner.cycle(np.ascontiguousarray(H[c]), PX[c], PY[c], first=first)
+            torch.cuda.synchronize()
+            for m in (m1, m2):
+                got = m.cpu().numpy()
+                assert got[first:first + n].tobytes() == o["rec"].tobytes(), "cycle %d" % c
+                assert not got[:first].any() and not got[first + n:].any(), "stores outside the slot range"
+    finally:
+        planner.set_record_mirrors([])
