@@ -480,6 +480,25 @@ int dp_mean_points(dp_ctx* c, int n_paths, const int32_t* path_off, const double
     return DP_OK;
 }
 
+int dp_nearest_id(dp_ctx* c, int n_paths, const int32_t* path_off, const double* px, const double* py, const double* qx, const double* qy,
+                  int32_t* out_id) {
+    if (!c || n_paths < 0 || !path_off || !qx || !qy || !out_id) return fail(DP_ERR_ARG, "dp_nearest_id: bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t np = (size_t)path_off[n_paths];
+    Tmp tmp; cudaError_t e;
+    std::vector<double2> hxy = interleave(px, py, np);
+    PUT(d_off, int32_t, path_off, (size_t)n_paths + 1);
+    PUT(d_pxy, double2, hxy.data(), np);
+    PUT(d_qx, double, qx, (size_t)n_paths);
+    PUT(d_qy, double, qy, (size_t)n_paths);
+    PUT(d_o, int32_t, (const int32_t*)nullptr, (size_t)n_paths);
+    CK(dp_launch_nearest(n_paths, d_off, d_pxy, d_qx, d_qy, d_o, c->st[0]));
+    ++c->launches;
+    CK(cudaMemcpyAsync(out_id, d_o, (size_t)n_paths * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+
 int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
                         int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min,
                         double lat_max, double clear_dis, int32_t* best_index, double* best_dis_lng, double* out_dis_lng) {

@@ -148,6 +148,7 @@ __device__ __forceinline__ void dp_publish(unsigned* flag, unsigned epoch, int l
 }
 __device__ __forceinline__ void dp_await(const unsigned* flag, unsigned epoch) {
     unsigned v = 0;
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 22); ++spin) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v == epoch) break;
@@ -703,19 +704,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         plan_dirty = true;
     }
     // ---- GetVhclLocalState (Planning.cpp:623-676) on last_Bpoints ----
-    double md = 9999.0;
-    int mi = 0x7fffffff;
-    for (int i = lane; i < DP_PATH_POINTS; i += 32) {
-        const double2 q = sm.plan[i];
-        const double d = dp_dist_plain(h.x, h.y, q.x, q.y);
-        if (d < md) { md = d; mi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(DP_FULL, md, o);
-        const int oi = __shfl_xor_sync(DP_FULL, mi, o);
-        if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
-    }
+    const int mi = dp_nearest_plain(sm.plan, DP_PATH_POINTS, h.x, h.y, lane);   // nearest of the 200 points (Planning.cpp:640-648)
     const int near_id = (mi == 0x7fffffff) ? carried_near_id : mi;
     const int front_id = near_id + 8;
     int idx = (near_id == 199) ? near_id - 1 : near_id;
@@ -728,10 +717,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         if (front_id < 0) ++ub;
         const int cnt = max(0, 199 - f0);
         __syncwarp();
-        for (int j = lane; j < cnt; j += 32) {
-            const double2 a = sm.plan[f0 + j], b = sm.plan[f0 + j + 1];
-            sm.scr[j] = dp_dist_plain(b.x, b.y, a.x, a.y);
-        }
+        for (int j = lane; j < cnt; j += 32) { const double2 a = sm.plan[f0 + j], b = sm.plan[f0 + j + 1]; sm.scr[j] = dp_dist_plain(b.x, b.y, a.x, a.y); }
         dp_pad_scr(sm, cnt, lane);
         __syncwarp();
         remain = dp_seq_sum(sm, cnt, 0.0);

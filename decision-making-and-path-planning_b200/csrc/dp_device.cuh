@@ -144,6 +144,49 @@ __device__ __forceinline__ SeqHit dp_seq_first(const WarpSmem& sm, int n, double
     return r;
 }
 
+// ---- CShare::NearestId / the nearest-point loop of GetVhclLocalState (Planning.cpp:640-648), one warp -----------------
+// Reference: d_i = sqrt(e_i) with e_i = dx*dx + dy*dy, strict '<' starting from 9999: the LOWEST index among the points
+// whose ROUNDED distance is minimal (0x7fffffff here when no distance is below 9999).  sqrt is monotone, so that distance
+// is sqrt(min e) and the answer is the lowest index with e == min e -- unless a DIFFERENT e within a few ulps of the
+// minimum rounds to the same sqrt.  So the squared distances are compared (one sqrt per query instead of n), and any e
+// within 2^-49 of the minimum but not equal to it sends the warp through the reference's own loop.
+__device__ __forceinline__ int dp_nearest_plain(const double2* pts, int n, double x, double y, int lane) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL), TOL = 1.0 + 0x1p-49;
+    double be = INF;
+    int bi = 0x7fffffff;
+    bool amb = false;
+    for (int i = lane; i < n; i += 32) {
+        const double2 q = pts[i];
+        const double dx = x - q.x, dy = y - q.y;
+        const double e = dx * dx + dy * dy;                 // the argument of the reference's sqrt, same operations
+        if (e < be) { amb = amb || (be <= e * TOL); be = e; bi = i; }   // (the displaced lower index may round to the same sqrt)
+    }
+    double ge = be;
+    int gi = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oe = __shfl_xor_sync(DP_FULL, ge, o);
+        const int oi = __shfl_xor_sync(DP_FULL, gi, o);
+        if (oe < ge || (oe == ge && oi < gi)) { ge = oe; gi = oi; }
+    }
+    amb = amb || (be != ge && be <= ge * TOL);
+    if (!__any_sync(DP_FULL, amb)) return (gi != 0x7fffffff && sqrt(ge) < 9999.0) ? gi : 0x7fffffff;
+    double md = 9999.0;                                     // near tie: the reference loop, verbatim
+    int mi = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) {
+        const double2 q = pts[i];
+        const double dd = dp_dist_plain(x, y, q.x, q.y);
+        if (dd < md) { md = dd; mi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(DP_FULL, md, o);
+        const int oi = __shfl_xor_sync(DP_FULL, mi, o);
+        if (od < md || (od == md && oi < mi)) { md = od; mi = oi; }
+    }
+    return mi;
+}
+
 // ---- TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP) with an mbarrier --------------
 __device__ __forceinline__ uint32_t dp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dp_bulk_prefetch(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* mbar, int lane) {

@@ -35,6 +35,8 @@ cudaError_t dp_launch_create(int n_paths, const int32_t* path_off, const double2
                              double2* out_xy, cudaStream_t st);
 cudaError_t dp_launch_bezier(int n, const double* poses, double* out_xy, cudaStream_t st);
 cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double2* pxy, double* out_xy, cudaStream_t st);
+cudaError_t dp_launch_nearest(int n_paths, const int32_t* path_off, const double2* pxy, const double* qx, const double* qy, int32_t* out_id,
+                              cudaStream_t st);
 cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
                             int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs,
                             double lat_min, double lat_max, double clear_dis, double* cand_dis_lng, unsigned long long* best_key,

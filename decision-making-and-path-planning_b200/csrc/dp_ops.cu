@@ -79,6 +79,17 @@ op_mean_kernel(int n_paths, const int32_t* __restrict__ path_off, const double2*
     }
 }
 
+// CShare::NearestId (call sites Decision.cpp:1889,2074,2383; loop shape Planning.cpp:640-648), one warp per (path, query)
+__global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32)
+op_nearest_kernel(int n_paths, const int32_t* __restrict__ path_off, const double2* __restrict__ pxy, const double* __restrict__ qx,
+                  const double* __restrict__ qy, int32_t* __restrict__ out_id) {
+    const int lane = threadIdx.x & 31, pid = blockIdx.x * DP_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (pid >= n_paths) return;
+    const int off = path_off[pid], P = path_off[pid + 1] - off;
+    const int id = dp_nearest_plain(pxy + off, P, qx[pid], qy[pid], lane);
+    if (lane == 0) out_id[pid] = (id == 0x7fffffff) ? 0 : id;   // the operator returns 0 when nothing is closer than 9999
+}
+
 // ------------------------------------------------------------------------------------------------
 // Dense candidate sweep (BASELINE config 3): one warp per candidate, SWEEP_WARPS candidates per
 // block.  The base polyline and its segment normals are staged once per block in shared memory,
@@ -248,6 +259,12 @@ cudaError_t dp_launch_bezier(int n, const double* poses, double* out_xy, cudaStr
 cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double2* pxy, double* out_xy, cudaStream_t st) {
     if (n_paths <= 0) return cudaSuccess;
     op_mean_kernel<<<(n_paths + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(n_paths, path_off, pxy, out_xy);
+    return cudaGetLastError();
+}
+cudaError_t dp_launch_nearest(int n_paths, const int32_t* path_off, const double2* pxy, const double* qx, const double* qy, int32_t* out_id,
+                              cudaStream_t st) {
+    if (n_paths <= 0) return cudaSuccess;
+    op_nearest_kernel<<<(n_paths + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(n_paths, path_off, pxy, qx, qy, out_id);
     return cudaGetLastError();
 }
 cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,

@@ -21,7 +21,7 @@ SYMBOLS = [
     "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
     "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
-    "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors",
+    "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id",
 ]
 
 _lib = None
@@ -188,6 +188,18 @@ class Planner:
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 6)
         out = np.zeros((poses.shape[0], 2, abi.PATH_POINTS))
         _ck(self.lib.dp_bezier_planning(self.ctx, C.c_int(poses.shape[0]), abi.ptr(poses), abi.ptr(out)), "dp_bezier_planning")
+        return out
+
+    def nearest_id(self, paths, qx, qy):
+        """CShare::NearestId, one query point per path"""
+        off = np.zeros(len(paths) + 1, np.int32)
+        off[1:] = np.cumsum([len(p[0]) for p in paths])
+        px = np.ascontiguousarray(np.concatenate([np.asarray(p[0], np.float64) for p in paths]))
+        py = np.ascontiguousarray(np.concatenate([np.asarray(p[1], np.float64) for p in paths]))
+        qx, qy = np.ascontiguousarray(qx, np.float64), np.ascontiguousarray(qy, np.float64)
+        out = np.zeros(len(paths), np.int32)
+        _ck(self.lib.dp_nearest_id(self.ctx, C.c_int(len(paths)), abi.ptr(off), abi.ptr(px), abi.ptr(py), abi.ptr(qx), abi.ptr(qy),
+                                   abi.ptr(out)), "dp_nearest_id")
         return out
 
     def mean_points(self, paths):

@@ -244,6 +244,11 @@ int dp_create_new_path(dp_ctx* ctx, int n_paths, const int32_t* path_off, const 
 /* CShare::BezierPlanning  (Planning.cpp:606,863): poses[n][6] = start x,y,dir, aim x,y,dir;
  * out[n][2][200] */
 int dp_bezier_planning(dp_ctx* ctx, int n, const double* poses, double* out_xy);
+/* CShare::NearestId       (Decision.cpp:1889,2074,2383; loop shape Planning.cpp:640-648): one query point per path;
+ * out_id[i] = index of the path point nearest to (qx[i], qy[i]): lowest index among the points whose rounded distance
+ * sqrt(dx*dx+dy*dy) is minimal, 0 when no distance is below 9999 */
+int dp_nearest_id(dp_ctx* ctx, int n_paths, const int32_t* path_off, const double* px,
+                  const double* py, const double* qx, const double* qy, int32_t* out_id);
 /* CShare::MeanPoints      (Planning.cpp:872): out[n][2][200] */
 int dp_mean_points(dp_ctx* ctx, int n_paths, const int32_t* path_off, const double* px,
                    const double* py, double* out_xy);

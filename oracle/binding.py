@@ -109,6 +109,10 @@ class Oracle(_Runner):
         self.lib.oracle_bezier(abi.ptr(poses6), abi.ptr(out), C.c_int(n))
         return out
 
+    def nearest_id(self, qx, qy, px, py):
+        px, py = (np.ascontiguousarray(a, np.float64) for a in (px, py))
+        return int(self.lib.oracle_nearest_id(C.c_double(qx), C.c_double(qy), abi.ptr(px), abi.ptr(py), C.c_int(px.size)))
+
     def mean_points(self, px, py, n_out=abi.PATH_POINTS):
         px, py = (np.ascontiguousarray(a, np.float64) for a in (px, py))
         out = np.zeros((2, n_out))

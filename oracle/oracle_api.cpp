@@ -98,6 +98,11 @@ void oracle_bezier(const double* poses6, double* out_xy /*[2][n]*/, int n) {
     spec::bezier_planning(spec::P3{poses6[0], poses6[1], poses6[2]}, spec::P3{poses6[3], poses6[4], poses6[5]}, o.data(), n);
     for (int i = 0; i < n; ++i) { out_xy[i] = o[i].x; out_xy[n + i] = o[i].y; }
 }
+int oracle_nearest_id(double qx, double qy, const double* px, const double* py, int n) {
+    std::vector<spec::P2> p(n > 0 ? n : 1);
+    for (int i = 0; i < n; ++i) p[i] = spec::P2{px[i], py[i]};
+    return spec::nearest_id(spec::P2{qx, qy}, p.data(), n);
+}
 void oracle_mean_points(const double* px, const double* py, int n_in, double* out_xy /*[2][n_out]*/, int n_out) {
     std::vector<spec::P2> p(n_in > 0 ? n_in : 1), o(n_out);
     for (int i = 0; i < n_in; ++i) p[i] = spec::P2{px[i], py[i]};

@@ -321,3 +321,30 @@ def test_record_mirrors(planner, the_map):
                 assert not got[:first].any() and not got[first + n:].any(), "stores outside the slot range"
     finally:
         planner.set_record_mirrors([])
+
+
+def test_nearest_id_operator_and_near_ties(planner, oracle):
+    """CShare::NearestId on the GPU compares SQUARED distances and falls back to the reference's sqrt loop when two different
+    squared distances lie within 2^-49 of each other.  Random paths, exact ties (duplicate points), and crafted near ties where
+    two squared distances differ by one ulp (so their sqrt may or may not round to the same double), in both index orders."""
+    rng = np.random.default_rng(11)
+    paths, qx, qy = [], [], []
+    for P in (1, 2, 31, 32, 33, 200, 257):
+        for _ in range(6):
+            paths.append((rng.uniform(-50, 50, P), rng.uniform(-50, 50, P))); qx.append(rng.uniform(-60, 60)); qy.append(rng.uniform(-60, 60))
+    x = rng.uniform(-5, 5, 200); y = rng.uniform(-5, 5, 200)
+    x[150] = x[20]; y[150] = y[20]; x[77] = x[20]; y[77] = y[20]          # exact ties: lowest index wins
+    paths.append((x, y)); qx.append(x[20] + 1e-3); qy.append(y[20] - 2e-3)
+    paths.append((np.full(200, 1e5), np.full(200, 1e5))); qx.append(0.0); qy.append(0.0)   # nothing closer than 9999 -> 0
+    for base in (1.0, 3.0, 0.75, 123.456, 1e-3, 777.0):
+        for lo_first in (True, False):
+            # query at the origin; point A at (2b, b) -> e = 5 b^2; point B at (2b, b') with b' = nextafter(b): e one or two ulps up
+            b = base; b2 = np.nextafter(b, np.inf)
+            x = np.full(64, 50.0 * b + 100.0); y = np.full(64, 50.0 * b + 100.0)
+            ia, ib = (5, 40) if lo_first else (40, 5)
+            x[ia] = 2 * b; y[ia] = b; x[ib] = 2 * b; y[ib] = b2
+            paths.append((x, y)); qx.append(0.0); qy.append(0.0)
+    got = planner.nearest_id(paths, qx, qy)
+    for i, p in enumerate(paths):
+        want = oracle.nearest_id(qx[i], qy[i], p[0], p[1])
+        assert int(got[i]) == want, (i, len(p[0]), int(got[i]), want)
