@@ -318,7 +318,7 @@ __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my
 }
 
 // spec_sincos_deg / spec_atan: fixed polynomials shared (as text, not as code) with the oracle.
-__device__ __forceinline__ void dp_sincos_deg(double a, double* c, double* s) {
+static __device__ __noinline__ void dp_sincos_deg(double a, double* c, double* s) {
     const double k = rint(a / 90.0);
     const double r = fma(-90.0, k, a);
     const double x = r * (3.14159265358979323846 / 180.0);
@@ -371,7 +371,7 @@ static __device__ __noinline__ double dp_atan(double z) {
 }
 
 // CalcGlobalDir / GetRoadAngle (Planning.cpp:719-750)
-__device__ __forceinline__ double dp_heading(double ax, double ay, double bx, double by, double eps, double pi) {
+static __device__ __noinline__ double dp_heading(double ax, double ay, double bx, double by, double eps, double pi) {
     double angle;
     if (fabs(bx - ax) < eps && fabs(by - ay) < eps) angle = 0;
     else if (fabs(bx - ax) < eps) angle = (by > ay) ? pi / 2 : 3 * pi / 2;
@@ -384,7 +384,7 @@ __device__ __forceinline__ double dp_heading(double ax, double ay, double bx, do
 }
 
 // GetLatDis (Planning.cpp:686-709), LEFT positive
-__device__ __forceinline__ double dp_lat_dis(double cx, double cy, double px, double py, double nx, double ny, double eps) {
+static __device__ __noinline__ double dp_lat_dis(double cx, double cy, double px, double py, double nx, double ny, double eps) {
     double l;
     if (fabs(px - nx) > eps) {
         const double k = (py - ny) / (px - nx);
