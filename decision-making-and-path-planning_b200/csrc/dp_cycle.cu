@@ -162,7 +162,12 @@ template <class T> __device__ __forceinline__ T dp_l2(const T* p) { return __ldc
 
 }  // namespace
 
-#define DP_MIN_BLOCKS 7
+#define DP_CARVEOUT 77
+// CTA size of the cycle kernel.  WPB = 4 (7 CTAs = 28 warps per SM) keeps a 4096-scene batch a single wave.  WPB = 1 (25 CTAs
+// per SM; the per-CTA shared-memory reservation costs three slots) recycles a warp's slot the moment ITS scene is done
+// instead of when the slowest scene of its CTA retires (sweep scenes last twice as long: ncu showed 21.6 of 28 warp slots
+// active at 65 536 scenes): 0.942 -> 0.857 ms there, but 1.8 % slower on the one-wave batch.  The launcher picks by batch size.
+#define DP_MIN_BLOCKS(WPB) ((WPB) == 1 ? 25 : 7)
 
 // PHASE 0: whole cycle in one launch.  PHASE 1 / 2: Decision half / Planning half as two back-to-back launches -- the
 // same work with half the code per kernel: with 28 warps per SM in different places of a ~11 k-instruction kernel the
@@ -184,15 +189,15 @@ extern "C" int dp_debug_timeline(long long* dst, int n_scenes) {
 #define DBG_END(ph, nt)
 #endif
 
-template <int PHASE>
-__global__ void __launch_bounds__(DP_WARPS_PER_BLOCK * 32, DP_MIN_BLOCKS)
+template <int PHASE, int WPB>
+__global__ void __launch_bounds__(WPB * 32, DP_MIN_BLOCKS(WPB))
 dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restrict__ hdr, const double* __restrict__ obs_x,
                 const double* __restrict__ obs_y, int max_obs, dp_carry* __restrict__ carry, double2* __restrict__ last_path,
                 dp_plan_record* __restrict__ rec, dp_trace_record* __restrict__ trace, double* __restrict__ path_xy,
                 double* __restrict__ path_ll, DpIo io) {
-    __shared__ WarpSmem smem[DP_WARPS_PER_BLOCK];
+    __shared__ WarpSmem smem[WPB];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int scene = blockIdx.x * DP_WARPS_PER_BLOCK + wib;
+    const int scene = blockIdx.x * WPB + wib;
     if (scene >= n_scenes) return;
 #ifdef DP_DEBUG_CLOCK
     if (lane == 0) {
@@ -868,39 +873,46 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
                             double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io) {
     if (n <= 0) return cudaSuccess;
     static bool configured = false;
-    if (!configured) {                                      // 196 of 256 KB as shared memory: 7 CTAs per SM, the rest stays L1
-        cudaFuncSetAttribute(dp_cycle_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 77);
-        cudaFuncSetAttribute(dp_cycle_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 77);
-        cudaFuncSetAttribute(dp_cycle_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 77);
+    static int sm_count = 0;
+    if (!configured) {                                      // 196 of 256 KB as shared memory, the rest stays L1
+        cudaFuncSetAttribute(dp_cycle_kernel<0, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+        cudaFuncSetAttribute(dp_cycle_kernel<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+        cudaFuncSetAttribute(dp_cycle_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+        cudaFuncSetAttribute(dp_cycle_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+        cudaFuncSetAttribute(dp_cycle_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
-    const int blocks = (n + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, threads = DP_WARPS_PER_BLOCK * 32;
     if (!split) {
         DpIo io0 = io; io0.done = nullptr;
-        dp_cycle_kernel<0><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io0);
+        const int blocks = (n + 3) / 4;
+        dp_cycle_kernel<0, 4><<<blocks, 128, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io0);
     } else {
+        // batches of at most one wave of 4-warp CTAs stay one wave; larger ones run one warp per CTA (see DP_MIN_BLOCKS)
+        const bool wide = n <= sm_count * DP_MIN_BLOCKS(4) * 4;
+        const int wpb = wide ? 4 : 1;
+        const int blocks = (n + wpb - 1) / wpb, threads = wpb * 32;
         // Decision launch ingests (hdr/ox/oy may be pinned host memory); Planning launch reads the staged device copies
         DpIo io1 = io; io1.n_mirror = 0;
         DpIo io2 = io; io2.hdr_stage = nullptr; io2.ox_stage = nullptr; io2.oy_stage = nullptr;
         if (split != 2) io1.done = io2.done = nullptr;
-        dp_cycle_kernel<1><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
+        if (wide) dp_cycle_kernel<1, 4><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
+        else dp_cycle_kernel<1, 1><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
         const dp_scene_hdr* hdr2 = io.hdr_stage ? io.hdr_stage : hdr;
         const double* ox2 = io.ox_stage ? io.ox_stage : ox; const double* oy2 = io.oy_stage ? io.oy_stage : oy;
-        if (io2.done) {
-            // programmatic dependent launch WITHOUT a grid-wide dependency wait in the kernel: scenes hand over one by one
-            // (dp_publish / dp_await), so Planning CTAs run in the slots the Decision launch frees while its tail finishes
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, dp_cycle_kernel<2>, m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy,
-                                               path_ll, io2);
-            if (e != cudaSuccess) return e;
-        } else {
-            dp_cycle_kernel<2><<<blocks, threads, 0, st>>>(m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2);
-        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        // programmatic dependent launch WITHOUT a grid-wide dependency wait in the kernel: scenes hand over one by one
+        // (dp_publish / dp_await), so Planning CTAs run in the slots the Decision launch frees while its tail finishes
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = io2.done ? 1 : 0;
+        cudaError_t e = wide ? cudaLaunchKernelEx(&cfg, dp_cycle_kernel<2, 4>, m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2)
+                             : cudaLaunchKernelEx(&cfg, dp_cycle_kernel<2, 1>, m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }

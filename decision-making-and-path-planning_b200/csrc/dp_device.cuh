@@ -21,7 +21,9 @@
 #define DP_FULL 0xffffffffu
 #define DP_TILE 120            // path points staged per warp per tile (= the reference's 120-point lane slice)
 #define DP_SCR 192             // sequential-sum terms per pass (multiple of 8)
-#define DP_WARPS_PER_BLOCK 4
+#ifndef DP_WARPS_PER_BLOCK
+#define DP_WARPS_PER_BLOCK 4                   // operator kernels; the cycle kernel is templated on its CTA size (dp_cycle.cu)
+#endif
 
 struct DevMap {
     const double2* xy;                         // AoS copy of (x, y), built at upload
@@ -34,8 +36,8 @@ struct DevMap {
     int n_roads, n_lanes, n_conn;
 };
 
-// 6864 bytes per warp: 7 CTAs of 4 warps fit the 196 KB shared-memory configuration and leave
-// 60 KB of L1 for the map gathers.
+// 6864 bytes per warp (+ 1 KB the system reserves per CTA): 7 CTAs of 4 warps (28 warps) or 25 one-warp CTAs fit the
+// 196 KB shared-memory configuration and leave 60 KB of L1 for the map gathers.
 struct __align__(16) WarpSmem {
     union {
         struct {
