@@ -9,6 +9,7 @@
 // Candidate paths exist only as shared-memory tiles; HBM sees the 128-byte scene header, the
 // obstacle SoA rows, the 128-byte carry, the previous local path (the reference's own cross-cycle
 // state, Planning.cpp:6) and the 128-byte plan record.
+#include <cstdlib>
 #include "dp_device.cuh"
 #include "dp_fused.cuh"
 #include "dp_kernels.h"
@@ -891,7 +892,9 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
         dp_cycle_kernel<0, 4><<<blocks, 128, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io0);
     } else {
         // batches of at most one wave of 4-warp CTAs stay one wave; larger ones run one warp per CTA (see DP_MIN_BLOCKS)
-        const bool wide = n <= sm_count * DP_MIN_BLOCKS(4) * 4;
+        static int force_wpb = -1;                          // DP_WPB=1|4 overrides the choice (experiments)
+        if (force_wpb < 0) { const char* e = getenv("DP_WPB"); force_wpb = e ? atoi(e) : 0; }
+        const bool wide = force_wpb ? force_wpb == 4 : n <= sm_count * DP_MIN_BLOCKS(4) * 4;
         const int wpb = wide ? 4 : 1;
         const int blocks = (n + wpb - 1) / wpb, threads = wpb * 32;
         // Decision launch ingests (hdr/ox/oy may be pinned host memory); Planning launch reads the staged device copies
