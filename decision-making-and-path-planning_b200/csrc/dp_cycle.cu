@@ -168,7 +168,10 @@ template <class T> __device__ __forceinline__ T dp_l2(const T* p) { return __ldc
 // per SM; the per-CTA shared-memory reservation costs three slots) recycles a warp's slot the moment ITS scene is done
 // instead of when the slowest scene of its CTA retires (sweep scenes last twice as long: ncu showed 21.6 of 28 warp slots
 // active at 65 536 scenes): 0.942 -> 0.857 ms there, but 1.8 % slower on the one-wave batch.  The launcher picks by batch size.
-#define DP_MIN_BLOCKS(WPB) ((WPB) == 1 ? 25 : 7)
+#ifndef DP_MIN_BLOCKS_W1
+#define DP_MIN_BLOCKS_W1 25
+#endif
+#define DP_MIN_BLOCKS(WPB) ((WPB) == 1 ? DP_MIN_BLOCKS_W1 : 7)
 
 // PHASE 0: whole cycle in one launch.  PHASE 1 / 2: Decision half / Planning half as two back-to-back launches -- the
 // same work with half the code per kernel: with 28 warps per SM in different places of a ~11 k-instruction kernel the

@@ -348,3 +348,19 @@ def test_nearest_id_operator_and_near_ties(planner, oracle):
     for i, p in enumerate(paths):
         want = oracle.nearest_id(qx[i], qy[i], p[0], p[1])
         assert int(got[i]) == want, (i, len(p[0]), int(got[i]), want)
+
+
+def test_multi_wave_batch_one_warp_ctas(oracle, the_map):
+    """Batches above one wave (> 4144 scenes on a B200) run the one-warp-per-CTA instantiation of the cycle kernels with the
+    overlapped launch; same parity bar: every record, trace slot, path sample and the final carry against the oracle."""
+    from dmpp_b200.planner import Planner
+    n = 6000
+    p = Planner(max_scenes=n, max_obs=12)
+    p.upload_map(the_map)
+    try:
+        H, got, want = run_both(p, oracle, the_map, np.arange(50_000, 50_000 + n), "highway", 10, 10)
+        check(got, want, "6000 scenes")
+        H, got, want = run_both(p, oracle, the_map, np.arange(70_000, 70_000 + n), "junction", 8, 10)
+        check(got, want, "6000 junction scenes")
+    finally:
+        p.close()
