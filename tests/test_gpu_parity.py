@@ -364,3 +364,43 @@ def test_multi_wave_batch_one_warp_ctas(oracle, the_map):
         check(got, want, "6000 junction scenes")
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_launch_modes_agree(planner, the_map, monkeypatch, split):
+    """DP_SPLIT=0 (one fused launch) and DP_SPLIT=1 (two launches back to back) must produce the bytes of the default
+    overlapped launch: records, traces, paths and carried state."""
+    from dmpp_b200 import scenes
+    from dmpp_b200.planner import Planner
+    n, cycles = 384, 10
+    for kind, seed0 in (("highway", 31_000), ("junction", 32_000)):
+        ep = scenes.Episodes(the_map, np.arange(seed0, seed0 + n), cycles=cycles, kind=kind, n_obs=10)
+        H, OX, OY = ep.all_cycles()
+        PX, PY = pad_obs(OX, OY, planner.max_obs)
+        want = planner.run_episodes(H, PX, PY)
+        monkeypatch.setenv("DP_SPLIT", split)                  # read by dp_create
+        alt = Planner(max_scenes=n, max_obs=planner.max_obs)
+        monkeypatch.delenv("DP_SPLIT")
+        alt.upload_map(the_map)
+        got = alt.run_episodes(H, PX, PY)
+        alt.close()
+        for k in ("rec", "trace", "path_xy", "path_ll", "carry", "last_path"):
+            assert got[k].tobytes() == want[k].tobytes(), (kind, split, k)
+
+
+def test_error_behaviour(planner, the_map):
+    """every entry point reports a negative status + dp_last_error instead of failing silently"""
+    from dmpp_b200 import abi
+    from dmpp_b200.planner import DpError, Planner
+    fresh = Planner(max_scenes=8, max_obs=4)
+    h = np.zeros(4, abi.scene_hdr); ox = np.zeros((4, 4)); oy = np.zeros((4, 4))
+    with pytest.raises(DpError, match="map not uploaded"):
+        fresh.cycle(h, ox, oy)
+    fresh.upload_map(the_map)
+    with pytest.raises(DpError):
+        fresh.cycle(np.zeros(16, abi.scene_hdr), np.zeros((16, 4)), np.zeros((16, 4)))      # more scenes than the context holds
+    with pytest.raises(DpError):
+        fresh.reset(4, 8)                                                                 # slot range out of bounds
+    with pytest.raises(DpError):
+        fresh.set_record_mirrors([0x1000] * 9)                                            # more mirrors than supported
+    fresh.close()
