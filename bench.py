@@ -213,6 +213,8 @@ def run_ours(args, rank, world, local_rank):
     gather_kind = "none"
     if world > 1:
         try:
+            if os.environ.get("DP_BENCH_NO_SYMM"):
+                raise RuntimeError("disabled by DP_BENCH_NO_SYMM")
             import torch.distributed._symmetric_memory as symm
             gath = [symm.empty((world * SCENES, 128), dtype=torch.uint8, device=dev) for _ in range(3)]
             hdl = [symm.rendezvous(g, dist.group.WORLD) for g in gath]
