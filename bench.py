@@ -128,7 +128,7 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": secs / cyc * min(SCENES, 4096) * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_desc(1),
             "plan_cycles_per_s": cyc / secs,
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": arm.kind,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": arm.kind, "per_core": val / max(cores, 1),
                              "sample": "%d steps, each = %d scenes x %d cycles (whole episodes), one process per core running "
                                        "the unmodified Decision.cpp/Planning.cpp objects" % (steps, min(SCENES, 4096), EPISODE)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -427,7 +427,7 @@ def run_ours(args, rank, world, local_rank):
                 t, dt, _ = arm.step()
                 t_traj += t; t_s += dt; n += 1
             arm.close()
-            line["cpu_baseline"] = {"value": t_traj / t_s, "unit": UNIT, "cores": cores, "kind": arm.kind,
+            line["cpu_baseline"] = {"value": t_traj / t_s, "unit": UNIT, "cores": cores, "kind": arm.kind, "per_core": t_traj / t_s / max(cores, 1),
                                     "sample": "%d passes over %d scenes x %d cycles, one process per core (unmodified reference "
                                               "objects when kind=reference)" % (n, min(SCENES, 4096), EPISODE)}
         except Exception as e:  # noqa: BLE001
