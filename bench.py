@@ -4,7 +4,7 @@ trajectories scored / s and plan cycles / s).
 
 Workload (BASELINE config 2): 4096 independent synthetic highway scenes per GPU, ego + 10
 vehicles, reference-derived default candidate set, 25-cycle scripted episodes.  One "step" = one
-fused Decision+Planning cycle for every scene of the batch (one launch of dp_cycle_kernel).
+Decision+Planning cycle for every scene of the batch (the Decision and the Planning launch of dp_cycle_kernel, overlapped).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path (one rank per GPU)
   python bench.py --impl reference [...]                       the reference's own CPU code (oracle/_ref)

@@ -1,4 +1,5 @@
-// csrc/dp_cycle.cu -- the fused Decision + Planning cycle kernel (sm_100a).
+// csrc/dp_cycle.cu -- the Decision + Planning cycle kernel (sm_100a): dp_cycle_kernel<PHASE, WPB>, launched as a Decision
+// half and a Planning half that overlap scene by scene (PHASE 1 / 2; PHASE 0 = both halves in one launch), see below.
 //
 // One WARP owns one scene for the whole cycle: LoadRefPath -> AroundObstacle -> BehaviorDecision
 // (with the in-lane avoid sweep) -> SpeedDecision/RefPath  (Decision.cpp:216-315, 323-486), then
