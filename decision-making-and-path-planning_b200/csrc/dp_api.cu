@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 #include "dp_kernels.h"
 
@@ -514,8 +515,11 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
                       d_vy = tmp.put<double>(dvy, (size_t)n_obs, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "staging", e); }
     PUT(d_dis, double, (const double*)nullptr, (size_t)n_cand);
     PUT(d_key, unsigned long long, (const unsigned long long*)nullptr, 1);
+    PUT(d_next, unsigned, (const unsigned*)nullptr, 1);
     CK(cudaMemsetAsync(d_key, 0xff, 8, c->st[0]));
-    CK(dp_launch_sweep(d_bx, d_by, n_base, d_off, d_np, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs, lat_min, lat_max, clear_dis, d_dis, d_key, c->st[0]));
+    CK(cudaMemsetAsync(d_next, 0, 4, c->st[0]));
+    CK(dp_launch_sweep(d_bx, d_by, n_base, d_off, d_np, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs, lat_min, lat_max, clear_dis, d_dis, d_key, nullptr, d_next,
+                       c->st[0]));
     ++c->launches;
     unsigned long long key = ~0ull;
     CK(cudaMemcpyAsync(&key, d_key, 8, cudaMemcpyDeviceToHost, c->st[0]));
@@ -537,6 +541,8 @@ struct dp_sweep {
     int n_base = 0, n_cand = 0, max_obs = 0;
     double *d_bx = nullptr, *d_by = nullptr, *d_off = nullptr, *d_obs = nullptr, *d_dis = nullptr;   // d_obs: [4][max_obs]
     int32_t* d_np = nullptr;
+    int32_t* d_order = nullptr;                             // candidates sorted longest first (processing order of the kernel)
+    unsigned* d_next = nullptr;                             // the kernel's work counter
     unsigned long long* d_key = nullptr;
     double* h_obs = nullptr;                                // pinned [4][max_obs]
     unsigned long long* h_key = nullptr;                    // pinned
@@ -562,6 +568,13 @@ int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const doubl
     CK(cudaMemcpy(s->d_bx, base_x, n_base * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->d_by, base_y, n_base * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_off, offset, (size_t)n_cand * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_np, n_pts, (size_t)n_cand * 4, cudaMemcpyHostToDevice));
+    {   // longest candidates first: the warps pull work from a counter, so the tail is one short candidate, not a long one
+        std::vector<int32_t> order((size_t)n_cand);
+        for (int i = 0; i < n_cand; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return n_pts[a] > n_pts[b]; });
+        CK(cudaMalloc((void**)&s->d_order, (size_t)n_cand * 4)); CK(cudaMalloc((void**)&s->d_next, 4));
+        CK(cudaMemcpy(s->d_order, order.data(), (size_t)n_cand * 4, cudaMemcpyHostToDevice));
+    }
     CK(cudaEventCreate(&s->e0)); CK(cudaEventCreate(&s->e1));
     *out = s;
     return DP_OK;
@@ -585,8 +598,9 @@ int dp_sweep_score(dp_sweep* s, const double* ox, const double* oy, const double
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         cudaMemcpyAsync(s->d_obs, s->h_obs, (size_t)4 * mo * 8, cudaMemcpyHostToDevice, st);
         cudaMemsetAsync(s->d_key, 0xff, 8, st);
+        cudaMemsetAsync(s->d_next, 0, 4, st);
         dp_launch_sweep(s->d_bx, s->d_by, s->n_base, s->d_off, s->d_np, s->n_cand, s->d_obs, s->d_obs + mo, s->d_obs + 2 * mo, s->d_obs + 3 * mo,
-                        n_obs, lat_min, lat_max, clear_dis, s->d_dis, s->d_key, st);
+                        n_obs, lat_min, lat_max, clear_dis, s->d_dis, s->d_key, s->d_order, s->d_next, st);
         cudaMemcpyAsync(s->h_key, s->d_key, 8, cudaMemcpyDeviceToHost, st);
         CK(cudaStreamEndCapture(st, &g));
         CK(cudaGraphInstantiate(&s->exec, g, 0));
@@ -615,6 +629,7 @@ int dp_sweep_destroy(dp_sweep* s) {
     cudaStreamSynchronize(s->c->st[0]);
     if (s->exec) cudaGraphExecDestroy(s->exec);
     cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_off); cudaFree(s->d_np); cudaFree(s->d_obs); cudaFree(s->d_dis); cudaFree(s->d_key);
+    cudaFree(s->d_order); cudaFree(s->d_next);
     cudaFreeHost(s->h_obs); cudaFreeHost(s->h_key);
     if (s->e0) cudaEventDestroy(s->e0);
     if (s->e1) cudaEventDestroy(s->e1);

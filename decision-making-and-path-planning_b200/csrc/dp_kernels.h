@@ -40,5 +40,5 @@ cudaError_t dp_launch_nearest(int n_paths, const int32_t* path_off, const double
 cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
                             int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs,
                             double lat_min, double lat_max, double clear_dis, double* cand_dis_lng, unsigned long long* best_key,
-                            cudaStream_t st);
+                            const int32_t* order, unsigned* next, cudaStream_t st);   // order: processing order (nullable); next: zeroed counter
 cudaError_t dp_launch_fma_peak(int which, float* sink, int iters, int blocks, cudaStream_t st);

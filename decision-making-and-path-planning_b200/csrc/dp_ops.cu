@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, 3)
 sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, const double* __restrict__ offset,
              const int32_t* __restrict__ n_pts, int n_cand, const double* __restrict__ ox, const double* __restrict__ oy,
              const double* __restrict__ dvx, const double* __restrict__ dvy, int n_obs, double lat_min, double lat_max,
-             double clear_dis, double* __restrict__ cand_dis_lng, unsigned long long* __restrict__ best_key) {
+             double clear_dis, double* __restrict__ cand_dis_lng, unsigned long long* __restrict__ best_key,
+             const int32_t* __restrict__ order, unsigned* __restrict__ next) {
     __shared__ double2 s_base[SWEEP_MAX_BASE];
     __shared__ double2 s_nrm[SWEEP_MAX_BASE];              // normal of segment j -> j+1
     __shared__ double4 s_obs[SWEEP_MAX_OBS];
@@ -128,7 +129,14 @@ sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_
     __syncthreads();
 
     unsigned long long mykey = ~0ull;
-    for (int c = blockIdx.x * SWEEP_WARPS + wib; c < n_cand; c += gridDim.x * SWEEP_WARPS) {
+    // Candidates differ 32x in length (8..256 points): a static round-robin leaves the slowest warp ~30 % behind the mean.
+    // Warps fetch the next candidate from a counter instead, in the order the session prepared (longest first).
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(next, 1u);
+        i = __shfl_sync(DP_FULL, i, 0);
+        if (i >= n_cand) break;
+        const int c = order ? order[i] : i;
         const int P = min(n_pts[c], n_base);
         const double off = offset[c];
         double dis_lng = DP_NOT_FOUND;
@@ -270,13 +278,13 @@ cudaError_t dp_launch_nearest(int n_paths, const int32_t* path_off, const double
 cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
                             int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs,
                             double lat_min, double lat_max, double clear_dis, double* cand_dis_lng, unsigned long long* best_key,
-                            cudaStream_t st) {
+                            const int32_t* order, unsigned* next, cudaStream_t st) {
     if (n_cand <= 0) return cudaSuccess;
     int blocks = (n_cand + SWEEP_WARPS - 1) / SWEEP_WARPS;
     const int cap = 148 * 3;                               // persistent-style: 3 CTAs x 8 warps per SM, grid-stride over candidates
     if (blocks > cap) blocks = cap;
     sweep_kernel<<<blocks, SWEEP_WARPS * 32, 0, st>>>(base_x, base_y, n_base, offset, n_pts, n_cand, ox, oy, dvx, dvy, n_obs, lat_min,
-                                                      lat_max, clear_dis, cand_dis_lng, best_key);
+                                                      lat_max, clear_dis, cand_dis_lng, best_key, order, next);
     return cudaGetLastError();
 }
 cudaError_t dp_launch_fma_peak(int which, float* sink, int iters, int blocks, cudaStream_t st) {
