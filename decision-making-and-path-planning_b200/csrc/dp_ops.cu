@@ -101,6 +101,9 @@ op_nearest_kernel(int n_paths, const int32_t* __restrict__ path_off, const doubl
 // Decision.cpp:944-953), deterministic whatever the launch geometry.
 // ------------------------------------------------------------------------------------------------
 #define SWEEP_WARPS 8
+#ifndef SWEEP_CTAS_PER_SM
+#define SWEEP_CTAS_PER_SM 3
+#endif
 #define SWEEP_MAX_BASE 256
 #define SWEEP_MAX_OBS 192
 
@@ -110,7 +113,7 @@ __device__ __forceinline__ void sweep_upd(double d2, int j, double& bb, int& bj)
     if (d2 < bb) { bb = d2; bj = j; }
 }
 
-__global__ void __launch_bounds__(SWEEP_WARPS * 32, 3)
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, SWEEP_CTAS_PER_SM)
 sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, const double* __restrict__ offset,
              const int32_t* __restrict__ n_pts, int n_cand, const double* __restrict__ ox, const double* __restrict__ oy,
              const double* __restrict__ dvx, const double* __restrict__ dvy, int n_obs, double lat_min, double lat_max,
@@ -281,7 +284,7 @@ cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_ba
                             const int32_t* order, unsigned* next, cudaStream_t st) {
     if (n_cand <= 0) return cudaSuccess;
     int blocks = (n_cand + SWEEP_WARPS - 1) / SWEEP_WARPS;
-    const int cap = 148 * 3;                               // persistent-style: 3 CTAs x 8 warps per SM, grid-stride over candidates
+    const int cap = 148 * SWEEP_CTAS_PER_SM;                               // persistent-style: 3 CTAs x 8 warps per SM, grid-stride over candidates
     if (blocks > cap) blocks = cap;
     sweep_kernel<<<blocks, SWEEP_WARPS * 32, 0, st>>>(base_x, base_y, n_base, offset, n_pts, n_cand, ox, oy, dvx, dvy, n_obs, lat_min,
                                                       lat_max, clear_dis, cand_dis_lng, best_key, order, next);
