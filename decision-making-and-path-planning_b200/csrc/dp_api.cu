@@ -68,7 +68,8 @@ namespace {
 // launch plumbing of one cycle call: hand-off flags, then the caller's pinned record buffer (if any) and the context's mirrors
 DpIo make_io(dp_ctx* c, int first, dp_plan_record* host_rec) {
     DpIo io = dp_io_none();
-    io.done = c->d_done + first; io.epoch = ++c->epoch;
+    if (++c->epoch == 0) ++c->epoch;                        // (0 is what never-written flags hold)
+    io.done = c->d_done + first; io.epoch = c->epoch;
     if (host_rec) io.mirror[io.n_mirror++] = host_rec;
     for (int k = 0; k < c->n_mirror; ++k) io.mirror[io.n_mirror++] = c->mirror[k] + first;
     return io;
