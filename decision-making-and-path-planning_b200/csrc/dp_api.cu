@@ -9,6 +9,8 @@
 #include <cstring>
 #include <string>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <vector>
 #include "dp_kernels.h"
 
@@ -59,6 +61,17 @@ struct dp_ctx {
     // overlapped split launch (split == 2): per-scene hand-off flags and the epoch of the next cycle
     unsigned* d_done = nullptr;
     unsigned epoch = 0;
+    // chained submits (dp_cycle_submit, DP_CHAIN=0 switches back to events): no event or stream wait sits between the launches,
+    // so cycle k+1's Decision launch can be a programmatic dependent of cycle k's Planning launch; inputs and completion are
+    // signalled through flags instead
+    int chain = 1;
+    unsigned* d_inflag = nullptr;                           // [2] "inputs of the cycle in staging set s are on the device"
+    unsigned* d_pdone = nullptr;                            // [max_scenes] per-scene "Planning finished" epoch
+    unsigned* d_tally = nullptr;                            // [2] finished Planning warps
+    unsigned* h_done = nullptr;                             // [2] page-locked: the last Planning warp of a cycle stores its epoch here
+                                                            // [2..3] page-locked source words of the in_flag copies
+    unsigned wait_epoch[2] = {0, 0};
+    unsigned chain_prev_epoch = 0; int chain_first = -1, chain_n = -1;
     // record mirrors (dp_set_record_mirrors): device-accessible bases indexed by carry slot
     dp_plan_record* mirror[DP_MAX_MIRRORS - 1] = {};
     int n_mirror = 0;
@@ -70,6 +83,7 @@ DpIo make_io(dp_ctx* c, int first, dp_plan_record* host_rec) {
     DpIo io = dp_io_none();
     if (++c->epoch == 0) ++c->epoch;                        // (0 is what never-written flags hold)
     io.done = c->d_done + first; io.epoch = c->epoch;
+    c->chain_prev_epoch = 0;                                // (dp_cycle_submit re-arms the chain after its own launch)
     if (host_rec) io.mirror[io.n_mirror++] = host_rec;
     for (int k = 0; k < c->n_mirror; ++k) io.mirror[io.n_mirror++] = c->mirror[k] + first;
     return io;
@@ -155,6 +169,12 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     if ((r = dev_alloc(&c->d_carry, (size_t)max_scenes))) { delete c; return r; }
     if ((r = dev_alloc(&c->d_last, (size_t)max_scenes * DP_PATH_POINTS))) { delete c; return r; }
     if ((r = dev_alloc(&c->d_done, (size_t)max_scenes))) { delete c; return r; }
+    if ((r = dev_alloc(&c->d_pdone, (size_t)max_scenes)) || (r = dev_alloc(&c->d_inflag, 2)) || (r = dev_alloc(&c->d_tally, 2))) { delete c; return r; }
+    CK(cudaMemset(c->d_pdone, 0, (size_t)max_scenes * sizeof(unsigned)));
+    CK(cudaMemset(c->d_inflag, 0, 2 * sizeof(unsigned))); CK(cudaMemset(c->d_tally, 0, 2 * sizeof(unsigned)));
+    CK(cudaHostAlloc((void**)&c->h_done, 4 * sizeof(unsigned), cudaHostAllocMapped));
+    c->h_done[0] = c->h_done[1] = c->h_done[2] = c->h_done[3] = 0;
+    if (const char* e = getenv("DP_CHAIN")) c->chain = atoi(e) != 0;
     CK(cudaMemset(c->d_done, 0, (size_t)max_scenes * sizeof(unsigned)));
     for (int s = 0; s < 2; ++s) {
         CK(cudaStreamCreateWithFlags(&c->st[s], cudaStreamNonBlocking));
@@ -179,7 +199,8 @@ int dp_destroy(dp_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->map_allocs) cudaFree(p);
-    cudaFree(c->d_carry); cudaFree(c->d_last); cudaFree(c->d_done);
+    cudaFree(c->d_carry); cudaFree(c->d_last); cudaFree(c->d_done); cudaFree(c->d_pdone); cudaFree(c->d_inflag); cudaFree(c->d_tally);
+    if (c->h_done) cudaFreeHost(c->h_done);
     for (int s = 0; s < 2; ++s) {
         cudaFree(c->d_hdr[s]); cudaFree(c->d_ox[s]); cudaFree(c->d_oy[s]); cudaFree(c->d_rec[s]);
         cudaFree(c->d_trace[s]); cudaFree(c->d_pxy[s]); cudaFree(c->d_pll[s]);
@@ -231,6 +252,7 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
 int dp_reset(dp_ctx* c, int first, int count) {
     if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_reset: range");
     if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_reset: submitted cycles in flight, call dp_cycle_wait first");
+    c->chain_prev_epoch = 0;
     CK(cudaSetDevice(c->device));
     CK(dp_launch_reset(c->d_carry, c->d_last, first, count, c->st[0]));
     ++c->launches;
@@ -258,6 +280,7 @@ int dp_carry_download(dp_ctx* c, int first, int count, dp_carry* hc, double* hl)
 int dp_carry_upload(dp_ctx* c, int first, int count, const dp_carry* hc, const double* hl) {
     if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_carry_upload: range");
     if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_carry_upload: submitted cycles in flight, call dp_cycle_wait first");
+    c->chain_prev_epoch = 0;
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     if (hc) CK(cudaMemcpy(c->d_carry + first, hc, (size_t)count * sizeof(dp_carry), cudaMemcpyHostToDevice));
@@ -367,27 +390,70 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
     // staging set s was last read by cycle (submitted - 2), which has been waited for: it is free.
     const int s = (int)(c->submitted & 1);
     const size_t mo = (size_t)c->max_obs;
-    CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
-    CK(cudaMemcpyAsync(c->d_ox[s], ox, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[1]));
-    CK(cudaMemcpyAsync(c->d_oy[s], oy, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[2]));
     cudaStream_t st = c->st[0];                             // one compute stream: cycle k+1 reads the carry cycle k wrote
-    for (int k = 0; k < 3; ++k) {
-        CK(cudaEventRecord(c->in_ready[s][k], c->cp[k]));
-        CK(cudaStreamWaitEvent(st, c->in_ready[s][k], 0));
+    if (c->chain && c->split == 2) {
+        // Chained: nothing but kernels goes into the compute stream.  The copy stream carries the three input DMAs and then a
+        // four-byte copy that raises in_flag; the Decision warps wait for that flag, and per scene for the previous cycle's
+        // Planning warp; the last Planning warp of the batch stores the epoch to page-locked host memory (dp_cycle_wait).
+        const unsigned prev = (c->chain_prev_epoch && c->chain_first == first && c->chain_n == n) ? c->chain_prev_epoch : 0u;
+        DpIo io = make_io(c, first, (dp_plan_record*)dv_rec);
+        CK(cudaMemsetAsync(c->d_tally + s, 0, sizeof(unsigned), c->cp[0]));
+        CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
+        CK(cudaMemcpyAsync(c->d_ox[s], ox, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[0]));
+        CK(cudaMemcpyAsync(c->d_oy[s], oy, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[0]));
+        // the flag goes up by a COPY, not a kernel: a one-thread kernel could find every SM slot taken by Decision and Planning
+        // CTAs that are waiting for exactly this flag
+        c->h_done[2 + s] = io.epoch;
+        CK(cudaMemcpyAsync(c->d_inflag + s, c->h_done + 2 + s, sizeof(unsigned), cudaMemcpyHostToDevice, c->cp[0]));
+        void* dv_done = nullptr;
+        CK(cudaHostGetDevicePointer(&dv_done, c->h_done, 0));
+        io.in_flag = c->d_inflag + s;
+        io.pdone = c->d_pdone + first; io.prev_epoch = prev;
+        io.tally = c->d_tally + s; io.tally_n = (unsigned)n; io.host_done = (unsigned*)dv_done + s;
+        c->wait_epoch[s] = n > 0 ? io.epoch : 0u;
+        CK(dp_launch_cycle(c->map, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
+                           c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, io));
+        c->chain_prev_epoch = io.epoch; c->chain_first = first; c->chain_n = n;
+    } else {
+        CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
+        CK(cudaMemcpyAsync(c->d_ox[s], ox, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[1]));
+        CK(cudaMemcpyAsync(c->d_oy[s], oy, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[2]));
+        for (int k = 0; k < 3; ++k) {
+            CK(cudaEventRecord(c->in_ready[s][k], c->cp[k]));
+            CK(cudaStreamWaitEvent(st, c->in_ready[s][k], 0));
+        }
+        CK(dp_launch_cycle(c->map, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
+                           c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, make_io(c, first, (dp_plan_record*)dv_rec)));
+        CK(cudaEventRecord(c->done[s], st));
+        c->wait_epoch[s] = 0;
     }
-    CK(dp_launch_cycle(c->map, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
-                       c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, make_io(c, first, (dp_plan_record*)dv_rec)));
     c->launches += c->split ? 2 : 1;
-    CK(cudaEventRecord(c->done[s], st));
     ++c->submitted;
     return DP_OK;
 }
-
 int dp_cycle_wait(dp_ctx* c) {
     if (!c) return fail(DP_ERR_ARG, "dp_cycle_wait: null context");
     if (c->submitted == c->waited) return fail(DP_ERR_STATE, "dp_cycle_wait: nothing in flight");
     CK(cudaSetDevice(c->device));
-    CK(cudaEventSynchronize(c->done[c->waited & 1]));
+    const int s = (int)(c->waited & 1);
+    if (c->chain && c->split == 2) {
+        const unsigned want = c->wait_epoch[s];
+        const volatile unsigned* flag = c->h_done + s;
+        if (want) {
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned long long spin = 0; *flag != want; ++spin) {
+                if ((spin & 0xfff) == 0xfff) {              // a kernel that trapped never raises the flag: ask the stream now and then
+                    const cudaError_t q = cudaStreamQuery(c->st[0]);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) return fail(DP_ERR_CUDA, "dp_cycle_wait", q);
+                    if (q == cudaSuccess && *flag != want) return fail(DP_ERR_CUDA, "dp_cycle_wait: the stream drained without the completion flag");
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) return fail(DP_ERR_CUDA, "dp_cycle_wait: timed out");
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
+    } else {
+        CK(cudaEventSynchronize(c->done[s]));
+    }
     ++c->waited;
     return DP_OK;
 }

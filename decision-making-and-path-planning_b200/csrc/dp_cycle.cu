@@ -182,12 +182,13 @@ template <class T> __device__ __forceinline__ T dp_l2(const T* p) { return __ldc
 #ifdef DP_DEBUG_CLOCK
 // instrumented build only (make debug, tools/scene_timeline.py): per scene and launch {start ns, end ns, SM id, n_traj,
 // regions done ns, sweep start ns, sweep end ns, -}
-__device__ long long g_dbg_timeline[65536 * 2 * 8];
+__device__ long long g_dbg_timeline[2 * 65536 * 2 * 8];   // [epoch parity][scene][phase][8]
 __device__ __forceinline__ long long dbg_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (long long)t; }
-#define DBG_MARK(ph, slot) if (lane == 0) g_dbg_timeline[((size_t)scene * 2 + (ph)) * 8 + (slot)] = dbg_now()
-#define DBG_END(ph, nt) if (lane == 0) { long long* g = g_dbg_timeline + ((size_t)scene * 2 + (ph)) * 8; g[1] = dbg_now(); g[3] = (nt); }
+#define DBG_MARK(ph, slot) if (lane == 0) g_dbg_timeline[(((size_t)(io.epoch & 1) * 65536 + scene) * 2 + (ph)) * 8 + (slot)] = dbg_now()
+#define DBG_END(ph, nt) if (lane == 0) { long long* g = g_dbg_timeline + (((size_t)(io.epoch & 1) * 65536 + scene) * 2 + (ph)) * 8; g[1] = dbg_now(); g[3] = (nt); }
 extern "C" int dp_debug_timeline(long long* dst, int n_scenes) {
-    return (int)cudaMemcpyFromSymbol(dst, g_dbg_timeline, (size_t)n_scenes * 16 * sizeof(long long));
+    (void)n_scenes;
+    return (int)cudaMemcpyFromSymbol(dst, g_dbg_timeline, sizeof(g_dbg_timeline));   // dst: [2][65536][2][8]
 }
 #else
 #define DBG_MARK(ph, slot)
@@ -208,7 +209,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     if (lane == 0) {
         unsigned sid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(sid));
-        long long* g = g_dbg_timeline + ((size_t)scene * 2 + (PHASE == 2 ? 1 : 0)) * 8;
+        long long* g = g_dbg_timeline + (((size_t)(io.epoch & 1) * 65536 + scene) * 2 + (PHASE == 2 ? 1 : 0)) * 8;
         g[0] = dbg_now(); g[2] = sid; g[4] = g[5] = g[6] = 0;
     }
     const long long dbg_t0 = clock64();
@@ -219,11 +220,13 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
 #endif
     WarpSmem& sm = smem[wib];
     if (PHASE == 1 && io.done) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // Planning CTAs may start filling in
+    if (PHASE == 2 && io.pdone) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // ... and the next cycle's Decision CTAs
+    if (PHASE == 1 && io.in_flag) dp_await(io.in_flag, io.epoch);                                // chained submit: inputs staged?
     if (PHASE == 2 && io.done) dp_await(io.done + scene, io.epoch);
     // the 128-byte scene header comes in with one coalesced warp load (from HBM, or straight from pinned host memory
     // over PCIe in the zero-copy mode of dp_cycle_batch) and is read from shared memory afterwards
-    sm.hdr[lane] = (PHASE == 2) ? dp_l2(reinterpret_cast<const uint32_t*>(hdr + scene) + lane)
-                                : reinterpret_cast<const uint32_t*>(hdr + scene)[lane];
+    sm.hdr[lane] = (PHASE == 2 || io.in_flag) ? dp_l2(reinterpret_cast<const uint32_t*>(hdr + scene) + lane)   // (staged by a concurrent launch / copy)
+                                              : reinterpret_cast<const uint32_t*>(hdr + scene)[lane];
     __syncwarp();
     const dp_scene_hdr& h = *reinterpret_cast<const dp_scene_hdr*>(sm.hdr);
     const double* ox = obs_x + (size_t)scene * max_obs;
@@ -239,10 +242,14 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     double2* lastp = last_path + (size_t)scene * DP_PATH_POINTS;
     dp_carry* const cg = carry + scene;
     dp_plan_record* const out = rec + scene;                // the record is assembled in place: fields are stored when final
+    // chained submit: the previous cycle's Planning warp of THIS scene may still be running (it reads the hand-off in the
+    // carry this warp is about to overwrite): wait for it, scene by scene
+    if (PHASE == 1 && io.prev_epoch) dp_await(io.pdone + scene, io.prev_epoch);
     const LaneMap lm = dp_lane_map(N, lane);
     // this lane's obstacle stays in registers for the whole cycle when N < 32
     const bool lm_act = (lm.nchunk > 1) && (lane < N * lm.nchunk);
-    const double mx = lm_act ? (PHASE == 2 ? dp_l2(ox + lm.o) : ox[lm.o]) : 0.0, my = lm_act ? (PHASE == 2 ? dp_l2(oy + lm.o) : oy[lm.o]) : 0.0;
+    const bool via_l2 = PHASE == 2 || io.in_flag != nullptr;
+    const double mx = lm_act ? (via_l2 ? dp_l2(ox + lm.o) : ox[lm.o]) : 0.0, my = lm_act ? (via_l2 ? dp_l2(oy + lm.o) : oy[lm.o]) : 0.0;
     dp_trace_record* tr = trace ? trace + scene : nullptr;
     if (tr && PHASE != 2) {                                 // zero the trace record cooperatively
         uint32_t* w = reinterpret_cast<uint32_t*>(tr);
@@ -351,7 +358,13 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         DBG_MARK(0, 4);
 
         // ---- BehaviorDecision (Decision.cpp:898-1773) ----
-        dp_carry c = *cg;
+        dp_carry c;
+        if (PHASE == 1) {                                   // through L2: in a chain the line was written by launches that may still be running
+            const int4* src = reinterpret_cast<const int4*>(cg);
+            int4* dst = reinterpret_cast<int4*>(&c);
+#pragma unroll
+            for (int k = 0; k < (int)(sizeof(dp_carry) / 16); ++k) dst[k] = __ldcg(src + k);
+        } else c = *cg;
         Beh cur;
         cur.behavior = c.behavior; cur.target = c.target_lanenum; cur.light = c.light_status;
         cur.lanechg = c.lanechg_status != 0; cur.obsavoid = c.obsavoid_status != 0; cur.dlg = c.behavior_to_dlg;
@@ -839,6 +852,18 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         for (int k = 0; k < DP_MAX_MIRRORS; ++k)             // (static indices: the parameter array stays in the constant bank)
             if (k < io.n_mirror) reinterpret_cast<uint32_t*>(io.mirror[k] + scene)[lane] = w;
     }
+    if (PHASE == 2 && io.pdone) {
+        // chained submit: this scene's cycle is complete -- its next Decision warp may go; the last warp of the batch tells the host
+        __threadfence();                                    // (every lane: its stores, the mirrors included, before the flags)
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(io.pdone + scene), "r"(io.epoch) : "memory");
+            if (io.host_done && atomicAdd(io.tally, 1u) == io.tally_n - 1u) {
+                __threadfence_system();                     // cumulative: everything the other warps fenced before their tally increment
+                *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
+            }
+        }
+    }
 }
 
 // ---- reset carry to constructor state (Decision.cpp:8-29, Planning.cpp:8-11,62) ----
@@ -891,7 +916,7 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
         configured = true;
     }
     if (!split) {
-        DpIo io0 = io; io0.done = nullptr;
+        DpIo io0 = io; io0.done = nullptr; io0.in_flag = nullptr; io0.pdone = nullptr; io0.prev_epoch = 0;
         const int blocks = (n + 3) / 4;
         dp_cycle_kernel<0, 4><<<blocks, 128, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io0);
     } else {
@@ -904,9 +929,20 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
         // Decision launch ingests (hdr/ox/oy may be pinned host memory); Planning launch reads the staged device copies
         DpIo io1 = io; io1.n_mirror = 0;
         DpIo io2 = io; io2.hdr_stage = nullptr; io2.ox_stage = nullptr; io2.oy_stage = nullptr;
-        if (split != 2) io1.done = io2.done = nullptr;
-        if (wide) dp_cycle_kernel<1, 4><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
-        else dp_cycle_kernel<1, 1><<<blocks, threads, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
+        if (split != 2) { io1.done = io2.done = nullptr; io1.in_flag = io2.in_flag = nullptr; io1.pdone = io2.pdone = nullptr; io1.prev_epoch = 0; }
+        {
+            // chained submit: the Decision half is a programmatic dependent of the previous cycle's Planning half (which triggers
+            // at entry); its warps wait per scene for that cycle's Planning warp (io.prev_epoch) and for the staged inputs
+            cudaLaunchConfig_t cfg1 = {};
+            cfg1.gridDim = dim3(blocks); cfg1.blockDim = dim3(threads); cfg1.dynamicSmemBytes = 0; cfg1.stream = st;
+            cudaLaunchAttribute at1[1];
+            at1[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at1[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg1.attrs = at1; cfg1.numAttrs = io1.prev_epoch ? 1 : 0;
+            cudaError_t e1 = wide ? cudaLaunchKernelEx(&cfg1, dp_cycle_kernel<1, 4>, m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1)
+                                  : cudaLaunchKernelEx(&cfg1, dp_cycle_kernel<1, 1>, m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
+            if (e1 != cudaSuccess) return e1;
+        }
         const dp_scene_hdr* hdr2 = io.hdr_stage ? io.hdr_stage : hdr;
         const double* ox2 = io.ox_stage ? io.ox_stage : ox; const double* oy2 = io.oy_stage ? io.oy_stage : oy;
         cudaLaunchConfig_t cfg = {};

@@ -16,12 +16,19 @@ struct DpIo {
     dp_scene_hdr* hdr_stage; double* ox_stage; double* oy_stage;
     dp_plan_record* mirror[DP_MAX_MIRRORS]; int n_mirror;
     unsigned* done; unsigned epoch;
+    // chained submits (dp_cycle_submit): consecutive cycles of the same scenes overlap as well, see dp_cycle.cu
+    const unsigned* in_flag;                   // *in_flag == epoch once this cycle's inputs are in the staging set
+    unsigned* pdone; unsigned prev_epoch;      // pdone[scene] = epoch of the last cycle whose Planning warp finished; the Decision warp
+                                               // of a scene waits for prev_epoch before it touches the carry (0: nothing to wait for)
+    unsigned* tally; unsigned tally_n;         // finished Planning warps of this cycle; the last one stores epoch to *host_done
+    unsigned* host_done;                       // (page-locked host memory)
 };
 inline DpIo dp_io_none() { DpIo io = {}; return io; }
 
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
                             double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io);   // split: 0 fused, 1 two launches, 2 overlapped
+// (io.prev_epoch != 0 additionally launches the Decision half as a programmatic dependent of the previous cycle's Planning half)
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st);
 cudaError_t dp_launch_map_prep(const double* x, const double* y, const int32_t* lane_pt_off, int n_lanes, double2* xy, double2* nrm,
                                double* lenp, cudaStream_t st);

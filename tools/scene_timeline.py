@@ -18,9 +18,11 @@ m = scenes.Map(); ep = scenes.Episodes(m, np.arange(n), cycles=K, n_obs=10); H, 
 p = Planner(n, 10); p.upload_map(m)
 for c in range(K):
     o = p.cycle(np.ascontiguousarray(H[c]), OX[c], OY[c])
-t = np.zeros((n, 2, 8), np.int64)
+T2 = np.zeros((2, 65536, 2, 8), np.int64)
 lib = load()
-assert lib.dp_debug_timeline(t.ctypes.data_as(C.c_void_p), C.c_int(n)) == 0
+assert lib.dp_debug_timeline(T2.ctypes.data_as(C.c_void_p), C.c_int(n)) == 0
+last = int(np.argmax(T2[:, :n, 1, 1].max(axis=1)))          # parity of the last cycle
+t = T2[last, :n]
 t0 = t[:, 0, 0].min()
 for ph, nm in ((0, "Decision"), (1, "Planning")):
     st, en, sm, nt = t[:, ph, 0] - t0, t[:, ph, 1] - t0, t[:, ph, 2], t[:, ph, 3]
