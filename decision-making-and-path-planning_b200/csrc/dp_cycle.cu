@@ -902,17 +902,19 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
                             double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io) {
     if (n <= 0) return cudaSuccess;
-    static bool configured = false;
-    static int sm_count = 0;
+    static bool configured_dev[64] = {};                    // (function attributes are per device)
+    static int sm_count_dev[64] = {};
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    bool& configured = configured_dev[dev_id & 63];
+    int& sm_count = sm_count_dev[dev_id & 63];
     if (!configured) {                                      // 196 of 256 KB as shared memory, the rest stays L1
         cudaFuncSetAttribute(dp_cycle_kernel<0, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
         cudaFuncSetAttribute(dp_cycle_kernel<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
         cudaFuncSetAttribute(dp_cycle_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
         cudaFuncSetAttribute(dp_cycle_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
         cudaFuncSetAttribute(dp_cycle_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id);
         configured = true;
     }
     if (!split) {

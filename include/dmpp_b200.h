@@ -148,6 +148,8 @@ typedef struct dp_carry {
     uint8_t pad[128 - 48 - 24 - 16 - 4];
 } dp_carry;
 
+/* A context belongs to one device and is NOT thread-safe: calls on one context must come from one thread at a time
+ * (different contexts are independent; dp_last_error is per process). */
 typedef struct dp_ctx dp_ctx;
 
 const char* dp_last_error(void);
