@@ -174,7 +174,7 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     CK(cudaMemset(c->d_inflag, 0, 2 * sizeof(unsigned))); CK(cudaMemset(c->d_tally, 0, 2 * sizeof(unsigned)));
     CK(cudaHostAlloc((void**)&c->h_done, 4 * sizeof(unsigned), cudaHostAllocMapped));
     c->h_done[0] = c->h_done[1] = c->h_done[2] = c->h_done[3] = 0;
-    if (const char* e = getenv("DP_CHAIN")) c->chain = atoi(e) != 0;
+    if (const char* e = getenv("DP_CHAIN")) c->chain = atoi(e);   // 0: events, 1: flags only, 2: flags + chained Decision launch
     CK(cudaMemset(c->d_done, 0, (size_t)max_scenes * sizeof(unsigned)));
     for (int s = 0; s < 2; ++s) {
         CK(cudaStreamCreateWithFlags(&c->st[s], cudaStreamNonBlocking));
@@ -305,6 +305,26 @@ int dp_cycle_batch_dev(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, con
     return DP_OK;
 }
 
+int dp_run_episode_dev(dp_ctx* c, int first, int n, int cycles, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec,
+                       void* stream) {
+    if (!c || !hdr || !ox || !oy || !rec || n < 0 || cycles < 0 || first < 0 || first + n > c->max_scenes)
+        return fail(DP_ERR_ARG, "dp_run_episode_dev: bad argument");
+    if (!c->have_map) return fail(DP_ERR_STATE, "dp_run_episode_dev: map not uploaded");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_run_episode_dev: submitted cycles in flight, call dp_cycle_wait first");
+    CK(cudaSetDevice(c->device));
+    const size_t mo = (size_t)c->max_obs;
+    // back-to-back launch pairs, no host involvement in between.  (Chaining cycle k+1's Decision launch to cycle k's Planning
+    // launch as dp_cycle_submit does was measured here too: 84 vs 66 us per 4096-scene cycle -- the early Decision CTAs spin in
+    // slots the Planning launch needs -- so the episode runner keeps the plain stream order.)
+    for (int k = 0; k < cycles; ++k) {
+        const DpIo io = make_io(c, first, nullptr);
+        CK(dp_launch_cycle(c->map, c->p, n, hdr + (size_t)k * n, ox + (size_t)k * n * mo, oy + (size_t)k * n * mo, c->max_obs, c->d_carry + first,
+                           c->d_last + (size_t)first * DP_PATH_POINTS, rec + (size_t)k * n, nullptr, nullptr, nullptr, (cudaStream_t)stream, c->split, io));
+        c->launches += c->split ? 2 : 1;
+    }
+    return DP_OK;
+}
+
 int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec,
                    dp_trace_record* trace, double* path_xy, double* path_ll) {
     if (!c || !hdr || !ox || !oy || !rec || n < 0 || first < 0 || first + n > c->max_scenes) return fail(DP_ERR_ARG, "dp_cycle_batch: bad argument");
@@ -395,7 +415,7 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
         // Chained: nothing but kernels goes into the compute stream.  The copy stream carries the three input DMAs and then a
         // four-byte copy that raises in_flag; the Decision warps wait for that flag, and per scene for the previous cycle's
         // Planning warp; the last Planning warp of the batch stores the epoch to page-locked host memory (dp_cycle_wait).
-        const unsigned prev = (c->chain_prev_epoch && c->chain_first == first && c->chain_n == n) ? c->chain_prev_epoch : 0u;
+        const unsigned prev = (c->chain >= 2 && c->chain_prev_epoch && c->chain_first == first && c->chain_n == n) ? c->chain_prev_epoch : 0u;
         DpIo io = make_io(c, first, (dp_plan_record*)dv_rec);
         CK(cudaMemsetAsync(c->d_tally + s, 0, sizeof(unsigned), c->cp[0]));
         CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));

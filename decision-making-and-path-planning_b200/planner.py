@@ -21,7 +21,7 @@ SYMBOLS = [
     "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
     "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
-    "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id",
+    "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev",
 ]
 
 _lib = None
@@ -114,6 +114,11 @@ class Planner:
         """bases: device-accessible addresses (ints); every finished record of slot s is also stored at base + 128 * s"""
         arr = (C.c_void_p * max(1, len(bases)))(*[C.c_void_p(int(b)) for b in bases])
         _ck(self.lib.dp_set_record_mirrors(self.ctx, C.c_int(len(bases)), arr), "dp_set_record_mirrors")
+
+    def run_episode_dev(self, n, cycles, d_hdr, d_ox, d_oy, d_rec, first=0, stream=0):
+        """`cycles` chained cycles of n scenes, all buffers device pointers: hdr[cycles][n], obs[cycles][n][max_obs], rec[cycles][n]"""
+        _ck(self.lib.dp_run_episode_dev(self.ctx, C.c_int(first), C.c_int(n), C.c_int(cycles), C.c_void_p(d_hdr), C.c_void_p(d_ox),
+                                        C.c_void_p(d_oy), C.c_void_p(d_rec), C.c_void_p(stream)), "dp_run_episode_dev")
 
     # ---- pipelined form: at most two cycles in flight, buffers page-locked (see include/dmpp_b200.h) ----
     def submit(self, hdr, ox, oy, rec, first=0):

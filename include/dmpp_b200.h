@@ -182,6 +182,14 @@ int dp_cycle_batch_dev(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scen
                        const double* obs_x, const double* obs_y, dp_plan_record* rec,
                        dp_trace_record* trace, double* path_xy, double* path_ll, void* stream);
 
+/* Whole scripted episodes with everything resident in HBM (replay / Monte-Carlo; SURVEY 8f rank 1, open loop): `cycles`
+ * consecutive cycles of the same n_scenes scenes, hdr[cycles][n_scenes], obs_x/obs_y[cycles][n_scenes][max_obs],
+ * rec[cycles][n_scenes], enqueued on `stream` in one call and asynchronous like dp_cycle_batch_dev.  The carry stays on the
+ * device between cycles (the hysteresis counters and the carried path of Decision.cpp:915-917 / Planning.cpp:6 evolve as in
+ * the reference) and nothing returns to the host until the caller synchronises the stream. */
+int dp_run_episode_dev(dp_ctx* ctx, int first_scene, int n_scenes, int cycles, const dp_scene_hdr* hdr,
+                       const double* obs_x, const double* obs_y, dp_plan_record* rec, void* stream);
+
 /* Host-pointer form (the drop-in call): copies inputs host->device, runs the cycle, copies the
  * requested outputs device->host, and returns when they are valid.  Buffers may be pageable or
  * pinned; dp_host_alloc returns pinned memory. */

@@ -404,3 +404,29 @@ def test_error_behaviour(planner, the_map):
     with pytest.raises(DpError):
         fresh.set_record_mirrors([0x1000] * 9)                                            # more mirrors than supported
     fresh.close()
+
+
+def test_run_episode_dev(planner, the_map):
+    """dp_run_episode_dev: whole episodes resident in HBM, one call -- records of every cycle and the final carry must be the
+    bytes the cycle-by-cycle host path produces."""
+    import torch
+    from dmpp_b200 import abi, scenes
+    n, cycles = 1500, 14
+    for kind, seed0 in (("highway", 61_000), ("junction", 62_000)):
+        ep = scenes.Episodes(the_map, np.arange(seed0, seed0 + n), cycles=cycles, kind=kind, n_obs=10)
+        H, OX, OY = ep.all_cycles()
+        PX, PY = pad_obs(OX, OY, planner.max_obs)
+        want = planner.run_episodes(H, PX, PY, trace=False, paths=False)
+        dev = torch.device("cuda", 0)
+        d_h = torch.from_numpy(H.view(np.uint8).reshape(cycles, n, 128)).to(dev)
+        d_x, d_y = torch.from_numpy(PX).to(dev), torch.from_numpy(PY).to(dev)
+        d_r = torch.zeros((cycles, n, 128), dtype=torch.uint8, device=dev)
+        planner.reset(0, n)
+        torch.cuda.synchronize()
+        planner.run_episode_dev(n, cycles, d_h.data_ptr(), d_x.data_ptr(), d_y.data_ptr(), d_r.data_ptr(),
+                                stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = d_r.cpu().numpy().view(abi.plan_record).reshape(cycles, n)
+        assert got.tobytes() == want["rec"].tobytes(), kind
+        carry, last = planner.download_carry(0, n)
+        assert carry.tobytes() == want["carry"].tobytes() and last.tobytes() == want["last_path"].tobytes(), kind
