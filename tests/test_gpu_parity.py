@@ -430,3 +430,12 @@ def test_run_episode_dev(planner, the_map):
         assert got.tobytes() == want["rec"].tobytes(), kind
         carry, last = planner.download_carry(0, n)
         assert carry.tobytes() == want["carry"].tobytes() and last.tobytes() == want["last_path"].tobytes(), kind
+
+
+@pytest.mark.parametrize("kind,n,cycles,n_obs,seed0", [("highway", 4096, 25, 7, 200_000), ("highway", 3000, 40, 16, 300_000),
+                                                       ("junction", 2000, 30, 3, 400_000), ("highway", 1024, 25, 33, 500_000)])
+def test_soak_other_seeds_and_obstacle_counts(planner, oracle, the_map, kind, n, cycles, n_obs, seed0):
+    """more of the same bar on other seeds, episode lengths and obstacle counts (7: three candidates per sweep pass with two idle
+    lanes; 16: two per pass; 3: eight per pass; 33: the grouped N >= 32 path inside the cycle kernel)"""
+    H, got, want = run_both(planner, oracle, the_map, np.arange(seed0, seed0 + n), kind, cycles, n_obs)
+    check(got, want, "%s n=%d N=%d" % (kind, n, n_obs))
