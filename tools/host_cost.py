@@ -17,7 +17,7 @@ for rep in range(6):
     t_all=time.perf_counter()
     for c in range(1,K):
         t0=time.perf_counter(); p.submit(Hh[c],OXh[c],OYh[c],recs[c&1]); t1=time.perf_counter(); p.wait(); t2=time.perf_counter()
-        s=int(recs[(c-1)&1]["n_traj"].sum(dtype=np.int64)); t3=time.perf_counter()
+        s=int(recs[(c-1)&1]["n_traj"].sum(dtype=np.int64)) if not os.environ.get("NOSUM") else 0; t3=time.perf_counter()
         if rep>=2: ts.append(t1-t0); tw.append(t2-t1); tsum.append(t3-t2)
     p.wait()
     if rep>=2: print("per step us", (time.perf_counter()-t_all)/(K-1)*1e6)
