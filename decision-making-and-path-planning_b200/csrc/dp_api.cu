@@ -38,6 +38,9 @@ struct dp_ctx {
     int max_scenes = 0, max_obs = 0;
     bool have_map = false;
     DevMap map;
+    DgMap gmap;                                             // the same tables + pruning bounds, as the group kernel takes them
+    long long* d_timeline = nullptr;                        // DP_TIMELINE=1: phase stamps of the last group launch (dp_debug_timeline)
+    int kernel = 1;                                         // 1: group kernel (dp_group.cuh), 0: round-1 warp-per-scene kernel (DP_KERNEL=warp)
     std::vector<void*> map_allocs;
     dp_carry* d_carry = nullptr;
     double2* d_last = nullptr;
@@ -87,6 +90,23 @@ DpIo make_io(dp_ctx* c, int first, dp_plan_record* host_rec) {
     if (host_rec) io.mirror[io.n_mirror++] = host_rec;
     for (int k = 0; k < c->n_mirror; ++k) io.mirror[io.n_mirror++] = c->mirror[k] + first;
     return io;
+}
+// one cycle of n scenes (carry slots first ..) on stream st
+cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec,
+                      dp_trace_record* trace, double* path_xy, double* path_ll, cudaStream_t st, const DpIo& io) {
+    if (c->kernel == 1) {
+        DgIo g = {};
+        for (int k = 0; k < io.n_mirror; ++k) g.mirror[k] = io.mirror[k];
+        g.n_mirror = io.n_mirror; g.tally = io.tally; g.tally_n = io.tally_n; g.host_done = io.host_done; g.epoch = io.epoch;
+        g.timeline = (n <= 8192) ? c->d_timeline : nullptr;
+        if (g.timeline) cudaMemsetAsync(c->d_timeline, 0, (size_t)8192 * 32 * 8, st);
+        c->launches += 1;
+        return dp_launch_group(c->gmap, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec,
+                               trace, path_xy, path_ll, st, g);
+    }
+    c->launches += c->split ? 2 : 1;
+    return dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace,
+                           path_xy, path_ll, st, c->split, io);
 }
 }  // namespace
 
@@ -164,6 +184,10 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     c->split = 2;
     if (const char* e = getenv("DP_SPLIT")) c->split = atoi(e);   // 0: one fused launch, 1: two launches back to back, 2: overlapped
     if (const char* e = getenv("DP_ZERO_COPY")) c->zero_copy = atoi(e) != 0;
+    if (const char* e = getenv("DP_KERNEL")) c->kernel = (strcmp(e, "warp") == 0) ? 0 : 1;
+    if (const char* e = getenv("DP_TIMELINE")) {
+        if (atoi(e)) { int rt = dev_alloc(&c->d_timeline, (size_t)8192 * 32); if (rt) { delete c; return rt; } cudaMemset(c->d_timeline, 0, (size_t)8192 * 32 * 8); }
+    }
     c->chunk = max_scenes < kChunk ? max_scenes : kChunk;
     int r;
     if ((r = dev_alloc(&c->d_carry, (size_t)max_scenes))) { delete c; return r; }
@@ -199,6 +223,7 @@ int dp_destroy(dp_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->map_allocs) cudaFree(p);
+    cudaFree(c->d_timeline);
     cudaFree(c->d_carry); cudaFree(c->d_last); cudaFree(c->d_done); cudaFree(c->d_pdone); cudaFree(c->d_inflag); cudaFree(c->d_tally);
     if (c->h_done) cudaFreeHost(c->h_done);
     for (int s = 0; s < 2; ++s) {
@@ -227,24 +252,47 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
         return DP_OK;
     };
     const size_t np = (size_t)m->n_points;
+    // the avoid sweep enumerates i < (W - Vw) / 0.6 candidates per side with no cap (Decision.cpp:940); this library holds
+    // DP_MAX_SWEEP of them: a lane wide enough to need more is rejected here instead of diverging silently
+    for (size_t i = 0; i < np; ++i)
+        if ((m->lane_width[i] / 100.0 - c->p.vehicle_width) / 0.6 > (double)DP_MAX_SWEEP)
+            return fail(DP_ERR_ARG, "dp_map_upload: lane too wide for DP_MAX_SWEEP avoid candidates per side");
+    for (int i = 0; i < m->n_lanes; ++i)
+        if (m->lane_pt_off[i + 1] - m->lane_pt_off[i] > 65535) return fail(DP_ERR_ARG, "dp_map_upload: lane longer than 65535 points");
     DevMap d;
     int r;
+    double* d_lenf = nullptr; float* d_hmax = nullptr; float* d_dnmax = nullptr; float* d_hmin = nullptr;
+    double* d_cump = nullptr; double* d_cerr = nullptr; int32_t* d_re0 = nullptr; int32_t* d_re1 = nullptr;
     if ((r = up(m->x, np * 8, (void**)&d.x))) return r;
     if ((r = up(m->y, np * 8, (void**)&d.y))) return r;
     if ((r = up(m->dir, np * 8, (void**)&d.dir))) return r;
     if ((r = up(nullptr, np * 16, (void**)&d.xy))) return r;
     if ((r = up(nullptr, np * 16, (void**)&d.nrm))) return r;
     if ((r = up(nullptr, np * 8, (void**)&d.lenp))) return r;
+    if ((r = up(nullptr, np * 8, (void**)&d_lenf))) return r;
+    if ((r = up(nullptr, (size_t)m->n_lanes * 4, (void**)&d_hmax))) return r;
+    if ((r = up(nullptr, (size_t)m->n_lanes * 4, (void**)&d_dnmax))) return r;
+    if ((r = up(nullptr, (size_t)m->n_lanes * 4, (void**)&d_hmin))) return r;
+    if ((r = up(nullptr, np * 8, (void**)&d_cump))) return r;
+    if ((r = up(nullptr, (size_t)m->n_lanes * 8, (void**)&d_cerr))) return r;
+    if ((r = up(nullptr, np * 4, (void**)&d_re0))) return r;
+    if ((r = up(nullptr, np * 4, (void**)&d_re1))) return r;
     if ((r = up(m->lane_width, np * 2, (void**)&d.width))) return r;
     if ((r = up(m->lanechg_attr, np * 2, (void**)&d.attr))) return r;
     if ((r = up(m->road_lane_base, (size_t)(m->n_roads + 1) * 4, (void**)&d.road_lane_base))) return r;
     if ((r = up(m->lane_pt_off, (size_t)(m->n_lanes + 1) * 4, (void**)&d.lane_pt_off))) return r;
     if ((r = up(m->conn, (size_t)m->n_conn * sizeof(dp_connector), (void**)&d.conn))) return r;
     d.n_roads = m->n_roads; d.n_lanes = m->n_lanes; d.n_conn = m->n_conn;
-    CK(dp_launch_map_prep(d.x, d.y, d.lane_pt_off, d.n_lanes, (double2*)d.xy, (double2*)d.nrm, (double*)d.lenp, c->st[0]));
-    ++c->launches;
+    CK(dp_launch_map_prep(d.x, d.y, d.attr, d.lane_pt_off, d.n_lanes, (double2*)d.xy, (double2*)d.nrm, (double*)d.lenp, d_lenf, d_hmax, d_hmin,
+                          d_dnmax, d_cump, d_cerr, d_re0, d_re1, c->st[0]));
+    c->launches += 2;
     CK(cudaStreamSynchronize(c->st[0]));
     c->map = d;
+    DgMap& g = c->gmap;
+    g.xy = d.xy; g.nrm = d.nrm; g.x = d.x; g.y = d.y; g.dir = d.dir; g.lenp = d.lenp; g.lenf = d_lenf; g.width = d.width; g.attr = d.attr;
+    g.road_lane_base = d.road_lane_base; g.lane_pt_off = d.lane_pt_off; g.conn = d.conn; g.lane_hmax = d_hmax; g.lane_dnmax = d_dnmax; g.lane_hmin = d_hmin;
+    g.cump = d_cump; g.lane_cerr = d_cerr; g.run_end0 = d_re0; g.run_end1 = d_re1;
+    g.n_roads = d.n_roads; g.n_lanes = d.n_lanes; g.n_conn = d.n_conn;
     c->have_map = true;
     return DP_OK;
 }
@@ -299,9 +347,8 @@ int dp_cycle_batch_dev(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, con
     if (!c || !hdr || !ox || !oy || !rec || n < 0 || first < 0 || first + n > c->max_scenes) return fail(DP_ERR_ARG, "dp_cycle_batch_dev: bad argument");
     if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_batch_dev: map not uploaded");
     CK(cudaSetDevice(c->device));
-    CK(dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace, path_xy,
-                       path_ll, (cudaStream_t)stream, c->split, make_io(c, first, nullptr)));
-    c->launches += c->split ? 2 : 1;
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_cycle_batch_dev: submitted cycles in flight, call dp_cycle_wait first");
+    CK(run_cycle(c, first, n, hdr, ox, oy, rec, trace, path_xy, path_ll, (cudaStream_t)stream, make_io(c, first, nullptr)));
     return DP_OK;
 }
 
@@ -318,9 +365,8 @@ int dp_run_episode_dev(dp_ctx* c, int first, int n, int cycles, const dp_scene_h
     // slots the Planning launch needs -- so the episode runner keeps the plain stream order.)
     for (int k = 0; k < cycles; ++k) {
         const DpIo io = make_io(c, first, nullptr);
-        CK(dp_launch_cycle(c->map, c->p, n, hdr + (size_t)k * n, ox + (size_t)k * n * mo, oy + (size_t)k * n * mo, c->max_obs, c->d_carry + first,
-                           c->d_last + (size_t)first * DP_PATH_POINTS, rec + (size_t)k * n, nullptr, nullptr, nullptr, (cudaStream_t)stream, c->split, io));
-        c->launches += c->split ? 2 : 1;
+        CK(run_cycle(c, first, n, hdr + (size_t)k * n, ox + (size_t)k * n * mo, oy + (size_t)k * n * mo, rec + (size_t)k * n, nullptr, nullptr,
+                     nullptr, (cudaStream_t)stream, io));
     }
     return DP_OK;
 }
@@ -347,7 +393,7 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         if (rs != DP_OK) return rs;
         return dp_cycle_wait(c);
     }
-    if (plain && c->zero_copy && c->split && pin_in && pin_rec && dv_hdr && dv_ox && dv_oy && dv_rec) {
+    if (plain && c->zero_copy && c->split && c->kernel == 0 && pin_in && pin_rec && dv_hdr && dv_ox && dv_oy && dv_rec) {
         // DP_ZERO_COPY=1: the Decision launch pulls the 128-byte headers and the obstacle rows straight out of the caller's
         // pinned buffers over PCIe (one coalesced load per scene) and leaves device copies for the Planning launch, which
         // pushes each finished record into the caller's pinned result buffer.  No copy engines -- but GPU-issued PCIe reads
@@ -380,10 +426,8 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         CK(cudaMemcpyAsync(c->d_hdr[s], sh, (size_t)cn * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(c->d_ox[s], sx, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(c->d_oy[s], sy, (size_t)cn * mo * 8, cudaMemcpyHostToDevice, st));
-        CK(dp_launch_cycle(c->map, c->p, cn, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first + i0,
-                           c->d_last + (size_t)(first + i0) * DP_PATH_POINTS, c->d_rec[s], trace ? c->d_trace[s] : nullptr,
-                           path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st, c->split, make_io(c, first + i0, nullptr)));
-        c->launches += c->split ? 2 : 1;
+        CK(run_cycle(c, first + i0, cn, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->d_rec[s], trace ? c->d_trace[s] : nullptr,
+                     path_xy ? c->d_pxy[s] : nullptr, path_ll ? c->d_pll[s] : nullptr, st, make_io(c, first + i0, nullptr)));
         CK(cudaMemcpyAsync(pin_rec ? rec + i0 : c->h_rec[s], c->d_rec[s], (size_t)cn * sizeof(dp_plan_record), cudaMemcpyDeviceToHost, st));
         if (trace) CK(cudaMemcpyAsync(trace + i0, c->d_trace[s], (size_t)cn * sizeof(dp_trace_record), cudaMemcpyDeviceToHost, st));
         if (path_xy) CK(cudaMemcpyAsync(path_xy + (size_t)i0 * 400, c->d_pxy[s], (size_t)cn * 400 * 8, cudaMemcpyDeviceToHost, st));
@@ -411,6 +455,26 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
     const int s = (int)(c->submitted & 1);
     const size_t mo = (size_t)c->max_obs;
     cudaStream_t st = c->st[0];                             // one compute stream: cycle k+1 reads the carry cycle k wrote
+    if (c->kernel == 1) {
+        // group kernel: the three input DMAs overlap on their own copy streams, the launch waits for their events; the kernel
+        // stores every record into the caller's page-locked buffer itself and its last CTA raises a flag in page-locked memory
+        // (dp_cycle_wait polls it: no event round trip).  The tally word is re-armed by that last CTA, not by a memset.
+        CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
+        CK(cudaMemcpyAsync(c->d_ox[s], ox, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[1]));
+        CK(cudaMemcpyAsync(c->d_oy[s], oy, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[2]));
+        for (int k = 0; k < 3; ++k) {
+            CK(cudaEventRecord(c->in_ready[s][k], c->cp[k]));
+            CK(cudaStreamWaitEvent(st, c->in_ready[s][k], 0));
+        }
+        DpIo io = make_io(c, first, (dp_plan_record*)dv_rec);
+        void* dv_done = nullptr;
+        CK(cudaHostGetDevicePointer(&dv_done, c->h_done, 0));
+        io.tally = c->d_tally + s; io.tally_n = (unsigned)n; io.host_done = (unsigned*)dv_done + s;
+        c->wait_epoch[s] = n > 0 ? io.epoch : 0u;
+        CK(run_cycle(c, first, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->d_rec[s], nullptr, nullptr, nullptr, st, io));
+        ++c->submitted;
+        return DP_OK;
+    }
     if (c->chain && c->split == 2) {
         // Chained: nothing but kernels goes into the compute stream.  The copy stream carries the three input DMAs and then a
         // four-byte copy that raises in_flag; the Decision warps wait for that flag, and per scene for the previous cycle's
@@ -456,7 +520,7 @@ int dp_cycle_wait(dp_ctx* c) {
     if (c->submitted == c->waited) return fail(DP_ERR_STATE, "dp_cycle_wait: nothing in flight");
     CK(cudaSetDevice(c->device));
     const int s = (int)(c->waited & 1);
-    if (c->chain && c->split == 2) {
+    if (c->kernel == 1 || (c->chain && c->split == 2)) {
         const unsigned want = c->wait_epoch[s];
         const volatile unsigned* flag = c->h_done + s;
         if (want) {
@@ -486,6 +550,15 @@ int dp_set_record_mirrors(dp_ctx* c, int n, void* const* bases) {
         c->mirror[k] = (dp_plan_record*)bases[k];
     }
     c->n_mirror = n;
+    return DP_OK;
+}
+
+int dp_debug_timeline(dp_ctx* c, long long* host_out, int n_blocks) {
+    if (!c || !host_out || n_blocks < 0 || n_blocks > 8192) return fail(DP_ERR_ARG, "dp_debug_timeline: bad argument");
+    if (!c->d_timeline) return fail(DP_ERR_STATE, "dp_debug_timeline: context was created without DP_TIMELINE=1");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host_out, c->d_timeline, (size_t)n_blocks * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
     return DP_OK;
 }
 

@@ -14,6 +14,7 @@
 #include "dp_device.cuh"
 #include "dp_fused.cuh"
 #include "dp_kernels.h"
+#include "dp_group.cuh"
 
 namespace {
 
@@ -878,23 +879,81 @@ __global__ void dp_reset_kernel(dp_carry* carry, double2* last_path, int first, 
     for (int k = 0; k < DP_PATH_POINTS; ++k) lp[k] = make_double2(0.0, 0.0);
 }
 
-// ---- map precompute: AoS points, per-point segment lengths (both idioms) and unit right normal ----
+// ---- map precompute: AoS points, per-point segment lengths (both idioms), unit right normal, per-lane pruning bounds ----
+// lane_hmax[gl] >= every segment length of lane gl, lane_dnmax[gl] >= |nrm[i+1]-nrm[i]| over its segments (FP32, rounded up):
+// the radii of the exactly pruned scan (dp_group.cuh).  Positive floats order like their bit patterns: atomicMax on the bits.
 __global__ void dp_map_prep_kernel(const double* x, const double* y, const int32_t* lane_pt_off, int n_lanes, double2* xy, double2* nrm,
-                                   double* lenp) {
+                                   double* lenp, double* lenf, float* lane_hmax, float* lane_hmin, float* lane_dnmax) {
     const int gl = blockIdx.x;
     if (gl >= n_lanes) return;
     const int off = lane_pt_off[gl], n = lane_pt_off[gl + 1] - off;
+    float hm = 0.f, hl = 1e30f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double2 nn = make_double2(0.0, 0.0);
-        double l = 0.0;
+        double l = 0.0, lf = 0.0;
         const double2 a = make_double2(x[off + i], y[off + i]);
         if (i + 1 < n) {
             const double2 b = make_double2(x[off + i + 1], y[off + i + 1]);
             nn = dp_normal(a, b);
             l = dp_dist_plain(b.x, b.y, a.x, a.y);
+            lf = sqrt(dp_sq2(b.x - a.x, b.y - a.y));
+            hm = fmaxf(hm, (float)lf * 1.0001f + 1e-6f);
+            hl = fminf(hl, (float)lf * 0.9999f);
         }
-        xy[off + i] = a; nrm[off + i] = nn; lenp[off + i] = l;
+        xy[off + i] = a; nrm[off + i] = nn; lenp[off + i] = l; lenf[off + i] = lf;
     }
+    atomicMax(reinterpret_cast<unsigned*>(lane_hmax + gl), __float_as_uint(hm));
+    atomicMin(reinterpret_cast<unsigned*>(lane_hmin + gl), __float_as_uint(hl));
+    __syncthreads();                                        // this block's normals are in memory (same block reads them back)
+    float dm = 0.f;
+    for (int i = threadIdx.x; i + 2 < n; i += blockDim.x) {
+        const double2 a = nrm[off + i], b = nrm[off + i + 1];
+        dm = fmaxf(dm, (float)sqrt(dp_sq2(b.x - a.x, b.y - a.y)) * 1.0001f + 1e-7f);
+    }
+    atomicMax(reinterpret_cast<unsigned*>(lane_dnmax + gl), __float_as_uint(dm));
+}
+
+// per lane, one thread per task: 0 = sequential prefix of lenp (+ the rounding bound of its differences), 1 / 2 = run ends
+// of the lane-change attribute tests `attr == 1` / `attr & 1` (Decision.cpp:1179-1190 and siblings; dg_run_exceeds)
+__global__ void dp_map_prep2_kernel(const double* lenp, const uint16_t* attr, const int32_t* lane_pt_off, int n_lanes, double* cump,
+                                    double* lane_cerr, int32_t* run_end0, int32_t* run_end1) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gl = t / 3, task = t - gl * 3;
+    if (gl >= n_lanes) return;
+    const int off = lane_pt_off[gl], n = lane_pt_off[gl + 1] - off;
+    if (task == 0) {
+        double acc = 0.0;
+        bool dyadic = true;                                 // every term a multiple of 2^-20: partial sums in any order are exact
+        for (int i = 0; i < n; ++i) {
+            const double t = lenp[off + i];
+            cump[off + i] = acc; acc += t;
+            if (t * 1048576.0 != rint(t * 1048576.0)) dyadic = false;
+        }
+        lane_cerr[gl] = (dyadic && acc < 1073741824.0) ? 0.0 : 4.0 * (double)n * 0x1p-53 * acc + 1e-12;
+    } else {
+        int32_t* re = (task == 1) ? run_end0 : run_end1;
+        if (n > 0) re[off + n - 1] = n - 1;
+        for (int i = n - 2; i >= 0; --i) {
+            const int a = attr[off + i + 1];
+            const bool ok = (task == 1) ? (a == 1) : ((a & 1) != 0);
+            re[off + i] = ok ? re[off + i + 1] : i;
+        }
+    }
+}
+
+// ---- the group kernel (dp_group.cuh): one CTA = g scenes ----
+template <int G, int TPB>
+__global__ void __launch_bounds__(TPB, (G <= 8) ? 4 : 2)   // G 16: 2 CTAs x 256 threads x 128 regs; G 8: 4 CTAs/SM (TPB 128: 128 regs, TPB 256: 64 regs)
+dp_group_kernel(DgMap m, dp_params p, int n_scenes, int g, const dp_scene_hdr* __restrict__ hdr, const double* __restrict__ obs_x,
+                const double* __restrict__ obs_y, int max_obs, dp_carry* __restrict__ carry, double2* __restrict__ last_path,
+                dp_plan_record* __restrict__ rec, dp_trace_record* __restrict__ trace, double* __restrict__ path_xy,
+                double* __restrict__ path_ll, DgIo io) {
+    extern __shared__ __align__(16) unsigned char dg_raw[];
+    DgSmem<G>& sm = *reinterpret_cast<DgSmem<G>*>(dg_raw);
+    const int first = blockIdx.x * g;
+    if (first >= n_scenes) return;
+    const int S = min(g, n_scenes - first);
+    dg_group_cycle<G, TPB>(m, p, first, S, hdr, obs_x, obs_y, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io, sm);
 }
 
 // ---- launchers (called from dp_api.cu) ----
@@ -966,8 +1025,62 @@ cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int 
     dp_reset_kernel<<<(count + 127) / 128, 128, 0, st>>>(carry, last_path, first, count);
     return cudaGetLastError();
 }
-cudaError_t dp_launch_map_prep(const double* x, const double* y, const int32_t* lane_pt_off, int n_lanes, double2* xy, double2* nrm,
-                               double* lenp, cudaStream_t st) {
-    dp_map_prep_kernel<<<n_lanes, 256, 0, st>>>(x, y, lane_pt_off, n_lanes, xy, nrm, lenp);
+cudaError_t dp_launch_map_prep(const double* x, const double* y, const uint16_t* attr, const int32_t* lane_pt_off, int n_lanes, double2* xy,
+                               double2* nrm, double* lenp, double* lenf, float* lane_hmax, float* lane_hmin, float* lane_dnmax, double* cump,
+                               double* lane_cerr, int32_t* run_end0, int32_t* run_end1, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(lane_hmax, 0, (size_t)n_lanes * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(lane_dnmax, 0, (size_t)n_lanes * sizeof(float), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(lane_hmin, 0x7f, (size_t)n_lanes * sizeof(float), st);   // 0x7f7f7f7f = 3.4e38: above every length
+    if (e != cudaSuccess) return e;
+    dp_map_prep_kernel<<<n_lanes, 256, 0, st>>>(x, y, lane_pt_off, n_lanes, xy, nrm, lenp, lenf, lane_hmax, lane_hmin, lane_dnmax);
+    dp_map_prep2_kernel<<<(3 * n_lanes + 63) / 64, 64, 0, st>>>(lenp, attr, lane_pt_off, n_lanes, cump, lane_cerr, run_end0, run_end1);
     return cudaGetLastError();
+}
+
+// Group kernel launch.  cfg 0: 16 scenes x 256 threads per CTA, 2 CTAs per SM; cfg 1: 8 scenes x 128 threads, 4 CTAs per SM.
+// Scenes per CTA: batches that fit one wave are spread evenly over the resident CTA slots (4096 scenes on 148 SMs: 14 per CTA,
+// 293 of 296 slots); larger batches run full groups.
+template <int G, int TPB>
+static cudaError_t dp_launch_group_t(const DgMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
+                                     int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
+                                     double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io, int sm_count, int force_g) {
+    static bool configured_dev[64] = {};
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    const size_t smem = sizeof(DgSmem<G>);
+    if (!configured_dev[dev_id & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(dp_group_kernel<G, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(dp_group_kernel<G, TPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured_dev[dev_id & 63] = true;
+    }
+    const int per_sm = (G <= 8) ? 4 : 2;
+    (void)0;
+    int g = (n + sm_count * per_sm - 1) / (sm_count * per_sm);
+    if (g < 1) g = 1;
+    if (g > G) g = G;
+    if (force_g > 0 && force_g <= G) g = force_g;
+    const int blocks = (n + g - 1) / g;
+    dp_group_kernel<G, TPB><<<blocks, TPB, smem, st>>>(m, p, n, g, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io);
+    return cudaGetLastError();
+}
+cudaError_t dp_launch_group(const DgMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
+                            int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
+                            double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io) {
+    if (n <= 0) return cudaSuccess;
+    static int sm_count_dev[64] = {};
+    static int cfg = -1, force_g = 0;
+    if (cfg < 0) {
+        const char* e = getenv("DP_GROUP_CFG"); cfg = e ? atoi(e) : 0;
+        const char* f = getenv("DP_GROUP_G"); force_g = f ? atoi(f) : 0;
+    }
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    int& sm_count = sm_count_dev[dev_id & 63];
+    if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id);
+    if (cfg == 1) return dp_launch_group_t<8, 128>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g);
+    if (cfg == 2) return dp_launch_group_t<8, 256>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g);
+    return dp_launch_group_t<16, 256>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g);
 }

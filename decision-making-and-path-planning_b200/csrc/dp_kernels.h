@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "dp_device.cuh"
+#include "dp_group.cuh"
 
 // optional plumbing of the cycle launches:
 //   *_stage   zero-copy ingest (DP_ZERO_COPY=1): the Decision launch reads hdr/obstacles from pinned host memory and leaves
@@ -30,8 +31,13 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
                             double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io);   // split: 0 fused, 1 two launches, 2 overlapped
 // (io.prev_epoch != 0 additionally launches the Decision half as a programmatic dependent of the previous cycle's Planning half)
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st);
-cudaError_t dp_launch_map_prep(const double* x, const double* y, const int32_t* lane_pt_off, int n_lanes, double2* xy, double2* nrm,
-                               double* lenp, cudaStream_t st);
+cudaError_t dp_launch_map_prep(const double* x, const double* y, const uint16_t* attr, const int32_t* lane_pt_off, int n_lanes, double2* xy,
+                               double2* nrm, double* lenp, double* lenf, float* lane_hmax, float* lane_hmin, float* lane_dnmax, double* cump,
+                               double* lane_cerr, int32_t* run_end0, int32_t* run_end1, cudaStream_t st);
+// the group kernel (dp_group.cuh): ONE launch per cycle, a CTA walks a group of scenes through the cycle phase by phase
+cudaError_t dp_launch_group(const DgMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
+                            int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
+                            double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io);
 
 // operator-level kernels (dp_ops.cu)
 // operator kernels take polylines as AoS double2 (the host entry points interleave x/y)

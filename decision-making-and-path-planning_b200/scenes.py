@@ -15,7 +15,13 @@ the left neighbour of lane n is lane n-1, Decision.cpp:602-604):
                                      (CreateNewPath(+-W), Decision.cpp:629-631,667-669)
   road 6  approach,  heading 90 deg, 2 lanes, 400 points, attribute 0     (junction scenes)
   road 7  departure, heading 180 deg,2 lanes, 400 points, attribute 0
+  road 8  straight, heading 75 deg,  3 lanes, attribute of lanes 1 and 2: 2 at every 128th point, 3 elsewhere; lane 3: 1
+                                     (the only shape on which the obstacle-motivated RIGHT change of Decision.cpp:1296-1424
+                                     can fire: attribute exactly 2 at the ego's point, odd attributes ahead, quirk 1)
   connectors 6->7: lane 1->1 and lane 2->2, quarter circle left turn
+
+`Episodes` draws seeded scenes; `Directed` scripts the scene families that the random mix (almost) never reaches -- the
+right lane change (behaviour 3) sites of the rule tree.
 """
 import ctypes as C
 import math
@@ -105,6 +111,10 @@ class Map:
         add_road(jx + 0 * sj, jy - (n_j - 1) * SPACING + sj, np.full(n_j, 90.0), [0, 0])
         Rc = 14.0                                    # left turn: north -> west
         add_road(jx - Rc - 0.5 - sj, jy + Rc + 0.5 + 0 * sj, np.full(n_j, 180.0), [0, 0])
+        # road 8: straight heading 75 deg; lanes 1/2 carry attribute 2 on isolated points, 3 in between
+        c8, s8 = math.cos(math.radians(75.0)), math.sin(math.radians(75.0))
+        a23 = np.where(ids % 128 == 0, 2, 3)
+        add_road(-2500.0 + s * c8, 900.0 + s * s8, np.full(N_PTS, 75.0), [a23, a23, 1])
         self.n_road_lanes = self.road_lane_base[-1]
         for l in (0, 1):                             # connector lane l+1 -> lane l+1
             r_l = Rc + (0.5 - l) * LANE_W            # left lane (l=0) has the smaller radius
@@ -352,6 +362,137 @@ class Episodes:
 
     def all_cycles(self):
         """[cycles][n] hdr and [cycles][n][n_obs] obstacle arrays (cycle-major)."""
+        H = np.zeros((self.cycles, self.n), dtype=abi.scene_hdr)
+        OX = np.zeros((self.cycles, self.n, self.n_obs))
+        OY = np.zeros((self.cycles, self.n, self.n_obs))
+        for c in range(self.cycles):
+            H[c] = self.hdr(c)
+            OX[c], OY[c] = self.obstacles(c)
+        return H, OX, OY
+
+
+# streams of the directed families
+(D_FAM, D_LANE, D_ID, D_GAP, D_LAT, D_SPEED, D_NAV, D_STALL, D_YAW, D_PERIOD, D_OTHER_S, D_OTHER_L, D_MOVE, D_WOB) = range(100, 114)
+
+
+class Directed:
+    """Scripted scene families that reach the RIGHT lane change of the rule tree (behaviour 3).  Same interface as
+    `Episodes` (hdr(c), obstacles(c), all_cycles()); every quantity is a stateless hash of (seed, stream, index).
+
+    family 'right_obstacle' -- Decision.cpp:1296-1424 (commit at :1382) and the right-lane aim walk with its loop-bound quirk
+        (Planning.cpp:473-501): road 8, ego STANDING on a point whose attribute is exactly 2 (the run of odd attributes ahead
+        is > 50 m), a standing vehicle 8-20 m ahead in its lane, right neighbour lane mostly clear; the signal timer passes
+        1500 ms after ~16 cycles.  Lane 1 scenes take the no-way-back branch (light 2, 50 m), lane 2 scenes the other one
+        (light 1, 10 m) and walk the right lane for the aim point.  At cycle `move_t` the ego appears on the target lane.
+    family 'right_nav' -- Decision.cpp:1086-1143 (commit at :1108): the navigation asks for a right change on a lane whose
+        attribute is 2.  The signal timer of that branch restarts every cycle unless light_status is already 2 (quirk 3), so
+        the commit needs either (a) ONE cycle period >= 2000 ms (a stalled cycle: `stall` sub-family, roads 1 and 3, lane 1),
+        or (b) light 2 carried over from an avoid-right manoeuvre on an attribute-0 stretch that ends (`carry` sub-family:
+        road 4 lane 1 crossing id 700 behind a vehicle that sits left of the lane centre).
+    """
+
+    def __init__(self, m: Map, seeds, family="right_obstacle", n_obs=10, cycles=40):
+        self.m, self.family, self.n_obs, self.cycles = m, family, int(n_obs), int(cycles)
+        self.seeds = np.asarray(seeds, dtype=np.uint64)
+        self.n = self.seeds.size
+        sd = self.seeds
+        n = self.n
+        self.lat_wob = (rnd(sd, D_WOB) - 0.5) * 0.16
+        if family == "right_obstacle":
+            self.road = np.full(n, 8, np.int64)
+            self.lane0 = 1 + (rnd(sd, D_LANE) * 2).astype(np.int64)             # lane 1 or 2
+            self.id0 = 128 * (2 + (rnd(sd, D_ID) * 10).astype(np.int64))        # attribute 2 exactly here
+            self.v = np.zeros(n)
+            self.gap = 8.0 + rnd(sd, D_GAP) * 12.0
+            self.lead_lat = (rnd(sd, D_LAT) - 0.5) * 1.0
+            self.lead_v = np.zeros(n)
+            self.move_t = 24 + (rnd(sd, D_MOVE) * 12).astype(np.int64)
+            self.nav = np.zeros((n, abi.LANESUM), np.uint16)
+            self.nav[:, :3] = [1, 2, 3]
+            self.stall_t = np.full(n, -1, np.int64)
+        elif family == "right_nav":
+            sub = rnd(sd, D_FAM) < 0.5                                          # True: stall, False: carry
+            self.sub_stall = sub
+            self.road = np.where(sub, np.where(rnd(sd, D_LANE) < 0.5, 1, 3), 4).astype(np.int64)
+            self.lane0 = np.ones(n, np.int64)
+            self.v = 25.0 + rnd(sd, D_SPEED) * 15.0
+            self.id0 = np.where(sub, 200 + (rnd(sd, D_ID) * 1200).astype(np.int64), 660 + (rnd(sd, D_ID) * 30).astype(np.int64))
+            self.gap = np.where(sub, 30.0 + rnd(sd, D_GAP) * 40.0, 9.0 + rnd(sd, D_GAP) * 4.0)
+            self.lead_lat = np.where(sub, (rnd(sd, D_LAT) - 0.5) * 0.6, 0.45 + rnd(sd, D_LAT) * 0.15)
+            self.lead_v = self.v / 3.6
+            self.move_t = np.full(n, 10 ** 6, np.int64)
+            self.nav = np.zeros((n, abi.LANESUM), np.uint16)
+            self.nav[:, 0] = 2 + (rnd(sd, D_NAV) * 2).astype(np.int64)          # exit lane 2 or 3: lane 1 must go right
+            self.stall_t = np.where(sub, 4 + (rnd(sd, D_STALL) * (cycles - 8)).astype(np.int64), -1)
+        else:
+            raise ValueError(family)
+        self.nl = (m.road_lane_base[self.road] - m.road_lane_base[self.road - 1]).astype(np.int64)
+        k = np.arange(1, self.n_obs, dtype=np.uint64)[None, :]
+        s2 = sd[:, None]
+        # the other vehicles: far lanes / far behind, a few in the right neighbour lane (then the change may never commit)
+        self.other_rel = -80.0 + rnd(s2, D_OTHER_S, k) * 200.0
+        ol = rnd(s2, D_OTHER_L, k)
+        self.other_lane = np.where(ol < 0.12, np.minimum(self.lane0[:, None] + 1, self.nl[:, None]), self.nl[:, None])
+        self.other_lane = np.where(ol > 0.9, self.lane0[:, None], self.other_lane)
+        self.other_rel = np.where(self.other_lane == self.lane0[:, None], -90.0 - rnd(s2, D_OTHER_S, k + np.uint64(500)) * 60.0, self.other_rel)
+        self._t_cache = {}
+
+    period_ticks_base = Episodes.period_ticks
+    _lane_xy = Episodes._lane_xy
+
+    def period_ticks(self, c):
+        t = 80 + (rnd(self.seeds, D_PERIOD, c) * 41.0).astype(np.int64)
+        return np.where(self.stall_t == c, 2000 + (rnd(self.seeds, D_STALL, 7) * 1000.0).astype(np.int64), t)
+
+    def elapsed_s(self, c):
+        if c not in self._t_cache:
+            t = np.zeros(self.n)
+            for i in range(c):
+                t = t + self.period_ticks(i) / 1000.0
+            self._t_cache[c] = t
+        return self._t_cache[c]
+
+    def hdr(self, c):
+        m = self.m
+        h = np.zeros(self.n, dtype=abi.scene_hdr)
+        h["period_ms"] = self.period_ticks(c).astype(np.float64)
+        t = self.elapsed_s(c)
+        s = self.id0 * SPACING + self.v / 3.6 * t
+        lane = np.where(c >= self.move_t, np.minimum(self.lane0 + 1, self.nl), self.lane0)
+        gl = m.road_lane_base[self.road - 1].astype(np.int64) + lane - 1
+        x, y, hd, idn = self._lane_xy(gl, s)
+        hr = np.radians(hd)
+        lat = self.lat_wob * np.sin(0.4 * c)
+        h["x"] = x - lat * np.sin(hr)
+        h["y"] = y + lat * np.cos(hr)
+        h["dir"] = np.mod(hd + (rnd(self.seeds, D_YAW, c) - 0.5) * 3.0 + 360.0, 360.0)
+        h["velocity"] = self.v
+        h["n_obs"] = self.n_obs
+        h["conn"] = -1
+        h["road_num"] = self.road
+        h["lane_num"] = lane
+        h["last_roadnum"] = 1; h["next_roadnum"] = 1; h["last_lanenum"] = 1; h["next_lanenum"] = 1
+        for l in range(abi.LANESUM):
+            h["id"][:, l] = np.where(l < self.nl, idn, 0)
+        h["out_lane_no"] = self.nav
+        return h
+
+    def obstacles(self, c):
+        m = self.m
+        t = self.elapsed_s(c)
+        S = np.zeros((self.n, self.n_obs)); L = np.zeros((self.n, self.n_obs), np.int64); LAT = np.zeros((self.n, self.n_obs))
+        S[:, 0] = self.id0 * SPACING + self.gap + self.lead_v * t
+        L[:, 0] = self.lane0
+        LAT[:, 0] = self.lead_lat
+        if self.n_obs > 1:
+            S[:, 1:] = (self.id0 * SPACING + self.v / 3.6 * t)[:, None] + self.other_rel
+            L[:, 1:] = self.other_lane
+        gl = m.road_lane_base[self.road - 1].astype(np.int64)[:, None] + L - 1
+        x, y, hd, _ = self._lane_xy(gl, S)
+        hr = np.radians(hd)
+        return np.ascontiguousarray(x - LAT * np.sin(hr)), np.ascontiguousarray(y + LAT * np.cos(hr))
+
+    def all_cycles(self):
         H = np.zeros((self.cycles, self.n), dtype=abi.scene_hdr)
         OX = np.zeros((self.cycles, self.n, self.n_obs))
         OY = np.zeros((self.cycles, self.n, self.n_obs))

@@ -269,6 +269,10 @@ int dp_mean_points(dp_ctx* ctx, int n_paths, const int32_t* path_off, const doub
 /* device properties + FMA micro-benchmark used as roofline denominator:
  * returns measured FP64 / FP32 FMA throughput in TFLOP/s on the context's device. */
 int dp_measure_fma_peak(dp_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
+/* diagnostic: phase time stamps (globaltimer, ns) of the most recent cycle launch, one row of 32 per CTA (row b = scenes
+ * [b*g, (b+1)*g) of the batch; stamp 0 = CTA start, stamp i = end of phase i of csrc/dp_group.cuh).  Only contexts created
+ * with DP_TIMELINE=1 in the environment record them; used by tools/group_timeline.py, never by the product path. */
+int dp_debug_timeline(dp_ctx* ctx, long long* host_out, int n_blocks);
 /* number of kernels this library has launched since dp_create (bench.py "gpu_launches") */
 int64_t dp_launch_count(dp_ctx* ctx);
 /* device pointer helpers so a Python/C++ caller can stage inputs for dp_cycle_batch_dev */

@@ -89,6 +89,15 @@ class Oracle(_Runner):
         o["traj"] = traj.value
         return o
 
+    BRANCHES = ["b3_nav_1108", "b3_obs_1382", "b3_both_1618", "b3_both_1711", "enter_1596", "enter_1688", "aim_right_473",
+                "aim_right_walk"]
+
+    def branch_hits(self, reset=True):
+        """hit counters of the right-lane-change sites since the last reset (planner_oracle.h BR_*)"""
+        out = np.zeros(len(self.BRANCHES), np.int64)
+        self.lib.oracle_branch_hits(abi.ptr(out), C.c_int(1 if reset else 0))
+        return dict(zip(self.BRANCHES, out.tolist()))
+
     # operator-level
     def search_obstacle(self, px, py, ox, oy, lo, hi):
         px, py, ox, oy = (np.ascontiguousarray(a, np.float64) for a in (px, py, ox, oy))

@@ -76,6 +76,14 @@ long long oracle_run_batch(const dp_params* p, int n, int cycles, int max_obs, c
     return ub.load();
 }
 
+// hit counters of the right-lane-change sites since the last reset (planner_oracle.h, BR_*)
+void oracle_branch_hits(long long* out, int reset) {
+    for (int i = 0; i < oracle::BR_COUNT; ++i) {
+        out[i] = oracle::g_branch_hits[i].load();
+        if (reset) oracle::g_branch_hits[i].store(0);
+    }
+}
+
 // ---- operator-level entry points (known-answer tests, GPU operator parity) ----
 void oracle_search_obstacle(const double* px, const double* py, int P, const double* ox, const double* oy, int N,
                             double lo, double hi, dp_search_slot* out) {

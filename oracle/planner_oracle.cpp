@@ -4,10 +4,16 @@
 #include <cmath>
 #include <cstring>
 
+#include <atomic>
+
 namespace oracle {
 using spec::P2;
 using spec::P3;
 typedef std::vector<P2> Path;
+
+// per-branch hit counters of the right-lane-change sites (tests assert that the directed scene families reach them)
+std::atomic<long long> g_branch_hits[BR_COUNT];
+static inline void hit(int b) { g_branch_hits[b].fetch_add(1, std::memory_order_relaxed); }
 
 void reset_state(SceneState& s) {
     std::memset(&s, 0, sizeof(s));
@@ -247,6 +253,7 @@ void segment_decision(Ctx& k, SceneState& st, Path& refpath) {
                         if (cur.light != 2) { cur.lanechg = true /* = 2, quirk 3 */; c.rightlight_time = 0; }
                         c.rightlight_time += period;
                         if (((gRF > gF + 10) || (gRF > 40)) && gRR > 15 && c.rightlight_time >= 2000) {
+                            hit(BR_B3_NAV_1108);
                             cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
                         } else keep(true);
                     } else { keep(true); cur.dlg = 4; }
@@ -306,6 +313,7 @@ void segment_decision(Ctx& k, SceneState& st, Path& refpath) {
                                     }
                                 }
                                 if (chg && gRF > gF + 10 && gRR > 10 && c.leftlight_time > 1500) {
+                                    hit(BR_B3_OBS_1382);
                                     c.frontobs_time = 0; cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
                                 } else keep(true);
                             } else keep(true);
@@ -328,10 +336,12 @@ void segment_decision(Ctx& k, SceneState& st, Path& refpath) {
                                     c.frontobs_time = 0; cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
                                 } else keep(true);
                             } else if (right_ok && !nb_right) {                      // :1596-1636
+                                hit(BR_ENTER_1596);
                                 if (cur.light != 2) { cur.light = 2; c.leftlight_time = 0; }
                                 tick();
                                 if (gRF > gF + 10) {
                                     if (gRR > 10 && c.leftlight_time > 2000) {
+                                        hit(BR_B3_BOTH_1618);
                                         c.frontobs_time = 0; cur.behavior = 3; cur.target = lane_cur + 1; cur.lanechg = true;
                                     } else keep(false);
                                 }
@@ -342,10 +352,12 @@ void segment_decision(Ctx& k, SceneState& st, Path& refpath) {
                                     c.frontobs_time = 0; cur.behavior = 2; cur.target = lane_cur - 1; cur.lanechg = true;
                                 } else keep(false);
                             } else if (right_ok) {                                   // :1688-1730
+                                hit(BR_ENTER_1688);
                                 if (cur.light != 2) { cur.light = 2; c.leftlight_time = 0; }
                                 tick();
                                 if (gRF > gF + 10) {
                                     if (gRR > 10 && c.leftlight_time > 2000) {
+                                        hit(BR_B3_BOTH_1711);
                                         c.frontobs_time = 0; cur.behavior = 3;
                                         lane_cur = 1; cur.target = 1;                // "= LaneNum_Cur = 1" (quirk 2)
                                         cur.lanechg = true;
@@ -493,6 +505,8 @@ void planning_cycle(Ctx& k, SceneState& st, const Path& refpath) {
             if (d_behavior == 2) {                      // :443-471 (quirk 7)
                 if (lane > 1) walk_lane(gl - 1, left_id, left_sum - 1, gl, left_sum - 2, left_sum - 1);
             } else if (d_behavior == 3) {               // :473-501 (quirk 7: bound is leftpoint_sum)
+                hit(BR_AIM_RIGHT_473);
+                if (lane < lane_sum && right_id < left_sum - 1) hit(BR_AIM_RIGHT_WALK);
                 if (lane < lane_sum) walk_lane(gl + 1, right_id, left_sum - 1, gl + 1, right_sum - 1, right_sum - 1);
                 else if (right_id < left_sum - 1) ++k.out.ub_hits;   // reference indexes a lane that does not exist
             }

@@ -14,7 +14,14 @@
 #include "cshare_spec.h"
 #include "ref_api.h"
 
+#include <atomic>
+
 namespace oracle {
+
+// hit counters of the right-lane-change sites (Decision.cpp:1108,1382,1618,1711; Planning.cpp:473-501)
+enum { BR_B3_NAV_1108, BR_B3_OBS_1382, BR_B3_BOTH_1618, BR_B3_BOTH_1711, BR_ENTER_1596, BR_ENTER_1688, BR_AIM_RIGHT_473,
+       BR_AIM_RIGHT_WALK, BR_COUNT };
+extern std::atomic<long long> g_branch_hits[BR_COUNT];
 
 struct MapView {
     dp_map_desc d;

@@ -1,31 +1,39 @@
-"""per-kernel executed-instruction breakdown by source line from `ncu --page source --csv` (file saved beforehand)
-usage: python tools/ncu_lines.py src.csv <kernel-substring> [top]"""
-import collections
-import csv
-import sys
-
-rows = csv.reader(open(sys.argv[1]))
-want = sys.argv[2]
-top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-cur = kern = None
-ix = None
-agg = collections.OrderedDict()
+"""per-source-line instruction / sample shares of an ncu report, aggregated over line ranges of dp_group.cuh
+usage: python tools/ncu_lines.py report.ncu-rep"""
+import csv, sys, subprocess, collections, re, os
+rep = sys.argv[1]
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'], capture_output=True, text=True).stdout
+rows = list(csv.reader(src.splitlines()))
+res = []; cur = None; h = None
 for r in rows:
-    if not r:
-        continue
-    if r[0] == "File Path":
-        cur = r[1].split("/")[-1]; continue
-    if r[0] == "Function Name":
-        kern = r[1]; continue
+    if not r: continue
+    if r[0] == "File Path": cur = r[1].split('/')[-1]; continue
+    if r[0] == "Function Name": continue
     if r[0] == "Line No":
-        ix = {c: i for i, c in enumerate(r) if c != "Source"}; continue
-    if r[0] != "" and ix and kern and want in kern:
-        try:
-            a = agg.setdefault((cur, int(r[0])), [r[1].strip()[:100], 0.0, 0.0])
-            a[1] += float(r[ix["Instructions Executed"]]); a[2] += float(r[ix["# Samples"]])
-        except (ValueError, KeyError):
-            pass
-ti = sum(a[1] for a in agg.values()); ts = sum(a[2] for a in agg.values())
-print("kernel %s: %d warp instructions, %d samples" % (want, ti, ts))
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    print("%-14s %4d inst %5.2f%% (%6.0f/scene@4096) smp %4.1f%% | %s" % (k[0][:14], k[1], 100 * a[1] / ti, a[1] / 4096, 100 * a[2] / max(ts, 1), a[0]))
+        h = r; ix = {c: i for i, c in enumerate(h) if c not in ('Source',)}; continue
+    if r[0] != "" and h:
+        try: res.append((cur, int(r[0]), float(r[ix['# Samples']]), float(r[ix['Instructions Executed']]), float(r[ix['Thread Instructions Executed']]) if 'Thread Instructions Executed' in ix else 0.0))
+        except Exception: pass
+base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'decision-making-and-path-planning_b200', 'csrc', 'dp_group.cuh')
+# section markers: function definitions and phase comments
+marks = []
+for i, l in enumerate(open(base), 1):
+    m = re.match(r'^(DG_FN|DG_NOINLINE|template <bool OFFS> DG_FN|template <bool OFFS>)\s*.*?(\w+)\(', l)
+    if m: marks.append((i, m.group(2)))
+    m = re.match(r'^\s*// ---- (P\w+)', l)
+    if m: marks.append((i, m.group(1)))
+marks.sort()
+def sec(line):
+    name = '?'
+    for i, n in marks:
+        if i <= line: name = n
+        else: break
+    return name
+agg = collections.Counter(); smp = collections.Counter(); thr = collections.Counter()
+for f, l, s, i, t in res:
+    k = sec(l) if f == 'dp_group.cuh' else f
+    agg[k] += i; smp[k] += s; thr[k] += t
+ti = sum(agg.values()); ts = sum(smp.values())
+print("total warp inst %.0f samples %.0f" % (ti, ts))
+for k, v in agg.most_common(40):
+    print("%-22s inst %5.1f%% (%9.0f, lanes %4.1f)  samples %5.1f%%" % (k, 100 * v / ti, v, thr[k] / max(v, 1), 100 * smp[k] / ts))
