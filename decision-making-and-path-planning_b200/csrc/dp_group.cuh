@@ -448,6 +448,37 @@ DG_FN double dg_seq_sum(const double* t, int n, int cap, double stop_above, Tail
     return sum;
 }
 
+// first index j < n whose running sum t[0] + ... + t[j] (index order) satisfies (sum - 4 > far), -1 if none: the walk of
+// SearchAimPoint (Planning.cpp:410-432, 505-530).  The first min(n, cap) terms come from shared memory, the rest through
+// tail(j); partial sums are evaluated 8 at a time with one exit test per block (terms >= 0: the test is monotone).
+template <class Tail>
+DG_FN int dg_first_hit(const double* t, int n, int cap, double far, Tail tail) {
+    double sum = 0.0;
+    const int m = dg_imin(n, cap);
+    int j = 0;
+    for (; j + 8 <= m; j += 8) {
+        const double s0 = sum + t[j], s1 = s0 + t[j + 1], s2 = s1 + t[j + 2], s3 = s2 + t[j + 3];
+        const double s4 = s3 + t[j + 4], s5 = s4 + t[j + 5], s6 = s5 + t[j + 6], s7 = s6 + t[j + 7];
+        if ((s7 - 4.0) > far) {
+            int hit = j + 7;
+            if ((s6 - 4.0) > far) hit = j + 6;
+            if ((s5 - 4.0) > far) hit = j + 5;
+            if ((s4 - 4.0) > far) hit = j + 4;
+            if ((s3 - 4.0) > far) hit = j + 3;
+            if ((s2 - 4.0) > far) hit = j + 2;
+            if ((s1 - 4.0) > far) hit = j + 1;
+            if ((s0 - 4.0) > far) hit = j;
+            return hit;
+        }
+        sum = s7;
+    }
+    for (; j < n; ++j) {
+        sum += (j < m) ? t[j] : tail(j);
+        if ((sum - 4.0) > far) return j;
+    }
+    return -1;
+}
+
 DG_FN void dg_put_slot(dp_search_slot* slot, const DgRes& r, int evaluated) {
     slot->dis_lat = r.dis_lat; slot->dis_lng = r.dis_lng; slot->ob_index = (int16_t)r.ob;
     slot->pathid = (uint16_t)r.pathid; slot->evaluated = (uint8_t)evaluated; slot->found = r.found ? 1 : 0;
@@ -474,6 +505,7 @@ struct DgCtl {
     int d_behavior, d_target;
     float faraim;
     int walk_kind, woff, wgl, wfrom, wto, fb_off, fb_idx, fb_n, fb_id;
+    int walk_hit, walk_exact;                      // look-ahead walk answered from the prefix table (-1: no hit); 1: the exact loop decides
     int first, near_id, front_id, afresh, cause, plan_dirty, req;   // req: 0 reuse, 1 Bezier, 2 MeanPoints, 3 zero path
     int mean_n, s0;
     unsigned hb2_bits, hmin2_bits, dl2_bits;       // local path: max / min squared segment length, max squared direction change (FP32 bits)
@@ -1251,6 +1283,39 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
         } else if (pos == 1 || pos == 2) {
             if (k.rp_n0 + k.rp_n1 - 1 > 0) k.walk_kind = 2;
         }
+        k.walk_hit = -1; k.walk_exact = 0;
+        if (k.walk_kind == 1) {
+            // "first point whose accumulated arclength - 4 exceeds faraim" (Planning.cpp:410-432) asked of the prefix table:
+            // cump[from + j + 1] - cump[from] equals the reference's running sum up to the rounding bound lane_cerr (0 for lanes
+            // whose sums are exact).  Terms lie in [hmin, hmax], so the first hit sits in a small index window: binary search
+            // there; if the decision at the hit or before it falls inside the rounding bracket, the reference's own loop decides.
+            const int cnt = k.wto - k.wfrom;
+            int hit = -1;
+            const double far = (double)faraim;
+            const double* cp = m.cump + k.woff + k.wfrom;
+            const double c0 = cp[0], ce = m.lane_cerr[k.wgl], err = ce > 0.0 ? ce + 1e-9 : 0.0;
+            const double tgt = far + 4.0;
+            const float hmx = m.lane_hmax[k.wgl], hmn = m.lane_hmin[k.wgl];
+            int lo = (int)((float)tgt / hmx) - 2, hi = (hmn > 1e-6f) ? (int)((float)tgt / hmn) + 3 : cnt - 1;
+            if (lo < 0) lo = 0;
+            if (hi > cnt - 1) hi = cnt - 1;
+            // invariant: no hit at j < lo (j terms of at most hmax stay below the target); first j in [lo, hi] with a definite hit
+            int first_def = hi + 1;
+            {
+                int a = lo, b = hi;
+                while (a <= b) {
+                    const int mid = (a + b) >> 1;
+                    if ((cp[mid + 1] - c0) - 4.0 > far + err) { first_def = mid; b = mid - 1; } else a = mid + 1;
+                }
+            }
+            bool exact_loop = false;
+            if (first_def <= hi) {
+                hit = k.wfrom + first_def;
+                if (err > 0.0 && first_def > 0 && (cp[first_def] - c0) - 4.0 >= far - err) exact_loop = true;   // the point before it is inside the bracket
+            } else if (hi < cnt - 1) exact_loop = true;     // (cannot happen with valid bounds; never guess)
+            else if (err > 0.0 && cnt > 0 && (cp[cnt] - c0) - 4.0 >= far - err) exact_loop = true;
+            k.walk_hit = hit; k.walk_exact = exact_loop ? 1 : 0;
+        }
     }
     DG_SYNC();
     DG_MARK(8);
@@ -1260,6 +1325,15 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
     dg_mbar_wait(&sm.mbar);
 #endif
     DG_PHASE(tid) {
+        {
+            const int lane = tid & 31;
+            for (int s = tid >> 5; s < S; s += TPB / 32) {  // walks the table could not decide: their terms, coalesced
+                const DgCtl& k = sm.ctl[s];
+                if (k.walk_kind != 1 || !k.walk_exact) continue;
+                const int nt = dg_imin(k.wto - k.wfrom, DG_SCR);
+                for (int j = lane; j < nt; j += 32) sm.scr[s][j] = m.lenp[k.woff + k.wfrom + j];
+            }
+        }
         if (sm.any_junction) {
             for (int it = tid; it < S * DG_SCR; it += TPB) {
                 const int s = it / DG_SCR, j = it - s * DG_SCR;
@@ -1292,41 +1366,10 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
         int aim_id = c.aim_id;
         const double far = (double)k.faraim;
         if (k.walk_kind == 1) {
-            // "first point whose accumulated arclength - 4 exceeds faraim" (Planning.cpp:410-432) asked of the prefix table:
-            // cump[from + j + 1] - cump[from] equals the reference's running sum up to the rounding bound lane_cerr (0 for lanes
-            // whose sums are exact).  Terms lie in [hmin, hmax], so the first hit sits in a small index window: binary search
-            // there; if the decision at the hit or before it falls inside the rounding bracket, the reference's own loop decides.
-            const int cnt = k.wto - k.wfrom;
-            int hit = -1;
-            const double* cp = m.cump + k.woff + k.wfrom;
-            const double c0 = cp[0], ce = m.lane_cerr[k.wgl], err = ce > 0.0 ? ce + 1e-9 : 0.0;
-            const double tgt = far + 4.0;
-            const float hmx = m.lane_hmax[k.wgl], hmn = m.lane_hmin[k.wgl];
-            int lo = (int)((float)tgt / hmx) - 2, hi = (hmn > 1e-6f) ? (int)((float)tgt / hmn) + 3 : cnt - 1;
-            if (lo < 0) lo = 0;
-            if (hi > cnt - 1) hi = cnt - 1;
-            // invariant: no hit at j < lo (j terms of at most hmax stay below the target); first j in [lo, hi] with a definite hit
-            int first_def = hi + 1;
-            {
-                int a = lo, b = hi;
-                while (a <= b) {
-                    const int mid = (a + b) >> 1;
-                    if ((cp[mid + 1] - c0) - 4.0 > far + err) { first_def = mid; b = mid - 1; } else a = mid + 1;
-                }
-            }
-            bool exact_loop = false;
-            if (first_def <= hi) {
-                hit = k.wfrom + first_def;
-                if (err > 0.0 && first_def > 0 && (cp[first_def] - c0) - 4.0 >= far - err) exact_loop = true;   // the point before it is inside the bracket
-            } else if (hi < cnt - 1) exact_loop = true;     // (cannot happen with valid bounds; never guess)
-            else if (err > 0.0 && cnt > 0 && (cp[cnt] - c0) - 4.0 >= far - err) exact_loop = true;
-            if (exact_loop) {
-                hit = -1;
-                double sum = 0.0;
-                for (int j = 0; j < cnt; ++j) {
-                    sum += m.lenp[k.woff + k.wfrom + j];
-                    if ((sum - 4.0) > far) { hit = k.wfrom + j; break; }
-                }
+            int hit = k.walk_hit;
+            if (k.walk_exact) {                             // inside the rounding bracket: the reference's loop on the staged terms
+                const int j = dg_first_hit(sm.scr[s], k.wto - k.wfrom, DG_SCR, far, [&](int q) { return m.lenp[k.woff + k.wfrom + q]; });
+                hit = j >= 0 ? k.wfrom + j : -1;
             }
             if (hit >= 0) {
                 aim_x = m.x[k.woff + hit]; aim_y = m.y[k.woff + hit]; aim_dir = m.dir[k.woff + hit]; aim_id = hit;
@@ -1338,35 +1381,10 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
         } else if (k.walk_kind == 2) {
             const DgView rv = dg_view(m, sm.path[s][0], nullptr);
             const int n = k.rp_n0 + k.rp_n1;
-            double sum = 0.0;
-            int hit = -1;
-            {
-                const int nt = n - 1, ms = dg_imin(nt, DG_SCR);
-                const double* t = sm.scr[s];
-                int j = 0;
-                for (; j + 8 <= ms && hit < 0; j += 8) {    // partial sums in index order, one exit test per block of 8
-                    const double s0 = sum + t[j], s1 = s0 + t[j + 1], s2 = s1 + t[j + 2], s3 = s2 + t[j + 3];
-                    const double s4 = s3 + t[j + 4], s5 = s4 + t[j + 5], s6 = s5 + t[j + 6], s7 = s6 + t[j + 7];
-                    if ((s7 - 4.0) > far) {
-                        hit = j + 7;
-                        if ((s6 - 4.0) > far) hit = j + 6;
-                        if ((s5 - 4.0) > far) hit = j + 5;
-                        if ((s4 - 4.0) > far) hit = j + 4;
-                        if ((s3 - 4.0) > far) hit = j + 3;
-                        if ((s2 - 4.0) > far) hit = j + 2;
-                        if ((s1 - 4.0) > far) hit = j + 1;
-                        if ((s0 - 4.0) > far) hit = j;
-                    }
-                    sum = s7;
-                }
-                for (; j < nt && hit < 0; ++j) {
-                    double tt;
-                    if (j < DG_SCR) tt = t[j];
-                    else { const double2 a = dg_pt(rv, j), b = dg_pt(rv, j + 1); tt = dg_dist_plain(a.x, a.y, b.x, b.y); }
-                    sum += tt;
-                    if ((sum - 4.0) > far) hit = j;
-                }
-            }
+            const int hit = dg_first_hit(sm.scr[s], n - 1, DG_SCR, far, [&](int q) {
+                const double2 a = dg_pt(rv, q), b = dg_pt(rv, q + 1);
+                return dg_dist_plain(a.x, a.y, b.x, b.y);
+            });
             if (hit >= 0) {
                 const double2 a = dg_pt(rv, hit);
                 aim_x = a.x; aim_y = a.y;
