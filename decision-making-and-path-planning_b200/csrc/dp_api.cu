@@ -37,10 +37,10 @@ struct dp_ctx {
     dp_params p;
     int max_scenes = 0, max_obs = 0;
     bool have_map = false;
-    DevMap map;
-    DgMap gmap;                                             // the same tables + pruning bounds, as the group kernel takes them
+    DgMap gmap;                                             // map tables + pruning bounds + prefix / run-end tables (both kernels)
+    DpLaunchCfg lc;                                         // per-context launch state (dp_kernels.h)
     long long* d_timeline = nullptr;                        // DP_TIMELINE=1: phase stamps of the last group launch (dp_debug_timeline)
-    int kernel = 1;                                         // 1: group kernel (dp_group.cuh), 0: round-1 warp-per-scene kernel (DP_KERNEL=warp)
+    int kernel = 0;                                         // 0: warp-per-scene kernel (dp_cycle.cu), 1: group kernel (dp_group.cuh); see dp_create
     std::vector<void*> map_allocs;
     dp_carry* d_carry = nullptr;
     double2* d_last = nullptr;
@@ -102,11 +102,11 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
         if (g.timeline) cudaMemsetAsync(c->d_timeline, 0, (size_t)8192 * 32 * 8, st);
         c->launches += 1;
         return dp_launch_group(c->gmap, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec,
-                               trace, path_xy, path_ll, st, g);
+                               trace, path_xy, path_ll, st, g, c->lc);
     }
     c->launches += c->split ? 2 : 1;
-    return dp_launch_cycle(c->map, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace,
-                           path_xy, path_ll, st, c->split, io);
+    return dp_launch_cycle(c->gmap, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace,
+                           path_xy, path_ll, st, c->split, io, c->lc);
 }
 }  // namespace
 
@@ -151,6 +151,40 @@ std::vector<double2> interleave(const double* x, const double* y, size_t n) {
     return v;
 }
 #define PUT(var, T, src, n) T* var = tmp.put<T>(src, n, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "operator staging", e)
+
+// Dense sweep: candidates that share an offset share their geometry (dp_ops.cu).  rows = distinct offsets (bit patterns),
+// groups = distinct point counts of a row, ascending; cand_group[c] = group of candidate c (-1: fewer than 2 points).
+struct SweepGroups {
+    std::vector<double> row_off;
+    std::vector<int32_t> row_gbeg, group_P, cand_group;
+};
+SweepGroups build_sweep_groups(const double* offset, const int32_t* n_pts, int n_cand, int n_base) {
+    SweepGroups g;
+    std::vector<std::pair<uint64_t, int32_t>> keyed((size_t)n_cand);   // (offset bits, P)
+    for (int c = 0; c < n_cand; ++c) {
+        uint64_t b; memcpy(&b, &offset[c], 8);
+        keyed[c] = {b, n_pts[c] < n_base ? n_pts[c] : n_base};
+    }
+    std::vector<int32_t> order((size_t)n_cand);
+    for (int c = 0; c < n_cand; ++c) order[c] = c;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return keyed[a] < keyed[b]; });
+    g.cand_group.assign((size_t)n_cand, -1);
+    g.row_gbeg.push_back(0);
+    bool have_row = false; uint64_t cur_bits = 0; int32_t cur_P = -1;
+    for (int32_t c : order) {
+        const uint64_t b = keyed[c].first; const int32_t P = keyed[c].second;
+        if (P < 2) continue;
+        if (!have_row || b != cur_bits) {
+            if (have_row) g.row_gbeg.push_back((int32_t)g.group_P.size());
+            double off; memcpy(&off, &b, 8);
+            g.row_off.push_back(off); have_row = true; cur_bits = b; cur_P = -1;
+        }
+        if (P != cur_P) { g.group_P.push_back(P); cur_P = P; }
+        g.cand_group[c] = (int32_t)g.group_P.size() - 1;
+    }
+    if (have_row) g.row_gbeg.push_back((int32_t)g.group_P.size());
+    return g;
+}
 }  // namespace
 
 extern "C" {
@@ -184,7 +218,15 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     c->split = 2;
     if (const char* e = getenv("DP_SPLIT")) c->split = atoi(e);   // 0: one fused launch, 1: two launches back to back, 2: overlapped
     if (const char* e = getenv("DP_ZERO_COPY")) c->zero_copy = atoi(e) != 0;
-    if (const char* e = getenv("DP_KERNEL")) c->kernel = (strcmp(e, "warp") == 0) ? 0 : 1;
+    // Kernel choice, from the measurements in profiles/README.md (round 2): the warp-per-scene kernel wins while a scene's
+    // obstacles fit one warp pass (N < 32: 71 vs 96 us per 4096-scene cycle at N = 10); the group kernel, whose scans are flat
+    // (trajectory, obstacle) lists with exact pruning, wins for crowded scenes (N = 200: 135 vs 212 us per 1024 junction scenes).
+    c->kernel = (max_obs >= 32) ? 1 : 0;
+    if (const char* e = getenv("DP_KERNEL")) c->kernel = (strcmp(e, "warp") == 0) ? 0 : (strcmp(e, "group") == 0) ? 1 : c->kernel;
+    CK(cudaDeviceGetAttribute(&c->lc.sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (const char* e = getenv("DP_WPB")) c->lc.force_wpb = atoi(e);
+    if (const char* e = getenv("DP_GROUP_CFG")) c->lc.group_cfg = atoi(e);
+    if (const char* e = getenv("DP_GROUP_G")) c->lc.group_g = atoi(e);
     if (const char* e = getenv("DP_TIMELINE")) {
         if (atoi(e)) { int rt = dev_alloc(&c->d_timeline, (size_t)8192 * 32); if (rt) { delete c; return rt; } cudaMemset(c->d_timeline, 0, (size_t)8192 * 32 * 8); }
     }
@@ -259,7 +301,7 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
             return fail(DP_ERR_ARG, "dp_map_upload: lane too wide for DP_MAX_SWEEP avoid candidates per side");
     for (int i = 0; i < m->n_lanes; ++i)
         if (m->lane_pt_off[i + 1] - m->lane_pt_off[i] > 65535) return fail(DP_ERR_ARG, "dp_map_upload: lane longer than 65535 points");
-    DevMap d;
+    DgMap d;
     int r;
     double* d_lenf = nullptr; float* d_hmax = nullptr; float* d_dnmax = nullptr; float* d_hmin = nullptr;
     double* d_cump = nullptr; double* d_cerr = nullptr; int32_t* d_re0 = nullptr; int32_t* d_re1 = nullptr;
@@ -287,12 +329,9 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
                           d_dnmax, d_cump, d_cerr, d_re0, d_re1, c->st[0]));
     c->launches += 2;
     CK(cudaStreamSynchronize(c->st[0]));
-    c->map = d;
-    DgMap& g = c->gmap;
-    g.xy = d.xy; g.nrm = d.nrm; g.x = d.x; g.y = d.y; g.dir = d.dir; g.lenp = d.lenp; g.lenf = d_lenf; g.width = d.width; g.attr = d.attr;
-    g.road_lane_base = d.road_lane_base; g.lane_pt_off = d.lane_pt_off; g.conn = d.conn; g.lane_hmax = d_hmax; g.lane_dnmax = d_dnmax; g.lane_hmin = d_hmin;
-    g.cump = d_cump; g.lane_cerr = d_cerr; g.run_end0 = d_re0; g.run_end1 = d_re1;
-    g.n_roads = d.n_roads; g.n_lanes = d.n_lanes; g.n_conn = d.n_conn;
+    d.lenf = d_lenf; d.lane_hmax = d_hmax; d.lane_dnmax = d_dnmax; d.lane_hmin = d_hmin;
+    d.cump = d_cump; d.lane_cerr = d_cerr; d.run_end0 = d_re0; d.run_end1 = d_re1;
+    c->gmap = d;
     c->have_map = true;
     return DP_OK;
 }
@@ -401,8 +440,8 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         cudaStream_t st = c->st[0];
         DpIo io = make_io(c, first, (dp_plan_record*)dv_rec);
         io.hdr_stage = c->d_hdr[0]; io.ox_stage = c->d_ox[0]; io.oy_stage = c->d_oy[0];
-        CK(dp_launch_cycle(c->map, c->p, n, (const dp_scene_hdr*)dv_hdr, (const double*)dv_ox, (const double*)dv_oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
-                           c->d_rec[0], nullptr, nullptr, nullptr, st, c->split, io));
+        CK(dp_launch_cycle(c->gmap, c->p, n, (const dp_scene_hdr*)dv_hdr, (const double*)dv_ox, (const double*)dv_oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
+                           c->d_rec[0], nullptr, nullptr, nullptr, st, c->split, io, c->lc));
         c->launches += 2;
         CK(cudaStreamSynchronize(st));
         return DP_OK;
@@ -495,8 +534,8 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
         io.pdone = c->d_pdone + first; io.prev_epoch = prev;
         io.tally = c->d_tally + s; io.tally_n = (unsigned)n; io.host_done = (unsigned*)dv_done + s;
         c->wait_epoch[s] = n > 0 ? io.epoch : 0u;
-        CK(dp_launch_cycle(c->map, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
-                           c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, io));
+        CK(dp_launch_cycle(c->gmap, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
+                           c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, io, c->lc));
         c->chain_prev_epoch = io.epoch; c->chain_first = first; c->chain_n = n;
     } else {
         CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
@@ -506,8 +545,8 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
             CK(cudaEventRecord(c->in_ready[s][k], c->cp[k]));
             CK(cudaStreamWaitEvent(st, c->in_ready[s][k], 0));
         }
-        CK(dp_launch_cycle(c->map, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
-                           c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, make_io(c, first, (dp_plan_record*)dv_rec)));
+        CK(dp_launch_cycle(c->gmap, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
+                           c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, make_io(c, first, (dp_plan_record*)dv_rec), c->lc));
         CK(cudaEventRecord(c->done[s], st));
         c->wait_epoch[s] = 0;
     }
@@ -667,19 +706,22 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
         return fail(DP_ERR_ARG, "dp_score_candidates: bad argument (n_base in [2,256], n_obs <= 192)");
     CK(cudaSetDevice(c->device));
     Tmp tmp; cudaError_t e;
+    const SweepGroups sg = build_sweep_groups(offset, n_pts, n_cand, n_base);
+    const int n_rows = (int)sg.row_off.size();
     PUT(d_bx, double, base_x, (size_t)n_base); PUT(d_by, double, base_y, (size_t)n_base);
-    PUT(d_off, double, offset, (size_t)n_cand); PUT(d_np, int32_t, n_pts, (size_t)n_cand);
+    PUT(d_roff, double, sg.row_off.data(), sg.row_off.size()); PUT(d_gbeg, int32_t, sg.row_gbeg.data(), sg.row_gbeg.size());
+    PUT(d_gP, int32_t, sg.group_P.data(), sg.group_P.size()); PUT(d_cg, int32_t, sg.cand_group.data(), (size_t)n_cand);
+    PUT(d_gdis, double, (const double*)nullptr, sg.group_P.size());
     PUT(d_ox, double, ox, (size_t)n_obs); PUT(d_oy, double, oy, (size_t)n_obs);
     double* d_vx = nullptr; double* d_vy = nullptr;
     if (dvx && dvy) { d_vx = tmp.put<double>(dvx, (size_t)n_obs, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "staging", e);
                       d_vy = tmp.put<double>(dvy, (size_t)n_obs, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "staging", e); }
     PUT(d_dis, double, (const double*)nullptr, (size_t)n_cand);
     PUT(d_key, unsigned long long, (const unsigned long long*)nullptr, 1);
-    PUT(d_next, unsigned, (const unsigned*)nullptr, 1);
     CK(cudaMemsetAsync(d_key, 0xff, 8, c->st[0]));
-    CK(cudaMemsetAsync(d_next, 0, 4, c->st[0]));
-    CK(dp_launch_sweep(d_bx, d_by, n_base, d_off, d_np, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs, lat_min, lat_max, clear_dis, d_dis, d_key, nullptr, d_next,
-                       c->st[0]));
+    CK(dp_launch_sweep(d_bx, d_by, n_base, n_rows, d_roff, d_gbeg, d_gP, d_cg, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs, lat_min, lat_max, clear_dis,
+                       d_gdis, d_dis, d_key, c->st[0]));
+    ++c->launches;
     ++c->launches;
     unsigned long long key = ~0ull;
     CK(cudaMemcpyAsync(&key, d_key, 8, cudaMemcpyDeviceToHost, c->st[0]));
@@ -699,10 +741,9 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
 struct dp_sweep {
     dp_ctx* c = nullptr;
     int n_base = 0, n_cand = 0, max_obs = 0;
-    double *d_bx = nullptr, *d_by = nullptr, *d_off = nullptr, *d_obs = nullptr, *d_dis = nullptr;   // d_obs: [4][max_obs]
-    int32_t* d_np = nullptr;
-    int32_t* d_order = nullptr;                             // candidates sorted longest first (processing order of the kernel)
-    unsigned* d_next = nullptr;                             // the kernel's work counter
+    double *d_bx = nullptr, *d_by = nullptr, *d_roff = nullptr, *d_obs = nullptr, *d_dis = nullptr, *d_gdis = nullptr;   // d_obs: [4][max_obs]
+    int32_t *d_gbeg = nullptr, *d_gP = nullptr, *d_cg = nullptr;   // rows / horizon groups of the candidate set (build_sweep_groups)
+    int n_rows = 0, n_groups = 0;
     unsigned long long* d_key = nullptr;
     double* h_obs = nullptr;                                // pinned [4][max_obs]
     unsigned long long* h_key = nullptr;                    // pinned
@@ -721,20 +762,19 @@ int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const doubl
     dp_sweep* s = new dp_sweep();
     s->c = c; s->n_base = n_base; s->n_cand = n_cand; s->max_obs = max_obs;
     CK(cudaMalloc((void**)&s->d_bx, n_base * 8)); CK(cudaMalloc((void**)&s->d_by, n_base * 8));
-    CK(cudaMalloc((void**)&s->d_off, (size_t)n_cand * 8)); CK(cudaMalloc((void**)&s->d_np, (size_t)n_cand * 4));
+    const SweepGroups sg = build_sweep_groups(offset, n_pts, n_cand, n_base);
+    s->n_rows = (int)sg.row_off.size(); s->n_groups = (int)sg.group_P.size();
+    CK(cudaMalloc((void**)&s->d_roff, (sg.row_off.size() + 1) * 8)); CK(cudaMalloc((void**)&s->d_gbeg, sg.row_gbeg.size() * 4));
+    CK(cudaMalloc((void**)&s->d_gP, (sg.group_P.size() + 1) * 4)); CK(cudaMalloc((void**)&s->d_cg, (size_t)n_cand * 4));
+    CK(cudaMalloc((void**)&s->d_gdis, (sg.group_P.size() + 1) * 8));
     CK(cudaMalloc((void**)&s->d_obs, (size_t)4 * max_obs * 8)); CK(cudaMalloc((void**)&s->d_dis, (size_t)n_cand * 8));
     CK(cudaMalloc((void**)&s->d_key, 8));
     CK(cudaMallocHost((void**)&s->h_obs, (size_t)4 * max_obs * 8)); CK(cudaMallocHost((void**)&s->h_key, 8));
     CK(cudaMemcpy(s->d_bx, base_x, n_base * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->d_by, base_y, n_base * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s->d_off, offset, (size_t)n_cand * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s->d_np, n_pts, (size_t)n_cand * 4, cudaMemcpyHostToDevice));
-    {   // longest candidates first: the warps pull work from a counter, so the tail is one short candidate, not a long one
-        std::vector<int32_t> order((size_t)n_cand);
-        for (int i = 0; i < n_cand; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return n_pts[a] > n_pts[b]; });
-        CK(cudaMalloc((void**)&s->d_order, (size_t)n_cand * 4)); CK(cudaMalloc((void**)&s->d_next, 4));
-        CK(cudaMemcpy(s->d_order, order.data(), (size_t)n_cand * 4, cudaMemcpyHostToDevice));
-    }
+    if (s->n_rows) CK(cudaMemcpy(s->d_roff, sg.row_off.data(), sg.row_off.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_gbeg, sg.row_gbeg.data(), sg.row_gbeg.size() * 4, cudaMemcpyHostToDevice));
+    if (s->n_groups) CK(cudaMemcpy(s->d_gP, sg.group_P.data(), sg.group_P.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->d_cg, sg.cand_group.data(), (size_t)n_cand * 4, cudaMemcpyHostToDevice));
     CK(cudaEventCreate(&s->e0)); CK(cudaEventCreate(&s->e1));
     *out = s;
     return DP_OK;
@@ -758,9 +798,8 @@ int dp_sweep_score(dp_sweep* s, const double* ox, const double* oy, const double
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         cudaMemcpyAsync(s->d_obs, s->h_obs, (size_t)4 * mo * 8, cudaMemcpyHostToDevice, st);
         cudaMemsetAsync(s->d_key, 0xff, 8, st);
-        cudaMemsetAsync(s->d_next, 0, 4, st);
-        dp_launch_sweep(s->d_bx, s->d_by, s->n_base, s->d_off, s->d_np, s->n_cand, s->d_obs, s->d_obs + mo, s->d_obs + 2 * mo, s->d_obs + 3 * mo,
-                        n_obs, lat_min, lat_max, clear_dis, s->d_dis, s->d_key, s->d_order, s->d_next, st);
+        dp_launch_sweep(s->d_bx, s->d_by, s->n_base, s->n_rows, s->d_roff, s->d_gbeg, s->d_gP, s->d_cg, s->n_cand, s->d_obs, s->d_obs + mo,
+                        s->d_obs + 2 * mo, s->d_obs + 3 * mo, n_obs, lat_min, lat_max, clear_dis, s->d_gdis, s->d_dis, s->d_key, st);
         cudaMemcpyAsync(s->h_key, s->d_key, 8, cudaMemcpyDeviceToHost, st);
         CK(cudaStreamEndCapture(st, &g));
         CK(cudaGraphInstantiate(&s->exec, g, 0));
@@ -769,7 +808,7 @@ int dp_sweep_score(dp_sweep* s, const double* ox, const double* oy, const double
     }
     if (device_ms) CK(cudaEventRecord(s->e0, st));
     CK(cudaGraphLaunch(s->exec, st));
-    c->launches += 1;
+    c->launches += 2;
     if (device_ms) CK(cudaEventRecord(s->e1, st));
     CK(cudaStreamSynchronize(st));
     if (device_ms) CK(cudaEventElapsedTime(device_ms, s->e0, s->e1));
@@ -788,8 +827,8 @@ int dp_sweep_destroy(dp_sweep* s) {
     cudaSetDevice(s->c->device);
     cudaStreamSynchronize(s->c->st[0]);
     if (s->exec) cudaGraphExecDestroy(s->exec);
-    cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_off); cudaFree(s->d_np); cudaFree(s->d_obs); cudaFree(s->d_dis); cudaFree(s->d_key);
-    cudaFree(s->d_order); cudaFree(s->d_next);
+    cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_roff); cudaFree(s->d_gbeg); cudaFree(s->d_gP); cudaFree(s->d_cg); cudaFree(s->d_gdis);
+    cudaFree(s->d_obs); cudaFree(s->d_dis); cudaFree(s->d_key);
     cudaFreeHost(s->h_obs); cudaFreeHost(s->h_key);
     if (s->e0) cudaEventDestroy(s->e0);
     if (s->e1) cudaEventDestroy(s->e1);

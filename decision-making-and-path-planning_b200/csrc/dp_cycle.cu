@@ -56,6 +56,14 @@ __device__ __forceinline__ Src slice_src(const DevMap& m, int base, int stride, 
 static __device__ __noinline__ bool run_exceeds(const DevMap& m, WarpSmem& sm, int gl, int id, int mode, double thr, int lane) {
     if (mode == 2) return 0.0 > thr;
     const int off = m.lane_pt_off[gl], n = m.lane_pt_off[gl + 1] - off;
+    if (id >= n - 1) return 0.0 > thr;
+    {   // the run ends at run_end[id]; its length is cump[end] - cump[id] up to the rounding bound lane_cerr: outside that
+        // bracket the answer needs no walk (dp_group.cuh, dg_run_exceeds)
+        const int e = (mode == 0 ? m.run_end0 : m.run_end1)[off + id];
+        const double approx = m.cump[off + e] - m.cump[off + id], err = m.lane_cerr[gl];
+        if (approx > thr + err) return true;
+        if (approx < thr - err) return false;
+    }
     double sum = 0.0;
     for (int i0 = id; i0 < n - 1; i0 += DP_SCR) {
         const int cnt = min(DP_SCR, n - 1 - i0);
@@ -134,8 +142,9 @@ __device__ __forceinline__ void junction_recipe(const DevMap& m, const dp_scene_
 
 // out-of-line copy for the rare trajectories (junction reference path, sweep with more than 16 obstacles)
 static __device__ __noinline__ SearchRes dp_search_cold(const Src s, double mx, double my, const double* ox, const double* oy, int N,
-                                                        const LaneMap lm, double lo, double hi, WarpSmem& sm, int lane) {
-    return dp_search(s, mx, my, ox, oy, N, lm, lo, hi, sm, lane);
+                                                        const LaneMap lm, double lo, double hi, WarpSmem& sm, int lane, float hb = 0.f,
+                                                        float dmax = 0.f) {
+    return dp_search(s, mx, my, ox, oy, N, lm, lo, hi, sm, lane, hb, dmax);
 }
 
 // ---- per-scene hand-off between the two overlapped launches ----------------------------------------------------------
@@ -165,6 +174,20 @@ template <class T> __device__ __forceinline__ T dp_l2(const T* p) { return __ldc
 
 }  // namespace
 
+// Which scans of the warp kernel use the exact pruning of dp_group.cuh (measured on the B200, profiles/README.md round 2):
+// in the avoid sweep a lane owns a whole 120-point scan of its (candidate, obstacle) pair and pruning pays (78 -> 70 us per
+// 4096-scene cycle); in the lane-region and local-path searches the lanes already split a path in chunks of ~40 points, the
+// sampling pass costs as much as it saves and the extra code hurts (70 -> 83 us): off.  Large batches run the one-warp CTAs,
+// whose instruction footprint matters more than the scan length: no pruning there either.
+#ifndef DP_PRUNE_REGION
+#define DP_PRUNE_REGION 0
+#endif
+#ifndef DP_PRUNE_LOCAL
+#define DP_PRUNE_LOCAL 0
+#endif
+#ifndef DP_PRUNE_SWEEP
+#define DP_PRUNE_SWEEP (WPB == 4)
+#endif
 #define DP_CARVEOUT 77
 // CTA size of the cycle kernel.  WPB = 4 (7 CTAs = 28 warps per SM) keeps a 4096-scene batch a single wave.  WPB = 1 (25 CTAs
 // per SM; the per-CTA shared-memory reservation costs three slots) recycles a warp's slot the moment ITS scene is done
@@ -312,20 +335,20 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         Slice F, R, NF, NR;
         NF.base = NR.base = 0; NF.stride = 1; NR.stride = -1; NF.P = NR.P = 0; NF.d = NR.d = 0.0;
         lane_slices(m, gl, id, p.id_more, F, R, ub);
-        int side = 0;
+        int side = 0, gn = gl;                              // gn: the lane the neighbour pair is read from
         if (lanechg == 1 || lanechg == 3) {
             side = 1;
             if (lane_n > 1) {
                 const int idl = (int)(uint16_t)h.id[lane_n - 2];
                 const int nl = m.lane_pt_off[gl] - m.lane_pt_off[gl - 1];
-                if (idl > 0 && idl < nl) lane_slices(m, gl - 1, idl, p.id_more, NF, NR, ub);
+                if (idl > 0 && idl < nl) { lane_slices(m, gl - 1, idl, p.id_more, NF, NR, ub); gn = gl - 1; }
             } else { NF = F; NF.d = -1 * W; NR = R; NR.d = -1 * W; }
         } else if (lanechg == 2) {
             side = 2;
             if (lane_n < lane_sum) {
                 const int idr = (int)(uint16_t)h.id[lane_n];
                 const int nr = m.lane_pt_off[gl + 2] - m.lane_pt_off[gl + 1];
-                if (idr > 0 && idr < nr) lane_slices(m, gl + 1, idr, p.id_more, NF, NR, ub);
+                if (idr > 0 && idr < nr) { lane_slices(m, gl + 1, idr, p.id_more, NF, NR, ub); gn = gl + 1; }
             } else { NF = F; NF.d = W; NR = R; NR.d = W; }
         }
         // ---- AroundObstacle (Decision.cpp:759-881): the four trajectories in ONE fused pass ----
@@ -337,6 +360,11 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             const double rd[4] = {0.0, 0.0, NF.d, NR.d};
             dp_region_stage(m, sm, rb, rs, rP, rd, lane);
             const double nlo = (side == 2) ? -0.5 * W : -0.5 * Vw, nhi = (side == 2) ? 0.5 * Vw : 0.5 * W;
+            // pruning bounds of the scans (dp_group.cuh): F / R from the ego lane, the neighbour pair from its lane (or the
+            // ego lane shifted by +-W when the neighbour is virtual)
+            float hbF, dmF, hbN, dmN;
+            dg_bounds(m, gl, 0.0, -0.5 * Vw, 0.5 * Vw, &hbF, &dmF);
+            dg_bounds(m, gn, NF.d, nlo, nhi, &hbN, &dmN);
             int qoff = 0;
 #pragma unroll 1
             for (int r = 0; r < 4; ++r) {                   // one copy of the search code, four staged trajectories
@@ -344,7 +372,8 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                 if (Pr != 0) {
                     Src sp = dp_src_run(m.xy, 1, Pr);
                     sp.q_off = qoff;
-                    const SearchRes sr = dp_search(sp, mx, my, ox, oy, N, lm, r < 2 ? -0.5 * Vw : nlo, r < 2 ? 0.5 * Vw : nhi, sm, lane);
+                    const SearchRes sr = dp_search(sp, mx, my, ox, oy, N, lm, r < 2 ? -0.5 * Vw : nlo, r < 2 ? 0.5 * Vw : nhi, sm, lane,
+                                                   DP_PRUNE_REGION ? (r < 2 ? hbF : hbN) : 0.f, r < 2 ? dmF : dmN);
                     ++n_traj; pts += Pr;
                     put_slot(tr ? &tr->region[r < 2 ? r : nslot + r - 2] : nullptr, sr, 1, lane);
                     if (r == 0) gF = sr.dis_lng; else if (r == 2) gNF = sr.dis_lng; else if (r == 3) gNR = sr.dis_lng;
@@ -391,6 +420,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                     DBG_MARK(0, 5);
                     if (shifted > 0 && N > 0 && N <= 16) {
                         dp_sweep_stage(m, sm, F.base, F.P, lane);
+                        const float hmaxF = m.lane_hmax[gl], hminF = m.lane_hmin[gl], dnF = m.lane_dnmax[gl];
                         const int per = min(8, 32 / N);
                         for (int u0 = 0; u0 < shifted && (sweep_pick < 0 || tr); u0 += per) {
                             const int cnt = min(per, shifted - u0);
@@ -400,14 +430,16 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                                 [&](int g, const SearchRes& r, bool before_first) {
                                     if (before_first && r.dis_lng > 25) first_g = g;
                                     if (tr) put_slot(&tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)], r, (none_yet && before_first) ? 1 : 2, lane);
-                                });
+                                }, DP_PRUNE_SWEEP ? hmaxF : -1.f, hminF, dnF);
                             if (sweep_pick < 0 && first >= 0) sweep_pick = first_g;
                         }
                     } else {
                         for (int u = 0; u < shifted && (sweep_pick < 0 || tr); ++u) {   // one candidate at a time (N > 16)
                             const int g = dp_sweep_g(u, K);
                             const double cd = dp_sweep_offset(g, K);
-                            const SearchRes s = dp_search_cold(slice_src(m, F.base, 1, F.P, cd), mx, my, ox, oy, N, lm, -0.5 * Vw, 0.5 * Vw, sm, lane);
+                            float hbC, dmC;
+                            dg_bounds(m, gl, cd, -0.5 * Vw, 0.5 * Vw, &hbC, &dmC);
+                            const SearchRes s = dp_search_cold(slice_src(m, F.base, 1, F.P, cd), mx, my, ox, oy, N, lm, -0.5 * Vw, 0.5 * Vw, sm, lane, hbC, dmC);
                             const bool before = sweep_pick < 0;
                             put_slot(tr ? &tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)] : nullptr, s, before ? 1 : 2, lane);
                             if (before && s.dis_lng > 25) sweep_pick = g;
@@ -657,9 +689,38 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             bool walk = true;
             if (wfrom < 0) { ++ub; walk = false; }
             if (wto > wn - 1) { ++ub; wto = wn - 1; if (wfrom >= wto) walk = false; }
+            // "first point whose accumulated arclength - 4 exceeds faraim" asked of the prefix table (dp_group.cuh, P6): binary
+            // search inside the index window the segment-length bounds allow; the exact loop below only runs when the decision at
+            // the hit (or at the last point) falls inside the rounding bracket of the table
+            bool table_done = false;
+            if (walk) {
+                const int cnt = wto - wfrom;
+                const double far = (double)faraim;
+                const double* cp = m.cump + woff + wfrom;
+                const double c0 = cp[0], ce = m.lane_cerr[wl], err = ce > 0.0 ? ce + 1e-9 : 0.0;
+                const double tgt = far + 4.0;
+                const float hmx = m.lane_hmax[wl], hmn = m.lane_hmin[wl];
+                int lo = (int)((float)tgt / hmx) - 2, hi = (hmn > 1e-6f) ? (int)((float)tgt / hmn) + 3 : cnt - 1;
+                if (lo < 0) lo = 0;
+                if (hi > cnt - 1) hi = cnt - 1;
+                int first_def = hi + 1;
+                {
+                    int a = lo, b = hi;
+                    while (a <= b) {
+                        const int mid = (a + b) >> 1;
+                        if ((cp[mid + 1] - c0) - 4.0 > far + err) { first_def = mid; b = mid - 1; } else a = mid + 1;
+                    }
+                }
+                bool exact_loop = false;
+                if (first_def <= hi) {
+                    if (err > 0.0 && first_def > 0 && (cp[first_def] - c0) - 4.0 >= far - err) exact_loop = true;
+                } else if (hi < cnt - 1) exact_loop = true;
+                else if (err > 0.0 && cnt > 0 && (cp[cnt] - c0) - 4.0 >= far - err) exact_loop = true;
+                if (!exact_loop) { table_done = true; hit = (first_def <= hi) ? wfrom + first_def : -1; }
+            }
             if (walk) {
                 double sum = 0.0;
-                for (int i0 = wfrom; i0 < wto && hit < 0; i0 += DP_SCR) {
+                for (int i0 = wfrom; i0 < wto && hit < 0 && !table_done; i0 += DP_SCR) {
                     const int cnt = min(DP_SCR, wto - i0);
                     __syncwarp();
                     for (int j = lane; j < cnt; j += 32) sm.scr[j] = m.lenp[woff + i0 + j];
@@ -805,7 +866,31 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     const int s0 = max(near_id, 0);
     Src rem = dp_src_run(sm.plan + s0, 1, DP_PATH_POINTS - s0);
     rem.q_off = s0;
-    const SearchRes ls = dp_search(rem, mx, my, ox, oy, N, lm, (double)(float)(-1.1), (double)(float)(1.1), sm, lane);
+    // pruning bounds of the local path (FP32, rounded outwards): longest / shortest segment, largest difference of consecutive
+    // segment vectors (|u/|u| - w/|w|| <= |u - w| / hmin bounds the change of direction)
+    float hbL, dmL;
+    {
+        float hmx = 0.f, hmn = __int_as_float(0x7f800000), dmx = 0.f;
+        for (int j = s0 + lane; j < DP_PATH_POINTS - 1; j += 32) {
+            const double2 a = sm.plan[j], b = sm.plan[j + 1];
+            const float ux = (float)(b.x - a.x), uy = (float)(b.y - a.y);
+            const float l2 = ux * ux + uy * uy;
+            hmx = fmaxf(hmx, l2); hmn = fminf(hmn, l2);
+            if (j + 2 < DP_PATH_POINTS) {
+                const double2 c = sm.plan[j + 2];
+                const float ex = (float)(c.x - b.x) - ux, ey = (float)(c.y - b.y) - uy;
+                dmx = fmaxf(dmx, ex * ex + ey * ey);
+            }
+        }
+        hmx = __uint_as_float(__reduce_max_sync(DP_FULL, __float_as_uint(hmx)));   // (non-negative floats order like their bit patterns)
+        hmn = __uint_as_float(__reduce_min_sync(DP_FULL, __float_as_uint(hmn)));
+        dmx = __uint_as_float(__reduce_max_sync(DP_FULL, __float_as_uint(dmx)));
+        hbL = sqrtf(hmx) * 1.0001f + 1e-4f;
+        const float hmin = sqrtf(hmn) * 0.9999f - 1e-6f;
+        const float delta = (hmin > 1e-6f) ? sqrtf(dmx) / hmin * 1.001f + 1e-4f : 2.0f;
+        dmL = dg_dmax((double)(float)(-1.1), (double)(float)(1.1), hbL, delta, hmin);
+    }
+    const SearchRes ls = dp_search(rem, mx, my, ox, oy, N, lm, (double)(float)(-1.1), (double)(float)(1.1), sm, lane, DP_PRUNE_LOCAL ? hbL : 0.f, dmL);
     ++n_traj; pts += DP_PATH_POINTS - s0;
     put_slot(tr ? &tr->local : nullptr, ls, 1, lane);
     // ---- SpeedPlanning (Planning.cpp:888-990) ----
@@ -959,31 +1044,24 @@ dp_group_kernel(DgMap m, dp_params p, int n_scenes, int g, const dp_scene_hdr* _
 // ---- launchers (called from dp_api.cu) ----
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                            double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io) {
+                            double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io, DpLaunchCfg& lc) {
     if (n <= 0) return cudaSuccess;
-    static bool configured_dev[64] = {};                    // (function attributes are per device)
-    static int sm_count_dev[64] = {};
-    int dev_id = 0;
-    cudaGetDevice(&dev_id);
-    bool& configured = configured_dev[dev_id & 63];
-    int& sm_count = sm_count_dev[dev_id & 63];
-    if (!configured) {                                      // 196 of 256 KB as shared memory, the rest stays L1
+    if (!lc.attr_warp) {                                    // 196 of 256 KB as shared memory, the rest stays L1 (per context: no process-wide state)
         cudaFuncSetAttribute(dp_cycle_kernel<0, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
         cudaFuncSetAttribute(dp_cycle_kernel<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
         cudaFuncSetAttribute(dp_cycle_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
         cudaFuncSetAttribute(dp_cycle_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
         cudaFuncSetAttribute(dp_cycle_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id);
-        configured = true;
+        lc.attr_warp = true;
     }
+    const int sm_count = lc.sm_count;
     if (!split) {
         DpIo io0 = io; io0.done = nullptr; io0.in_flag = nullptr; io0.pdone = nullptr; io0.prev_epoch = 0;
         const int blocks = (n + 3) / 4;
         dp_cycle_kernel<0, 4><<<blocks, 128, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io0);
     } else {
         // batches of at most one wave of 4-warp CTAs stay one wave; larger ones run one warp per CTA (see DP_MIN_BLOCKS)
-        static int force_wpb = -1;                          // DP_WPB=1|4 overrides the choice (experiments)
-        if (force_wpb < 0) { const char* e = getenv("DP_WPB"); force_wpb = e ? atoi(e) : 0; }
+        const int force_wpb = lc.force_wpb;                 // DP_WPB=1|4 overrides the choice (experiments)
         const bool wide = force_wpb ? force_wpb == 4 : n <= sm_count * DP_MIN_BLOCKS(4) * 4;
         const int wpb = wide ? 4 : 1;
         const int blocks = (n + wpb - 1) / wpb, threads = wpb * 32;
@@ -1045,16 +1123,13 @@ cudaError_t dp_launch_map_prep(const double* x, const double* y, const uint16_t*
 template <int G, int TPB>
 static cudaError_t dp_launch_group_t(const DgMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                                      int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                                     double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io, int sm_count, int force_g) {
-    static bool configured_dev[64] = {};
-    int dev_id = 0;
-    cudaGetDevice(&dev_id);
+                                     double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io, int sm_count, int force_g, bool& configured) {
     const size_t smem = sizeof(DgSmem<G>);
-    if (!configured_dev[dev_id & 63]) {
+    if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(dp_group_kernel<G, TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(dp_group_kernel<G, TPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured_dev[dev_id & 63] = true;
+        configured = true;
     }
     const int per_sm = (G <= 8) ? 4 : 2;
     (void)0;
@@ -1068,19 +1143,10 @@ static cudaError_t dp_launch_group_t(const DgMap& m, const dp_params& p, int n, 
 }
 cudaError_t dp_launch_group(const DgMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                            double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io) {
+                            double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io, DpLaunchCfg& lc) {
     if (n <= 0) return cudaSuccess;
-    static int sm_count_dev[64] = {};
-    static int cfg = -1, force_g = 0;
-    if (cfg < 0) {
-        const char* e = getenv("DP_GROUP_CFG"); cfg = e ? atoi(e) : 0;
-        const char* f = getenv("DP_GROUP_G"); force_g = f ? atoi(f) : 0;
-    }
-    int dev_id = 0;
-    cudaGetDevice(&dev_id);
-    int& sm_count = sm_count_dev[dev_id & 63];
-    if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id);
-    if (cfg == 1) return dp_launch_group_t<8, 128>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g);
-    if (cfg == 2) return dp_launch_group_t<8, 256>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g);
-    return dp_launch_group_t<16, 256>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g);
+    const int cfg = lc.group_cfg, force_g = lc.group_g, sm_count = lc.sm_count;
+    if (cfg == 1) return dp_launch_group_t<8, 128>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g, lc.attr_group[1]);
+    if (cfg == 2) return dp_launch_group_t<8, 256>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g, lc.attr_group[2]);
+    return dp_launch_group_t<16, 256>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, st, io, sm_count, force_g, lc.attr_group[0]);
 }

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/dmpp_b200.h"
+#include "dp_group.cuh"
 
 #define DP_FULL 0xffffffffu
 #define DP_TILE 120            // path points staged per warp per tile (= the reference's 120-point lane slice)
@@ -25,16 +26,8 @@
 #define DP_WARPS_PER_BLOCK 4                   // operator kernels; the cycle kernel is templated on its CTA size (dp_cycle.cu)
 #endif
 
-struct DevMap {
-    const double2* xy;                         // AoS copy of (x, y), built at upload
-    const double* x; const double* y; const double* dir;
-    const double2* nrm;                        // unit RIGHT normal of segment i -> i+1 (0 at a lane's last point)
-    const double* lenp;                        // |p[i+1]-p[i]| as sqrt(dx*dx+dy*dy)        (CalcDistance idiom)
-    const uint16_t* width; const uint16_t* attr;
-    const int32_t* road_lane_base; const int32_t* lane_pt_off;
-    const dp_connector* conn;
-    int n_roads, n_lanes, n_conn;
-};
+// the map tables (+ pruning bounds, prefix / run-end tables) are shared with the group kernel
+typedef DgMap DevMap;
 
 // 6864 bytes per warp (+ 1 KB the system reserves per CTA): 7 CTAs of 4 warps (28 warps) or 25 one-warp CTAs fit the
 // 196 KB shared-memory configuration and leave 60 KB of L1 for the map gathers.
@@ -216,9 +209,12 @@ __device__ __forceinline__ void dp_bulk_wait(unsigned long long* mbar) {
 // One copy of this code serves every trajectory of the cycle (noinline keeps the kernel inside the
 // instruction cache).  (mx, my): this lane's obstacle when N < 32 (kept in registers for the whole
 // cycle); ox/oy: the scene's obstacle rows in global memory for the grouped N >= 32 case.
+// hb > 0 switches on the exactly pruned scan of dp_group.cuh (hb >= the path's segment lengths, dmax = reach of the corridor):
+// a lane samples one point per cell of 8 of ITS chunk and scans only the cells that can hold a point within
+// min(best sample, dmax); an obstacle whose best point is farther than dmax cannot be in the corridor and is dropped.
 __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my, const double* __restrict__ ox,
                                                    const double* __restrict__ oy, int N, const LaneMap lm, double lo, double hi,
-                                                   WarpSmem& sm, int lane) {
+                                                   WarpSmem& sm, int lane, const float hb = 0.f, const float dmax = 0.f) {
     SearchRes r;
     r.found = false; r.dis_lat = DP_NOT_FOUND; r.dis_lng = DP_NOT_FOUND; r.ob = -1; r.pathid = 0;
     const int P = s.n0 + s.n1;
@@ -242,7 +238,24 @@ __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my
         double b0 = INF, b1 = INF, b2 = INF, b3 = INF;
         int i0 = jlo, i1 = jlo, i2 = jlo, i3 = jlo;
         const int tstep = in_plan ? P : DP_TILE;
-        for (int t0 = 0; t0 < P; t0 += tstep) {
+        const bool prune = hb > 0.f && one_tile;
+        if (prune) {
+            if (!in_plan && g == 0) {                       // stage the (single) tile: coalesced gather, offset fused
+                __syncwarp();
+                for (int j = lane; j < P; j += 32) sm.tile[j] = dp_src_point(s, j);
+                __syncwarp();
+            }
+            const int len = jhi - jlo;
+            if (len > 0) {
+                const double2* q = pts + jlo;
+                const unsigned long long mk = dg_coarse_f([&](int j) { return q[j]; }, len, mx, my, hb, dmax);
+                if (mk) {
+                    const DgArg a = dg_refine_f([&](int j) { return q[j]; }, len, mx, my, mk);
+                    b0 = a.bd; i0 = jlo + a.bj;
+                }
+            }
+        }
+        for (int t0 = 0; t0 < P && !prune; t0 += tstep) {
             const int tn = min(tstep, P - t0);
             if (!in_plan && (g == 0 || !one_tile)) {        // stage the tile: coalesced gather, offset fused
                 __syncwarp();
@@ -282,7 +295,7 @@ __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my
             const int oj = __shfl_sync(DP_FULL, bj, src);
             if (lane < N && od < bd) { bd = od; bj = oj; }
         }
-        const bool owner = (nchunk == 1) ? active : (lane < N);
+        const bool owner = ((nchunk == 1) ? active : (lane < N)) && (!prune || (bd < INF && dg_within_reach(bd, dmax)));
         if (owner) {
             const int k = (bj == P - 1) ? P - 2 : bj;
             const double2 pk = one_tile ? pts[k] : dp_src_point(s, k), pk1 = one_tile ? pts[k + 1] : dp_src_point(s, k + 1);

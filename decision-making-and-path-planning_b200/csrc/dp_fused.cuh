@@ -119,8 +119,11 @@ __device__ __forceinline__ double dp_sweep_offset(int g, int K) { return (g < K)
 // with need_all == false the arclength of a candidate is only resolved as far as the `> clear` decision needs and
 // candidates after the first feasible one are skipped.  Returns the index (0..cnt-1) of the first feasible candidate or -1.
 template <class Sink>
+// hmax / hmin / dn: pruning bounds of F's lane (longest / shortest segment, largest change of normal); each lane derives the
+// bounds of ITS shifted candidate from them (dg_bounds) and runs the exactly pruned scan of dp_group.cuh.
 __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int u0, int cnt, int K, double mx, double my, int N, const LaneMap lm,
-                                             double lo, double hi, double clear, bool need_all, int lane, Sink sink) {
+                                             double lo, double hi, double clear, bool need_all, int lane, Sink sink,
+                                             const float hmax, const float hmin, const float dn) {
     const int ci_me = lane / N, o = lane - ci_me * N;       // N <= 16 here
     const bool active = ci_me < cnt;
     const int g_me = dp_sweep_g(u0 + ci_me, K);
@@ -129,35 +132,19 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int u0, int cn
     unsigned key = 0xffffffffu;
     double dlat = 0.0;
     if (active && P >= 2) {
-        // scan all P points of MY candidate for MY obstacle; the candidate point is rolled out in registers
-        const double INF = __longlong_as_double(0x7ff0000000000000LL);
-        double b0 = INF, b1 = INF, b2 = INF, b3 = INF;
-        int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-        int j = 0;
-#pragma unroll 2
-        for (; j + 4 <= P; j += 4) {                        // 4 independent running minima, 8 points in flight
-            const double2 q0 = dp_sweep_point(sm, j, dc), q1 = dp_sweep_point(sm, j + 1, dc);
-            const double2 q2 = dp_sweep_point(sm, j + 2, dc), q3 = dp_sweep_point(sm, j + 3, dc);
-            const double x0 = mx - q0.x, y0 = my - q0.y, x1 = mx - q1.x, y1 = my - q1.y;
-            const double x2 = mx - q2.x, y2 = my - q2.y, x3 = mx - q3.x, y3 = my - q3.y;
-            const double d0 = fma(x0, x0, y0 * y0), d1 = fma(x1, x1, y1 * y1);
-            const double d2 = fma(x2, x2, y2 * y2), d3 = fma(x3, x3, y3 * y3);
-            if (d0 < b0) { b0 = d0; i0 = j; }
-            if (d1 < b1) { b1 = d1; i1 = j + 1; }
-            if (d2 < b2) { b2 = d2; i2 = j + 2; }
-            if (d3 < b3) { b3 = d3; i3 = j + 3; }
-        }
-        for (; j < P; ++j) {
-            const double2 q0 = dp_sweep_point(sm, j, dc);
-            const double x0 = mx - q0.x, y0 = my - q0.y;
-            const double d0 = fma(x0, x0, y0 * y0);
-            if (d0 < b0) { b0 = d0; i0 = j; }
-        }
-        if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
-        if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
-        if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
+        // MY candidate against MY obstacle; the candidate point p + d n is rolled out in registers, never stored
+        const float ad = (float)fabs(dc) * 1.0001f;
+        const float hb = hmax + ad * dn + 1e-4f;
+        float delta = dn;
+        if (ad > 0.f) delta = (hmin > 1e-6f) ? dn * (1.0f + 4.0f * ad / hmin) * 1.0001f + 1e-6f : 2.0f;
+        const float dmax = (hmax < 0.f) ? dg_inff() : dg_dmax(lo, hi, hb, delta, hmin - ad * dn);   // (hmax < 0: pruning switched off)
+        const unsigned long long mk = (hmax < 0.f) ? ~0ull >> (64 - (P + 7) / 8) : dg_coarse_f([&](int j) { return dp_sweep_point(sm, j, dc); }, P, mx, my, hb, dmax);
+        DgArg a; a.bd = __longlong_as_double(0x7ff0000000000000LL); a.bj = 0;
+        if (mk) a = dg_refine_f([&](int j) { return dp_sweep_point(sm, j, dc); }, P, mx, my, mk);
+        const int i0 = a.bj;
+        const bool reach = mk && dg_within_reach(a.bd, dmax);
         const int bj = i0, k = (bj == P - 1) ? P - 2 : bj;
-        key = dp_owner_key(dp_sweep_point(sm, k, dc), dp_sweep_point(sm, k + 1, dc), bj, P, o, mx, my, lo, hi, &dlat);
+        if (reach) key = dp_owner_key(dp_sweep_point(sm, k, dc), dp_sweep_point(sm, k + 1, dc), bj, P, o, mx, my, lo, hi, &dlat);
     }
     // per-candidate selection: min of the packed key over the candidate's N lanes (xor butterfly restricted by compare)
     // done with full-warp shuffles so that every lane takes part: lanes of other candidates are ignored by index

@@ -296,8 +296,8 @@ struct DgArg { double bd; int bj; };
 // ties), step 1 of the SearchObstacle specification (oracle/cshare_spec.h), restricted to obstacles within dmax of the path.
 // Pass 1 (dg_coarse): one sample per cell of 8 points; a cell can hold a point at distance <= X only if its sample is within
 // X + 4 hb.  X = min(best sample so far, dmax).  Returns the cells to visit as a bit mask (bit = cell index, P <= 512).
-template <int MODE>
-DG_FN unsigned long long dg_coarse(const DgView& v, const int P, const double ox, const double oy, const float hb, const float dmax) {
+template <class PF>
+DG_FN unsigned long long dg_coarse_f(PF pt, const int P, const double ox, const double oy, const float hb, const float dmax) {
     const float FINF = dg_inff();
     float ubf = FINF;                              // upper bound of the minimum DISTANCE over the path, FP32, rounded up
     const float R = 4.0f * hb * 1.0001f + 1e-3f;   // a cell's points are at most 4 index steps from its sample
@@ -310,7 +310,7 @@ DG_FN unsigned long long dg_coarse(const DgView& v, const int P, const double ox
             const int j0 = c0 + 8 * c;
             float f = FINF;
             if (j0 < P) {
-                const double2 q = dg_jpt<MODE>(v, dg_imin(j0 + 4, P - 1));
+                const double2 q = pt(dg_imin(j0 + 4, P - 1));
                 const double dx = ox - q.x, dy = oy - q.y;
                 f = (float)fma(dx, dx, dy * dy);
             }
@@ -328,8 +328,8 @@ DG_FN unsigned long long dg_coarse(const DgView& v, const int P, const double ox
     return mask;
 }
 // Pass 2 (dg_refine): the marked cells in index order, strict '<' keeps the lowest index
-template <int MODE>
-DG_FN DgArg dg_refine(const DgView& v, const int P, const double ox, const double oy, unsigned long long mask) {
+template <class PF>
+DG_FN DgArg dg_refine_f(PF pt, const int P, const double ox, const double oy, unsigned long long mask) {
     const double INF = dg_inf();
     DgArg r; r.bd = INF; r.bj = 0;
     while (mask) {
@@ -344,7 +344,7 @@ DG_FN DgArg dg_refine(const DgView& v, const int P, const double ox, const doubl
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int j = jb + k;
-            const double2 q = dg_jpt<MODE>(v, dg_imin(j, P - 1));
+            const double2 q = pt(dg_imin(j, P - 1));
             const double dx = ox - q.x, dy = oy - q.y;
             e[k] = (j < P) ? fma(dx, dx, dy * dy) : INF;
         }
@@ -362,6 +362,18 @@ DG_FN DgArg dg_refine(const DgView& v, const int P, const double ox, const doubl
     }
     return r;
 }
+template <int MODE>
+DG_FN unsigned long long dg_coarse(const DgView& v, const int P, const double ox, const double oy, const float hb, const float dmax) {
+    return dg_coarse_f([&](int j) { return dg_jpt<MODE>(v, j); }, P, ox, oy, hb, dmax);
+}
+template <int MODE>
+DG_FN DgArg dg_refine(const DgView& v, const int P, const double ox, const double oy, unsigned long long mask) {
+    return dg_refine_f([&](int j) { return dg_jpt<MODE>(v, j); }, P, ox, oy, mask);
+}
+// The cells that survive the reach filter hold the true nearest point whenever it lies within dmax; when it does not, the
+// best point found may be a different one (and its lateral offset meaningless): such an obstacle cannot be in the corridor
+// and is dropped by comparing the FP64 minimum with dmax (dmax already carries its rounding margins).
+DG_FN bool dg_within_reach(double bd, float dmax) { return !(bd > (double)dmax * (double)dmax); }
 // paths longer than 512 points: both passes chunk by chunk in one thread (bj = -1: nothing within reach)
 DG_NOINLINE DgArg dg_scan_long(const DgView v, const int P, const double ox, const double oy, const float hb, const float dmax) {
     const float FINF = dg_inff();
@@ -650,7 +662,7 @@ DG_BODY dg_scan_phase(DgSmem<G>& sm, const int njobs, const int first, const dou
                 const double ox = obs_x[ob], oy = obs_y[ob];
                 if (jq.P > 512) {                  // longer than the 64-cell mask: the whole search in this thread
                     const DgArg a = dg_scan_long(jq.v, jq.P, ox, oy, jq.hb, jq.dmax);
-                    if (a.bj >= 0) {
+                    if (a.bj >= 0 && dg_within_reach(a.bd, jq.dmax)) {
                         double d;
                         const unsigned key = dg_key(jq.v, jq.P, a.bj, o, ox, oy, jq.lo, jq.hi, &d);
                         if (key != 0xffffffffu) dg_atomic_min_u32(jq.key, key);
@@ -677,6 +689,7 @@ DG_BODY dg_scan_phase(DgSmem<G>& sm, const int njobs, const int first, const dou
                 const double ox = obs_x[ob], oy = obs_y[ob];
                 const bool plain = (jq.v.n1 == 0 && jq.v.d == 0.0);
                 const DgArg a = plain ? dg_refine<0>(jq.v, jq.P, ox, oy, masks[e]) : dg_refine<1>(jq.v, jq.P, ox, oy, masks[e]);
+                if (!dg_within_reach(a.bd, jq.dmax)) continue;
                 double d;
                 const unsigned key = dg_key(jq.v, jq.P, a.bj, o, ox, oy, jq.lo, jq.hi, &d);
                 if (key != 0xffffffffu) dg_atomic_min_u32(jq.key, key);

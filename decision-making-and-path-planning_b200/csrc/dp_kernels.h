@@ -26,9 +26,19 @@ struct DpIo {
 };
 inline DpIo dp_io_none() { DpIo io = {}; return io; }
 
+// launch-time state of ONE context (no process-wide statics: two threads may own two contexts): device properties, which
+// kernels already carry their shared-memory attributes, and the experiment switches read from the environment by dp_create
+struct DpLaunchCfg {
+    int sm_count = 0;
+    bool attr_warp = false, attr_group[3] = {false, false, false};
+    int force_wpb = 0;                         // DP_WPB = 1 | 4: CTA size of the warp kernel (0: by batch size)
+    int group_cfg = 0;                         // DP_GROUP_CFG = 0 | 1 | 2: CTA shape of the group kernel (16 x 256, 8 x 128, 8 x 256)
+    int group_g = 0;                           // DP_GROUP_G: scenes per CTA (0: spread one wave evenly)
+};
+
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                            double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io);   // split: 0 fused, 1 two launches, 2 overlapped
+                            double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io, DpLaunchCfg& lc);   // split: 0 fused, 1 two launches, 2 overlapped
 // (io.prev_epoch != 0 additionally launches the Decision half as a programmatic dependent of the previous cycle's Planning half)
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st);
 cudaError_t dp_launch_map_prep(const double* x, const double* y, const uint16_t* attr, const int32_t* lane_pt_off, int n_lanes, double2* xy,
@@ -37,7 +47,7 @@ cudaError_t dp_launch_map_prep(const double* x, const double* y, const uint16_t*
 // the group kernel (dp_group.cuh): ONE launch per cycle, a CTA walks a group of scenes through the cycle phase by phase
 cudaError_t dp_launch_group(const DgMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
-                            double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io);
+                            double* path_xy, double* path_ll, cudaStream_t st, const DgIo& io, DpLaunchCfg& lc);
 
 // operator-level kernels (dp_ops.cu)
 // operator kernels take polylines as AoS double2 (the host entry points interleave x/y)
@@ -50,8 +60,9 @@ cudaError_t dp_launch_bezier(int n, const double* poses, double* out_xy, cudaStr
 cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double2* pxy, double* out_xy, cudaStream_t st);
 cudaError_t dp_launch_nearest(int n_paths, const int32_t* path_off, const double2* pxy, const double* qx, const double* qy, int32_t* out_id,
                               cudaStream_t st);
-cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
-                            int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs,
-                            double lat_min, double lat_max, double clear_dis, double* cand_dis_lng, unsigned long long* best_key,
-                            const int32_t* order, unsigned* next, cudaStream_t st);   // order: processing order (nullable); next: zeroed counter
+// dense candidate sweep (dp_ops.cu): candidates grouped on the host by (offset = row, point count = horizon group)
+cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, int n_rows, const double* row_off, const int32_t* row_gbeg,
+                            const int32_t* group_P, const int32_t* cand_group, int n_cand, const double* ox, const double* oy, const double* dvx,
+                            const double* dvy, int n_obs, double lat_min, double lat_max, double clear_dis, double* group_dis,
+                            double* cand_dis_lng, unsigned long long* best_key, cudaStream_t st);
 cudaError_t dp_launch_fma_peak(int which, float* sink, int iters, int blocks, cudaStream_t st);

@@ -91,142 +91,129 @@ op_nearest_kernel(int n_paths, const int32_t* __restrict__ path_off, const doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// Dense candidate sweep (BASELINE config 3): one warp per candidate, SWEEP_WARPS candidates per
-// block.  The base polyline and its segment normals are staged once per block in shared memory,
-// obstacle tracks (x, y, dvx, dvy) too; each warp materialises ITS candidate (offset copy of a
-// prefix of the base line) in its own shared-memory slab, then lanes = obstacles run the fused
-// rollout -> nearest-point -> corridor check; arclength is summed in index order.  Selection is
-// a packed (cost bits << 32 | candidate index) 64-bit atomicMin: feasible candidates have cost 0,
-// so the minimum is the LOWEST feasible index (the reference's first-feasible `break`,
-// Decision.cpp:944-953), deterministic whatever the launch geometry.
+// Dense candidate sweep (BASELINE config 3).  A candidate = CreateNewPath(first P points of the base line, offset), scored by
+// SearchObstacle against obstacle tracks o(j) = o0 + j dv.  Candidates that share an offset ("row") share their geometry:
+// the candidate with P points consists of the row points q_j = b_j + off n_j, j < P-1, plus ONE own last point
+// b_{P-1} + off n_{P-2} (CreateNewPath gives the last point the normal of the last segment, oracle/cshare_spec.h).  So the
+// nearest-point search of every horizon of a row is ONE pass over the row per obstacle: the running argmin over q_0..q_{P-2}
+// is the state, each horizon adds its own last point, runs the gates / lateral offset / corridor test with its own P, and
+// min-reduces its packed (path index << 16 | obstacle) key; the arclength to the selected point is a look-up in the row's
+// sequential prefix of segment lengths (every horizon starts at q_0, so the prefix IS the reference's sum).  Same bits as
+// scoring each candidate alone (tests/test_gpu_parity.py::test_dense_sweep*), rows x obstacles x points evaluations instead
+// of candidates x obstacles x points: 0.8 M instead of 250 M on the 64 x 32 x 32 grid.
+//   sweep_rows_kernel   one CTA per row: threads = obstacles (+ one warp for the prefix sum)
+//   sweep_select_kernel one thread per candidate: cost of its (row, horizon) group, lowest feasible index by a packed
+//                       (cost bits << 32 | index) 64-bit atomicMin: the reference's first-feasible `break` (Decision.cpp:944-953)
 // ------------------------------------------------------------------------------------------------
-#define SWEEP_WARPS 8
-#ifndef SWEEP_CTAS_PER_SM
-#define SWEEP_CTAS_PER_SM 3
-#endif
 #define SWEEP_MAX_BASE 256
 #define SWEEP_MAX_OBS 192
 
-// argmin update (a 64-bit integer compare on the bit patterns was tried to unload the FP64 pipe: 2 ISETP + 3 SEL cost more
-// issue slots than DSETP + 3 SEL, and this kernel is issue-bound -- profiles/README.md)
-__device__ __forceinline__ void sweep_upd(double d2, int j, double& bb, int& bj) {
-    if (d2 < bb) { bb = d2; bj = j; }
+__global__ void __launch_bounds__(SWEEP_MAX_OBS + 32)
+sweep_rows_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, const double* __restrict__ row_off,
+                  const int32_t* __restrict__ row_gbeg, const int32_t* __restrict__ group_P, const double* __restrict__ ox,
+                  const double* __restrict__ oy, const double* __restrict__ dvx, const double* __restrict__ dvy, int n_obs, double lat_min,
+                  double lat_max, double* __restrict__ group_dis) {
+    __shared__ double2 s_b[SWEEP_MAX_BASE];                 // base line
+    __shared__ double2 s_n[SWEEP_MAX_BASE];                 // unit right normal of segment j -> j+1
+    __shared__ double2 s_q[SWEEP_MAX_BASE];                 // row points b_j + off n_j
+    __shared__ double s_cum[SWEEP_MAX_BASE];                // sequential prefix of |q_{j+1} - q_j|
+    __shared__ unsigned s_key[SWEEP_MAX_BASE];              // per horizon group of the row
+    const int row = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int g0 = row_gbeg[row], ng = row_gbeg[row + 1] - g0;
+    const double off = row_off[row];
+    const int Pmax = ng > 0 ? group_P[g0 + ng - 1] : 0;     // horizons are sorted ascending
+    for (int j = tid; j < Pmax; j += nthr) s_b[j] = make_double2(base_x[j], base_y[j]);
+    for (int g = tid; g < ng; g += nthr) s_key[g] = 0xffffffffu;
+    __syncthreads();
+    for (int j = tid; j + 1 < Pmax; j += nthr) {
+        const double2 n = dp_normal(s_b[j], s_b[j + 1]);
+        s_n[j] = n;
+        s_q[j] = make_double2(fma(off, n.x, s_b[j].x), fma(off, n.y, s_b[j].y));
+    }
+    __syncthreads();
+    const int scan_threads = nthr - 32;
+    if (tid >= scan_threads) {
+        // the last warp: segment lengths of the row, then their sequential prefix (one lane)
+        const int lane = tid - scan_threads;
+        for (int j = lane; j + 2 < Pmax; j += 32) s_cum[j + 1] = sqrt(dp_sq2(s_q[j + 1].x - s_q[j].x, s_q[j + 1].y - s_q[j].y));
+        __syncwarp();
+        if (lane == 0) {
+            double acc = 0.0;
+            s_cum[0] = 0.0;
+            for (int j = 1; j + 1 < Pmax; ++j) { acc += s_cum[j]; s_cum[j] = acc; }   // s_cum[j] = arclength from q_0 to q_j, j <= Pmax-2
+        }
+    } else if (tid < n_obs) {
+        const int o = tid;
+        const double x0 = ox[o], y0 = oy[o], vx = dvx ? dvx[o] : 0.0, vy = dvy ? dvy[o] : 0.0;
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        double bd = INF;
+        int bj = 0;
+        int g = 0, Pn = group_P[g0];                        // next horizon to serve
+        double jd = 0.0;
+        for (int j = 0; j < Pmax; ++j, jd += 1.0) {
+            const double mx = fma(jd, vx, x0), my = fma(jd, vy, y0);   // obstacle when the ego reaches path point j
+            while (g < ng && Pn == j + 1) {
+                // horizon P = j + 1: its points are q_0 .. q_{P-2} (state bd, bj) and its own last point
+                const int P = Pn;
+                const double2 nl = s_n[P - 2], bl = s_b[P - 1];
+                const double2 ql = make_double2(fma(off, nl.x, bl.x), fma(off, nl.y, bl.y));
+                const double dx = mx - ql.x, dy = my - ql.y;
+                const double dl = fma(dx, dx, dy * dy);
+                int cj = bj;
+                if (dl < bd || P == 1) cj = P - 1;          // strict '<': the last index only wins when strictly closer
+                // gates, lateral offset, corridor with THIS horizon's P; the obstacle position is the one at step cj
+                const double hx = fma((double)cj, vx, x0), hy = fma((double)cj, vy, y0);
+                const int k = (cj == P - 1) ? P - 2 : cj;
+                const double2 pk = s_q[k], pk1 = (k + 1 == P - 1) ? ql : s_q[k + 1];
+                double dd;
+                const unsigned key = dp_owner_key(pk, pk1, cj, P, o, hx, hy, lat_min, lat_max, &dd);
+                if (key != 0xffffffffu) atomicMin(&s_key[g], key);
+                ++g;
+                Pn = (g < ng) ? group_P[g0 + g] : 0;
+            }
+            if (j + 1 < Pmax) {                             // row point j enters the running argmin (it is point j of every longer horizon)
+                const double2 q = s_q[j];
+                const double dx = mx - q.x, dy = my - q.y;
+                const double d = fma(dx, dx, dy * dy);
+                if (d < bd) { bd = d; bj = j; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int g = tid; g < ng; g += nthr) {
+        const unsigned key = s_key[g];
+        double dis = DP_NOT_FOUND;
+        if (key != 0xffffffffu) {
+            const int P = group_P[g0 + g], jstar = (int)(key >> 16);
+            if (jstar <= P - 2) dis = s_cum[jstar];
+            else {                                          // the horizon's own last point: one more term after the prefix to q_{P-2}
+                const double2 nl = s_n[P - 2], bl = s_b[P - 1];
+                const double2 ql = make_double2(fma(off, nl.x, bl.x), fma(off, nl.y, bl.y));
+                const double2 qp = s_q[P - 2];
+                dis = s_cum[P - 2] + sqrt(dp_sq2(ql.x - qp.x, ql.y - qp.y));
+            }
+        }
+        group_dis[g0 + g] = dis;
+    }
 }
 
-__global__ void __launch_bounds__(SWEEP_WARPS * 32, SWEEP_CTAS_PER_SM)
-sweep_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, const double* __restrict__ offset,
-             const int32_t* __restrict__ n_pts, int n_cand, const double* __restrict__ ox, const double* __restrict__ oy,
-             const double* __restrict__ dvx, const double* __restrict__ dvy, int n_obs, double lat_min, double lat_max,
-             double clear_dis, double* __restrict__ cand_dis_lng, unsigned long long* __restrict__ best_key,
-             const int32_t* __restrict__ order, unsigned* __restrict__ next) {
-    __shared__ double2 s_base[SWEEP_MAX_BASE];
-    __shared__ double2 s_nrm[SWEEP_MAX_BASE];              // normal of segment j -> j+1
-    __shared__ double4 s_obs[SWEEP_MAX_OBS];
-    __shared__ double2 s_cand[SWEEP_WARPS][SWEEP_MAX_BASE]; // the warp's candidate; reused for the arclength terms afterwards
-    __shared__ unsigned long long s_key[SWEEP_WARPS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    for (int j = threadIdx.x; j < n_base; j += blockDim.x) s_base[j] = make_double2(base_x[j], base_y[j]);
-    for (int o = threadIdx.x; o < n_obs; o += blockDim.x) s_obs[o] = make_double4(ox[o], oy[o], dvx ? dvx[o] : 0.0, dvy ? dvy[o] : 0.0);
-    __syncthreads();
-    for (int j = threadIdx.x; j + 1 < n_base; j += blockDim.x) s_nrm[j] = dp_normal(s_base[j], s_base[j + 1]);
-    __syncthreads();
-
-    unsigned long long mykey = ~0ull;
-    // Candidates differ 32x in length (8..256 points): a static round-robin leaves the slowest warp ~30 % behind the mean.
-    // Warps fetch the next candidate from a counter instead, in the order the session prepared (longest first).
-    for (;;) {
-        int i = 0;
-        if (lane == 0) i = (int)atomicAdd(next, 1u);
-        i = __shfl_sync(DP_FULL, i, 0);
-        if (i >= n_cand) break;
-        const int c = order ? order[i] : i;
-        const int P = min(n_pts[c], n_base);
-        const double off = offset[c];
-        double dis_lng = DP_NOT_FOUND;
-        if (P >= 2) {
-            double2* q = s_cand[wib];
-            __syncwarp();
-            for (int j = lane; j < P; j += 32) {           // rollout: offset copy, never leaves the SM
-                const double2 b = s_base[j], n = s_nrm[min(j, P - 2)];
-                q[j] = make_double2(fma(off, n.x, b.x), fma(off, n.y, b.y));
-            }
-            __syncwarp();
-            unsigned bestkey = 0xffffffffu;
-            for (int g = 0; g * 32 < n_obs; ++g) {
-                const int o = g * 32 + lane;
-                if (o < n_obs) {
-                    const double4 ob = s_obs[o];
-                    // 4 independent running minima (j mod 4): lexicographic (d2, j) min == sequential strict-'<' argmin
-                    const double INF = __longlong_as_double(0x7ff0000000000000LL);
-                    double b0 = INF, b1 = INF, b2 = INF, b3 = INF;
-                    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-                    int j = 0;
-                    double jd = 0.0;                        // (double)j, kept as a running exact integer
-                    for (; j + 4 <= P; j += 4, jd += 4.0) {
-                        const double2 p0 = q[j], p1 = q[j + 1], p2 = q[j + 2], p3 = q[j + 3];
-                        const double t0 = jd, t1 = jd + 1.0, t2 = jd + 2.0, t3 = jd + 3.0;
-                        const double x0 = fma(t0, ob.z, ob.x) - p0.x, y0 = fma(t0, ob.w, ob.y) - p0.y;
-                        const double x1 = fma(t1, ob.z, ob.x) - p1.x, y1 = fma(t1, ob.w, ob.y) - p1.y;
-                        const double x2 = fma(t2, ob.z, ob.x) - p2.x, y2 = fma(t2, ob.w, ob.y) - p2.y;
-                        const double x3 = fma(t3, ob.z, ob.x) - p3.x, y3 = fma(t3, ob.w, ob.y) - p3.y;
-                        sweep_upd(fma(x0, x0, y0 * y0), j, b0, i0);
-                        sweep_upd(fma(x1, x1, y1 * y1), j + 1, b1, i1);
-                        sweep_upd(fma(x2, x2, y2 * y2), j + 2, b2, i2);
-                        sweep_upd(fma(x3, x3, y3 * y3), j + 3, b3, i3);
-                    }
-                    for (; j < P; ++j, jd += 1.0) {
-                        const double2 p0 = q[j];
-                        const double t0 = jd;
-                        const double x0 = fma(t0, ob.z, ob.x) - p0.x, y0 = fma(t0, ob.w, ob.y) - p0.y;
-                        sweep_upd(fma(x0, x0, y0 * y0), j, b0, i0);
-                    }
-                    if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
-                    if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
-                    if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
-                    const int bj = i0;
-                    const double mx = fma((double)bj, ob.z, ob.x), my = fma((double)bj, ob.w, ob.y);
-                    const int k = (bj == P - 1) ? P - 2 : bj;
-                    double dd;
-                    bestkey = min(bestkey, dp_owner_key(q[k], q[k + 1], bj, P, o, mx, my, lat_min, lat_max, &dd));
-                }
-            }
-            const unsigned gmin = __reduce_min_sync(DP_FULL, bestkey);
-            if (gmin != 0xffffffffu) {
-                const int jstar = (int)(gmin >> 16);
-                double t[(SWEEP_MAX_BASE + 31) / 32];
-#pragma unroll
-                for (int u = 0; u < (SWEEP_MAX_BASE + 31) / 32; ++u) {
-                    const int j = lane + 32 * u;
-                    t[u] = (j < jstar) ? sqrt(dp_sq2(q[j + 1].x - q[j].x, q[j + 1].y - q[j].y)) : 0.0;
-                }
-                __syncwarp();                               // every lane is done with q: reuse it for the terms
-                double* len = reinterpret_cast<double*>(q);
-#pragma unroll
-                for (int u = 0; u < (SWEEP_MAX_BASE + 31) / 32; ++u) len[lane + 32 * u] = t[u];   // zero padded to 256
-                __syncwarp();
-                double sum = 0.0;
-                for (int j = 0; j < jstar; j += 8) {        // index order; the zero padding does not change the sum
-                    const double a0 = len[j], a1 = len[j + 1], a2 = len[j + 2], a3 = len[j + 3];
-                    const double a4 = len[j + 4], a5 = len[j + 5], a6 = len[j + 6], a7 = len[j + 7];
-                    sum += a0; sum += a1; sum += a2; sum += a3; sum += a4; sum += a5; sum += a6; sum += a7;
-                }
-                dis_lng = sum;
-            }
-        }
-        if (lane == 0) {
-            cand_dis_lng[c] = dis_lng;
-            const float cost = (dis_lng > clear_dis) ? 0.0f : __int_as_float(0x7f800000);
-            const unsigned long long key = ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)c;
-            mykey = min(mykey, key);
-        }
+__global__ void sweep_select_kernel(const int32_t* __restrict__ cand_group, int n_cand, const double* __restrict__ group_dis, double clear_dis,
+                                    double* __restrict__ cand_dis_lng, unsigned long long* __restrict__ best_key) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long key = ~0ull;
+    if (c < n_cand) {
+        const int g = cand_group[c];
+        const double dis = g >= 0 ? group_dis[g] : DP_NOT_FOUND;          // fewer than 2 points: SearchObstacle finds nothing
+        if (cand_dis_lng) cand_dis_lng[c] = dis;
+        const float cost = (dis > clear_dis) ? 0.0f : __int_as_float(0x7f800000);
+        key = ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)c;
     }
-    if (lane == 0) s_key[wib] = mykey;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long k = s_key[0];
-        for (int w = 1; w < SWEEP_WARPS; ++w) k = min(k, s_key[w]);
-        if (k != ~0ull) atomicMin(best_key, k);
+    // lowest key of the warp, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(DP_FULL, key, o);
+        key = other < key ? other : key;
     }
+    if ((threadIdx.x & 31) == 0 && key != ~0ull) atomicMin(best_key, key);
 }
 
 // FMA micro-benchmark: 8 independent accumulator chains per thread
@@ -278,16 +265,17 @@ cudaError_t dp_launch_nearest(int n_paths, const int32_t* path_off, const double
     op_nearest_kernel<<<(n_paths + DP_WARPS_PER_BLOCK - 1) / DP_WARPS_PER_BLOCK, DP_WARPS_PER_BLOCK * 32, 0, st>>>(n_paths, path_off, pxy, qx, qy, out_id);
     return cudaGetLastError();
 }
-cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, const double* offset, const int32_t* n_pts,
-                            int n_cand, const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs,
-                            double lat_min, double lat_max, double clear_dis, double* cand_dis_lng, unsigned long long* best_key,
-                            const int32_t* order, unsigned* next, cudaStream_t st) {
+cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, int n_rows, const double* row_off, const int32_t* row_gbeg,
+                            const int32_t* group_P, const int32_t* cand_group, int n_cand, const double* ox, const double* oy, const double* dvx,
+                            const double* dvy, int n_obs, double lat_min, double lat_max, double clear_dis, double* group_dis,
+                            double* cand_dis_lng, unsigned long long* best_key, cudaStream_t st) {
     if (n_cand <= 0) return cudaSuccess;
-    int blocks = (n_cand + SWEEP_WARPS - 1) / SWEEP_WARPS;
-    const int cap = 148 * SWEEP_CTAS_PER_SM;                               // persistent-style: 3 CTAs x 8 warps per SM, grid-stride over candidates
-    if (blocks > cap) blocks = cap;
-    sweep_kernel<<<blocks, SWEEP_WARPS * 32, 0, st>>>(base_x, base_y, n_base, offset, n_pts, n_cand, ox, oy, dvx, dvy, n_obs, lat_min,
-                                                      lat_max, clear_dis, cand_dis_lng, best_key, order, next);
+    if (n_rows > 0) {
+        const int threads = ((n_obs + 31) / 32) * 32 + 32;  // obstacles + the prefix-sum warp
+        sweep_rows_kernel<<<n_rows, threads, 0, st>>>(base_x, base_y, n_base, row_off, row_gbeg, group_P, ox, oy, dvx, dvy, n_obs, lat_min, lat_max,
+                                                      group_dis);
+    }
+    sweep_select_kernel<<<(n_cand + 255) / 256, 256, 0, st>>>(cand_group, n_cand, group_dis, clear_dis, cand_dis_lng, best_key);
     return cudaGetLastError();
 }
 cudaError_t dp_launch_fma_peak(int which, float* sink, int iters, int blocks, cudaStream_t st) {

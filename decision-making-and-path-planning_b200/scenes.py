@@ -455,7 +455,7 @@ class Directed:
     def hdr(self, c):
         m = self.m
         h = np.zeros(self.n, dtype=abi.scene_hdr)
-        h["period_ms"] = self.period_ticks(c).astype(np.float64)
+        h["period_ms"] = self.period_ticks(c).astype(np.float64) / 1000.0 * 1000.0        # == what the reference computes
         t = self.elapsed_s(c)
         s = self.id0 * SPACING + self.v / 3.6 * t
         lane = np.where(c >= self.move_t, np.minimum(self.lane0 + 1, self.nl), self.lane0)

@@ -19,7 +19,16 @@ CASES = {
     "highway_10": ("highway", 0, 48, 25, 10),
     "highway_40": ("highway", 31337, 16, 30, 40),
     "junction_10": ("junction", 555000, 24, 80, 10),
+    # directed families that reach the right lane change (behaviour 3), scenes.Directed
+    "right_obstacle_10": ("right_obstacle", 0, 32, 40, 10),
+    "right_nav_10": ("right_nav", 0, 32, 70, 10),
 }
+
+
+def episodes(m, kind, seeds, cycles, n_obs):
+    if kind.startswith("right_"):
+        return scenes.Directed(m, seeds, family=kind, cycles=cycles, n_obs=n_obs)
+    return scenes.Episodes(m, seeds, cycles=cycles, kind=kind, n_obs=n_obs)
 
 
 def sig(a, axis_from):
@@ -38,7 +47,7 @@ def main():
     ref.set_map(m)
     here = os.path.dirname(os.path.abspath(__file__))
     for name, (kind, s0, n, cyc, nobs) in CASES.items():
-        ep = scenes.Episodes(m, np.arange(s0, s0 + n), cycles=cyc, kind=kind, n_obs=nobs)
+        ep = episodes(m, kind, np.arange(s0, s0 + n), cyc, nobs)
         H, OX, OY = ep.all_cycles()
         o = ref.run(H, OX, OY)
         # checksum of the inputs so that a drift of the generator is detected, not silently absorbed

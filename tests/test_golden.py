@@ -11,7 +11,7 @@ import pytest
 from conftest import ROOT, assert_records_equal, same
 
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-from make_golden import sig  # noqa: E402
+from make_golden import episodes, sig  # noqa: E402
 
 FILES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
 REC = ["velocity_expect", "path_lat_dis", "remain_dis", "mindist_lon", "brakespeed", "des_acc", "radius", "aim_x", "aim_y",
@@ -20,10 +20,9 @@ REC = ["velocity_expect", "path_lat_dis", "remain_dis", "mindist_lon", "brakespe
 
 
 def load(path, the_map):
-    from dmpp_b200 import scenes
     g = np.load(path)
     s0, n, cyc, nobs = (int(v) for v in g["meta"])
-    ep = scenes.Episodes(the_map, np.arange(s0, s0 + n), cycles=cyc, kind=str(g["kind"]), n_obs=nobs)
+    ep = episodes(the_map, str(g["kind"]), np.arange(s0, s0 + n), cyc, nobs)
     H, OX, OY = ep.all_cycles()
     inp = np.array([np.frombuffer(H.tobytes(), np.uint8).astype(np.uint64).sum(), OX.sum(), OY.sum()])
     assert np.array_equal(inp, g["inputs"]), "scene generator drifted: regenerate the fixtures deliberately"
@@ -31,7 +30,7 @@ def load(path, the_map):
 
 
 def test_fixtures_exist():
-    assert len(FILES) >= 3
+    assert len(FILES) >= 5
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f) for f in FILES])

@@ -366,10 +366,11 @@ def test_multi_wave_batch_one_warp_ctas(oracle, the_map):
         p.close()
 
 
-@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("split", ["0", "1", "warp", "group", "group1", "group2"])
 def test_launch_modes_agree(planner, the_map, monkeypatch, split):
-    """DP_SPLIT=0 (one fused launch) and DP_SPLIT=1 (two launches back to back) must produce the bytes of the default
-    overlapped launch: records, traces, paths and carried state."""
+    """Every way the cycle can be launched must produce the same bytes (records, traces, paths, carried state) as the
+    module's default planner: the warp-per-scene kernel as one fused launch (DP_SPLIT=0), as two launches back to back
+    (DP_SPLIT=1) or overlapped (default), and the group kernel in its three CTA shapes (DP_GROUP_CFG 0/1/2)."""
     from dmpp_b200 import scenes
     from dmpp_b200.planner import Planner
     n, cycles = 384, 10
@@ -378,9 +379,14 @@ def test_launch_modes_agree(planner, the_map, monkeypatch, split):
         H, OX, OY = ep.all_cycles()
         PX, PY = pad_obs(OX, OY, planner.max_obs)
         want = planner.run_episodes(H, PX, PY)
-        monkeypatch.setenv("DP_SPLIT", split)                  # read by dp_create
+        env = {"0": {"DP_KERNEL": "warp", "DP_SPLIT": "0"}, "1": {"DP_KERNEL": "warp", "DP_SPLIT": "1"}, "warp": {"DP_KERNEL": "warp"},
+               "group": {"DP_KERNEL": "group"}, "group1": {"DP_KERNEL": "group", "DP_GROUP_CFG": "1"},
+               "group2": {"DP_KERNEL": "group", "DP_GROUP_CFG": "2"}}[split]
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)                           # read by dp_create (DP_GROUP_CFG: at the first group launch of the process)
         alt = Planner(max_scenes=n, max_obs=planner.max_obs)
-        monkeypatch.delenv("DP_SPLIT")
+        for k in env:
+            monkeypatch.delenv(k)
         alt.upload_map(the_map)
         got = alt.run_episodes(H, PX, PY)
         alt.close()
