@@ -156,7 +156,7 @@ std::vector<double2> interleave(const double* x, const double* y, size_t n) {
 // groups = distinct point counts of a row, ascending; cand_group[c] = group of candidate c (-1: fewer than 2 points).
 struct SweepGroups {
     std::vector<double> row_off;
-    std::vector<int32_t> row_gbeg, group_P, cand_group;
+    std::vector<int32_t> row_gbeg, group_P, group_row, cand_group;
 };
 SweepGroups build_sweep_groups(const double* offset, const int32_t* n_pts, int n_cand, int n_base) {
     SweepGroups g;
@@ -179,7 +179,7 @@ SweepGroups build_sweep_groups(const double* offset, const int32_t* n_pts, int n
             double off; memcpy(&off, &b, 8);
             g.row_off.push_back(off); have_row = true; cur_bits = b; cur_P = -1;
         }
-        if (P != cur_P) { g.group_P.push_back(P); cur_P = P; }
+        if (P != cur_P) { g.group_P.push_back(P); g.group_row.push_back((int32_t)g.row_off.size() - 1); cur_P = P; }
         g.cand_group[c] = (int32_t)g.group_P.size() - 1;
     }
     if (have_row) g.row_gbeg.push_back((int32_t)g.group_P.size());
@@ -711,7 +711,9 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
     PUT(d_bx, double, base_x, (size_t)n_base); PUT(d_by, double, base_y, (size_t)n_base);
     PUT(d_roff, double, sg.row_off.data(), sg.row_off.size()); PUT(d_gbeg, int32_t, sg.row_gbeg.data(), sg.row_gbeg.size());
     PUT(d_gP, int32_t, sg.group_P.data(), sg.group_P.size()); PUT(d_cg, int32_t, sg.cand_group.data(), (size_t)n_cand);
-    PUT(d_gdis, double, (const double*)nullptr, sg.group_P.size());
+    PUT(d_grow, int32_t, sg.group_row.data(), sg.group_row.size());
+    PUT(d_rcum, double, (const double*)nullptr, sg.row_off.size() * 256);
+    PUT(d_gkey, unsigned, (const unsigned*)nullptr, sg.group_P.size());
     PUT(d_ox, double, ox, (size_t)n_obs); PUT(d_oy, double, oy, (size_t)n_obs);
     double* d_vx = nullptr; double* d_vy = nullptr;
     if (dvx && dvy) { d_vx = tmp.put<double>(dvx, (size_t)n_obs, e); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "staging", e);
@@ -719,9 +721,10 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
     PUT(d_dis, double, (const double*)nullptr, (size_t)n_cand);
     PUT(d_key, unsigned long long, (const unsigned long long*)nullptr, 1);
     CK(cudaMemsetAsync(d_key, 0xff, 8, c->st[0]));
-    CK(dp_launch_sweep(d_bx, d_by, n_base, n_rows, d_roff, d_gbeg, d_gP, d_cg, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs, lat_min, lat_max, clear_dis,
-                       d_gdis, d_dis, d_key, c->st[0]));
-    ++c->launches;
+    CK(dp_launch_sweep_prefix(d_bx, d_by, n_rows, d_roff, d_gbeg, d_gP, d_rcum, c->st[0]));
+    CK(dp_launch_sweep(d_bx, d_by, n_base, n_rows, (int)sg.group_P.size(), d_roff, d_gbeg, d_gP, d_grow, d_cg, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs,
+                       lat_min, lat_max, clear_dis, d_gkey, d_rcum, d_dis, d_key, c->st[0]));
+    c->launches += 3;
     ++c->launches;
     unsigned long long key = ~0ull;
     CK(cudaMemcpyAsync(&key, d_key, 8, cudaMemcpyDeviceToHost, c->st[0]));
@@ -741,8 +744,9 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
 struct dp_sweep {
     dp_ctx* c = nullptr;
     int n_base = 0, n_cand = 0, max_obs = 0;
-    double *d_bx = nullptr, *d_by = nullptr, *d_roff = nullptr, *d_obs = nullptr, *d_dis = nullptr, *d_gdis = nullptr;   // d_obs: [4][max_obs]
-    int32_t *d_gbeg = nullptr, *d_gP = nullptr, *d_cg = nullptr;   // rows / horizon groups of the candidate set (build_sweep_groups)
+    double *d_bx = nullptr, *d_by = nullptr, *d_roff = nullptr, *d_obs = nullptr, *d_dis = nullptr, *d_rcum = nullptr;   // d_obs: [4][max_obs]
+    int32_t *d_gbeg = nullptr, *d_gP = nullptr, *d_grow = nullptr, *d_cg = nullptr;   // rows / horizon groups of the candidate set (build_sweep_groups)
+    unsigned* d_gkey = nullptr;
     int n_rows = 0, n_groups = 0;
     unsigned long long* d_key = nullptr;
     double* h_obs = nullptr;                                // pinned [4][max_obs]
@@ -766,7 +770,8 @@ int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const doubl
     s->n_rows = (int)sg.row_off.size(); s->n_groups = (int)sg.group_P.size();
     CK(cudaMalloc((void**)&s->d_roff, (sg.row_off.size() + 1) * 8)); CK(cudaMalloc((void**)&s->d_gbeg, sg.row_gbeg.size() * 4));
     CK(cudaMalloc((void**)&s->d_gP, (sg.group_P.size() + 1) * 4)); CK(cudaMalloc((void**)&s->d_cg, (size_t)n_cand * 4));
-    CK(cudaMalloc((void**)&s->d_gdis, (sg.group_P.size() + 1) * 8));
+    CK(cudaMalloc((void**)&s->d_rcum, (sg.row_off.size() + 1) * 256 * 8)); CK(cudaMalloc((void**)&s->d_grow, (sg.group_P.size() + 1) * 4));
+    CK(cudaMalloc((void**)&s->d_gkey, (sg.group_P.size() + 1) * 4));
     CK(cudaMalloc((void**)&s->d_obs, (size_t)4 * max_obs * 8)); CK(cudaMalloc((void**)&s->d_dis, (size_t)n_cand * 8));
     CK(cudaMalloc((void**)&s->d_key, 8));
     CK(cudaMallocHost((void**)&s->h_obs, (size_t)4 * max_obs * 8)); CK(cudaMallocHost((void**)&s->h_key, 8));
@@ -775,6 +780,11 @@ int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const doubl
     CK(cudaMemcpy(s->d_gbeg, sg.row_gbeg.data(), sg.row_gbeg.size() * 4, cudaMemcpyHostToDevice));
     if (s->n_groups) CK(cudaMemcpy(s->d_gP, sg.group_P.data(), sg.group_P.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_cg, sg.cand_group.data(), (size_t)n_cand * 4, cudaMemcpyHostToDevice));
+    if (s->n_groups) CK(cudaMemcpy(s->d_grow, sg.group_row.data(), sg.group_row.size() * 4, cudaMemcpyHostToDevice));
+    // the arclength prefix of every row does not depend on the obstacles: once, here
+    CK(dp_launch_sweep_prefix(s->d_bx, s->d_by, s->n_rows, s->d_roff, s->d_gbeg, s->d_gP, s->d_rcum, c->st[0]));
+    ++c->launches;
+    CK(cudaStreamSynchronize(c->st[0]));
     CK(cudaEventCreate(&s->e0)); CK(cudaEventCreate(&s->e1));
     *out = s;
     return DP_OK;
@@ -798,8 +808,9 @@ int dp_sweep_score(dp_sweep* s, const double* ox, const double* oy, const double
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         cudaMemcpyAsync(s->d_obs, s->h_obs, (size_t)4 * mo * 8, cudaMemcpyHostToDevice, st);
         cudaMemsetAsync(s->d_key, 0xff, 8, st);
-        dp_launch_sweep(s->d_bx, s->d_by, s->n_base, s->n_rows, s->d_roff, s->d_gbeg, s->d_gP, s->d_cg, s->n_cand, s->d_obs, s->d_obs + mo,
-                        s->d_obs + 2 * mo, s->d_obs + 3 * mo, n_obs, lat_min, lat_max, clear_dis, s->d_gdis, s->d_dis, s->d_key, st);
+        dp_launch_sweep(s->d_bx, s->d_by, s->n_base, s->n_rows, s->n_groups, s->d_roff, s->d_gbeg, s->d_gP, s->d_grow, s->d_cg, s->n_cand,
+                        s->d_obs, s->d_obs + mo, s->d_obs + 2 * mo, s->d_obs + 3 * mo, n_obs, lat_min, lat_max, clear_dis, s->d_gkey, s->d_rcum,
+                        s->d_dis, s->d_key, st);
         cudaMemcpyAsync(s->h_key, s->d_key, 8, cudaMemcpyDeviceToHost, st);
         CK(cudaStreamEndCapture(st, &g));
         CK(cudaGraphInstantiate(&s->exec, g, 0));
@@ -827,7 +838,7 @@ int dp_sweep_destroy(dp_sweep* s) {
     cudaSetDevice(s->c->device);
     cudaStreamSynchronize(s->c->st[0]);
     if (s->exec) cudaGraphExecDestroy(s->exec);
-    cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_roff); cudaFree(s->d_gbeg); cudaFree(s->d_gP); cudaFree(s->d_cg); cudaFree(s->d_gdis);
+    cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_roff); cudaFree(s->d_gbeg); cudaFree(s->d_gP); cudaFree(s->d_cg); cudaFree(s->d_rcum); cudaFree(s->d_grow); cudaFree(s->d_gkey);
     cudaFree(s->d_obs); cudaFree(s->d_dis); cudaFree(s->d_key);
     cudaFreeHost(s->h_obs); cudaFreeHost(s->h_key);
     if (s->e0) cudaEventDestroy(s->e0);

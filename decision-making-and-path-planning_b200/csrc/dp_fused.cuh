@@ -51,12 +51,20 @@ __device__ __forceinline__ unsigned dp_owner_key(double2 pk, double2 pk1, int bj
     bool pass = true;
     if (bj == 0) pass = fma(mx - pk.x, sx, (my - pk.y) * sy) >= 0.0;
     else if (bj == P - 1) pass = fma(mx - pk1.x, sx, (my - pk1.y) * sy) <= 0.0;
-    const double len = sqrt(dp_sq2(sx, sy));
+    *dout = 0.0;
+    if (!pass) return 0xffffffffu;
+    const double cross = fma(mx - pk.x, sy, -((my - pk.y) * sx));
+    const double len2 = dp_sq2(sx, sy);
+    {   // FP32 pre-reject of obstacles far outside the corridor (|d| = |cross| / len): saves the FP64 sqrt and division
+        const float cf = (float)cross, lf = (float)len2;
+        const float wm = (float)fmax(fabs(lo), fabs(hi)) * 1.001f + 0.01f;
+        if (cf * cf > wm * wm * lf * 1.001f) return 0xffffffffu;
+    }
+    const double len = sqrt(len2);
     double d = 0.0;
-    if (len > 0) d = fma(mx - pk.x, sy, -((my - pk.y) * sx)) / len;
-    pass = pass && (d >= lo && d <= hi);
+    if (len > 0) d = cross / len;
     *dout = d;
-    return pass ? (((unsigned)bj << 16) | (unsigned)o) : 0xffffffffu;
+    return (d >= lo && d <= hi) ? (((unsigned)bj << 16) | (unsigned)o) : 0xffffffffu;
 }
 
 // ---- the four lane-region trajectories share one staging round trip -------------------------------------------
