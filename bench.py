@@ -432,6 +432,7 @@ def run_ours(args, rank, world, local_rank):
                 extras["config4_shard"] = config4_line(torch, dist, P_, m, dev, rank, world, local_rank, 131072)
             else:
                 extras["config4"] = config4_line(torch, dist, P_, m, dev, rank, world, local_rank, 1048576)
+                extras["config3_split"] = config3_split_line(torch, dist, P_, m, dev, rank, world, local_rank)
             extras["config5"] = config5_line(torch, dist, P_, m, dev, rank, world, local_rank)
         except Exception as e:  # noqa: BLE001
             extras["extras_error"] = repr(e)
@@ -570,23 +571,11 @@ def device_cycles(torch, planner, n, d_hdr, d_ox, d_oy, d_rec, episode, warmup, 
 def config3_line(planner_cls, m, calls=10000):
     """BASELINE config 3: one scene, 65 536 candidates (64 lateral offsets x 32 aim distances x 32 horizons), 50 obstacle
     tracks, latency mode: one CUDA-graph replay per call, p50 / p99 over `calls` calls (host buffers in, winner out)."""
-    rng = np.random.default_rng(2024)
-    gl = m.lane_index(3, 2)
-    o = m.lane_pt_off[gl] + 900
-    bx, by = m.x[o:o + 256], m.y[o:o + 256]
-    lat = -3.15 + 0.1 * np.arange(64)
-    aim = 10.0 + 2.5 * np.arange(32)
-    hor = 8 * (1 + np.arange(32))
-    L, A, Hh = np.meshgrid(lat, aim, hor, indexing="ij")
-    n_pts = np.minimum(Hh, np.maximum(2, (A / 0.5).astype(np.int64))).astype(np.int32).ravel()
-    offset = L.ravel()
-    N = 50
+    bx, by, offset, n_pts, ox0, oy0, dvx, dvy = config3_grid(m)
+    N = ox0.size
     p = planner_cls(16, 64)
     p.upload_map(m)
     sess = p.sweep_session(bx, by, offset, n_pts, 64)
-    idx = rng.integers(5, 250, N)
-    ox0, oy0 = bx[idx] + rng.normal(0, 1.5, N), by[idx] + rng.normal(0, 1.5, N)
-    dvx, dvy = rng.normal(0, 0.04, N), rng.normal(0, 0.04, N)
     wall, dev = np.zeros(calls), np.zeros(calls)
     for i in range(50):
         sess.score(ox0, oy0, dvx, dvy, want_dis=False)
@@ -618,6 +607,57 @@ def config3_line(planner_cls, m, calls=10000):
                          "note": "row-sharing formulation: candidates of one lateral offset share one pass per obstacle (3136 distinct (offset, "
                                  "horizon) groups, 64 rows); latency mode is bound by the dependent chain of one (row, obstacle) pass and the "
                                  "graph's launch latency, not by the FMA roofline"}}
+
+
+def config3_grid(m):
+    rng = np.random.default_rng(2024)
+    gl = m.lane_index(3, 2)
+    o = m.lane_pt_off[gl] + 900
+    bx, by = m.x[o:o + 256], m.y[o:o + 256]
+    lat = -3.15 + 0.1 * np.arange(64)
+    aim = 10.0 + 2.5 * np.arange(32)
+    hor = 8 * (1 + np.arange(32))
+    L, A, Hh = np.meshgrid(lat, aim, hor, indexing="ij")
+    n_pts = np.minimum(Hh, np.maximum(2, (A / 0.5).astype(np.int64))).astype(np.int32).ravel()
+    offset = L.ravel()
+    N = 50
+    idx = rng.integers(5, 250, N)
+    ox0, oy0 = bx[idx] + rng.normal(0, 1.5, N), by[idx] + rng.normal(0, 1.5, N)
+    dvx, dvy = rng.normal(0, 0.04, N), rng.normal(0, 0.04, N)
+    return bx, by, offset, n_pts, ox0, oy0, dvx, dvy
+
+
+def config3_split_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, calls=2000):
+    """cross-GPU argmin: ONE scene's 65 536 candidates split over the ranks by contiguous index ranges; every
+    rank scores its range (dp_sweep_score), the winners meet in a packed (cost bits << 32 | global index) int64 MIN all-reduce
+    over NCCL: lowest cost first, lowest global index on ties -- the reference's first feasible candidate."""
+    from dmpp_b200 import parallel
+    bx, by, offset, n_pts, ox0, oy0, dvx, dvy = config3_grid(m)
+    lo, hi = parallel.scene_range(offset.size, rank, world)
+    p = planner_cls(16, 64, device=local_rank)
+    p.upload_map(m)
+    sess = p.sweep_session(bx, by, np.ascontiguousarray(offset[lo:hi]), np.ascontiguousarray(n_pts[lo:hi]), 64)
+    full = p.sweep_session(bx, by, offset, n_pts, 64) if rank == 0 else None
+    wall = np.zeros(calls)
+    agree = True
+    for i in range(calls + 20):
+        ox = ox0 + 0.01 * (i % 97) - (2.0 if i % 5 == 0 else 0.0)           # the obstacles move between calls
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        best, _, _ = sess.score(ox, oy0, dvx, dvy, want_dis=False)
+        cost, win = parallel.global_argmin(0.0 if best >= 0 else float("inf"), (best + lo) if best >= 0 else 0xFFFFFFFF, device=dev)
+        if i >= 20:
+            wall[i - 20] = time.perf_counter() - t0
+        if rank == 0 and i % 50 == 0:
+            fb, _, _ = full.score(ox, oy0, dvx, dvy, want_dis=False)
+            agree = agree and ((fb < 0 and cost == float("inf")) or (fb >= 0 and cost == 0.0 and win == fb))
+    sess.close()
+    if full is not None:
+        full.close()
+    p.close()
+    return {"workload": "config3 split %d-way: 65536 candidates of ONE scene by contiguous index ranges, packed int64 MIN all-reduce (NCCL) of the winners" % world,
+            "calls": calls, "latency_ms": {"p50": float(np.percentile(wall, 50) * 1e3), "p99": float(np.percentile(wall, 99) * 1e3)},
+            "winner_equals_single_gpu": bool(agree)}
 
 
 def config4_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, total_scenes, episode=12, warmup=2, steps=10):
@@ -668,37 +708,66 @@ def config4_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, tota
 
 
 def config5_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, n=1024, n_obs=200, episode=40, warmup=3, steps=20):
-    """BASELINE config 5 shape with the reference's own (static-obstacle) semantics: urban junction scenes (lane + connector
-    reference path, pos 0 -> 1 -> 2 -> 0), 200 agents per scene, Decision rule tree in the same launch (group kernel).
-    Weak scaling: n scenes per GPU."""
+    """BASELINE config 5: urban junction scenes (reference path = lane + connector, ~400 points, pos 1 / 2), 200 agents per scene
+    with constant-turn-rate predicted tracks, T = 400 steps of 0.02 s (8 s horizon): every step rolls the [T x N] track tiles out
+    on the device (dp_set_tracks_dev) and runs the cycle -- junction search against the moving agents, Decision rule tree, Planning
+    -- in one launch of the group kernel.  Weak scaling: n scenes per GPU.  The rollout is inside the timed region."""
     seeds = np.arange(7_000_000 + rank * n, 7_000_000 + (rank + 1) * n)
-    ep = scenes.Episodes(m, seeds, cycles=episode, n_obs=n_obs, kind="junction")
-    H, OX, OY = ep.all_cycles()
+    ep = scenes.Episodes(m, seeds, cycles=episode, n_obs=n_obs, kind="urban")
+    H, OX, OY, VX, VY, DTH = ep.all_cycles_tracks()
+    T = ep.TRACK_T
     p = planner_cls(max_scenes=n, max_obs=n_obs, device=local_rank)
     p.upload_map(m)
     d_hdr = torch.from_numpy(H.view(np.uint8).reshape(episode, n, 128)).to(dev)
     d_ox = torch.from_numpy(OX).to(dev); d_oy = torch.from_numpy(OY).to(dev)
+    d_vx = torch.from_numpy(VX).to(dev); d_vy = torch.from_numpy(VY).to(dev); d_dth = torch.from_numpy(DTH).to(dev)
     d_rec = torch.empty((n, 128), dtype=torch.uint8, device=dev)
+    d_tr = torch.zeros((n, abi.trace_record.itemsize), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    ms, traj, pts = [], 0, 0
     l0 = p.launch_count()
-    ms, traj = device_cycles(torch, p, n, d_hdr, d_ox, d_oy, d_rec, episode, warmup, steps, flush=flush)
+    for i in range(warmup + steps):
+        c = i % episode
+        if c == 0:
+            torch.cuda.synchronize()
+            p.reset(0, n)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        p.set_tracks_dev(n, T, d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_vx[c].data_ptr(), d_vy[c].data_ptr(), d_dth[c].data_ptr(),
+                         stream=st.cuda_stream)
+        p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec.data_ptr(), d_trace=d_tr.data_ptr(), stream=st.cuda_stream)
+        e1.record(st)
+        if i >= warmup:
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+            traj += traj_of(torch, d_rec)
+            pts += int(d_tr.view(torch.int32)[:, abi.trace_record.fields["pts_scored"][1] // 4].to(torch.int64).sum().item())
     launches = p.launch_count() - l0
+    ms = np.array(ms)
     t = torch.tensor([ms.sum()], dtype=torch.float64, device=dev)
-    tr = torch.tensor([float(traj)], dtype=torch.float64, device=dev)
+    tr = torch.tensor([float(traj), float(pts)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+    fp64, _ = p.measure_fma_peak()
     p.close()
     secs = float(t.item()) * 1e-3
-    return {"workload": "config5 shape: %d junction scenes/GPU x %d agents, lane + connector reference path, %d-cycle episodes (pos 0 -> 1 -> 2 -> 0), "
-                        "static obstacles as in the reference (Decision.cpp:162-163); group kernel" % (n, n_obs, episode),
-            "scenes_per_gpu": n, "agents": n_obs, "steps": steps, "warmup": warmup,
-            "value": float(tr.item()) / secs, "unit": UNIT, "plan_cycles_per_s": n * world * steps / secs,
-            "agent_checks_per_s": float(tr.item()) * n_obs / secs,
+    flops = alg_flops(float(tr[1].item()), float(tr[0].item()), n_obs)
+    return {"workload": "config5: %d urban junction scenes/GPU x %d agents with constant-turn-rate tracks (T = %d x 0.02 s), lane + connector "
+                        "reference path (~400 points), %d-cycle episodes; track rollout + cycle (group kernel) per step" % (n, n_obs, T, episode),
+            "scenes_per_gpu": n, "agents": n_obs, "track_steps": T, "steps": steps, "warmup": warmup,
+            "value": float(tr[0].item()) / secs, "unit": UNIT, "plan_cycles_per_s": n * world * steps / secs,
+            "agent_checks_per_s": float(tr[0].item()) * n_obs / secs, "path_points_per_trajectory": float(tr[1].item()) / max(float(tr[0].item()), 1.0),
             "ms_per_step": secs / steps * 1e3, "p50_ms": float(np.percentile(ms, 50)), "p99_ms": float(np.percentile(ms, 99)),
-            "gpu_launches": int(launches), "scaling": "weak", "l2": "256 MiB buffer written between timed steps"}
-
+            "gpu_launches": int(launches), "scaling": "weak", "l2": "256 MiB buffer written between timed steps",
+            "roofline": {"bound": "fp64", "kernel": "dp_group_kernel", "unit": "TFLOP/s", "achieved": flops / secs / 1e12 / world, "peak": fp64,
+                         "frac": flops / secs / 1e12 / world / fp64, "note": "algorithmic flops F(P,N) = 18 P + N (5 P + 12) of the trajectories scored "
+                         "(SURVEY.md 8d), per GPU; the pruned search evaluates a fraction of the P x N pairs, so this is work done per second, "
+                         "not FMA-pipe utilisation"},
+            "hbm": {"tile_bytes_per_step_per_gpu": 16 * T * n_obs * n, "what": "track tiles written by the rollout each step (then read sparsely)"}}
 
 
 _OUT_FD = None

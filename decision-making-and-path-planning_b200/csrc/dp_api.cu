@@ -39,6 +39,9 @@ struct dp_ctx {
     bool have_map = false;
     DgMap gmap;                                             // map tables + pruning bounds + prefix / run-end tables (both kernels)
     DpLaunchCfg lc;                                         // per-context launch state (dp_kernels.h)
+    // predicted agent tracks (dp_set_tracks): [max_scenes][T][max_obs] tiles + per-agent step bounds; tracks_T == 0: static obstacles
+    double* d_tile_x = nullptr; double* d_tile_y = nullptr; float* d_tile_step = nullptr; double* d_trk = nullptr;
+    int tracks_T = 0, tile_cap_T = 0;
     long long* d_timeline = nullptr;                        // DP_TIMELINE=1: phase stamps of the last group launch (dp_debug_timeline)
     int kernel = 0;                                         // 0: warp-per-scene kernel (dp_cycle.cu), 1: group kernel (dp_group.cuh); see dp_create
     std::vector<void*> map_allocs;
@@ -94,8 +97,12 @@ DpIo make_io(dp_ctx* c, int first, dp_plan_record* host_rec) {
 // one cycle of n scenes (carry slots first ..) on stream st
 cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec,
                       dp_trace_record* trace, double* path_xy, double* path_ll, cudaStream_t st, const DpIo& io) {
-    if (c->kernel == 1) {
+    if (c->kernel == 1 || c->tracks_T > 0) {                // (track tiles are only read by the group kernel)
         DgIo g = {};
+        if (c->tracks_T > 0) {
+            const size_t tb = (size_t)first * c->tracks_T * c->max_obs;
+            g.tile_x = c->d_tile_x + tb; g.tile_y = c->d_tile_y + tb; g.tile_step = c->d_tile_step + (size_t)first * c->max_obs; g.tile_T = c->tracks_T;
+        }
         for (int k = 0; k < io.n_mirror; ++k) g.mirror[k] = io.mirror[k];
         g.n_mirror = io.n_mirror; g.tally = io.tally; g.tally_n = io.tally_n; g.host_done = io.host_done; g.epoch = io.epoch;
         g.timeline = (n <= 8192) ? c->d_timeline : nullptr;
@@ -265,7 +272,7 @@ int dp_destroy(dp_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->map_allocs) cudaFree(p);
-    cudaFree(c->d_timeline);
+    cudaFree(c->d_timeline); cudaFree(c->d_tile_x); cudaFree(c->d_tile_y); cudaFree(c->d_tile_step); cudaFree(c->d_trk);
     cudaFree(c->d_carry); cudaFree(c->d_last); cudaFree(c->d_done); cudaFree(c->d_pdone); cudaFree(c->d_inflag); cudaFree(c->d_tally);
     if (c->h_done) cudaFreeHost(c->h_done);
     for (int s = 0; s < 2; ++s) {
@@ -494,7 +501,7 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
     const int s = (int)(c->submitted & 1);
     const size_t mo = (size_t)c->max_obs;
     cudaStream_t st = c->st[0];                             // one compute stream: cycle k+1 reads the carry cycle k wrote
-    if (c->kernel == 1) {
+    if (c->kernel == 1 || c->tracks_T > 0) {
         // group kernel: the three input DMAs overlap on their own copy streams, the launch waits for their events; the kernel
         // stores every record into the caller's page-locked buffer itself and its last CTA raises a flag in page-locked memory
         // (dp_cycle_wait polls it: no event round trip).  The tally word is re-armed by that last CTA, not by a memset.
@@ -559,7 +566,7 @@ int dp_cycle_wait(dp_ctx* c) {
     if (c->submitted == c->waited) return fail(DP_ERR_STATE, "dp_cycle_wait: nothing in flight");
     CK(cudaSetDevice(c->device));
     const int s = (int)(c->waited & 1);
-    if (c->kernel == 1 || (c->chain && c->split == 2)) {
+    if (c->kernel == 1 || c->tracks_T > 0 || (c->chain && c->split == 2)) {
         const unsigned want = c->wait_epoch[s];
         const volatile unsigned* flag = c->h_done + s;
         if (want) {
@@ -589,6 +596,50 @@ int dp_set_record_mirrors(dp_ctx* c, int n, void* const* bases) {
         c->mirror[k] = (dp_plan_record*)bases[k];
     }
     c->n_mirror = n;
+    return DP_OK;
+}
+
+int dp_set_tracks_dev(dp_ctx* c, int first, int n, int T, const double* ox, const double* oy, const double* vx, const double* vy,
+                      const double* dth, void* stream) {
+    if (!c || first < 0 || n < 0 || first + n > c->max_scenes || T < 1 || T > 4096 || !ox || !oy || !vx || !vy || !dth)
+        return fail(DP_ERR_ARG, "dp_set_tracks_dev: bad argument (T in [1, 4096])");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_set_tracks_dev: submitted cycles in flight, call dp_cycle_wait first");
+    CK(cudaSetDevice(c->device));
+    if (T > c->tile_cap_T) {                                // (re)allocate the tiles for the longest horizon seen
+        CK(cudaDeviceSynchronize());
+        cudaFree(c->d_tile_x); cudaFree(c->d_tile_y); cudaFree(c->d_tile_step);
+        c->d_tile_x = c->d_tile_y = nullptr; c->d_tile_step = nullptr; c->tile_cap_T = 0;
+        const size_t cells = (size_t)c->max_scenes * T * c->max_obs;
+        int r;
+        if ((r = dev_alloc(&c->d_tile_x, cells)) || (r = dev_alloc(&c->d_tile_y, cells)) || (r = dev_alloc(&c->d_tile_step, (size_t)c->max_scenes * c->max_obs)))
+            return r;
+        c->tile_cap_T = T;
+    }
+    if (c->tracks_T != 0 && c->tracks_T != T) return fail(DP_ERR_STATE, "dp_set_tracks_dev: one horizon per context (dp_clear_tracks first)");
+    const size_t tb = (size_t)first * T * c->max_obs;
+    CK(dp_launch_tracks(n, c->max_obs, T, ox, oy, vx, vy, dth, c->d_tile_x + tb, c->d_tile_y + tb, c->d_tile_step + (size_t)first * c->max_obs,
+                        (cudaStream_t)stream));
+    ++c->launches;
+    c->tracks_T = T;
+    return DP_OK;
+}
+int dp_set_tracks(dp_ctx* c, int first, int n, int T, const double* ox, const double* oy, const double* vx, const double* vy, const double* dth) {
+    if (!c || n < 0 || !ox || !oy || !vx || !vy || !dth) return fail(DP_ERR_ARG, "dp_set_tracks: bad argument");
+    CK(cudaSetDevice(c->device));
+    const size_t cnt = (size_t)n * c->max_obs;
+    if (!c->d_trk) { int r = dev_alloc(&c->d_trk, (size_t)c->max_scenes * c->max_obs * 5); if (r) return r; }
+    const double* src[5] = {ox, oy, vx, vy, dth};
+    for (int k = 0; k < 5; ++k) CK(cudaMemcpyAsync(c->d_trk + (size_t)k * c->max_scenes * c->max_obs, src[k], cnt * 8, cudaMemcpyHostToDevice, c->st[0]));
+    const size_t st = (size_t)c->max_scenes * c->max_obs;
+    int r = dp_set_tracks_dev(c, first, n, T, c->d_trk, c->d_trk + st, c->d_trk + 2 * st, c->d_trk + 3 * st, c->d_trk + 4 * st, c->st[0]);
+    if (r != DP_OK) return r;
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+int dp_clear_tracks(dp_ctx* c) {
+    if (!c) return fail(DP_ERR_ARG, "dp_clear_tracks: null context");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_clear_tracks: submitted cycles in flight, call dp_cycle_wait first");
+    c->tracks_T = 0;
     return DP_OK;
 }
 

@@ -1,8 +1,11 @@
 // host/PlannerBatch.h -- batched host mirror of the two reference classes: what `CDecision::Instance()` +
 // `CPlanning::Instance()` (Decision.h:105-107, Planning.h:38-40) become when N independent scenes are planned at
 // once.  One `Cycle()` = one iteration of CDecisionThread (Decision.cpp:119-206) + one of CPlanningThread
-// (Planning.cpp:64-226) for every scene, in ONE fused CUDA launch.  Thin, header-only wrapper of the C ABI.
+// (Planning.cpp:64-226) for every scene (one launch of the group kernel, or the overlapped Decision / Planning launch pair of
+// the warp-per-scene kernel: csrc/dp_cycle.cu).  Thin, header-only wrapper of the C ABI; the class surface of the two
+// reference singletons on top of it is in BatchFacade.h.  Compiled and run by tests/test_facade_cpp.py.
 #pragma once
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>

@@ -22,6 +22,7 @@ SYMBOLS = [
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
     "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
     "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev", "dp_debug_timeline",
+    "dp_set_tracks", "dp_set_tracks_dev", "dp_clear_tracks",
 ]
 
 _lib = None
@@ -109,6 +110,38 @@ class Planner:
                                     abi.ptr(o.get("path_xy") if paths else None),
                                     abi.ptr(o.get("path_ll") if paths else None)), "dp_cycle_batch")
         return o
+
+    # ---- predicted agent tracks (BASELINE config 5): constant-turn-rate parameters per obstacle point ----
+    def set_tracks(self, ox, oy, vx, vy, dth, T, first=0):
+        n = ox.shape[0]
+        assert all(a.shape == (n, self.max_obs) for a in (ox, oy, vx, vy, dth))
+        _ck(self.lib.dp_set_tracks(self.ctx, C.c_int(first), C.c_int(n), C.c_int(T), abi.ptr(ox), abi.ptr(oy), abi.ptr(vx), abi.ptr(vy),
+                                   abi.ptr(dth)), "dp_set_tracks")
+
+    def set_tracks_dev(self, n, T, d_ox, d_oy, d_vx, d_vy, d_dth, first=0, stream=0):
+        _ck(self.lib.dp_set_tracks_dev(self.ctx, C.c_int(first), C.c_int(n), C.c_int(T), C.c_void_p(d_ox), C.c_void_p(d_oy), C.c_void_p(d_vx),
+                                       C.c_void_p(d_vy), C.c_void_p(d_dth), C.c_void_p(stream)), "dp_set_tracks_dev")
+
+    def clear_tracks(self):
+        _ck(self.lib.dp_clear_tracks(self.ctx), "dp_clear_tracks")
+
+    def run_episodes_tracks(self, H, OX, OY, VX, VY, DTH, T, trace=True, paths=True):
+        """run_episodes with a fresh track tile before every cycle"""
+        cycles, n = H.shape
+        self.reset(0, n)
+        out = {"rec": np.zeros((cycles, n), abi.plan_record),
+               "trace": np.zeros((cycles, n), abi.trace_record) if trace else None,
+               "path_xy": np.zeros((cycles, n, 2, abi.PATH_POINTS)) if paths else None,
+               "path_ll": np.zeros((cycles, n, 2, abi.OUT_POINTS)) if paths else None}
+        for c in range(cycles):
+            o = {"rec": out["rec"][c], "trace": out["trace"][c] if trace else None,
+                 "path_xy": out["path_xy"][c] if paths else None, "path_ll": out["path_ll"][c] if paths else None}
+            cc = np.ascontiguousarray
+            self.set_tracks(cc(OX[c]), cc(OY[c]), cc(VX[c]), cc(VY[c]), cc(DTH[c]), T)
+            self.cycle(cc(H[c]), cc(OX[c]), cc(OY[c]), trace=trace, paths=paths, out=o)
+        self.clear_tracks()
+        out["carry"], out["last_path"] = self.download_carry(0, n)
+        return out
 
     def set_record_mirrors(self, bases):
         """bases: device-accessible addresses (ints); every finished record of slot s is also stored at base + 128 * s"""

@@ -172,8 +172,12 @@ class Map:
 class Episodes:
     """Scripted (open-loop) episodes: `hdr(c)`, `obstacles(c)` give the inputs of cycle c for all scenes.
 
-    kind: 'highway' (roads 1-5, pos 0) or 'junction' (roads 6/7 + connector, pos 0 -> 1 -> 2 -> 0).
+    kind: 'highway' (roads 1-5, pos 0), 'junction' (roads 6/7 + connector, pos 0 -> 1 -> 2 -> 0) or 'urban' (BASELINE config 5:
+    the same junction approached from far away with the whole approach treated as the pre-junction zone, so the reference
+    path lane + connector has ~400 points; `tracks(c)` gives every agent a constant-turn-rate prediction, T = 400 steps of 0.02 s).
     """
+    TRACK_T = 400
+    TRACK_DT = 0.02
 
     def __init__(self, m: Map, seeds, n_obs=10, kind="highway", cycles=25, roads=None):
         self.m = m
@@ -199,6 +203,8 @@ class Episodes:
             self.nl = np.full(self.n, 2, np.int64)
             self.lane0 = 1 + (rnd(sd, S_LANE) * 2).astype(np.int64)
             self.s0 = 150.0 + rnd(sd, S_ID0) * 35.0           # 14.5 .. 49.5 m before the stop line
+            if kind == "urban":                               # 70 % of the scenes start 170-190 m before it
+                self.s0 = np.where(rnd(sd, S_KIND) < 0.7, 10.0 + rnd(sd, S_ID0) * 20.0, self.s0)
             self.v = 12.0 + rnd(sd, S_SPEED) * 25.0
         self.wob_a = rnd(sd, S_WOB_A) * 0.3
         self.wob_w = 0.2 + rnd(sd, S_WOB_W) * 0.6
@@ -315,7 +321,7 @@ class Episodes:
             h["x"] = x - wob * np.sin(hr)
             h["y"] = y + wob * np.cos(hr)
             h["dir"] = np.mod(hd + yaw + 360.0, 360.0)
-            pre = in_app & (s > app_len - 30.0)                    # pre-junction zone: last 30 m
+            pre = in_app & ((s > app_len - 30.0) | (self.kind == "urban"))   # pre-junction zone: last 30 m (urban: the whole approach)
             h["pos"] = np.where(in_con, 2, np.where(pre, 1, 0))
             h["road_num"] = np.where(in_app, 6, 7)                 # in the junction: NEXT road (Decision.cpp:417)
             h["lane_num"] = lane
@@ -369,6 +375,36 @@ class Episodes:
             H[c] = self.hdr(c)
             OX[c], OY[c] = self.obstacles(c)
         return H, OX, OY
+
+    def tracks(self, c):
+        """constant-turn-rate prediction of every agent at cycle c: per-step displacement (vx, vy) [m per 0.02 s step] along the
+        heading of the lane it is on, and a small constant heading change per step [deg]; each [n, n_obs]."""
+        m = self.m
+        t = self.elapsed_s(c)[:, None]
+        s = self.ob_s0 + self.ob_v * t
+        app_len = 399 * SPACING
+        gl6 = m.road_lane_base[5].astype(np.int64) + self.ob_lane - 1
+        gl7 = m.road_lane_base[6].astype(np.int64) + self.ob_lane - 1
+        gc = m.conn["lane"][self.ob_lane - 1].astype(np.int64)
+        clen = (m.lane_pt_off[gc + 1] - m.lane_pt_off[gc] - 1) * SPACING
+        in_app = s < app_len
+        in_con = (~in_app) & (s < app_len + clen)
+        _, _, ha, _ = self._lane_xy(gl6, np.clip(s, 0.0, app_len))
+        _, _, hc, _ = self._lane_xy(gc, np.clip(s - app_len, 0.0, clen))
+        _, _, hdd, _ = self._lane_xy(gl7, np.maximum(s - app_len - clen, 0.0))
+        hr = np.radians(np.where(in_app, ha, np.where(in_con, hc, hdd)))
+        step = self.ob_v * self.TRACK_DT
+        k = np.arange(self.n_obs, dtype=np.uint64)[None, :]
+        dth = (rnd(self.seeds[:, None], S_YAW, k + np.uint64(7000)) - 0.5) * 0.1
+        return np.ascontiguousarray(step * np.cos(hr)), np.ascontiguousarray(step * np.sin(hr)), np.ascontiguousarray(dth)
+
+    def all_cycles_tracks(self):
+        """all_cycles() plus the track parameters VX, VY, DTH, each [cycles][n][n_obs]"""
+        H, OX, OY = self.all_cycles()
+        VX = np.zeros_like(OX); VY = np.zeros_like(OX); DTH = np.zeros_like(OX)
+        for c in range(self.cycles):
+            VX[c], VY[c], DTH[c] = self.tracks(c)
+        return H, OX, OY, VX, VY, DTH
 
 
 # streams of the directed families

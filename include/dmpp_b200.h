@@ -269,6 +269,21 @@ int dp_mean_points(dp_ctx* ctx, int n_paths, const int32_t* path_off, const doub
 /* device properties + FMA micro-benchmark used as roofline denominator:
  * returns measured FP64 / FP32 FMA throughput in TFLOP/s on the context's device. */
 int dp_measure_fma_peak(dp_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
+/* Predicted agent tracks (BASELINE config 5; a generalisation: the reference has the members z_DynaObs_front/rear, Decision.h:14-15,
+ * but their getters are commented out, Decision.cpp:162-163).  Every obstacle point of scenes [first, first+n) gets a constant-
+ * turn-rate prediction of T steps: position j+1 = position j + v_j, v_{j+1} = v_j rotated by dtheta degrees (vx, vy: metres per
+ * step at step 0; arrays [n][max_obs]; operations pinned in oracle/cshare_spec.h rollout_ctr).  The [T x max_obs] tile of each
+ * scene is rolled out on the device; from then on the junction search (Decision.cpp:370, :455: pos 1 / 2) of every cycle runs
+ * against the moving agents -- agent o is at tile[min(j, T-1)][o] when the ego reaches path point j -- while the lane-region,
+ * avoid and local-path searches keep the static positions of the cycle call, as in the reference.  Cycles then use the group
+ * kernel whatever the context's kernel choice.  Call again before each cycle whose agents moved; dp_clear_tracks switches back.
+ * _dev: device pointers, asynchronous on `stream` (the cycle must be launched on the same stream). */
+int dp_set_tracks(dp_ctx* ctx, int first_scene, int n_scenes, int T, const double* obs_x, const double* obs_y, const double* vx,
+                  const double* vy, const double* dtheta_deg);
+int dp_set_tracks_dev(dp_ctx* ctx, int first_scene, int n_scenes, int T, const double* obs_x, const double* obs_y, const double* vx,
+                      const double* vy, const double* dtheta_deg, void* stream);
+int dp_clear_tracks(dp_ctx* ctx);
+
 /* diagnostic: phase time stamps (globaltimer, ns) of the most recent cycle launch, one row of 32 per CTA (row b = scenes
  * [b*g, (b+1)*g) of the batch; stamp 0 = CTA start, stamp i = end of phase i of csrc/dp_group.cuh).  Only contexts created
  * with DP_TIMELINE=1 in the environment record them; used by tools/group_timeline.py, never by the product path. */

@@ -55,6 +55,7 @@ class Oracle(_Runner):
         if self.lib is None:
             raise RuntimeError("oracle/liboracle.so missing: run __graft_entry__.build()")
         self.lib.oracle_run_batch.restype = C.c_longlong
+        self.lib.oracle_run_batch_tracks.restype = C.c_longlong
         self.lib.oracle_atan.restype = C.c_double
         self.lib.oracle_atan.argtypes = [C.c_double]
         self.lib.oracle_calc_global_dir.restype = C.c_double
@@ -88,6 +89,28 @@ class Oracle(_Runner):
         o["seconds"] = sec.value
         o["traj"] = traj.value
         return o
+
+    def run_tracks(self, H, OX, OY, VX, VY, DTH, T, paths=True, trace=True, threads=1):
+        """episodes with predicted agent tracks (BASELINE config 5): constant-turn-rate parameters per cycle / scene / agent"""
+        cycles, n = H.shape
+        max_obs = OX.shape[2]
+        o = self._alloc(n, cycles, paths, False, trace)
+        sec = C.c_double(0)
+        ub = self.lib.oracle_run_batch_tracks(
+            C.byref(self.params), C.c_int(n), C.c_int(cycles), C.c_int(max_obs), abi.ptr(H), abi.ptr(OX), abi.ptr(OY), abi.ptr(VX),
+            abi.ptr(VY), abi.ptr(DTH), C.c_int(T), abi.ptr(o["rec"]), abi.ptr(o["trace"]), abi.ptr(o["path_xy"]), abi.ptr(o["path_ll"]),
+            abi.ptr(o["carry"]), abi.ptr(o["last_path"]), C.c_int(threads), C.byref(sec))
+        if ub < 0:
+            raise RuntimeError("oracle_run_batch_tracks failed: %d" % ub)
+        o["ub_hits"] = ub
+        o["seconds"] = sec.value
+        return o
+
+    def rollout_ctr(self, x0, y0, vx, vy, dth, T):
+        ox, oy = np.zeros(T), np.zeros(T)
+        self.lib.oracle_rollout_ctr.argtypes = [C.c_double] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.oracle_rollout_ctr(x0, y0, vx, vy, dth, T, abi.ptr(ox), abi.ptr(oy))
+        return ox, oy
 
     BRANCHES = ["b3_nav_1108", "b3_obs_1382", "b3_both_1618", "b3_both_1711", "enter_1596", "enter_1688", "aim_right_473",
                 "aim_right_walk"]

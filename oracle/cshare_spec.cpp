@@ -183,6 +183,55 @@ SearchResult search_obstacle_tracks(const P2* p, int P, const P2* obs, const P2*
     return r;
 }
 
+void rollout_ctr(double x0, double y0, double vx, double vy, double dtheta_deg, int T, double* out_x, double* out_y, int stride) {
+    double c, s;
+    spec_sincos_deg(dtheta_deg, &c, &s);
+    double x = x0, y = y0;
+    for (int j = 0; j < T; ++j) {
+        out_x[(size_t)j * stride] = x; out_y[(size_t)j * stride] = y;
+        x = x + vx; y = y + vy;
+        const double nvx = std::fma(c, vx, -(s * vy)), nvy = std::fma(s, vx, c * vy);
+        vx = nvx; vy = nvy;
+    }
+}
+
+SearchResult search_obstacle_tile(const P2* p, int P, const double* tx, const double* ty, int T, int N, double lat_min, double lat_max) {
+    SearchResult r{false, NOT_FOUND, NOT_FOUND, -1, 0};
+    if (P < 2 || T < 1) return r;
+    int best_j = P;
+    for (int o = 0; o < N; ++o) {
+        double bd = 0; int bj = 0;
+        for (int j = 0; j < P; ++j) {
+            const int jt = j < T ? j : T - 1;
+            const double ox = tx[(size_t)jt * N + o], oy = ty[(size_t)jt * N + o];
+            double d = sq2(ox - p[j].x, oy - p[j].y);
+            if (j == 0 || d < bd) { bd = d; bj = j; }
+        }
+        const int jt = bj < T ? bj : T - 1;
+        const double ox = tx[(size_t)jt * N + o], oy = ty[(size_t)jt * N + o];
+        int k = (bj == P - 1) ? P - 2 : bj;
+        double sx = p[k + 1].x - p[k].x, sy = p[k + 1].y - p[k].y;
+        if (bj == 0) {
+            double dot = std::fma(ox - p[0].x, sx, (oy - p[0].y) * sy);
+            if (!(dot >= 0)) continue;
+        } else if (bj == P - 1) {
+            double dot = std::fma(ox - p[P - 1].x, sx, (oy - p[P - 1].y) * sy);
+            if (!(dot <= 0)) continue;
+        }
+        double len = std::sqrt(sq2(sx, sy));
+        double d = 0;
+        if (len > 0) d = std::fma(ox - p[k].x, sy, -((oy - p[k].y) * sx)) / len;
+        if (!(d >= lat_min && d <= lat_max)) continue;
+        if (bj < best_j) { best_j = bj; r.found = true; r.dis_lat = d; r.ob_index = o; r.pathid = bj; }
+    }
+    if (r.found) {
+        double s = 0;
+        for (int i = 0; i < r.pathid; ++i) s += std::sqrt(sq2(p[i + 1].x - p[i].x, p[i + 1].y - p[i].y));
+        r.dis_lng = s;
+    }
+    return r;
+}
+
 void create_new_path(const P2* p, int P, double d, P2* out) {
     if (P < 2) {
         for (int j = 0; j < P; ++j) out[j] = p[j];

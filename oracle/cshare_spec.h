@@ -92,6 +92,19 @@ SearchResult search_obstacle(const P2* path, int P, const P2* obs, int N,
 SearchResult search_obstacle_tracks(const P2* path, int P, const P2* obs, const P2* dv, int N,
                                     double lat_min, double lat_max);
 
+// Predicted agent tracks of BASELINE config 5 (the reference has no prediction: Decision.cpp:162-163 comments the dynamic
+// obstacle getters out).  Constant-turn-rate rollout, T positions per agent, every operation pinned:
+//   (c, s) = spec_sincos_deg(dtheta);  x_0 = x0, y_0 = y0, v_0 = (vx, vy)  [metres per step];
+//   x_{j+1} = x_j + vx_j;  y_{j+1} = y_j + vy_j;  vx_{j+1} = fma(c, vx_j, -(s * vy_j));  vy_{j+1} = fma(s, vx_j, c * vy_j).
+// out_x / out_y are written with stride `stride` (the [T x N] track tile of a scene: element j of agent o at j * N + o).
+void rollout_ctr(double x0, double y0, double vx, double vy, double dtheta_deg, int T, double* out_x, double* out_y, int stride);
+
+// search_obstacle against a [T x N] track tile: agent o is at (tile_x[j' * N + o], tile_y[j' * N + o]), j' = min(j, T-1), when
+// the ego reaches path point j (an agent keeps its last predicted position beyond the horizon).  Step 1 compares
+// |o(j) - p_j|^2 over j; steps 2-5 use the position at j = j*.  T == 1 is exactly search_obstacle.
+SearchResult search_obstacle_tile(const P2* path, int P, const double* tile_x, const double* tile_y, int T, int N,
+                                  double lat_min, double lat_max);
+
 // CShare::CreateNewPath(path, d): lateral-offset copy, d > 0 shifts to the RIGHT of the direction
 // of travel (Decision.cpp:629 uses -W for the left lane, :942 -0.3*i for "left avoid").
 //   segment for point j: (j, j+1), last point reuses (P-2, P-1);

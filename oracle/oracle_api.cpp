@@ -76,6 +76,68 @@ long long oracle_run_batch(const dp_params* p, int n, int cycles, int max_obs, c
     return ub.load();
 }
 
+// Same as oracle_run_batch with predicted agent tracks (BASELINE config 5): per cycle and scene the constant-turn-rate parameters
+// trk_vx / trk_vy [m per step] and trk_dth [deg per step], [cycles][n][max_obs]; the [T x n_obs] tile of a scene is rolled out from
+// its obstacle positions (spec::rollout_ctr) and the junction search runs against it.  No reference counterpart exists.
+long long oracle_run_batch_tracks(const dp_params* p, int n, int cycles, int max_obs, const dp_scene_hdr* hdr, const double* ox,
+                                  const double* oy, const double* trk_vx, const double* trk_vy, const double* trk_dth, int T,
+                                  dp_plan_record* rec, dp_trace_record* trace, double* path_xy, double* path_ll, dp_carry* carry_out,
+                                  double* last_path_out, int threads, double* seconds) {
+    if (!g_have_map) return -1;
+    if (threads < 1) threads = 1;
+    std::atomic<long long> ub(0);
+    auto work = [&](int s0, int s1) {
+        std::vector<double> tx((size_t)T * max_obs), ty((size_t)T * max_obs);
+        long long lub = 0;
+        for (int s = s0; s < s1; ++s) {
+            oracle::SceneState st;
+            oracle::reset_state(st);
+            for (int c = 0; c < cycles; ++c) {
+                size_t e = (size_t)c * n + s;
+                const int no = hdr[e].n_obs < max_obs ? hdr[e].n_obs : max_obs;
+                for (int o = 0; o < no; ++o)
+                    spec::rollout_ctr(ox[e * max_obs + o], oy[e * max_obs + o], trk_vx[e * max_obs + o], trk_vy[e * max_obs + o],
+                                      trk_dth[e * max_obs + o], T, tx.data() + o, ty.data() + o, no);
+                oracle::CycleOut o{};
+                o.rec = rec + e;
+                o.trace = trace ? trace + e : nullptr;
+                o.path_xy = path_xy ? path_xy + e * 400 : nullptr;
+                o.path_ll = path_ll ? path_ll + e * 200 : nullptr;
+                o.tile_x = tx.data(); o.tile_y = ty.data(); o.tile_T = T;
+                oracle::cycle(g_map, *p, hdr[e], ox + e * max_obs, oy + e * max_obs, st, o, true);
+                lub += o.ub_hits;
+            }
+            if (carry_out) carry_out[s] = st.c;
+            if (last_path_out) {
+                std::memcpy(last_path_out + (size_t)s * 400, st.last_x, sizeof(st.last_x));
+                std::memcpy(last_path_out + (size_t)s * 400 + 200, st.last_y, sizeof(st.last_y));
+            }
+        }
+        ub += lub;
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    if (threads == 1) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; ++t) th.emplace_back(work, (int)((long long)n * t / threads), (int)((long long)n * (t + 1) / threads));
+        for (auto& x : th) x.join();
+    }
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return ub.load();
+}
+void oracle_search_obstacle_tile(const double* px, const double* py, int P, const double* tx, const double* ty, int T, int N, double lo,
+                                 double hi, dp_search_slot* out) {
+    std::vector<spec::P2> path(P);
+    for (int i = 0; i < P; ++i) path[i] = spec::P2{px[i], py[i]};
+    spec::SearchResult r = spec::search_obstacle_tile(path.data(), P, tx, ty, T, N, lo, hi);
+    std::memset(out, 0, sizeof(*out));
+    out->dis_lat = r.dis_lat; out->dis_lng = r.dis_lng; out->ob_index = (int16_t)r.ob_index; out->pathid = (uint16_t)r.pathid;
+    out->evaluated = 1; out->found = r.found;
+}
+void oracle_rollout_ctr(double x0, double y0, double vx, double vy, double dth, int T, double* out_x, double* out_y) {
+    spec::rollout_ctr(x0, y0, vx, vy, dth, T, out_x, out_y, 1);
+}
+
 // hit counters of the right-lane-change sites since the last reset (planner_oracle.h, BR_*)
 void oracle_branch_hits(long long* out, int reset) {
     for (int i = 0; i < oracle::BR_COUNT; ++i) {

@@ -408,7 +408,16 @@ void junction_decision(Ctx& k, SceneState& st, Path& refpath) {
         for (int i = 0; i < std::min(60, n); ++i) F.push_back(k.m.pt(gl, i));       // :446-452
     }
     const double Vw = k.p.vehicle_width;
-    spec::SearchResult s = search(k, F, -0.5 * Vw, 0.5 * Vw, k.out.trace ? &k.out.trace->junction : nullptr);   // :370 / :455
+    spec::SearchResult s;
+    if (k.out.tile_x && k.out.tile_T > 0) {                 // predicted tracks: the same call against the scene's track tile
+        s = spec::search_obstacle_tile(F.data(), (int)F.size(), k.out.tile_x, k.out.tile_y, k.out.tile_T, k.n_obs, -0.5 * Vw, 0.5 * Vw);
+        ++k.out.n_calls; ++k.n_traj; k.pts += (long)F.size();
+        if (k.out.trace) {
+            dp_search_slot* slot = &k.out.trace->junction;
+            slot->dis_lat = s.dis_lat; slot->dis_lng = s.dis_lng; slot->ob_index = (int16_t)s.ob_index;
+            slot->pathid = (uint16_t)s.pathid; slot->evaluated = 1; slot->found = s.found;
+        }
+    } else s = search(k, F, -0.5 * Vw, 0.5 * Vw, k.out.trace ? &k.out.trace->junction : nullptr);   // :370 / :455
     if (s.dis_lng < 13) {
         double v = s.dis_lng - 3;
         c.velocity_expect = v > 0 ? v : 0;              // max(dis_lng - 3, 0)

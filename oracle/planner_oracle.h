@@ -50,6 +50,9 @@ struct CycleOut {
     int calls_cap;
     int n_calls;                   // out
     int ub_hits;                   // out: reference UB sites the restatement had to define (should stay 0)
+    // in (BASELINE config 5 generalisation, nullable): the scene's [T x n_obs] predicted track tile; the junction search
+    // (Decision.cpp:370, :455) then runs against moving agents (spec::search_obstacle_tile).  Everything else stays static.
+    const double* tile_x = nullptr; const double* tile_y = nullptr; int tile_T = 0;
 };
 
 // exhaustive_sweep: also evaluate the avoid candidates the reference skips after its `break`

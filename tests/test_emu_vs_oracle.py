@@ -33,3 +33,17 @@ def test_group_kernel_logic_matches_oracle(emu, oracle, the_map, kind, seed0, n,
     check(got, want, kind)
     fast = emu.run(H, OX, OY, group=group, trace=False, paths=False)   # the untraced path stops its sums early: same records
     assert fast["rec"].tobytes() == got["rec"].tobytes()
+
+
+@pytest.mark.parametrize("n_obs,n,group", [(50, 64, 14), (200, 16, 16)])
+def test_group_kernel_logic_with_predicted_tracks(emu, oracle, the_map, n_obs, n, group):
+    """BASELINE config 5: junction search against constant-turn-rate track tiles (T = 400), ~400-point reference paths"""
+    from dmpp_b200 import scenes
+    ep = scenes.Episodes(the_map, np.arange(900, 900 + n), cycles=40, kind="urban", n_obs=n_obs)
+    H, OX, OY, VX, VY, DTH = ep.all_cycles_tracks()
+    want = oracle.run_tracks(H, OX, OY, VX, VY, DTH, ep.TRACK_T, threads=4)
+    static = oracle.run(H, OX, OY, threads=4)
+    assert (want["trace"]["junction"]["pathid"] != static["trace"]["junction"]["pathid"]).mean() > 0.3   # the tracks matter
+    assert np.percentile(want["trace"]["refpath_len"], 50) > 300
+    got = emu.run_tracks(H, OX, OY, VX, VY, DTH, ep.TRACK_T, group=group)
+    check(got, want, "urban tracks")

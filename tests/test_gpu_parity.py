@@ -103,6 +103,26 @@ def test_urban_junction_200_agents(oracle, the_map):
     assert set(np.unique(H["pos"]).tolist()) == {0, 1, 2}
 
 
+@pytest.mark.parametrize("n_obs,n", [(200, 96), (10, 256)])
+def test_urban_predicted_tracks(oracle, the_map, n_obs, n):
+    """BASELINE config 5: ~400-point lane + connector reference paths, every agent with a constant-turn-rate track of T = 400
+    steps rolled out on the device (dp_set_tracks); the junction search runs against the moving agents.  Bit-exact vs the
+    oracle's tile search; N = 10 goes through a context that would otherwise use the warp kernel."""
+    from dmpp_b200 import scenes
+    from dmpp_b200.planner import Planner
+    ep = scenes.Episodes(the_map, np.arange(40_000, 40_000 + n), cycles=40, kind="urban", n_obs=n_obs)
+    H, OX, OY, VX, VY, DTH = ep.all_cycles_tracks()
+    want = oracle.run_tracks(H, OX, OY, VX, VY, DTH, ep.TRACK_T, threads=8)
+    p = Planner(max_scenes=n, max_obs=n_obs)
+    p.upload_map(the_map)
+    got = p.run_episodes_tracks(H, OX, OY, VX, VY, DTH, ep.TRACK_T)
+    check(got, want, "urban tracks N=%d" % n_obs)
+    static = p.run_episodes(H, OX, OY)                      # tracks cleared: the reference's static semantics again
+    p.close()
+    check(static, oracle.run(H, OX, OY, threads=8), "urban static N=%d" % n_obs)
+    assert (got["trace"]["junction"]["pathid"] != static["trace"]["junction"]["pathid"]).mean() > 0.3
+
+
 def test_zero_obstacles_and_ragged(planner, oracle, the_map):
     from dmpp_b200 import scenes
     ep = scenes.Episodes(the_map, np.arange(300, 300 + 256), cycles=8, n_obs=12)

@@ -128,3 +128,28 @@ def test_mean_points_345_polyline(oracle):
     assert np.all(one[0] == 2.0) and np.all(one[1] == 5.0)
     dup = oracle.mean_points([1.0, 1.0, 2.0], [0.0, 0.0, 0.0])   # zero-length first segment
     assert dup[0, 0] == 1.0 and dup[0, -1] == 2.0 and np.all(np.diff(dup[0]) >= 0)
+
+
+def test_ctr_rollout_and_tile_search(oracle):
+    """constant-turn-rate rollout: a quarter turn per step walks the unit square; a tile of T = 1 is the static search"""
+    import ctypes as C
+    from dmpp_b200 import abi
+    x, y = oracle.rollout_ctr(0.0, 0.0, 1.0, 0.0, 90.0, 5)
+    assert np.allclose(x, [0, 1, 1, 0, 0], atol=1e-15) and np.allclose(y, [0, 0, 1, 1, 0], atol=1e-15)
+    x, y = oracle.rollout_ctr(3.0, -2.0, 0.25, 0.1, 0.0, 9)            # no turn: exact arithmetic progression of binary fractions
+    assert np.array_equal(x, 3.0 + 0.25 * np.arange(9))
+    px, py = straight(120)
+    ox = np.array([10.2, 30.1, 55.0]); oy = np.array([0.3, -0.5, 2.5])
+    want = oracle.search_obstacle(px, py, ox, oy, -0.9, 0.9)
+    out = np.zeros(1, abi.search_slot)
+    oracle.lib.oracle_search_obstacle_tile(abi.ptr(np.ascontiguousarray(px)), abi.ptr(np.ascontiguousarray(py)), C.c_int(120),
+                                           abi.ptr(ox), abi.ptr(oy), C.c_int(1), C.c_int(3), C.c_double(-0.9), C.c_double(0.9), abi.ptr(out))
+    for f in ("dis_lat", "dis_lng", "ob_index", "pathid", "found"):
+        assert out[0][f] == want[f], f
+    # an agent that drives away along the path at the ego's pace is met later than a parked one
+    T = 120
+    tx = np.zeros((T, 1)); ty = np.zeros((T, 1))
+    tx[:, 0] = 20.0 + 0.25 * np.arange(T)
+    oracle.lib.oracle_search_obstacle_tile(abi.ptr(np.ascontiguousarray(px)), abi.ptr(np.ascontiguousarray(py)), C.c_int(120),
+                                           abi.ptr(tx), abi.ptr(ty), C.c_int(T), C.c_int(1), C.c_double(-0.9), C.c_double(0.9), abi.ptr(out))
+    assert out[0]["found"] == 1 and out[0]["pathid"] == 80 and out[0]["dis_lng"] == 40.0

@@ -32,6 +32,21 @@ class Emu:
         self._desc = m.desc()
         assert self.lib.emu_set_map(C.byref(self._desc)) == 0
 
+    def run_tracks(self, H, OX, OY, VX, VY, DTH, T, trace=True, paths=True, group=14):
+        cycles, n = H.shape
+        max_obs = OX.shape[2]
+        o = {"rec": np.zeros((cycles, n), abi.plan_record),
+             "trace": np.zeros((cycles, n), abi.trace_record) if trace else None,
+             "path_xy": np.zeros((cycles, n, 2, abi.PATH_POINTS)) if paths else None,
+             "path_ll": np.zeros((cycles, n, 2, abi.OUT_POINTS)) if paths else None,
+             "carry": np.zeros(n, abi.carry), "last_path": np.zeros((n, 2, abi.PATH_POINTS))}
+        rc = self.lib.emu_run_batch_tracks(C.byref(self.params), C.c_int(n), C.c_int(cycles), C.c_int(max_obs), abi.ptr(H), abi.ptr(OX),
+                                           abi.ptr(OY), abi.ptr(VX), abi.ptr(VY), abi.ptr(DTH), C.c_int(T), abi.ptr(o["rec"]),
+                                           abi.ptr(o["trace"]), abi.ptr(o["path_xy"]), abi.ptr(o["path_ll"]), abi.ptr(o["carry"]),
+                                           abi.ptr(o["last_path"]), C.c_int(group))
+        assert rc == 0, rc
+        return o
+
     def run(self, H, OX, OY, trace=True, paths=True, group=14):
         cycles, n = H.shape
         max_obs = OX.shape[2]
