@@ -709,9 +709,9 @@ def config4_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, tota
 
 def config5_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, n=1024, n_obs=200, episode=40, warmup=3, steps=20):
     """BASELINE config 5: urban junction scenes (reference path = lane + connector, ~400 points, pos 1 / 2), 200 agents per scene
-    with constant-turn-rate predicted tracks, T = 400 steps of 0.02 s (8 s horizon): every step rolls the [T x N] track tiles out
-    on the device (dp_set_tracks_dev) and runs the cycle -- junction search against the moving agents, Decision rule tree, Planning
-    -- in one launch of the group kernel.  Weak scaling: n scenes per GPU.  The rollout is inside the timed region."""
+    with constant-turn-rate predicted tracks, T = 400 steps of 0.02 s (8 s horizon): one launch of the group kernel per step --
+    track rollout fused into the junction search against the moving agents (never materialised), Decision rule tree, Planning.
+    Weak scaling: n scenes per GPU."""
     seeds = np.arange(7_000_000 + rank * n, 7_000_000 + (rank + 1) * n)
     ep = scenes.Episodes(m, seeds, cycles=episode, n_obs=n_obs, kind="urban")
     H, OX, OY, VX, VY, DTH = ep.all_cycles_tracks()
@@ -735,8 +735,7 @@ def config5_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, n=10
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        p.set_tracks_dev(n, T, d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_vx[c].data_ptr(), d_vy[c].data_ptr(), d_dth[c].data_ptr(),
-                         stream=st.cuda_stream)
+        p.set_tracks_dev(T, d_vx[c].data_ptr(), d_vy[c].data_ptr(), d_dth[c].data_ptr())
         p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec.data_ptr(), d_trace=d_tr.data_ptr(), stream=st.cuda_stream)
         e1.record(st)
         if i >= warmup:
@@ -757,7 +756,7 @@ def config5_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, n=10
     secs = float(t.item()) * 1e-3
     flops = alg_flops(float(tr[1].item()), float(tr[0].item()), n_obs)
     return {"workload": "config5: %d urban junction scenes/GPU x %d agents with constant-turn-rate tracks (T = %d x 0.02 s), lane + connector "
-                        "reference path (~400 points), %d-cycle episodes; track rollout + cycle (group kernel) per step" % (n, n_obs, T, episode),
+                        "reference path (~400 points), %d-cycle episodes; one group-kernel launch per step" % (n, n_obs, T, episode),
             "scenes_per_gpu": n, "agents": n_obs, "track_steps": T, "steps": steps, "warmup": warmup,
             "value": float(tr[0].item()) / secs, "unit": UNIT, "plan_cycles_per_s": n * world * steps / secs,
             "agent_checks_per_s": float(tr[0].item()) * n_obs / secs, "path_points_per_trajectory": float(tr[1].item()) / max(float(tr[0].item()), 1.0),
@@ -767,7 +766,7 @@ def config5_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, n=10
                          "frac": flops / secs / 1e12 / world / fp64, "note": "algorithmic flops F(P,N) = 18 P + N (5 P + 12) of the trajectories scored "
                          "(SURVEY.md 8d), per GPU; the pruned search evaluates a fraction of the P x N pairs, so this is work done per second, "
                          "not FMA-pipe utilisation"},
-            "hbm": {"tile_bytes_per_step_per_gpu": 16 * T * n_obs * n, "what": "track tiles written by the rollout each step (then read sparsely)"}}
+            "tracks": "constant-turn-rate rollout fused into the search: T x N positions per scene exist only in registers"}
 
 
 _OUT_FD = None

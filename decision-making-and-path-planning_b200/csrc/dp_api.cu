@@ -39,9 +39,11 @@ struct dp_ctx {
     bool have_map = false;
     DgMap gmap;                                             // map tables + pruning bounds + prefix / run-end tables (both kernels)
     DpLaunchCfg lc;                                         // per-context launch state (dp_kernels.h)
-    // predicted agent tracks (dp_set_tracks): [max_scenes][T][max_obs] tiles + per-agent step bounds; tracks_T == 0: static obstacles
-    double* d_tile_x = nullptr; double* d_tile_y = nullptr; float* d_tile_step = nullptr; double* d_trk = nullptr;
-    int tracks_T = 0, tile_cap_T = 0;
+    // predicted agent tracks (dp_set_tracks): constant-turn-rate parameters of every obstacle point, indexed by carry slot;
+    // tracks_T == 0: static obstacles.  d_trk: the context's own copy for the host-pointer form ([3][max_scenes][max_obs])
+    const double* trk_vx = nullptr; const double* trk_vy = nullptr; const double* trk_dth = nullptr;
+    double* d_trk = nullptr;
+    int tracks_T = 0;
     long long* d_timeline = nullptr;                        // DP_TIMELINE=1: phase stamps of the last group launch (dp_debug_timeline)
     int kernel = 0;                                         // 0: warp-per-scene kernel (dp_cycle.cu), 1: group kernel (dp_group.cuh); see dp_create
     std::vector<void*> map_allocs;
@@ -100,8 +102,8 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
     if (c->kernel == 1 || c->tracks_T > 0) {                // (track tiles are only read by the group kernel)
         DgIo g = {};
         if (c->tracks_T > 0) {
-            const size_t tb = (size_t)first * c->tracks_T * c->max_obs;
-            g.tile_x = c->d_tile_x + tb; g.tile_y = c->d_tile_y + tb; g.tile_step = c->d_tile_step + (size_t)first * c->max_obs; g.tile_T = c->tracks_T;
+            const size_t tb = (size_t)first * c->max_obs;
+            g.trk_vx = c->trk_vx + tb; g.trk_vy = c->trk_vy + tb; g.trk_dth = c->trk_dth + tb; g.trk_T = c->tracks_T;
         }
         for (int k = 0; k < io.n_mirror; ++k) g.mirror[k] = io.mirror[k];
         g.n_mirror = io.n_mirror; g.tally = io.tally; g.tally_n = io.tally_n; g.host_done = io.host_done; g.epoch = io.epoch;
@@ -272,7 +274,7 @@ int dp_destroy(dp_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->map_allocs) cudaFree(p);
-    cudaFree(c->d_timeline); cudaFree(c->d_tile_x); cudaFree(c->d_tile_y); cudaFree(c->d_tile_step); cudaFree(c->d_trk);
+    cudaFree(c->d_timeline); cudaFree(c->d_trk);
     cudaFree(c->d_carry); cudaFree(c->d_last); cudaFree(c->d_done); cudaFree(c->d_pdone); cudaFree(c->d_inflag); cudaFree(c->d_tally);
     if (c->h_done) cudaFreeHost(c->h_done);
     for (int s = 0; s < 2; ++s) {
@@ -599,41 +601,22 @@ int dp_set_record_mirrors(dp_ctx* c, int n, void* const* bases) {
     return DP_OK;
 }
 
-int dp_set_tracks_dev(dp_ctx* c, int first, int n, int T, const double* ox, const double* oy, const double* vx, const double* vy,
-                      const double* dth, void* stream) {
-    if (!c || first < 0 || n < 0 || first + n > c->max_scenes || T < 1 || T > 4096 || !ox || !oy || !vx || !vy || !dth)
-        return fail(DP_ERR_ARG, "dp_set_tracks_dev: bad argument (T in [1, 4096])");
+int dp_set_tracks_dev(dp_ctx* c, int T, const double* vx, const double* vy, const double* dth) {
+    if (!c || T < 1 || !vx || !vy || !dth) return fail(DP_ERR_ARG, "dp_set_tracks_dev: bad argument");
     if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_set_tracks_dev: submitted cycles in flight, call dp_cycle_wait first");
-    CK(cudaSetDevice(c->device));
-    if (T > c->tile_cap_T) {                                // (re)allocate the tiles for the longest horizon seen
-        CK(cudaDeviceSynchronize());
-        cudaFree(c->d_tile_x); cudaFree(c->d_tile_y); cudaFree(c->d_tile_step);
-        c->d_tile_x = c->d_tile_y = nullptr; c->d_tile_step = nullptr; c->tile_cap_T = 0;
-        const size_t cells = (size_t)c->max_scenes * T * c->max_obs;
-        int r;
-        if ((r = dev_alloc(&c->d_tile_x, cells)) || (r = dev_alloc(&c->d_tile_y, cells)) || (r = dev_alloc(&c->d_tile_step, (size_t)c->max_scenes * c->max_obs)))
-            return r;
-        c->tile_cap_T = T;
-    }
-    if (c->tracks_T != 0 && c->tracks_T != T) return fail(DP_ERR_STATE, "dp_set_tracks_dev: one horizon per context (dp_clear_tracks first)");
-    const size_t tb = (size_t)first * T * c->max_obs;
-    CK(dp_launch_tracks(n, c->max_obs, T, ox, oy, vx, vy, dth, c->d_tile_x + tb, c->d_tile_y + tb, c->d_tile_step + (size_t)first * c->max_obs,
-                        (cudaStream_t)stream));
-    ++c->launches;
-    c->tracks_T = T;
+    c->trk_vx = vx; c->trk_vy = vy; c->trk_dth = dth; c->tracks_T = T;
     return DP_OK;
 }
-int dp_set_tracks(dp_ctx* c, int first, int n, int T, const double* ox, const double* oy, const double* vx, const double* vy, const double* dth) {
-    if (!c || n < 0 || !ox || !oy || !vx || !vy || !dth) return fail(DP_ERR_ARG, "dp_set_tracks: bad argument");
+int dp_set_tracks(dp_ctx* c, int first, int n, int T, const double* vx, const double* vy, const double* dth) {
+    if (!c || first < 0 || n < 0 || first + n > c->max_scenes || T < 1 || !vx || !vy || !dth) return fail(DP_ERR_ARG, "dp_set_tracks: bad argument");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_set_tracks: submitted cycles in flight, call dp_cycle_wait first");
     CK(cudaSetDevice(c->device));
-    const size_t cnt = (size_t)n * c->max_obs;
-    if (!c->d_trk) { int r = dev_alloc(&c->d_trk, (size_t)c->max_scenes * c->max_obs * 5); if (r) return r; }
-    const double* src[5] = {ox, oy, vx, vy, dth};
-    for (int k = 0; k < 5; ++k) CK(cudaMemcpyAsync(c->d_trk + (size_t)k * c->max_scenes * c->max_obs, src[k], cnt * 8, cudaMemcpyHostToDevice, c->st[0]));
-    const size_t st = (size_t)c->max_scenes * c->max_obs;
-    int r = dp_set_tracks_dev(c, first, n, T, c->d_trk, c->d_trk + st, c->d_trk + 2 * st, c->d_trk + 3 * st, c->d_trk + 4 * st, c->st[0]);
-    if (r != DP_OK) return r;
+    const size_t st = (size_t)c->max_scenes * c->max_obs, cnt = (size_t)n * c->max_obs, off = (size_t)first * c->max_obs;
+    if (!c->d_trk) { int r = dev_alloc(&c->d_trk, st * 3); if (r) return r; CK(cudaMemset(c->d_trk, 0, st * 3 * 8)); }
+    const double* src[3] = {vx, vy, dth};
+    for (int k = 0; k < 3; ++k) CK(cudaMemcpyAsync(c->d_trk + (size_t)k * st + off, src[k], cnt * 8, cudaMemcpyHostToDevice, c->st[0]));
     CK(cudaStreamSynchronize(c->st[0]));
+    c->trk_vx = c->d_trk; c->trk_vy = c->d_trk + st; c->trk_dth = c->d_trk + 2 * st; c->tracks_T = T;
     return DP_OK;
 }
 int dp_clear_tracks(dp_ctx* c) {

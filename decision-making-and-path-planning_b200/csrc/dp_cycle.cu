@@ -1026,19 +1026,6 @@ __global__ void dp_map_prep2_kernel(const double* lenp, const uint16_t* attr, co
     }
 }
 
-// ---- predicted agent tracks (BASELINE config 5): one thread per (scene, agent) rolls the constant-turn-rate model out into the
-// scene's [T x max_obs] tile (adjacent threads = adjacent agents: the T row writes are coalesced) and leaves the bound of one
-// step's displacement that the pruned search needs (dp_group.cuh, dg_rollout_ctr) ----
-__global__ void dp_tracks_kernel(int n_scenes, int max_obs, int T, const double* __restrict__ ox, const double* __restrict__ oy,
-                                 const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ dth,
-                                 double* __restrict__ tile_x, double* __restrict__ tile_y, float* __restrict__ tile_step) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_scenes * max_obs) return;
-    const int s = i / max_obs, o = i - s * max_obs;
-    const size_t base = (size_t)s * T * max_obs + o;
-    tile_step[i] = dg_rollout_ctr(ox[i], oy[i], vx[i], vy[i], dth[i], T, tile_x + base, tile_y + base, max_obs);
-}
-
 // ---- the group kernel (dp_group.cuh): one CTA = g scenes ----
 template <int G, int TPB>
 __global__ void __launch_bounds__(TPB, (G <= 8) ? 4 : 2)   // G 16: 2 CTAs x 256 threads x 128 regs; G 8: 4 CTAs/SM (TPB 128: 128 regs, TPB 256: 64 regs)
@@ -1109,13 +1096,6 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
                              : cudaLaunchKernelEx(&cfg, dp_cycle_kernel<2, 1>, m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2);
         if (e != cudaSuccess) return e;
     }
-    return cudaGetLastError();
-}
-cudaError_t dp_launch_tracks(int n_scenes, int max_obs, int T, const double* ox, const double* oy, const double* vx, const double* vy,
-                             const double* dth, double* tile_x, double* tile_y, float* tile_step, cudaStream_t st) {
-    if (n_scenes <= 0) return cudaSuccess;
-    const int total = n_scenes * max_obs;
-    dp_tracks_kernel<<<(total + 127) / 128, 128, 0, st>>>(n_scenes, max_obs, T, ox, oy, vx, vy, dth, tile_x, tile_y, tile_step);
     return cudaGetLastError();
 }
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st) {

@@ -95,9 +95,9 @@ struct DgIo {
     dp_plan_record* mirror[DG_MAX_MIRRORS]; int n_mirror;
     unsigned* tally; unsigned tally_n; unsigned* host_done; unsigned epoch;
     long long* timeline;                           // instrumented runs only (tools/group_timeline.py): [block][32] globaltimer stamps
-    // predicted agent tracks (BASELINE config 5, dp_set_tracks): [scene][T][max_obs] positions rolled out by dp_tracks_kernel and
-    // the per-agent bound of one step's displacement; null = static obstacles (the reference's own semantics)
-    const double* tile_x; const double* tile_y; const float* tile_step; int tile_T;
+    // predicted agent tracks (BASELINE config 5, dp_set_tracks): constant-turn-rate parameters [scene][max_obs] -- displacement of
+    // step 0 (vx, vy) and heading change per step (deg) -- and the horizon T; null = static obstacles (the reference's semantics)
+    const double* trk_vx; const double* trk_vy; const double* trk_dth; int trk_T;
 };
 
 // ---- small portable helpers ---------------------------------------------------------------------------------------------
@@ -365,74 +365,40 @@ DG_FN DgArg dg_refine_f(PF pt, const int P, const double ox, const double oy, un
     }
     return r;
 }
-// Moving obstacles (track tiles): ob(j) is the agent's position when the ego reaches path point j.  |ob(j) - p_j| changes by at
-// most hb + step per index step (both ends move), so the same cell filter holds with that radius; the corridor reach filter
-// is not used (its derivation assumes a fixed point), dmax = +inf.
-template <class PF, class OB>
-DG_FN unsigned long long dg_coarse_mv(PF pt, OB ob, const int P, const float hbs) {
-    const float FINF = dg_inff();
-    float ubf = FINF;
-    const float R = 4.0f * hbs * 1.0001f + 1e-3f;
-    unsigned long long mask = 0;
-    for (int c0 = 0, ch = 0; c0 < P; c0 += 128, ++ch) {
-        float dc[16];
-        float mn = FINF;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const int j0 = c0 + 8 * c;
-            float f = FINF;
-            if (j0 < P) {
-                const int jm = dg_imin(j0 + 4, P - 1);
-                const double2 q = pt(jm), o = ob(jm);
-                const double dx = o.x - q.x, dy = o.y - q.y;
-                f = (float)fma(dx, dx, dy * dy);
-            }
-            dc[c] = f;
-            mn = fminf(mn, f);
-        }
-        ubf = fminf(ubf, sqrtf(mn) * 1.0001f + 1e-3f);
-        const float thr = ubf + R;
-        const float thr2 = thr * thr * 1.0001f;
-        unsigned m16 = 0;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) m16 |= (dc[c] <= thr2) ? (1u << c) : 0u;
-        mask |= (unsigned long long)m16 << (16 * ch);
-    }
-    return mask;
-}
-template <class PF, class OB>
-DG_FN DgArg dg_refine_mv(PF pt, OB ob, const int P, unsigned long long mask) {
-    const double INF = dg_inf();
-    DgArg r; r.bd = INF; r.bj = 0;
-    while (mask) {
-#if defined(DP_EMU)
-        const int c = __builtin_ctzll(mask);
-#else
-        const int c = __ffsll((long long)mask) - 1;
-#endif
-        mask &= mask - 1;
-        for (int j = 8 * c; j < dg_imin(8 * c + 8, P); ++j) {
-            const double2 q = pt(j), o = ob(j);
-            const double dx = o.x - q.x, dy = o.y - q.y;
-            const double e = fma(dx, dx, dy * dy);
-            if (e < r.bd) { r.bd = e; r.bj = j; }
+// Moving agents (BASELINE config 5): fused rollout -> nearest-point search of ONE agent against ONE trajectory.  The agent follows
+// the constant-turn-rate model of oracle/cshare_spec.h (rollout_ctr): position j+1 = position j + v_j, v_{j+1} = v_j rotated by
+// dtheta, frozen after step T-1; it is at position j when the ego reaches path point j.  The predicted track is never
+// materialised: the recurrence advances in registers while the path is walked, strict '<' keeps the lowest index, and the
+// agent's position at the argmin is what steps 2-5 of SearchObstacle (gates, lateral offset, corridor) see.
+struct DgTrk { double x, y; DgArg a; };
+template <class PF>
+DG_FN DgTrk dg_track_search(PF pt, const int P, double x, double y, double vx, double vy, const double dth, const int T) {
+    double c, s;
+    dg_sincos_deg(dth, &c, &s);
+    DgTrk r; r.x = x; r.y = y; r.a.bd = dg_inf(); r.a.bj = 0;
+    for (int j = 0; j < P; ++j) {
+        const double2 q = pt(j);
+        const double dx = x - q.x, dy = y - q.y;
+        const double e = fma(dx, dx, dy * dy);
+        if (e < r.a.bd) { r.a.bd = e; r.a.bj = j; r.x = x; r.y = y; }
+        if (j + 1 < T) {
+            x = x + vx; y = y + vy;
+            const double nvx = fma(c, vx, -(s * vy)), nvy = fma(s, vx, c * vy);
+            vx = nvx; vy = nvy;
         }
     }
     return r;
 }
-// constant-turn-rate rollout of one agent (oracle/cshare_spec.h rollout_ctr): T positions, written with stride `stride`
-DG_FN float dg_rollout_ctr(double x, double y, double vx, double vy, double dth, int T, double* out_x, double* out_y, int stride) {
+// the agent's position at step j (the same recurrence, for the one selected agent of a trajectory)
+DG_FN double2 dg_track_pos(double x, double y, double vx, double vy, const double dth, const int T, const int j) {
     double c, s;
     dg_sincos_deg(dth, &c, &s);
-    float step2 = 0.f;
-    for (int j = 0; j < T; ++j) {
-        out_x[(size_t)j * stride] = x; out_y[(size_t)j * stride] = y;
-        step2 = fmaxf(step2, (float)(vx * vx + vy * vy));
+    for (int i = 0; i < j && i + 1 < T; ++i) {
         x = x + vx; y = y + vy;
         const double nvx = fma(c, vx, -(s * vy)), nvy = fma(s, vx, c * vy);
         vx = nvx; vy = nvy;
     }
-    return sqrtf(step2) * 1.001f + 1e-6f;          // bound of one step's displacement
+    return make_double2(x, y);
 }
 
 template <int MODE>
@@ -599,7 +565,7 @@ struct DgCtl {
 // one trajectory of a scan phase, by value
 struct DgJob {
     DgView v; double lo, hi; unsigned* key; int P, scene; float hb, dmax;
-    const double* tx; const double* ty; const float* tstep; int tT, tN;   // the scene's track tile (null: static obstacles)
+    const double* tvx; const double* tvy; const double* tdth; int tT;     // the scene's agent tracks (null: static obstacles)
 };
 
 template <int G>
@@ -736,31 +702,12 @@ DG_BODY dg_scan_phase(DgSmem<G>& sm, const int njobs, const int first, const dou
                 if (jq.P < 2 || o >= sm.ctl[jq.scene].N) continue;
                 const size_t ob = (size_t)(first + jq.scene) * max_obs + o;
                 const double ox = obs_x[ob], oy = obs_y[ob];
-                if (jq.tx) {                       // predicted tracks: the agent moves while the ego advances along the path
-                    const int T = jq.tT, N = jq.tN;
+                if (jq.tvx) {                      // predicted tracks: fused rollout + search of this agent, no survivor list
                     const DgView& vv = jq.v;
-                    if (jq.P > 512) {              // longer than the 64-cell mask: every point, in this thread
-                        double bd = dg_inf(); int bj = 0;
-                        for (int j = 0; j < jq.P; ++j) {
-                            const double2 q = dg_point_any(vv, j);
-                            const size_t qi = (size_t)dg_imin(j, T - 1) * N + o;
-                            const double dx = jq.tx[qi] - q.x, dy = jq.ty[qi] - q.y;
-                            const double e = fma(dx, dx, dy * dy);
-                            if (e < bd) { bd = e; bj = j; }
-                        }
-                        const size_t qi = (size_t)dg_imin(bj, T - 1) * N + o;
-                        double d;
-                        const unsigned key = dg_key(vv, jq.P, bj, o, jq.tx[qi], jq.ty[qi], jq.lo, jq.hi, &d);
-                        if (key != 0xffffffffu) dg_atomic_min_u32(jq.key, key);
-                        continue;
-                    }
-                    const unsigned long long mk = dg_coarse_mv([&](int j) { return dg_point_any(vv, j); },
-                        [&](int j) { const size_t q = (size_t)dg_imin(j, T - 1) * N + o; return make_double2(jq.tx[q], jq.ty[q]); },
-                        jq.P, jq.hb + jq.tstep[o]);
-                    if (mk) {
-                        const int pos = dg_atomic_add_i32(cnt, 1);
-                        list[pos] = (unsigned)(it - t0); masks[pos] = mk;
-                    }
+                    const DgTrk t = dg_track_search([&](int j) { return dg_point_any(vv, j); }, jq.P, ox, oy, jq.tvx[o], jq.tvy[o], jq.tdth[o], jq.tT);
+                    double d;
+                    const unsigned key = dg_key(vv, jq.P, t.a.bj, o, t.x, t.y, jq.lo, jq.hi, &d);
+                    if (key != 0xffffffffu) dg_atomic_min_u32(jq.key, key);
                     continue;
                 }
                 if (jq.P > 512) {                  // longer than the 64-cell mask: the whole search in this thread
@@ -790,17 +737,6 @@ DG_BODY dg_scan_phase(DgSmem<G>& sm, const int njobs, const int first, const dou
                 const DgJob jq = job(jb);
                 const size_t ob = (size_t)(first + jq.scene) * max_obs + o;
                 const double ox = obs_x[ob], oy = obs_y[ob];
-                if (jq.tx) {
-                    const int T = jq.tT, N = jq.tN;
-                    const DgView& vv = jq.v;
-                    const DgArg a = dg_refine_mv([&](int j) { return dg_point_any(vv, j); },
-                        [&](int j) { const size_t q = (size_t)dg_imin(j, T - 1) * N + o; return make_double2(jq.tx[q], jq.ty[q]); }, jq.P, masks[e]);
-                    const size_t q = (size_t)dg_imin(a.bj, T - 1) * N + o;          // steps 2-5 use the agent's position at j = j*
-                    double d;
-                    const unsigned key = dg_key(jq.v, jq.P, a.bj, o, jq.tx[q], jq.ty[q], jq.lo, jq.hi, &d);
-                    if (key != 0xffffffffu) dg_atomic_min_u32(jq.key, key);
-                    continue;
-                }
                 const bool plain = (jq.v.n1 == 0 && jq.v.d == 0.0);
                 const DgArg a = plain ? dg_refine<0>(jq.v, jq.P, ox, oy, masks[e]) : dg_refine<1>(jq.v, jq.P, ox, oy, masks[e]);
                 if (!dg_within_reach(a.bd, jq.dmax)) continue;
@@ -993,10 +929,10 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
         DgPath& pa = sm.path[s][r];
         DgJob j;
         j.v = dg_view(m, pa, nullptr); j.lo = pa.lo; j.hi = pa.hi; j.key = &pa.key; j.P = pa.n0 + pa.n1; j.scene = s; j.hb = pa.hb; j.dmax = pa.dmax;
-        j.tx = nullptr; j.ty = nullptr; j.tstep = nullptr; j.tT = 0; j.tN = max_obs;
-        if (io.tile_x && r == 0 && sm.ctl[s].pos != 0) {      // the junction search (Decision.cpp:370, :455) against the scene's track tile
-            const size_t tb = (size_t)(first + s) * io.tile_T * max_obs;
-            j.tx = io.tile_x + tb; j.ty = io.tile_y + tb; j.tstep = io.tile_step + (size_t)(first + s) * max_obs; j.tT = io.tile_T;
+        j.tvx = nullptr; j.tvy = nullptr; j.tdth = nullptr; j.tT = 0;
+        if (io.trk_vx && r == 0 && sm.ctl[s].pos != 0) {      // the junction search (Decision.cpp:370, :455) against the moving agents
+            const size_t tb = (size_t)(first + s) * max_obs;
+            j.tvx = io.trk_vx + tb; j.tvy = io.trk_vy + tb; j.tdth = io.trk_dth + tb; j.tT = io.trk_T;
         }
         return j;
     });
@@ -1028,11 +964,12 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
         const size_t ob = (size_t)(first + s) * max_obs;
         const DgView v = dg_view(m, pa, nullptr);
         DgRes res;
-        if (io.tile_x && r == 0 && sm.ctl[s].pos != 0 && pa.key != 0xffffffffu && P >= 2) {
+        if (io.trk_vx && r == 0 && sm.ctl[s].pos != 0 && pa.key != 0xffffffffu && P >= 2) {
             const int jstar = (int)(pa.key >> 16), ostar = (int)(pa.key & 0xffffu);
-            const size_t q = ((size_t)(first + s) * io.tile_T + dg_imin(jstar, io.tile_T - 1)) * max_obs + ostar;
+            const size_t q = ob + ostar;
+            const double2 at = dg_track_pos(obs_x[q], obs_y[q], io.trk_vx[q], io.trk_vy[q], io.trk_dth[q], io.trk_T, jstar);
             double d;
-            dg_key(v, P, jstar, ostar, io.tile_x[q], io.tile_y[q], pa.lo, pa.hi, &d);
+            dg_key(v, P, jstar, ostar, at.x, at.y, pa.lo, pa.hi, &d);
             res = dg_res_none(); res.found = 1; res.pathid = jstar; res.ob = ostar; res.dis_lat = d;
         } else res = dg_selected(v, P, pa.key, obs_x + ob, obs_y + ob, pa.lo, pa.hi);
         if (res.found) {
@@ -1269,7 +1206,7 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
             DgPath pa = sm.path[s][0];
             DgJob j;
             j.scene = s; j.lo = -0.5 * Vw; j.hi = 0.5 * Vw; j.key = &sm.swkey[s][u];
-            j.tx = nullptr; j.ty = nullptr; j.tstep = nullptr; j.tT = 0; j.tN = max_obs;
+            j.tvx = nullptr; j.tvy = nullptr; j.tdth = nullptr; j.tT = 0;
             if (u >= k.sweep_cnt) { j.P = 0; j.hb = 0.f; j.dmax = 0.f; j.v = dg_view(m, pa, nullptr); return j; }
             pa.d = dg_sweep_offset(dg_sweep_g(u, k.K), k.K);
             j.v = dg_view(m, pa, nullptr); j.P = pa.n0;
@@ -1856,7 +1793,7 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
         const DgCtl& k = sm.ctl[s];
         DgJob j;
         j.v = dg_view(m, pa, sm.plan[s]); j.lo = pa.lo; j.hi = pa.hi; j.key = &pa.key; j.P = pa.n0; j.scene = s;
-        j.tx = nullptr; j.ty = nullptr; j.tstep = nullptr; j.tT = 0; j.tN = max_obs;
+        j.tvx = nullptr; j.tvy = nullptr; j.tdth = nullptr; j.tT = 0;
         j.hb = sqrtf(dg_bits_float(k.hb2_bits)) * 1.0001f + 1e-4f;
         const float hmin = sqrtf(dg_bits_float(k.hmin2_bits)) * 0.9999f - 1e-6f;
         // |u/|u| - w/|w|| <= 2 |u - w| / (|u| + |w|) <= |u - w| / hmin for consecutive segment vectors u, w

@@ -112,15 +112,14 @@ class Planner:
         return o
 
     # ---- predicted agent tracks (BASELINE config 5): constant-turn-rate parameters per obstacle point ----
-    def set_tracks(self, ox, oy, vx, vy, dth, T, first=0):
-        n = ox.shape[0]
-        assert all(a.shape == (n, self.max_obs) for a in (ox, oy, vx, vy, dth))
-        _ck(self.lib.dp_set_tracks(self.ctx, C.c_int(first), C.c_int(n), C.c_int(T), abi.ptr(ox), abi.ptr(oy), abi.ptr(vx), abi.ptr(vy),
-                                   abi.ptr(dth)), "dp_set_tracks")
+    def set_tracks(self, vx, vy, dth, T, first=0):
+        n = vx.shape[0]
+        assert all(a.shape == (n, self.max_obs) for a in (vx, vy, dth))
+        _ck(self.lib.dp_set_tracks(self.ctx, C.c_int(first), C.c_int(n), C.c_int(T), abi.ptr(vx), abi.ptr(vy), abi.ptr(dth)), "dp_set_tracks")
 
-    def set_tracks_dev(self, n, T, d_ox, d_oy, d_vx, d_vy, d_dth, first=0, stream=0):
-        _ck(self.lib.dp_set_tracks_dev(self.ctx, C.c_int(first), C.c_int(n), C.c_int(T), C.c_void_p(d_ox), C.c_void_p(d_oy), C.c_void_p(d_vx),
-                                       C.c_void_p(d_vy), C.c_void_p(d_dth), C.c_void_p(stream)), "dp_set_tracks_dev")
+    def set_tracks_dev(self, T, d_vx, d_vy, d_dth):
+        """device arrays [max_scenes][max_obs], referenced until clear_tracks / the next set"""
+        _ck(self.lib.dp_set_tracks_dev(self.ctx, C.c_int(T), C.c_void_p(d_vx), C.c_void_p(d_vy), C.c_void_p(d_dth)), "dp_set_tracks_dev")
 
     def clear_tracks(self):
         _ck(self.lib.dp_clear_tracks(self.ctx), "dp_clear_tracks")
@@ -137,7 +136,7 @@ class Planner:
             o = {"rec": out["rec"][c], "trace": out["trace"][c] if trace else None,
                  "path_xy": out["path_xy"][c] if paths else None, "path_ll": out["path_ll"][c] if paths else None}
             cc = np.ascontiguousarray
-            self.set_tracks(cc(OX[c]), cc(OY[c]), cc(VX[c]), cc(VY[c]), cc(DTH[c]), T)
+            self.set_tracks(cc(VX[c]), cc(VY[c]), cc(DTH[c]), T)
             self.cycle(cc(H[c]), cc(OX[c]), cc(OY[c]), trace=trace, paths=paths, out=o)
         self.clear_tracks()
         out["carry"], out["last_path"] = self.download_carry(0, n)

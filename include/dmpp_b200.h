@@ -270,18 +270,18 @@ int dp_mean_points(dp_ctx* ctx, int n_paths, const int32_t* path_off, const doub
  * returns measured FP64 / FP32 FMA throughput in TFLOP/s on the context's device. */
 int dp_measure_fma_peak(dp_ctx* ctx, double* fp64_tflops, double* fp32_tflops);
 /* Predicted agent tracks (BASELINE config 5; a generalisation: the reference has the members z_DynaObs_front/rear, Decision.h:14-15,
- * but their getters are commented out, Decision.cpp:162-163).  Every obstacle point of scenes [first, first+n) gets a constant-
- * turn-rate prediction of T steps: position j+1 = position j + v_j, v_{j+1} = v_j rotated by dtheta degrees (vx, vy: metres per
- * step at step 0; arrays [n][max_obs]; operations pinned in oracle/cshare_spec.h rollout_ctr).  The [T x max_obs] tile of each
- * scene is rolled out on the device; from then on the junction search (Decision.cpp:370, :455: pos 1 / 2) of every cycle runs
- * against the moving agents -- agent o is at tile[min(j, T-1)][o] when the ego reaches path point j -- while the lane-region,
- * avoid and local-path searches keep the static positions of the cycle call, as in the reference.  Cycles then use the group
- * kernel whatever the context's kernel choice.  Call again before each cycle whose agents moved; dp_clear_tracks switches back.
- * _dev: device pointers, asynchronous on `stream` (the cycle must be launched on the same stream). */
-int dp_set_tracks(dp_ctx* ctx, int first_scene, int n_scenes, int T, const double* obs_x, const double* obs_y, const double* vx,
-                  const double* vy, const double* dtheta_deg);
-int dp_set_tracks_dev(dp_ctx* ctx, int first_scene, int n_scenes, int T, const double* obs_x, const double* obs_y, const double* vx,
-                      const double* vy, const double* dtheta_deg, void* stream);
+ * but their getters are commented out, Decision.cpp:162-163).  Every obstacle point gets a constant-turn-rate prediction of T
+ * steps: position 0 = the obstacle point of the cycle call, position j+1 = position j + v_j, v_{j+1} = v_j rotated by dtheta
+ * degrees, frozen after step T-1 (vx, vy: metres per step at step 0; operations pinned in oracle/cshare_spec.h rollout_ctr).
+ * From then on the junction search of every cycle (Decision.cpp:370, :455: pos 1 / 2) runs against the moving agents -- agent o is
+ * at its position j when the ego reaches path point j; the rollout is fused into the search, the track is never materialised --
+ * while the lane-region, avoid and local-path searches keep the static positions, as in the reference.  Cycles then use the
+ * group kernel whatever the context's kernel choice.  dp_clear_tracks switches back.
+ *   dp_set_tracks     host arrays [n_scenes][max_obs] for carry slots first_scene .., copied into the context;
+ *   dp_set_tracks_dev device arrays [max_scenes][max_obs] indexed by carry slot, referenced (not copied): they must stay valid,
+ *                     and may be rewritten between cycles in stream order. */
+int dp_set_tracks(dp_ctx* ctx, int first_scene, int n_scenes, int T, const double* vx, const double* vy, const double* dtheta_deg);
+int dp_set_tracks_dev(dp_ctx* ctx, int T, const double* vx, const double* vy, const double* dtheta_deg);
 int dp_clear_tracks(dp_ctx* ctx);
 
 /* diagnostic: phase time stamps (globaltimer, ns) of the most recent cycle launch, one row of 32 per CTA (row b = scenes

@@ -90,8 +90,7 @@ int emu_run_batch(const dp_params* p, int n, int cycles, int max_obs, const dp_s
     return emu_run_batch_tracks(p, n, cycles, max_obs, hdr, ox, oy, nullptr, nullptr, nullptr, 0, rec, trace, path_xy, path_ll, carry_out,
                                 last_path_out, group);
 }
-// with predicted agent tracks (vx != null): the tile of every scene is rolled out on the host before each cycle, exactly what
-// dp_tracks_kernel does on the device
+// with predicted agent tracks (vx != null): constant-turn-rate parameters [cycles][n][max_obs]
 int emu_run_batch_tracks(const dp_params* p, int n, int cycles, int max_obs, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                          const double* vx, const double* vy, const double* dth, int T, dp_plan_record* rec, dp_trace_record* trace,
                          double* path_xy, double* path_ll, dp_carry* carry_out, double* last_path_out, int group) {
@@ -106,19 +105,9 @@ int emu_run_batch_tracks(const dp_params* p, int n, int cycles, int max_obs, con
     }
     DgSmem<G>* sm = new DgSmem<G>();
     DgIo io; std::memset(&io, 0, sizeof(io));
-    std::vector<double> tx, ty; std::vector<float> tstep;
-    if (vx) { tx.resize((size_t)n * T * max_obs); ty.resize(tx.size()); tstep.resize((size_t)n * max_obs); }
     for (int c = 0; c < cycles; ++c) {
         const size_t e = (size_t)c * n;
-        if (vx) {
-            for (int s = 0; s < n; ++s)
-                for (int o = 0; o < max_obs; ++o) {
-                    const size_t q = (e + s) * max_obs + o;
-                    tstep[(size_t)s * max_obs + o] = dg_rollout_ctr(ox[q], oy[q], vx[q], vy[q], dth[q], T, &tx[((size_t)s * T) * max_obs + o],
-                                                                    &ty[((size_t)s * T) * max_obs + o], max_obs);
-                }
-            io.tile_x = tx.data(); io.tile_y = ty.data(); io.tile_step = tstep.data(); io.tile_T = T;
-        }
+        if (vx) { io.trk_vx = vx + e * max_obs; io.trk_vy = vy + e * max_obs; io.trk_dth = dth + e * max_obs; io.trk_T = T; }
         for (int first = 0; first < n; first += group) {
             const int S = (n - first < group) ? n - first : group;
             std::memset(sm, 0xA5, sizeof(*sm));             // uninitialised shared memory
