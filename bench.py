@@ -216,9 +216,21 @@ def run_ours(args, rank, world, local_rank):
     # collective is a barrier, run on a side stream beside the next step's kernels.  Three gathered buffers rotate so that a
     # step never overwrites records a peer may still be reading.
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    gath = hdl = None
+    gath = hdl = gat = None
     gather_kind = "none"
-    if world > 1:
+    if world > 1 and not os.environ.get("DP_BENCH_NO_IPC"):
+        try:   # the C ABI's own fused gather: CUDA IPC peer mapping, records + completion flags stored by the cycle kernel
+            from dmpp_b200.planner import Gather
+            gat = Gather(planner, world, rank, SCENES, depth=4)
+            hs = [None] * world
+            dist.all_gather_object(hs, gat.my_handle())
+            gat.attach(hs)
+            gather_kind = ("dp_gather_* (C ABI): peer stores + completion flags from the cycle kernel over NVLink (CUDA IPC mapping), "
+                           "a one-thread wait kernel one step behind the launches")
+        except Exception as e:  # noqa: BLE001
+            print("dp_gather unavailable (%s): falling back to torch symmetric memory" % e, file=sys.stderr)
+            gat = None
+    if world > 1 and gat is None:
         try:
             if os.environ.get("DP_BENCH_NO_SYMM"):
                 raise RuntimeError("disabled by DP_BENCH_NO_SYMM")
@@ -263,6 +275,19 @@ def run_ours(args, rank, world, local_rank):
                 planner.reset(0, SCENES)
             flush.zero_()
             rec_i = d_recs[i % 3]
+            if gat is not None:
+                # step i+1 of the fused gather: the kernel stores records and flags on every rank; the wait for the PREVIOUS
+                # step's flags follows the launch on the same stream (depth 4: nobody overwrites a slice a peer still waits for)
+                gat.arm(i + 1)
+                ev[i][0].record(stream)
+                planner.cycle_dev(SCENES, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), rec_i.data_ptr(),
+                                  stream=stream.cuda_stream)
+                ev[i][1].record(stream)
+                if pending is not None:
+                    gat.wait(pending[0] + 1, stream=stream.cuda_stream)
+                ev[i][2].record(stream)
+                pending = (i, rec_i)
+                continue
             if hdl is not None:                              # this step's records go to slice `rank` of every rank's buffer i % 3
                 planner.set_record_mirrors([p + rank * SCENES * 128 for p in hdl[i % 3].buffer_ptrs])
             ev[i][0].record(stream)
@@ -281,7 +306,10 @@ def run_ours(args, rank, world, local_rank):
             pending = (i, rec_i) if world > 1 else None
         if world > 1:
             tail_ev[0].record(stream)
-            finish_gather(*pending)
+            if gat is not None:
+                gat.wait(pending[0] + 1, stream=stream.cuda_stream)
+            else:
+                finish_gather(*pending)
             tail_ev[1].record(stream)
         return pending
 
@@ -291,7 +319,20 @@ def run_ours(args, rank, world, local_rank):
     l0 = planner.launch_count()
     last = dev_loop(W, K)
     barrier()
-    if world > 1:                                            # the gathered buffer of the last step holds every rank's records
+    if world > 1 and gat is not None:                        # my gathered buffer of the last step holds every rank's records
+        import ctypes as C_
+        host = np.zeros((world, SCENES, 128), np.uint8)
+        assert planner.lib.dp_memcpy_d2h(planner.ctx, abi.ptr(host), C_.c_void_p(gat.buffer(last[0] + 1)), C_.c_size_t(host.nbytes),
+                                         C_.c_void_p(stream.cuda_stream)) == 0
+        torch.cuda.synchronize()
+        mine = last[1].cpu().numpy()
+        assert np.array_equal(host[rank], mine), "own slice of the gathered records differs"
+        allrec = [torch.zeros_like(last[1]) for _ in range(world)]
+        dist.all_gather(allrec, last[1])
+        for r in range(world):
+            assert np.array_equal(host[r], allrec[r].cpu().numpy()), "gathered slice of rank %d differs" % r
+        gat.disarm()
+    elif world > 1:                                          # the gathered buffer of the last step holds every rank's records
         g = gath[last[0] % 3].view(world, SCENES, 128)
         assert torch.equal(g[rank], last[1]), "own slice of the gathered records differs"
         chk = torch.tensor([float(last[1][:, :].sum(dtype=torch.int64).item())], dtype=torch.float64, device=dev)
@@ -339,6 +380,7 @@ def run_ours(args, rank, world, local_rank):
                           "what": "the same without the first cycle of each %d-cycle episode, where every scene runs InitialPlanning and "
                                   "writes its whole carried path (Planning.cpp:124-128)" % EPISODE},
                "histogram": {"edges_ms": [float(e) for e in edges], "counts": [int(h) for h in hist]},
+               "p50_by_cycle_of_episode": [float(np.percentile(lms[np.arange(LAT_N) % EPISODE == c_], 50)) for c_ in range(EPISODE)],
                "what": "device time of one Decision+Planning cycle of %d scenes, CUDA events, cold L2 (256 MiB flush before every cycle)" % SCENES}
         barrier()
 
@@ -351,13 +393,21 @@ def run_ours(args, rank, world, local_rank):
     e2e_t = np.zeros(W + K)
     # N > 1: the end-to-end loops keep the gather: every record also goes to every peer's gathered buffer (mirrors set once,
     # buffer 0) and each step ends with the barrier that makes the gathered buffer readable
-    if world > 1 and hdl is not None:
+    if world > 1 and gat is None and hdl is not None:
         torch.cuda.synchronize()
         planner.set_record_mirrors([p + rank * SCENES * 128 for p in hdl[0].buffer_ptrs])
+    gstep = [W + K + 1]                                      # fused-gather step numbers continue after the device loops
+
+    def arm_gather():
+        if gat is not None:
+            gstep[0] += 1
+            gat.arm(gstep[0])
 
     def step_gather():
         if world > 1:
-            if hdl is not None:
+            if gat is not None:
+                gat.wait(gstep[0], stream=stream.cuda_stream)
+            elif hdl is not None:
                 hdl[0].barrier()
             else:
                 dist.all_gather_into_tensor(gath[0], d_recs[0])
@@ -371,6 +421,7 @@ def run_ours(args, rank, world, local_rank):
         if i == W:
             barrier()
         t0 = time.perf_counter()
+        arm_gather()
         planner.cycle(Hh[c], OXh[c], OYh[c], out=out)
         step_gather()
         e2e_t[i] = time.perf_counter() - t0
@@ -399,6 +450,7 @@ def run_ours(args, rank, world, local_rank):
                 s1 = min(SCENES, s0 + CH)
                 if len(pend) == 2:
                     planner.wait(); got += int(pend.pop(0)["n_traj"].sum(dtype=np.int64))
+                arm_gather()
                 planner.submit(Hh[c, s0:s1], OXh[c, s0:s1], OYh[c, s0:s1], recs2[i & 1][s0:s1], first=s0)
                 pend.append(recs2[i & 1][s0:s1])
         while pend:
@@ -420,6 +472,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_val = float(traj.item()) / float(e2e_p.item())
     if world > 1:
         torch.cuda.synchronize()
+        if gat is not None:
+            gat.disarm()
         planner.set_record_mirrors([])
 
     # ---- the other BASELINE configs (extra keys of the same line) ----
@@ -439,6 +493,10 @@ def run_ours(args, rank, world, local_rank):
     sampler.stop = True
     sampler.join(timeout=2)
 
+    if gat is not None:                                      # every rank is done with the peers' buffers before anyone unmaps them
+        torch.cuda.synchronize()
+        dist.barrier()
+        gat.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -542,7 +600,7 @@ def traj_of(torch, d_rec):
     return int(v.sum().item())
 
 
-def device_cycles(torch, planner, n, d_hdr, d_ox, d_oy, d_rec, episode, warmup, steps, flush=None, after=None):
+def device_cycles(torch, planner, n, d_hdr, d_ox, d_oy, d_rec, episode, warmup, steps, flush=None, after=None, before=None):
     """`warmup + steps` cycles of n scenes with inputs resident in HBM; per-step device ms (CUDA events on the launching
     stream) of the timed ones and the trajectories they scored.  `after(i)`: work enqueued after the cycle inside the timed
     region (the record gather of a multi-GPU run)."""
@@ -555,6 +613,8 @@ def device_cycles(torch, planner, n, d_hdr, d_ox, d_oy, d_rec, episode, warmup, 
             planner.reset(0, n)
         if flush is not None:
             flush.zero_()
+        if before is not None:
+            before(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
         planner.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec.data_ptr(), stream=st.cuda_stream)
@@ -673,8 +733,26 @@ def config4_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, tota
     d_hdr = torch.from_numpy(H.view(np.uint8).reshape(episode, n, 128)).to(dev)
     d_ox = torch.from_numpy(OX).to(dev); d_oy = torch.from_numpy(OY).to(dev)
     d_rec = torch.empty((n, 128), dtype=torch.uint8, device=dev)
-    gather = "none"; after = None; hdl = None
-    if world > 1:
+    gather = "none"; after = None; hdl = None; gat = None
+    if world > 1 and not os.environ.get("DP_BENCH_NO_IPC"):
+        try:
+            from dmpp_b200.planner import Gather
+            gat = Gather(p, world, rank, n, depth=2)
+            hs = [None] * world
+            dist.all_gather_object(hs, gat.my_handle())
+            gat.attach(hs)
+            st_ = torch.cuda.current_stream()
+            cnt = [0]
+
+            def before(i):
+                cnt[0] += 1
+                gat.arm(cnt[0])
+            after = lambda i: gat.wait(cnt[0], stream=st_.cuda_stream)   # noqa: E731
+            gather = "dp_gather_* (C ABI, CUDA IPC): peer stores + flags from the kernel, wait for every rank's flag inside the timed step"
+        except Exception as e:  # noqa: BLE001
+            gat = None
+            gather = "dp_gather failed (%s)" % type(e).__name__
+    if world > 1 and gat is None:
         try:
             import torch.distributed._symmetric_memory as symm
             g = symm.empty((world * n, 128), dtype=torch.uint8, device=dev)
@@ -687,7 +765,7 @@ def config4_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, tota
             after = lambda i: dist.all_gather_into_tensor(gbuf, d_rec)   # noqa: E731
             gather = "all_gather_into_tensor inside the timed step (%s)" % type(e).__name__
     l0 = p.launch_count()
-    ms, traj = device_cycles(torch, p, n, d_hdr, d_ox, d_oy, d_rec, episode, warmup, steps, after=after)
+    ms, traj = device_cycles(torch, p, n, d_hdr, d_ox, d_oy, d_rec, episode, warmup, steps, after=after, before=before if gat is not None else None)
     launches = p.launch_count() - l0
     t = torch.tensor([ms.sum()], dtype=torch.float64, device=dev)
     tr = torch.tensor([float(traj)], dtype=torch.float64, device=dev)
@@ -695,6 +773,8 @@ def config4_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, tota
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+        if gat is not None:
+            gat.close()
         p.set_record_mirrors([])
     p.close()
     secs = float(t.item()) * 1e-3

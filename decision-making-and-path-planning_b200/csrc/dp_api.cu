@@ -83,6 +83,10 @@ struct dp_ctx {
     // record mirrors (dp_set_record_mirrors): device-accessible bases indexed by carry slot
     dp_plan_record* mirror[DP_MAX_MIRRORS - 1] = {};
     int n_mirror = 0;
+    // fused gather (dp_gather_*): flags the next cycle launch raises on every rank when its last record is out
+    unsigned* peer_flag[DP_MAX_MIRRORS] = {};
+    int n_peer_flag = 0; unsigned flag_value = 0;
+    unsigned* d_tally_g = nullptr;
 };
 
 namespace {
@@ -94,6 +98,8 @@ DpIo make_io(dp_ctx* c, int first, dp_plan_record* host_rec) {
     c->chain_prev_epoch = 0;                                // (dp_cycle_submit re-arms the chain after its own launch)
     if (host_rec) io.mirror[io.n_mirror++] = host_rec;
     for (int k = 0; k < c->n_mirror; ++k) io.mirror[io.n_mirror++] = c->mirror[k] + first;
+    for (int k = 0; k < c->n_peer_flag; ++k) io.peer_flag[k] = c->peer_flag[k];
+    io.n_peer_flag = c->n_peer_flag; io.flag_value = c->flag_value;
     return io;
 }
 // one cycle of n scenes (carry slots first ..) on stream st
@@ -107,6 +113,9 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
         }
         for (int k = 0; k < io.n_mirror; ++k) g.mirror[k] = io.mirror[k];
         g.n_mirror = io.n_mirror; g.tally = io.tally; g.tally_n = io.tally_n; g.host_done = io.host_done; g.epoch = io.epoch;
+        for (int k = 0; k < io.n_peer_flag; ++k) g.peer_flag[k] = io.peer_flag[k];
+        g.n_peer_flag = io.n_peer_flag; g.flag_value = io.flag_value;
+        if (g.n_peer_flag && !g.tally) { g.tally = c->d_tally_g; g.tally_n = (unsigned)n; }
         g.timeline = (n <= 8192) ? c->d_timeline : nullptr;
         if (g.timeline) cudaMemsetAsync(c->d_timeline, 0, (size_t)8192 * 32 * 8, st);
         c->launches += 1;
@@ -114,8 +123,10 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
                                trace, path_xy, path_ll, st, g, c->lc);
     }
     c->launches += c->split ? 2 : 1;
+    DpIo iow = io;
+    if (iow.n_peer_flag && !iow.tally) { iow.tally = c->d_tally_g; iow.tally_n = (unsigned)n; }
     return dp_launch_cycle(c->gmap, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace,
-                           path_xy, path_ll, st, c->split, io, c->lc);
+                           path_xy, path_ll, st, c->split, iow, c->lc);
 }
 }  // namespace
 
@@ -244,7 +255,9 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     if ((r = dev_alloc(&c->d_carry, (size_t)max_scenes))) { delete c; return r; }
     if ((r = dev_alloc(&c->d_last, (size_t)max_scenes * DP_PATH_POINTS))) { delete c; return r; }
     if ((r = dev_alloc(&c->d_done, (size_t)max_scenes))) { delete c; return r; }
-    if ((r = dev_alloc(&c->d_pdone, (size_t)max_scenes)) || (r = dev_alloc(&c->d_inflag, 2)) || (r = dev_alloc(&c->d_tally, 2))) { delete c; return r; }
+    if ((r = dev_alloc(&c->d_pdone, (size_t)max_scenes)) || (r = dev_alloc(&c->d_inflag, 2)) || (r = dev_alloc(&c->d_tally, 2)) ||
+        (r = dev_alloc(&c->d_tally_g, 1))) { delete c; return r; }
+    CK(cudaMemset(c->d_tally_g, 0, sizeof(unsigned)));
     CK(cudaMemset(c->d_pdone, 0, (size_t)max_scenes * sizeof(unsigned)));
     CK(cudaMemset(c->d_inflag, 0, 2 * sizeof(unsigned))); CK(cudaMemset(c->d_tally, 0, 2 * sizeof(unsigned)));
     CK(cudaHostAlloc((void**)&c->h_done, 4 * sizeof(unsigned), cudaHostAllocMapped));
@@ -275,7 +288,7 @@ int dp_destroy(dp_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->map_allocs) cudaFree(p);
     cudaFree(c->d_timeline); cudaFree(c->d_trk);
-    cudaFree(c->d_carry); cudaFree(c->d_last); cudaFree(c->d_done); cudaFree(c->d_pdone); cudaFree(c->d_inflag); cudaFree(c->d_tally);
+    cudaFree(c->d_carry); cudaFree(c->d_last); cudaFree(c->d_done); cudaFree(c->d_pdone); cudaFree(c->d_inflag); cudaFree(c->d_tally); cudaFree(c->d_tally_g);
     if (c->h_done) cudaFreeHost(c->h_done);
     for (int s = 0; s < 2; ++s) {
         cudaFree(c->d_hdr[s]); cudaFree(c->d_ox[s]); cudaFree(c->d_oy[s]); cudaFree(c->d_rec[s]);
@@ -632,6 +645,89 @@ int dp_debug_timeline(dp_ctx* c, long long* host_out, int n_blocks) {
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(host_out, c->d_timeline, (size_t)n_blocks * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return DP_OK;
+}
+
+// ---- fused gather of plan records across the GPUs of one box, through the C ABI (CUDA IPC) ----
+struct dp_gather {
+    dp_ctx* c = nullptr;
+    int world = 0, rank = 0, slots = 0, depth = 0;
+    unsigned char* base[DP_MAX_MIRRORS] = {};               // every rank's allocation as seen from here (own: the local pointer)
+    bool opened[DP_MAX_MIRRORS] = {};
+    size_t rec_bytes = 0;                                   // records come first ([depth][world][slots]), the flags ([depth][world] u32) follow
+};
+static_assert(DP_IPC_BYTES >= sizeof(cudaIpcMemHandle_t), "DP_IPC_BYTES");
+
+int dp_gather_create(dp_ctx* c, int world, int rank, int slots, int depth, dp_gather** out, void* handle_out) {
+    if (!c || !out || !handle_out || world < 1 || world > DP_MAX_MIRRORS - 1 || rank < 0 || rank >= world || slots < 1 || slots > c->max_scenes || depth < 1)
+        return fail(DP_ERR_ARG, "dp_gather_create: bad argument (world <= 8)");
+    CK(cudaSetDevice(c->device));
+    dp_gather* g = new dp_gather();
+    g->c = c; g->world = world; g->rank = rank; g->slots = slots; g->depth = depth;
+    g->rec_bytes = (size_t)depth * world * slots * sizeof(dp_plan_record);
+    const size_t bytes = g->rec_bytes + (size_t)depth * world * sizeof(unsigned);
+    cudaError_t e = cudaMalloc((void**)&g->base[rank], bytes);
+    if (e != cudaSuccess) { delete g; return fail(DP_ERR_NOMEM, "dp_gather_create: cudaMalloc", e); }
+    CK(cudaMemset(g->base[rank], 0, bytes));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, g->base[rank]));
+    memset(handle_out, 0, DP_IPC_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    *out = g;
+    return DP_OK;
+}
+int dp_gather_attach(dp_gather* g, const void* handles) {
+    if (!g || !handles) return fail(DP_ERR_ARG, "dp_gather_attach: bad argument");
+    CK(cudaSetDevice(g->c->device));
+    for (int r = 0; r < g->world; ++r) {
+        if (r == g->rank || g->opened[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char*)handles + (size_t)r * DP_IPC_BYTES, sizeof(h));
+        CK(cudaIpcOpenMemHandle((void**)&g->base[r], h, cudaIpcMemLazyEnablePeerAccess));
+        g->opened[r] = true;
+    }
+    return DP_OK;
+}
+int dp_gather_arm(dp_gather* g, unsigned step) {
+    if (!g || step == 0) return fail(DP_ERR_ARG, "dp_gather_arm: bad argument (steps count from 1)");
+    dp_ctx* c = g->c;                                       // (only read by the NEXT launch call of this thread: fine between pipelined submits)
+    const size_t b = step % (unsigned)g->depth;
+    c->n_mirror = 0; c->n_peer_flag = 0;
+    for (int r = 0; r < g->world; ++r) {
+        if (!g->base[r]) return fail(DP_ERR_STATE, "dp_gather_arm: dp_gather_attach first");
+        c->mirror[c->n_mirror++] = reinterpret_cast<dp_plan_record*>(g->base[r]) + (b * g->world + g->rank) * g->slots;
+        c->peer_flag[c->n_peer_flag++] = reinterpret_cast<unsigned*>(g->base[r] + g->rec_bytes) + b * g->world + g->rank;
+    }
+    c->flag_value = step;
+    return DP_OK;
+}
+int dp_gather_disarm(dp_gather* g) {
+    if (!g) return fail(DP_ERR_ARG, "dp_gather_disarm: null");
+    g->c->n_mirror = 0; g->c->n_peer_flag = 0;
+    return DP_OK;
+}
+int dp_gather_wait(dp_gather* g, unsigned step, void* stream) {
+    if (!g || step == 0) return fail(DP_ERR_ARG, "dp_gather_wait: bad argument");
+    CK(cudaSetDevice(g->c->device));
+    const size_t b = step % (unsigned)g->depth;
+    CK(dp_launch_gather_wait(reinterpret_cast<const unsigned*>(g->base[g->rank] + g->rec_bytes) + b * g->world, g->world, step, (cudaStream_t)stream));
+    ++g->c->launches;
+    return DP_OK;
+}
+const void* dp_gather_buffer(dp_gather* g, unsigned step) {
+    if (!g) return nullptr;
+    return g->base[g->rank] + (size_t)(step % (unsigned)g->depth) * g->world * g->slots * sizeof(dp_plan_record);
+}
+int dp_gather_destroy(dp_gather* g) {
+    if (!g) return DP_OK;
+    cudaSetDevice(g->c->device);
+    cudaDeviceSynchronize();
+    dp_gather_disarm(g);
+    for (int r = 0; r < g->world; ++r) {
+        if (r == g->rank) cudaFree(g->base[r]);
+        else if (g->opened[r]) cudaIpcCloseMemHandle(g->base[r]);
+    }
+    delete g;
     return DP_OK;
 }
 

@@ -938,6 +938,19 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         for (int k = 0; k < DP_MAX_MIRRORS; ++k)             // (static indices: the parameter array stays in the constant bank)
             if (k < io.n_mirror) reinterpret_cast<uint32_t*>(io.mirror[k] + scene)[lane] = w;
     }
+    if (PHASE != 1 && io.tally && !io.pdone) {
+        // completion of the whole launch without the chain: the last warp tells the host (page-locked flag) and / or the peers
+        __threadfence();                                    // (every lane: its stores, the mirrors included, before the tally)
+        __syncwarp();
+        if (lane == 0 && atomicAdd(io.tally, 1u) == io.tally_n - 1u) {
+            *io.tally = 0;
+            __threadfence_system();                         // cumulative: everything the other warps fenced before their tally increment
+            if (io.host_done) *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
+#pragma unroll
+            for (int k = 0; k < DP_MAX_MIRRORS; ++k)
+                if (k < io.n_peer_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+        }
+    }
     if (PHASE == 2 && io.pdone) {
         // chained submit: this scene's cycle is complete -- its next Decision warp may go; the last warp of the batch tells the host
         __threadfence();                                    // (every lane: its stores, the mirrors included, before the flags)
@@ -1026,6 +1039,19 @@ __global__ void dp_map_prep2_kernel(const double* lenp, const uint16_t* attr, co
     }
 }
 
+// ---- fused gather: wait until every rank's flag of this step has arrived in MY gathered buffer (one thread) ----
+__global__ void dp_gather_wait_kernel(const unsigned* flags, int world, unsigned step) {
+    for (int r = 0; r < world; ++r) {
+        unsigned v = 0;
+        for (long spin = 0; spin < (1L << 26); ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+            if (v == step) break;
+            __nanosleep(200);
+        }
+        if (v != step) __trap();                            // never spin forever on a rank that is not there
+    }
+}
+
 // ---- the group kernel (dp_group.cuh): one CTA = g scenes ----
 template <int G, int TPB>
 __global__ void __launch_bounds__(TPB, (G <= 8) ? 4 : 2)   // G 16: 2 CTAs x 256 threads x 128 regs; G 8: 4 CTAs/SM (TPB 128: 128 regs, TPB 256: 64 regs)
@@ -1096,6 +1122,10 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
                              : cudaLaunchKernelEx(&cfg, dp_cycle_kernel<2, 1>, m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2);
         if (e != cudaSuccess) return e;
     }
+    return cudaGetLastError();
+}
+cudaError_t dp_launch_gather_wait(const unsigned* flags, int world, unsigned step, cudaStream_t st) {
+    dp_gather_wait_kernel<<<1, 1, 0, st>>>(flags, world, step);
     return cudaGetLastError();
 }
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st) {

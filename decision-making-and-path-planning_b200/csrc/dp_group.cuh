@@ -94,6 +94,9 @@ struct DgMap {
 struct DgIo {
     dp_plan_record* mirror[DG_MAX_MIRRORS]; int n_mirror;
     unsigned* tally; unsigned tally_n; unsigned* host_done; unsigned epoch;
+    // fused record gather of a multi-GPU job (dp_gather_*): when the LAST record of the launch is out, flag_value is stored to
+    // peer_flag[k] of every rank (st.release.sys after a system fence): "rank's slice of this step is complete in your buffer"
+    unsigned* peer_flag[DG_MAX_MIRRORS]; int n_peer_flag; unsigned flag_value;
     long long* timeline;                           // instrumented runs only (tools/group_timeline.py): [block][32] globaltimer stamps
     // predicted agent tracks (BASELINE config 5, dp_set_tracks): constant-turn-rate parameters [scene][max_obs] -- displacement of
     // step 0 (vx, vy) and heading change per step (deg) -- and the horizon T; null = static obstacles (the reference's semantics)
@@ -376,17 +379,16 @@ DG_FN DgTrk dg_track_search(PF pt, const int P, double x, double y, double vx, d
     double c, s;
     dg_sincos_deg(dth, &c, &s);
     DgTrk r; r.x = x; r.y = y; r.a.bd = dg_inf(); r.a.bj = 0;
-    for (int j = 0; j < P; ++j) {
-        const double2 q = pt(j);
-        const double dx = x - q.x, dy = y - q.y;
-        const double e = fma(dx, dx, dy * dy);
-        if (e < r.a.bd) { r.a.bd = e; r.a.bj = j; r.x = x; r.y = y; }
-        if (j + 1 < T) {
-            x = x + vx; y = y + vy;
-            const double nvx = fma(c, vx, -(s * vy)), nvy = fma(s, vx, c * vy);
-            vx = nvx; vy = nvy;
-        }
+    int j = 0;
+    for (; j + 4 <= P; j += 4) {                   // four path points in flight per trip: their loads do not wait for the recurrence
+        const double2 q0 = pt(j), q1 = pt(j + 1), q2 = pt(j + 2), q3 = pt(j + 3);
+#define DG_TRK_STEP(q, jj) { const double dx = x - (q).x, dy = y - (q).y; const double e = fma(dx, dx, dy * dy); \
+                             if (e < r.a.bd) { r.a.bd = e; r.a.bj = (jj); r.x = x; r.y = y; } \
+                             if ((jj) + 1 < T) { x = x + vx; y = y + vy; const double nvx = fma(c, vx, -(s * vy)), nvy = fma(s, vx, c * vy); vx = nvx; vy = nvy; } }
+        DG_TRK_STEP(q0, j) DG_TRK_STEP(q1, j + 1) DG_TRK_STEP(q2, j + 2) DG_TRK_STEP(q3, j + 3)
     }
+    for (; j < P; ++j) { const double2 q = pt(j); DG_TRK_STEP(q, j) }
+#undef DG_TRK_STEP
     return r;
 }
 // the agent's position at step j (the same recurrence, for the one selected agent of a trajectory)
@@ -1862,14 +1864,17 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
     }
     DG_MARK(23);
 #if !defined(DP_EMU)
-    if (io.host_done) {
+    if (io.tally) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();                         // cumulative: the CTA's stores (ordered before the barrier) before the tally
             if (atomicAdd(io.tally, (unsigned)S) + (unsigned)S == io.tally_n) {
                 *io.tally = 0;                              // re-armed for the next cycle that uses this word
                 __threadfence_system();
-                *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
+                if (io.host_done) *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
+#pragma unroll
+                for (int q = 0; q < DG_MAX_MIRRORS; ++q)
+                    if (q < io.n_peer_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[q]), "r"(io.flag_value) : "memory");
             }
         }
     }

@@ -23,6 +23,7 @@ struct DpIo {
                                                // of a scene waits for prev_epoch before it touches the carry (0: nothing to wait for)
     unsigned* tally; unsigned tally_n;         // finished Planning warps of this cycle; the last one stores epoch to *host_done
     unsigned* host_done;                       // (page-locked host memory)
+    unsigned* peer_flag[DP_MAX_MIRRORS]; int n_peer_flag; unsigned flag_value;   // fused gather (dp_gather_*), see DgIo
 };
 inline DpIo dp_io_none() { DpIo io = {}; return io; }
 
@@ -40,6 +41,7 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
                             double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io, DpLaunchCfg& lc);   // split: 0 fused, 1 two launches, 2 overlapped
 // (io.prev_epoch != 0 additionally launches the Decision half as a programmatic dependent of the previous cycle's Planning half)
+cudaError_t dp_launch_gather_wait(const unsigned* flags, int world, unsigned step, cudaStream_t st);
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st);
 cudaError_t dp_launch_map_prep(const double* x, const double* y, const uint16_t* attr, const int32_t* lane_pt_off, int n_lanes, double2* xy,
                                double2* nrm, double* lenp, double* lenf, float* lane_hmax, float* lane_hmin, float* lane_dnmax, double* cump,

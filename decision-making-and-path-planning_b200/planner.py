@@ -23,6 +23,7 @@ SYMBOLS = [
     "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
     "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev", "dp_debug_timeline",
     "dp_set_tracks", "dp_set_tracks_dev", "dp_clear_tracks",
+    "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
 ]
 
 _lib = None
@@ -272,6 +273,44 @@ class Planner:
         a, b = C.c_double(0), C.c_double(0)
         _ck(self.lib.dp_measure_fma_peak(self.ctx, C.byref(a), C.byref(b)), "dp_measure_fma_peak")
         return a.value, b.value
+
+
+class Gather:
+    """fused record gather across the GPUs of one box through the C ABI (CUDA IPC), see include/dmpp_b200.h dp_gather_*"""
+    IPC_BYTES = 64
+
+    def __init__(self, planner, world, rank, slots, depth=4):
+        self.lib, self.planner, self.world, self.rank, self.slots = planner.lib, planner, world, rank, slots
+        self.h = C.c_void_p()
+        self.handle = (C.c_ubyte * self.IPC_BYTES)()
+        _ck(self.lib.dp_gather_create(planner.ctx, C.c_int(world), C.c_int(rank), C.c_int(slots), C.c_int(depth), C.byref(self.h), self.handle),
+            "dp_gather_create")
+        self.lib.dp_gather_buffer.restype = C.c_void_p
+
+    def my_handle(self):
+        return bytes(self.handle)
+
+    def attach(self, handles):
+        """handles: list of `world` 64-byte handles, index = rank"""
+        buf = (C.c_ubyte * (self.IPC_BYTES * self.world))(*b"".join(handles))
+        _ck(self.lib.dp_gather_attach(self.h, buf), "dp_gather_attach")
+
+    def arm(self, step):
+        _ck(self.lib.dp_gather_arm(self.h, C.c_uint(step)), "dp_gather_arm")
+
+    def disarm(self):
+        _ck(self.lib.dp_gather_disarm(self.h), "dp_gather_disarm")
+
+    def wait(self, step, stream=0):
+        _ck(self.lib.dp_gather_wait(self.h, C.c_uint(step), C.c_void_p(stream)), "dp_gather_wait")
+
+    def buffer(self, step):
+        return int(self.lib.dp_gather_buffer(self.h, C.c_uint(step)))
+
+    def close(self):
+        if self.h:
+            self.lib.dp_gather_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class SweepSession:

@@ -218,6 +218,26 @@ int dp_cycle_wait(dp_ctx* ctx);
  * the peer's buffer, the per-step all-gather of plan records happens inside the Planning launch as 128-byte
  * peer stores instead of a separate collective; the caller only needs a barrier before it reads the gathered buffer. */
 int dp_set_record_mirrors(dp_ctx* ctx, int n, void* const* bases);
+/* Fused gather of the plan records of a multi-GPU job (one process per GPU of one box) through the C ABI alone -- no
+ * collective library, no framework: every rank owns a buffer rec[depth][world][slots] + flags, the buffers are mapped into every
+ * process over NVLink with CUDA IPC, and the cycle kernel itself stores each finished record into its rank's slice of EVERY
+ * rank's buffer (dp_set_record_mirrors under the hood) and, when its last record is out, raises its flag on every rank.
+ *   dp_gather_create   allocate my buffer, return its 64-byte IPC handle; the caller exchanges the handles (any transport)
+ *   dp_gather_attach   handles[world][DP_IPC_BYTES] of all ranks (own entry ignored): map the peers
+ *   dp_gather_arm      the NEXT cycle launch of ctx writes step `step` (>= 1, increasing): buffer step % depth, slice `rank`
+ *   dp_gather_wait     enqueue on `stream` a wait for all `world` flags of that step in MY buffer; work that follows on the
+ *                      stream may read dp_gather_buffer(step) = device pointer to rec[world][slots] of that step
+ * A rank may run ahead of a peer: with waits enqueued one step behind the launches (launch s, launch s+1, wait s, ...), depth 4
+ * guarantees that a slice is never overwritten before every peer has waited for it. */
+#define DP_IPC_BYTES 64
+typedef struct dp_gather dp_gather;
+int dp_gather_create(dp_ctx* ctx, int world, int rank, int slots_per_rank, int depth, dp_gather** out, void* my_handle_out);
+int dp_gather_attach(dp_gather* g, const void* handles);
+int dp_gather_arm(dp_gather* g, unsigned step);
+int dp_gather_disarm(dp_gather* g);
+int dp_gather_wait(dp_gather* g, unsigned step, void* stream);
+const void* dp_gather_buffer(dp_gather* g, unsigned step);
+int dp_gather_destroy(dp_gather* g);
 int dp_host_alloc(void** p, size_t bytes);
 int dp_host_free(void* p);
 

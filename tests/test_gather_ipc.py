@@ -1,0 +1,71 @@
+"""Fused record gather through the C ABI alone (dp_gather_*: CUDA IPC peer mapping + completion flags raised by the cycle kernel).
+Two processes share cuda:0 as "ranks" of a two-GPU job: after each step both must hold both ranks' plan records, bit for bit, for
+both kernels (N = 10: warp-per-scene, N = 40: group)."""
+import multiprocessing as mp
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def worker(rank, world, conn, n, n_obs, cycles, q):
+    import ctypes as C
+    import torch
+    import dmpp_b200  # noqa: F401
+    from dmpp_b200 import abi, scenes
+    from dmpp_b200.planner import Gather, Planner
+    dev = torch.device("cuda", 0)
+    m = scenes.Map()
+    ep = scenes.Episodes(m, np.arange(rank * n, (rank + 1) * n), cycles=cycles, n_obs=n_obs)
+    H, OX, OY = ep.all_cycles()
+    p = Planner(n, n_obs)
+    p.upload_map(m)
+    g = Gather(p, world, rank, n, depth=4)
+    conn.send(g.my_handle())
+    handles = conn.recv()                                    # all ranks' handles, index = rank
+    g.attach(handles)
+    d_hdr = torch.from_numpy(H.view(np.uint8).reshape(cycles, n, 128)).to(dev)
+    d_ox, d_oy = torch.from_numpy(OX).to(dev), torch.from_numpy(OY).to(dev)
+    d_rec = torch.empty((n, 128), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    got = []
+    for c in range(cycles):
+        step = c + 1
+        g.arm(step)
+        p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec.data_ptr(), stream=st.cuda_stream)
+        g.wait(step, stream=st.cuda_stream)
+        host = np.zeros((world * n, 128), np.uint8)
+        assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
+        assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
+        got.append((host.copy(), d_rec.cpu().numpy().copy()))
+    q.put((rank, got))
+    conn.recv()                                              # keep the mapping alive until the peer has finished too
+    g.close(); p.close()
+
+
+@pytest.mark.parametrize("n_obs", [10, 40])
+def test_two_processes_gather_through_cuda_ipc(n_obs):
+    world, n, cycles = 2, 96, 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    pipes = [ctx.Pipe() for _ in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, pipes[r][1], n, n_obs, cycles, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    handles = [pipes[r][0].recv() for r in range(world)]
+    for r in range(world):
+        pipes[r][0].send(handles)
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for r in range(world):
+        pipes[r][0].send("done")
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    for c in range(cycles):
+        own = [res[r][c][1] for r in range(world)]           # what each rank computed this step
+        assert own[0].any()
+        for r in range(world):
+            gathered = res[r][c][0].reshape(world, n, 128)
+            for k in range(world):
+                assert np.array_equal(gathered[k], own[k]), "step %d: rank %d does not hold rank %d's records" % (c, r, k)

@@ -6,6 +6,7 @@ import os
 import sys
 
 os.environ["DP_TIMELINE"] = "1"
+os.environ.setdefault("DP_KERNEL", "group")
 import numpy as np
 import torch
 
