@@ -960,6 +960,9 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             if (io.host_done && atomicAdd(io.tally, 1u) == io.tally_n - 1u) {
                 __threadfence_system();                     // cumulative: everything the other warps fenced before their tally increment
                 *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
+#pragma unroll
+                for (int k = 0; k < DP_MAX_MIRRORS; ++k)     // fused gather: this rank's slice of the step is complete on every rank
+                    if (k < io.n_peer_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
             }
         }
     }

@@ -39,6 +39,21 @@ def worker(rank, world, conn, n, n_obs, cycles, q):
         assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
         assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
         got.append((host.copy(), d_rec.cpu().numpy().copy()))
+    # the host-pointer call (pinned buffers -> dp_cycle_submit + dp_cycle_wait under the hood) raises the flags too
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
+    Hh = pin(H.view(np.uint8).reshape(cycles, n, 128)).view(abi.scene_hdr).reshape(cycles, n)
+    OXh, OYh = pin(OX), pin(OY)
+    rec_h = torch.empty((n, 128), dtype=torch.uint8).pin_memory().numpy().view(abi.plan_record).reshape(n)
+    p.reset(0, n)
+    for c in range(cycles):
+        step = cycles + c + 1
+        g.arm(step)
+        p.cycle(Hh[c], OXh[c], OYh[c], out={"rec": rec_h})
+        g.wait(step, stream=st.cuda_stream)
+        host = np.zeros((world * n, 128), np.uint8)
+        assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
+        assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
+        got.append((host.copy(), rec_h.view(np.uint8).reshape(n, 128).copy()))
     q.put((rank, got))
     conn.recv()                                              # keep the mapping alive until the peer has finished too
     g.close(); p.close()
@@ -62,7 +77,7 @@ def test_two_processes_gather_through_cuda_ipc(n_obs):
     for pr in procs:
         pr.join(timeout=120)
         assert pr.exitcode == 0
-    for c in range(cycles):
+    for c in range(2 * cycles):
         own = [res[r][c][1] for r in range(world)]           # what each rank computed this step
         assert own[0].any()
         for r in range(world):
