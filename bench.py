@@ -279,12 +279,11 @@ def run_ours(args, rank, world, local_rank):
                 # step i+1 of the fused gather: the kernel stores records and flags on every rank; the wait for the PREVIOUS
                 # step's flags follows the launch on the same stream (depth 4: nobody overwrites a slice a peer still waits for)
                 gat.arm(i + 1)
+                gat.chain(pending[0] + 1 if pending is not None else 0)   # the wait for step i rides in the launch of step i+1
                 ev[i][0].record(stream)
                 planner.cycle_dev(SCENES, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), rec_i.data_ptr(),
                                   stream=stream.cuda_stream)
                 ev[i][1].record(stream)
-                if pending is not None:
-                    gat.wait(pending[0] + 1, stream=stream.cuda_stream)
                 ev[i][2].record(stream)
                 pending = (i, rec_i)
                 continue
@@ -398,10 +397,11 @@ def run_ours(args, rank, world, local_rank):
         planner.set_record_mirrors([p + rank * SCENES * 128 for p in hdl[0].buffer_ptrs])
     gstep = [W + K + 1]                                      # fused-gather step numbers continue after the device loops
 
-    def arm_gather():
+    def arm_gather(chain=False):
         if gat is not None:
             gstep[0] += 1
             gat.arm(gstep[0])
+            gat.chain(gstep[0] - 1 if chain else 0)          # pipelined: the wait for the step before rides in this launch
 
     def step_gather():
         if world > 1:
@@ -450,7 +450,7 @@ def run_ours(args, rank, world, local_rank):
                 s1 = min(SCENES, s0 + CH)
                 if len(pend) == 2:
                     planner.wait(); got += int(pend.pop(0)["n_traj"].sum(dtype=np.int64))
-                arm_gather()
+                arm_gather(chain=True)
                 planner.submit(Hh[c, s0:s1], OXh[c, s0:s1], OYh[c, s0:s1], recs2[i & 1][s0:s1], first=s0)
                 pend.append(recs2[i & 1][s0:s1])
         while pend:

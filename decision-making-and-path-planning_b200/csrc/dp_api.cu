@@ -86,6 +86,7 @@ struct dp_ctx {
     // fused gather (dp_gather_*): flags the next cycle launch raises on every rank when its last record is out
     unsigned* peer_flag[DP_MAX_MIRRORS] = {};
     int n_peer_flag = 0; unsigned flag_value = 0;
+    const unsigned* wait_flag = nullptr; int n_wait = 0; unsigned wait_value = 0;
     unsigned* d_tally_g = nullptr;
 };
 
@@ -100,6 +101,7 @@ DpIo make_io(dp_ctx* c, int first, dp_plan_record* host_rec) {
     for (int k = 0; k < c->n_mirror; ++k) io.mirror[io.n_mirror++] = c->mirror[k] + first;
     for (int k = 0; k < c->n_peer_flag; ++k) io.peer_flag[k] = c->peer_flag[k];
     io.n_peer_flag = c->n_peer_flag; io.flag_value = c->flag_value;
+    io.wait_flag = c->wait_flag; io.n_wait = c->n_wait; io.wait_value = c->wait_value;
     return io;
 }
 // one cycle of n scenes (carry slots first ..) on stream st
@@ -115,7 +117,8 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
         g.n_mirror = io.n_mirror; g.tally = io.tally; g.tally_n = io.tally_n; g.host_done = io.host_done; g.epoch = io.epoch;
         for (int k = 0; k < io.n_peer_flag; ++k) g.peer_flag[k] = io.peer_flag[k];
         g.n_peer_flag = io.n_peer_flag; g.flag_value = io.flag_value;
-        if (g.n_peer_flag && !g.tally) { g.tally = c->d_tally_g; g.tally_n = (unsigned)n; }
+        g.wait_flag = io.wait_flag; g.n_wait = io.n_wait; g.wait_value = io.wait_value;
+        if ((g.n_peer_flag || g.n_wait) && !g.tally) { g.tally = c->d_tally_g; g.tally_n = (unsigned)n; }
         g.timeline = (n <= 8192) ? c->d_timeline : nullptr;
         if (g.timeline) cudaMemsetAsync(c->d_timeline, 0, (size_t)8192 * 32 * 8, st);
         c->launches += 1;
@@ -124,7 +127,7 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
     }
     c->launches += c->split ? 2 : 1;
     DpIo iow = io;
-    if (iow.n_peer_flag && !iow.tally) { iow.tally = c->d_tally_g; iow.tally_n = (unsigned)n; }
+    if ((iow.n_peer_flag || iow.n_wait) && !iow.tally) { iow.tally = c->d_tally_g; iow.tally_n = (unsigned)n; }
     return dp_launch_cycle(c->gmap, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace,
                            path_xy, path_ll, st, c->split, iow, c->lc);
 }
@@ -701,9 +704,19 @@ int dp_gather_arm(dp_gather* g, unsigned step) {
     c->flag_value = step;
     return DP_OK;
 }
+int dp_gather_chain(dp_gather* g, unsigned prev_step) {
+    if (!g) return fail(DP_ERR_ARG, "dp_gather_chain: null");
+    dp_ctx* c = g->c;
+    if (prev_step == 0) { c->wait_flag = nullptr; c->n_wait = 0; c->wait_value = 0; return DP_OK; }
+    if (!g->base[g->rank]) return fail(DP_ERR_STATE, "dp_gather_chain: dp_gather_attach first");
+    c->wait_flag = reinterpret_cast<const unsigned*>(g->base[g->rank] + g->rec_bytes) + (size_t)(prev_step % (unsigned)g->depth) * g->world;
+    c->n_wait = g->world; c->wait_value = prev_step;
+    return DP_OK;
+}
 int dp_gather_disarm(dp_gather* g) {
     if (!g) return fail(DP_ERR_ARG, "dp_gather_disarm: null");
     g->c->n_mirror = 0; g->c->n_peer_flag = 0;
+    g->c->wait_flag = nullptr; g->c->n_wait = 0; g->c->wait_value = 0;
     return DP_OK;
 }
 int dp_gather_wait(dp_gather* g, unsigned step, void* stream) {

@@ -945,10 +945,11 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         if (lane == 0 && atomicAdd(io.tally, 1u) == io.tally_n - 1u) {
             *io.tally = 0;
             __threadfence_system();                         // cumulative: everything the other warps fenced before their tally increment
-            if (io.host_done) *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
 #pragma unroll
             for (int k = 0; k < DP_MAX_MIRRORS; ++k)
-                if (k < io.n_peer_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+                if (k < io.n_peer_flag) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+            dg_wait_flags(io.wait_flag, io.n_wait, io.wait_value);
+            if (io.host_done) *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
         }
     }
     if (PHASE == 2 && io.pdone) {
@@ -959,10 +960,11 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(io.pdone + scene), "r"(io.epoch) : "memory");
             if (io.host_done && atomicAdd(io.tally, 1u) == io.tally_n - 1u) {
                 __threadfence_system();                     // cumulative: everything the other warps fenced before their tally increment
-                *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
 #pragma unroll
                 for (int k = 0; k < DP_MAX_MIRRORS; ++k)     // fused gather: this rank's slice of the step is complete on every rank
-                    if (k < io.n_peer_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+                    if (k < io.n_peer_flag) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+                dg_wait_flags(io.wait_flag, io.n_wait, io.wait_value);
+                *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
             }
         }
     }
@@ -1043,17 +1045,7 @@ __global__ void dp_map_prep2_kernel(const double* lenp, const uint16_t* attr, co
 }
 
 // ---- fused gather: wait until every rank's flag of this step has arrived in MY gathered buffer (one thread) ----
-__global__ void dp_gather_wait_kernel(const unsigned* flags, int world, unsigned step) {
-    for (int r = 0; r < world; ++r) {
-        unsigned v = 0;
-        for (long spin = 0; spin < (1L << 26); ++spin) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-            if (v == step) break;
-            __nanosleep(200);
-        }
-        if (v != step) __trap();                            // never spin forever on a rank that is not there
-    }
-}
+__global__ void dp_gather_wait_kernel(const unsigned* flags, int world, unsigned step) { dg_wait_flags(flags, world, step); }
 
 // ---- the group kernel (dp_group.cuh): one CTA = g scenes ----
 template <int G, int TPB>

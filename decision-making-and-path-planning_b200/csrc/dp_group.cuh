@@ -95,13 +95,32 @@ struct DgIo {
     dp_plan_record* mirror[DG_MAX_MIRRORS]; int n_mirror;
     unsigned* tally; unsigned tally_n; unsigned* host_done; unsigned epoch;
     // fused record gather of a multi-GPU job (dp_gather_*): when the LAST record of the launch is out, flag_value is stored to
-    // peer_flag[k] of every rank (st.release.sys after a system fence): "rank's slice of this step is complete in your buffer"
+    // peer_flag[k] of every rank (one system fence, then relaxed system-scope stores): "rank's slice of this step is complete in your buffer"
     unsigned* peer_flag[DG_MAX_MIRRORS]; int n_peer_flag; unsigned flag_value;
+    // ... and the barrier of the PREVIOUS step folded into this launch: after raising its own flags the last warp / CTA waits
+    // until wait_flag[0..n_wait) (this rank's flag words of that step, one per rank) all hold wait_value, and only then tells the
+    // host -- "this launch is complete" implies "every rank's records of the step before are in my gathered buffer"
+    const unsigned* wait_flag; int n_wait; unsigned wait_value;
     long long* timeline;                           // instrumented runs only (tools/group_timeline.py): [block][32] globaltimer stamps
     // predicted agent tracks (BASELINE config 5, dp_set_tracks): constant-turn-rate parameters [scene][max_obs] -- displacement of
     // step 0 (vx, vy) and heading change per step (deg) -- and the horizon T; null = static obstacles (the reference's semantics)
     const double* trk_vx; const double* trk_vy; const double* trk_dth; int trk_T;
 };
+
+#if !defined(DP_EMU)
+// one thread: every flag word of a step has arrived (ld.acquire.sys pairs with the st.release.sys of the peers' last warps)
+__device__ __forceinline__ void dg_wait_flags(const unsigned* flags, int n, unsigned value) {
+    for (int r = 0; r < n; ++r) {
+        unsigned v = 0;
+        for (long spin = 0; spin < (1L << 26); ++spin) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+            if (v == value) break;
+            __nanosleep(100);
+        }
+        if (v != value) __trap();                           // never spin forever on a rank that is not there
+    }
+}
+#endif
 
 // ---- small portable helpers ---------------------------------------------------------------------------------------------
 DG_FN int dg_imin(int a, int b) { return a < b ? a : b; }
@@ -1867,14 +1886,15 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
     if (io.tally) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();                         // cumulative: the CTA's stores (ordered before the barrier) before the tally
+            __threadfence();                                // cumulative: the CTA's stores (ordered before the barrier) before the tally
             if (atomicAdd(io.tally, (unsigned)S) + (unsigned)S == io.tally_n) {
                 *io.tally = 0;                              // re-armed for the next cycle that uses this word
                 __threadfence_system();
-                if (io.host_done) *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
 #pragma unroll
                 for (int q = 0; q < DG_MAX_MIRRORS; ++q)
-                    if (q < io.n_peer_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[q]), "r"(io.flag_value) : "memory");
+                    if (q < io.n_peer_flag) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[q]), "r"(io.flag_value) : "memory");
+                dg_wait_flags(io.wait_flag, io.n_wait, io.wait_value);
+                if (io.host_done) *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
             }
         }
     }

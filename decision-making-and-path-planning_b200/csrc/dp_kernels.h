@@ -24,6 +24,7 @@ struct DpIo {
     unsigned* tally; unsigned tally_n;         // finished Planning warps of this cycle; the last one stores epoch to *host_done
     unsigned* host_done;                       // (page-locked host memory)
     unsigned* peer_flag[DP_MAX_MIRRORS]; int n_peer_flag; unsigned flag_value;   // fused gather (dp_gather_*), see DgIo
+    const unsigned* wait_flag; int n_wait; unsigned wait_value;                  // the previous step's barrier, folded in (DgIo)
 };
 inline DpIo dp_io_none() { DpIo io = {}; return io; }
 

@@ -23,7 +23,7 @@ SYMBOLS = [
     "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
     "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev", "dp_debug_timeline",
     "dp_set_tracks", "dp_set_tracks_dev", "dp_clear_tracks",
-    "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
+    "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_chain", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
 ]
 
 _lib = None
@@ -297,6 +297,10 @@ class Gather:
 
     def arm(self, step):
         _ck(self.lib.dp_gather_arm(self.h, C.c_uint(step)), "dp_gather_arm")
+
+    def chain(self, prev_step):
+        """the next cycle launch also waits (in its last warp) for every rank's flag of prev_step; 0 = off"""
+        _ck(self.lib.dp_gather_chain(self.h, C.c_uint(prev_step)), "dp_gather_chain")
 
     def disarm(self):
         _ck(self.lib.dp_gather_disarm(self.h), "dp_gather_disarm")

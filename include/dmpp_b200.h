@@ -227,6 +227,10 @@ int dp_set_record_mirrors(dp_ctx* ctx, int n, void* const* bases);
  *   dp_gather_arm      the NEXT cycle launch of ctx writes step `step` (>= 1, increasing): buffer step % depth, slice `rank`
  *   dp_gather_wait     enqueue on `stream` a wait for all `world` flags of that step in MY buffer; work that follows on the
  *                      stream may read dp_gather_buffer(step) = device pointer to rec[world][slots] of that step
+ *   dp_gather_chain    fold that wait into the NEXT cycle launch instead of a launch of its own: after raising its own flags the
+ *                      last warp of that launch waits for all flags of `prev_step` (0 = off) before the launch completes (and
+ *                      before dp_cycle_wait's host flag): kernel of step s done => dp_gather_buffer(prev_step) is complete.
+ *                      Deadlock-free as long as every rank launched prev_step before: no launch waits for a LATER step.
  * A rank may run ahead of a peer: with waits enqueued one step behind the launches (launch s, launch s+1, wait s, ...), depth 4
  * guarantees that a slice is never overwritten before every peer has waited for it. */
 #define DP_IPC_BYTES 64
@@ -234,6 +238,7 @@ typedef struct dp_gather dp_gather;
 int dp_gather_create(dp_ctx* ctx, int world, int rank, int slots_per_rank, int depth, dp_gather** out, void* my_handle_out);
 int dp_gather_attach(dp_gather* g, const void* handles);
 int dp_gather_arm(dp_gather* g, unsigned step);
+int dp_gather_chain(dp_gather* g, unsigned prev_step);
 int dp_gather_disarm(dp_gather* g);
 int dp_gather_wait(dp_gather* g, unsigned step, void* stream);
 const void* dp_gather_buffer(dp_gather* g, unsigned step);

@@ -54,6 +54,24 @@ def worker(rank, world, conn, n, n_obs, cycles, q):
         assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
         assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
         got.append((host.copy(), rec_h.view(np.uint8).reshape(n, 128).copy()))
+    # chained: no wait launches -- the launch of step s carries the wait for step s-1 (dp_gather_chain); the gathered buffer of
+    # s-1 is read right behind the kernel of s, the last one after an explicit wait
+    p.reset(0, n)
+    own = []
+    for c in range(cycles + 1):
+        step = 2 * cycles + c + 1
+        if c < cycles:
+            g.arm(step)
+            g.chain(step - 1 if c else 0)
+            p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec.data_ptr(), stream=st.cuda_stream)
+            own.append(d_rec.cpu().numpy().copy())
+        else:
+            g.wait(step - 1, stream=st.cuda_stream)
+        if c:
+            host = np.zeros((world * n, 128), np.uint8)
+            assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step - 1)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
+            assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
+            got.append((host.copy(), own[c - 1]))
     q.put((rank, got))
     conn.recv()                                              # keep the mapping alive until the peer has finished too
     g.close(); p.close()
@@ -77,7 +95,7 @@ def test_two_processes_gather_through_cuda_ipc(n_obs):
     for pr in procs:
         pr.join(timeout=120)
         assert pr.exitcode == 0
-    for c in range(2 * cycles):
+    for c in range(3 * cycles):
         own = [res[r][c][1] for r in range(world)]           # what each rank computed this step
         assert own[0].any()
         for r in range(world):
