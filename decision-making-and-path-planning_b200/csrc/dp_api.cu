@@ -179,7 +179,9 @@ std::vector<double2> interleave(const double* x, const double* y, size_t n) {
 // groups = distinct point counts of a row, ascending; cand_group[c] = group of candidate c (-1: fewer than 2 points).
 struct SweepGroups {
     std::vector<double> row_off;
-    std::vector<int32_t> row_gbeg, group_P, group_row, cand_group;
+    std::vector<int32_t> row_gbeg, group_P, group_row, cand_group, group_first;   // group_first: lowest candidate index of the group
+    int32_t first_nogroup = -1;                             // lowest candidate with fewer than 2 points
+    std::vector<int32_t> row_info;                          // per row {first group, groups, longest horizon, 0}
 };
 SweepGroups build_sweep_groups(const double* offset, const int32_t* n_pts, int n_cand, int n_base) {
     SweepGroups g;
@@ -202,10 +204,16 @@ SweepGroups build_sweep_groups(const double* offset, const int32_t* n_pts, int n
             double off; memcpy(&off, &b, 8);
             g.row_off.push_back(off); have_row = true; cur_bits = b; cur_P = -1;
         }
-        if (P != cur_P) { g.group_P.push_back(P); g.group_row.push_back((int32_t)g.row_off.size() - 1); cur_P = P; }
+        if (P != cur_P) { g.group_P.push_back(P); g.group_row.push_back((int32_t)g.row_off.size() - 1); g.group_first.push_back(c); cur_P = P; }
         g.cand_group[c] = (int32_t)g.group_P.size() - 1;
+        if (c < g.group_first.back()) g.group_first.back() = c;
     }
+    for (int c = 0; c < n_cand; ++c) if (g.cand_group[c] < 0) { g.first_nogroup = c; break; }
     if (have_row) g.row_gbeg.push_back((int32_t)g.group_P.size());
+    for (size_t r = 0; r + 1 < g.row_gbeg.size(); ++r) {
+        const int32_t g0 = g.row_gbeg[r], ng = g.row_gbeg[r + 1] - g0;
+        g.row_info.insert(g.row_info.end(), {g0, ng, ng > 0 ? g.group_P[(size_t)g0 + ng - 1] : 0, 0});   // (horizons ascend within a row)
+    }
     return g;
 }
 }  // namespace
@@ -854,6 +862,7 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
     PUT(d_bx, double, base_x, (size_t)n_base); PUT(d_by, double, base_y, (size_t)n_base);
     PUT(d_roff, double, sg.row_off.data(), sg.row_off.size()); PUT(d_gbeg, int32_t, sg.row_gbeg.data(), sg.row_gbeg.size());
     PUT(d_gP, int32_t, sg.group_P.data(), sg.group_P.size()); PUT(d_cg, int32_t, sg.cand_group.data(), (size_t)n_cand);
+    PUT(d_rinfo, int32_t, sg.row_info.data(), sg.row_info.size());
     PUT(d_grow, int32_t, sg.group_row.data(), sg.group_row.size());
     PUT(d_rcum, double, (const double*)nullptr, sg.row_off.size() * 256);
     PUT(d_gkey, unsigned, (const unsigned*)nullptr, sg.group_P.size());
@@ -865,7 +874,7 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
     PUT(d_key, unsigned long long, (const unsigned long long*)nullptr, 1);
     CK(cudaMemsetAsync(d_key, 0xff, 8, c->st[0]));
     CK(dp_launch_sweep_prefix(d_bx, d_by, n_rows, d_roff, d_gbeg, d_gP, d_rcum, c->st[0]));
-    CK(dp_launch_sweep(d_bx, d_by, n_base, n_rows, (int)sg.group_P.size(), d_roff, d_gbeg, d_gP, d_grow, d_cg, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs,
+    CK(dp_launch_sweep(d_bx, d_by, n_base, n_rows, (int)sg.group_P.size(), d_roff, reinterpret_cast<const int4*>(d_rinfo), d_gP, d_grow, d_cg, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs,
                        lat_min, lat_max, clear_dis, d_gkey, d_rcum, d_dis, d_key, c->st[0]));
     c->launches += 3;
     ++c->launches;
@@ -887,17 +896,17 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
 struct dp_sweep {
     dp_ctx* c = nullptr;
     int n_base = 0, n_cand = 0, max_obs = 0;
-    double *d_bx = nullptr, *d_by = nullptr, *d_roff = nullptr, *d_obs = nullptr, *d_dis = nullptr, *d_rcum = nullptr;   // d_obs: [4][max_obs]
-    int32_t *d_gbeg = nullptr, *d_gP = nullptr, *d_grow = nullptr, *d_cg = nullptr;   // rows / horizon groups of the candidate set (build_sweep_groups)
-    unsigned* d_gkey = nullptr;
-    int n_rows = 0, n_groups = 0;
-    unsigned long long* d_key = nullptr;
-    double* h_obs = nullptr;                                // pinned [4][max_obs]
-    unsigned long long* h_key = nullptr;                    // pinned
-    double* h_args = nullptr;                               // pinned {lat_min, lat_max, clear}
-    cudaGraphExec_t exec = nullptr;
-    int graph_n_obs = -1;
-    double g_lo = 0, g_hi = 0, g_clear = 0;
+    double *d_bx = nullptr, *d_by = nullptr, *d_roff = nullptr, *d_rcum = nullptr;
+    int32_t *d_gbeg = nullptr, *d_gP = nullptr, *d_rinfo = nullptr;   // rows / horizon groups of the candidate set (build_sweep_groups)
+    int32_t* d_gfirst = nullptr;                            // lowest candidate index per group
+    unsigned* d_done = nullptr;                             // row counter of the fused launch (0 between calls)
+    int n_rows = 0, n_groups = 0, first_nogroup = -1;
+    unsigned long long* d_res = nullptr;                    // {packed key, dis_lng bits} per row of the call in flight
+    double* h_obs = nullptr;                                // [4][max_obs] staging of the caller's obstacle arrays
+    unsigned long long* h_out = nullptr;                    // page-locked {packed key, dis_lng bits, sequence}: written by the grid's last CTA
+    unsigned long long* h_out_dev = nullptr;                // ... as the device addresses it
+    unsigned long long seq = 0;
+    long long* d_dbg = nullptr;                             // DP_SWEEP_DBG=1: phase stamps of the row owners (tools/sweep_probe.py)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
@@ -912,18 +921,23 @@ int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const doubl
     const SweepGroups sg = build_sweep_groups(offset, n_pts, n_cand, n_base);
     s->n_rows = (int)sg.row_off.size(); s->n_groups = (int)sg.group_P.size();
     CK(cudaMalloc((void**)&s->d_roff, (sg.row_off.size() + 1) * 8)); CK(cudaMalloc((void**)&s->d_gbeg, sg.row_gbeg.size() * 4));
-    CK(cudaMalloc((void**)&s->d_gP, (sg.group_P.size() + 1) * 4)); CK(cudaMalloc((void**)&s->d_cg, (size_t)n_cand * 4));
-    CK(cudaMalloc((void**)&s->d_rcum, (sg.row_off.size() + 1) * 256 * 8)); CK(cudaMalloc((void**)&s->d_grow, (sg.group_P.size() + 1) * 4));
-    CK(cudaMalloc((void**)&s->d_gkey, (sg.group_P.size() + 1) * 4));
-    CK(cudaMalloc((void**)&s->d_obs, (size_t)4 * max_obs * 8)); CK(cudaMalloc((void**)&s->d_dis, (size_t)n_cand * 8));
-    CK(cudaMalloc((void**)&s->d_key, 8));
-    CK(cudaMallocHost((void**)&s->h_obs, (size_t)4 * max_obs * 8)); CK(cudaMallocHost((void**)&s->h_key, 8));
+    CK(cudaMalloc((void**)&s->d_gP, (sg.group_P.size() + 1) * 4)); CK(cudaMalloc((void**)&s->d_rinfo, (sg.row_info.size() + 4) * 4));
+    CK(cudaMalloc((void**)&s->d_rcum, (sg.row_off.size() + 1) * 256 * 8));
+    CK(cudaMalloc((void**)&s->d_gfirst, (sg.group_P.size() + 1) * 4)); CK(cudaMalloc((void**)&s->d_res, (sg.row_off.size() + 1) * 16));
+    CK(cudaMalloc((void**)&s->d_done, 4));
+    CK(cudaMemset(s->d_done, 0, 4));
+    CK(cudaHostAlloc((void**)&s->h_obs, (size_t)4 * 192 * 8, cudaHostAllocMapped));
+    CK(cudaHostAlloc((void**)&s->h_out, 3 * 8, cudaHostAllocMapped));
+    s->h_out[0] = s->h_out[1] = s->h_out[2] = 0;
+    CK(cudaHostGetDevicePointer((void**)&s->h_out_dev, s->h_out, 0));
+    s->first_nogroup = sg.first_nogroup;
+    if (getenv("DP_SWEEP_DBG")) { CK(cudaMalloc((void**)&s->d_dbg, (size_t)(s->n_rows + 1) * 64)); CK(cudaMemset(s->d_dbg, 0, (size_t)(s->n_rows + 1) * 64)); }
     CK(cudaMemcpy(s->d_bx, base_x, n_base * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->d_by, base_y, n_base * 8, cudaMemcpyHostToDevice));
     if (s->n_rows) CK(cudaMemcpy(s->d_roff, sg.row_off.data(), sg.row_off.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->d_gbeg, sg.row_gbeg.data(), sg.row_gbeg.size() * 4, cudaMemcpyHostToDevice));
     if (s->n_groups) CK(cudaMemcpy(s->d_gP, sg.group_P.data(), sg.group_P.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s->d_cg, sg.cand_group.data(), (size_t)n_cand * 4, cudaMemcpyHostToDevice));
-    if (s->n_groups) CK(cudaMemcpy(s->d_grow, sg.group_row.data(), sg.group_row.size() * 4, cudaMemcpyHostToDevice));
+    if (s->n_rows) CK(cudaMemcpy(s->d_rinfo, sg.row_info.data(), sg.row_info.size() * 4, cudaMemcpyHostToDevice));
+    if (s->n_groups) CK(cudaMemcpy(s->d_gfirst, sg.group_first.data(), sg.group_first.size() * 4, cudaMemcpyHostToDevice));
     // the arclength prefix of every row does not depend on the obstacles: once, here
     CK(dp_launch_sweep_prefix(s->d_bx, s->d_by, s->n_rows, s->d_roff, s->d_gbeg, s->d_gP, s->d_rcum, c->st[0]));
     ++c->launches;
@@ -939,40 +953,45 @@ int dp_sweep_score(dp_sweep* s, const double* ox, const double* oy, const double
     dp_ctx* c = s->c;
     CK(cudaSetDevice(c->device));
     cudaStream_t st = c->st[0];
-    const int mo = s->max_obs;
+    const int mo = 192;                                      // staging stride (SWEEP_MAX_OBS)
     for (int i = 0; i < n_obs; ++i) {
         s->h_obs[i] = ox[i]; s->h_obs[mo + i] = oy[i];
         s->h_obs[2 * mo + i] = dvx ? dvx[i] : 0.0; s->h_obs[3 * mo + i] = dvy ? dvy[i] : 0.0;
     }
-    if (!s->exec || s->graph_n_obs != n_obs || s->g_lo != lat_min || s->g_hi != lat_max || s->g_clear != clear_dis) {
-        // (re)capture: the graph bakes in the scalar arguments; in the steady state of a planning loop they do not change
-        if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
-        cudaGraph_t g = nullptr;
-        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        cudaMemcpyAsync(s->d_obs, s->h_obs, (size_t)4 * mo * 8, cudaMemcpyHostToDevice, st);
-        cudaMemsetAsync(s->d_key, 0xff, 8, st);
-        dp_launch_sweep(s->d_bx, s->d_by, s->n_base, s->n_rows, s->n_groups, s->d_roff, s->d_gbeg, s->d_gP, s->d_grow, s->d_cg, s->n_cand,
-                        s->d_obs, s->d_obs + mo, s->d_obs + 2 * mo, s->d_obs + 3 * mo, n_obs, lat_min, lat_max, clear_dis, s->d_gkey, s->d_rcum,
-                        s->d_dis, s->d_key, st);
-        cudaMemcpyAsync(s->h_key, s->d_key, 8, cudaMemcpyDeviceToHost, st);
-        CK(cudaStreamEndCapture(st, &g));
-        CK(cudaGraphInstantiate(&s->exec, g, 0));
-        cudaGraphDestroy(g);
-        s->graph_n_obs = n_obs; s->g_lo = lat_min; s->g_hi = lat_max; s->g_clear = clear_dis;
-    }
+    // ONE launch: the obstacle tracks travel in the kernel parameters, the grid's last CTA writes the winner into page-locked
+    // memory and re-arms the device state; the host watches the sequence word instead of synchronising the stream
+    const unsigned long long seq = ++s->seq;
     if (device_ms) CK(cudaEventRecord(s->e0, st));
-    CK(cudaGraphLaunch(s->exec, st));
-    c->launches += 2;
+    CK(dp_launch_sweep_fused(s->d_bx, s->d_by, s->n_base, s->n_rows, s->d_roff, reinterpret_cast<const int4*>(s->d_rinfo), s->d_gP, s->d_gfirst,
+                             s->first_nogroup, s->h_obs, mo, n_obs, lat_min, lat_max, clear_dis, s->d_rcum, s->d_res, s->d_done, s->h_out_dev, seq,
+                             s->d_dbg, st));
+    ++c->launches;
     if (device_ms) CK(cudaEventRecord(s->e1, st));
-    CK(cudaStreamSynchronize(st));
-    if (device_ms) CK(cudaEventElapsedTime(device_ms, s->e0, s->e1));
-    const unsigned long long key = *s->h_key;
+    volatile unsigned long long* ho = s->h_out;
+    for (unsigned spin = 1; ho[2] != seq; ++spin) {
+        if ((spin & 0xfffff) == 0) {                        // every ~million polls: has the launch died?
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(DP_ERR_CUDA, "dp_sweep_score: launch failed", q);
+            if (q == cudaSuccess && ho[2] != seq) return fail(DP_ERR_CUDA, "dp_sweep_score: launch finished without a result");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const unsigned long long key = ho[0], dbits = ho[1];
+    if (device_ms) { CK(cudaEventSynchronize(s->e1)); CK(cudaEventElapsedTime(device_ms, s->e0, s->e1)); }
     const bool feasible = (key >> 32) == 0;
     *best_index = feasible ? (int32_t)(key & 0xffffffffu) : -1;
     if (best_dis_lng) {
         *best_dis_lng = DP_NOT_FOUND;
-        if (feasible) CK(cudaMemcpy(best_dis_lng, s->d_dis + *best_index, 8, cudaMemcpyDeviceToHost));
+        if (feasible) memcpy(best_dis_lng, &dbits, 8);
     }
+    return DP_OK;
+}
+/* diagnostic: globaltimer stamps [n_rows][8] of the last dp_sweep_score (sessions created with DP_SWEEP_DBG=1 only) */
+int dp_sweep_debug(dp_sweep* s, long long* out, int n_rows) {
+    if (!s || !out || !s->d_dbg || n_rows > s->n_rows + 1) return fail(DP_ERR_STATE, "dp_sweep_debug: session was created without DP_SWEEP_DBG=1");
+    CK(cudaSetDevice(s->c->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, s->d_dbg, (size_t)n_rows * 64, cudaMemcpyDeviceToHost));
     return DP_OK;
 }
 
@@ -980,10 +999,9 @@ int dp_sweep_destroy(dp_sweep* s) {
     if (!s) return DP_OK;
     cudaSetDevice(s->c->device);
     cudaStreamSynchronize(s->c->st[0]);
-    if (s->exec) cudaGraphExecDestroy(s->exec);
-    cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_roff); cudaFree(s->d_gbeg); cudaFree(s->d_gP); cudaFree(s->d_cg); cudaFree(s->d_rcum); cudaFree(s->d_grow); cudaFree(s->d_gkey);
-    cudaFree(s->d_obs); cudaFree(s->d_dis); cudaFree(s->d_key);
-    cudaFreeHost(s->h_obs); cudaFreeHost(s->h_key);
+    cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_roff); cudaFree(s->d_gbeg); cudaFree(s->d_gP); cudaFree(s->d_rinfo); cudaFree(s->d_rcum);
+    cudaFree(s->d_dbg); cudaFree(s->d_gfirst); cudaFree(s->d_res); cudaFree(s->d_done);
+    cudaFreeHost(s->h_obs); cudaFreeHost(s->h_out);
     if (s->e0) cudaEventDestroy(s->e0);
     if (s->e1) cudaEventDestroy(s->e1);
     delete s;

@@ -210,7 +210,7 @@ __device__ long long g_dbg_timeline[2 * 65536 * 2 * 8];   // [epoch parity][scen
 __device__ __forceinline__ long long dbg_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (long long)t; }
 #define DBG_MARK(ph, slot) if (lane == 0) g_dbg_timeline[(((size_t)(io.epoch & 1) * 65536 + scene) * 2 + (ph)) * 8 + (slot)] = dbg_now()
 #define DBG_END(ph, nt) if (lane == 0) { long long* g = g_dbg_timeline + (((size_t)(io.epoch & 1) * 65536 + scene) * 2 + (ph)) * 8; g[1] = dbg_now(); g[3] = (nt); }
-extern "C" int dp_debug_timeline(long long* dst, int n_scenes) {
+extern "C" int dp_debug_scene_timeline(long long* dst, int n_scenes) {
     (void)n_scenes;
     return (int)cudaMemcpyFromSymbol(dst, g_dbg_timeline, sizeof(g_dbg_timeline));   // dst: [2][65536][2][8]
 }

@@ -1,6 +1,9 @@
 // csrc/dp_ops.cu -- operator-level kernels behind the CShare seam, the
 // dense candidate sweep of BASELINE config 3, and the FMA micro-benchmark that provides the
 // roofline denominator (MEASURED_PEAKS.json has no FP64/FP32 CUDA-core figure).
+#include <cstdlib>
+#include <cstring>
+#include <cooperative_groups.h>
 #include "dp_device.cuh"
 #include "dp_fused.cuh"
 #include "dp_kernels.h"
@@ -101,105 +104,247 @@ op_nearest_kernel(int n_paths, const int32_t* __restrict__ path_off, const doubl
 // sequential prefix of segment lengths (every horizon starts at q_0, so the prefix IS the reference's sum).  Same bits as
 // scoring each candidate alone (tests/test_gpu_parity.py::test_dense_sweep*), rows x obstacles x points evaluations instead
 // of candidates x obstacles x points: 0.8 M instead of 250 M on the 64 x 32 x 32 grid.
-//   sweep_rows_kernel   one CTA per (row, block of 32 obstacles): 8 threads per obstacle, each owns an eighth of the row
-//                       (pass A: argmin of the part; pass B: the part again from the state the earlier parts left)
+//   sweep_rows_kernel   one thread-block CLUSTER per row, one CTA per block of 32 obstacles, a warp per part of the row: every
+//                       lane of a warp walks the same row points and meets the same horizons at the same step (no divergence,
+//                       row points broadcast); pass A: argmin of the part; pass B: the part again from the state the earlier
+//                       parts left.  The CTAs of a row min-reduce their packed keys into the shared memory of the cluster's
+//                       first CTA (distributed shared memory, remote atomicMin), which then owns the row's result.
+//                       FUSED (latency session, dp_sweep_score): that CTA also selects among the row's horizon groups, the
+//                       grid's last CTA writes the winner into page-locked host memory and re-arms the state -- one launch
+//                       per call, obstacles in the kernel parameters, no copy / memset / graph nodes
 //   sweep_prefix_kernel one CTA per row: sequential prefix of the row's segment lengths (obstacle-independent: once per candidate set)
-//   sweep_select_kernel one thread per candidate: cost of its (row, horizon) group, lowest feasible index by a packed
-//                       (cost bits << 32 | index) 64-bit atomicMin: the reference's first-feasible `break` (Decision.cpp:944-953)
+//   sweep_select_kernel (dp_score_candidates only) one thread per candidate: cost of its (row, horizon) group, lowest feasible
+//                       index by a packed (cost bits << 32 | index) 64-bit atomicMin: the reference's first-feasible `break`
+//                       (Decision.cpp:944-953)
 // ------------------------------------------------------------------------------------------------
 #define SWEEP_MAX_BASE 256
 #define SWEEP_MAX_OBS 192
+#define SWEEP_MAXW 32                                       // warps (= parts of the row) per CTA at most
 
-#define SWEEP_Q 8                                           // threads per (row, obstacle): eighths of the row
-#define SWEEP_OB 32                                         // obstacles per CTA
-__global__ void __launch_bounds__(SWEEP_Q * SWEEP_OB)
-sweep_rows_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, const double* __restrict__ row_off,
-                  const int32_t* __restrict__ row_gbeg, const int32_t* __restrict__ group_P, const double* __restrict__ ox,
-                  const double* __restrict__ oy, const double* __restrict__ dvx, const double* __restrict__ dvy, int n_obs, int ob0, double lat_min,
-                  double lat_max, unsigned* __restrict__ group_key) {
-    __shared__ double2 s_b[SWEEP_MAX_BASE];                 // base line
-    __shared__ double2 s_n[SWEEP_MAX_BASE];                 // unit right normal of segment j -> j+1
-    __shared__ double2 s_q[SWEEP_MAX_BASE];                 // row points b_j + off n_j
-    __shared__ unsigned s_key[SWEEP_MAX_BASE];              // per horizon group of the row
-    __shared__ double s_pd[SWEEP_OB][SWEEP_Q];              // running-argmin state at the end of each part of the row, per obstacle
-    __shared__ int s_pj[SWEEP_OB][SWEEP_Q];
-    __shared__ int s_gP[SWEEP_MAX_BASE];                    // the row's horizons (point counts), ascending
-    const int row = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
-    const int g0 = row_gbeg[row], ng = row_gbeg[row + 1] - g0;
-    const double off = row_off[row];
-    const int Pmax = ng > 0 ? group_P[g0 + ng - 1] : 0;     // horizons are sorted ascending
-    for (int j = tid; j < Pmax; j += nthr) s_b[j] = make_double2(base_x[j], base_y[j]);
-    for (int g = tid; g < ng; g += nthr) { s_key[g] = 0xffffffffu; s_gP[g] = group_P[g0 + g]; }
-    __syncthreads();
+struct SweepObs { double v[4][SWEEP_MAX_OBS]; };            // x0, y0, dvx, dvy: travels in the kernel parameters (6 KB)
+struct SweepSmem {
+    double2 b[SWEEP_MAX_BASE];                              // base line
+    double2 n[SWEEP_MAX_BASE];                              // unit right normal of segment j -> j+1
+    double2 q[SWEEP_MAX_BASE];                              // row points b_j + off n_j
+    unsigned key[SWEEP_MAX_BASE];                           // per horizon group of the row (first CTA of the cluster: the row's)
+    int gP[SWEEP_MAX_BASE];                                 // the row's horizons (point counts), ascending
+    double pd[SWEEP_MAXW][32];                              // running-argmin state at the end of each part of the row, per obstacle
+    int pj[SWEEP_MAXW][32];
+    double obs[4][32];                                      // this CTA's obstacle block
+    unsigned long long red[SWEEP_MAXW];
+    double redd[SWEEP_MAXW];
+    int last;
+};
+
+// one row against this CTA's 32 obstacles (o0 ..): min-reduces the packed selection key of every horizon group of the row into
+// rkey[0..ng) (the row owner's shared memory).  warp = part of the row; obs(k, o) = component k of obstacle track o
+template <class ObsFn>
+__device__ __forceinline__ void sweep_row_pass(SweepSmem& s, unsigned* rkey, const double* __restrict__ base_x, const double* __restrict__ base_y,
+                                               double off, const int32_t* __restrict__ gP, int ng, int Pmax, int n_obs, int o0, int PT,
+                                               double lat_min, double lat_max, ObsFn obs) {
+    namespace cg = cooperative_groups;
+    const int tid = threadIdx.x, nthr = blockDim.x, qt = tid >> 5, lane = tid & 31;
+    for (int g = tid; g < ng; g += nthr) { s.key[g] = 0xffffffffu; s.gP[g] = gP[g]; }
+    if (tid < 128) { const int k = tid >> 5, o = o0 + lane; s.obs[k][lane] = (o < n_obs) ? obs(k, o) : 0.0; }
+    cg::this_cluster().sync();                              // (the owner's keys are armed before any CTA of the row reduces into them)
     for (int j = tid; j + 1 < Pmax; j += nthr) {
-        const double2 n = dp_normal(s_b[j], s_b[j + 1]);
-        s_n[j] = n;
-        s_q[j] = make_double2(fma(off, n.x, s_b[j].x), fma(off, n.y, s_b[j].y));
+        const double2 n = dp_normal(s.b[j], s.b[j + 1]);
+        s.n[j] = n;
+        s.q[j] = make_double2(fma(off, n.x, s.b[j].x), fma(off, n.y, s.b[j].y));
     }
     __syncthreads();
-    // thread (obstacle ol, part qt): row points [j0, j1) of the running argmin; the obstacle block of this CTA
-    const int ol = tid / SWEEP_Q, qt = tid - ol * SWEEP_Q, o = ob0 + blockIdx.y * SWEEP_OB + ol;
-    const bool act = tid < SWEEP_OB * SWEEP_Q && o < n_obs;
+    const int o = o0 + lane;
+    const bool act = qt < PT && o < n_obs;
     const int nrow = Pmax > 0 ? Pmax - 1 : 0;               // row points q_0 .. q_{Pmax-2}
-    const int qlen = (nrow + SWEEP_Q - 1) / SWEEP_Q, j0 = qt * qlen, j1 = min(nrow, j0 + qlen);
+    const int qlen = (nrow + PT - 1) / PT, j0 = qt * qlen, j1 = min(nrow, j0 + qlen);
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    double x0 = 0, y0 = 0, vx = 0, vy = 0;
-    if (act) { x0 = ox[o]; y0 = oy[o]; vx = dvx ? dvx[o] : 0.0; vy = dvy ? dvy[o] : 0.0; }
-    {   // pass A: argmin of the own quarter
+    const double x0 = s.obs[0][lane], y0 = s.obs[1][lane], vx = s.obs[2][lane], vy = s.obs[3][lane];
+    if (qt < PT) {   // pass A: argmin of the own part
         double bd = INF; int bj = 0;
         if (act) {
             double jd = (double)j0;
             for (int j = j0; j < j1; ++j, jd += 1.0) {
-                const double2 q = s_q[j];
+                const double2 q = s.q[j];
                 const double dx = fma(jd, vx, x0) - q.x, dy = fma(jd, vy, y0) - q.y;
                 const double d = fma(dx, dx, dy * dy);
                 if (d < bd) { bd = d; bj = j; }
             }
-            s_pd[ol][qt] = bd; s_pj[ol][qt] = bj;
         }
+        s.pd[qt][lane] = bd; s.pj[qt][lane] = bj;
     }
     __syncthreads();
     if (act) {
-        // pass B: start from the state at the end of the quarters before mine (index order, strict '<': lowest index on ties),
-        // walk my quarter again and serve the horizons whose last row point falls into it
+        // pass B: start from the state at the end of the parts before mine (index order, strict '<': lowest index on ties),
+        // walk my part again and serve the horizons whose last row point falls into it
         double bd = INF; int bj = 0;
-        for (int q = 0; q < qt; ++q) if (s_pd[ol][q] < bd) { bd = s_pd[ol][q]; bj = s_pj[ol][q]; }
-        // horizon P needs the state over q_0 .. q_{P-2}: it is served by the quarter that holds row point P-2 ... i.e. when the
-        // walk is about to add row point j = P-1 (or, for the last horizon, at the end of the last quarter)
+        for (int q = 0; q < qt; ++q) {
+            const double od = s.pd[q][lane];
+            if (od < bd) { bd = od; bj = s.pj[q][lane]; }
+        }
+        // horizon P needs the state over q_0 .. q_{P-2}: it is served by the part that holds row point P-2 ... i.e. when the
+        // walk is about to add row point j = P-1 (or, for the last horizon, at the end of the last part)
         int g = 0;
-        while (g < ng && s_gP[g] - 1 < j0) ++g;             // horizons served by earlier parts (P-1 < j0); P-1 == j0 is mine
-        int Pn = (g < ng) ? s_gP[g] : 0;
-        const int jend = (qt == SWEEP_Q - 1 || j1 >= nrow) ? nrow + 1 : j1;   // the last quarter also serves P = Pmax (after the last row point)
+        for (int hi = ng; g < hi;) {                        // first horizon with P-1 >= j0 (earlier ones are served by earlier parts)
+            const int mid = (g + hi) >> 1;
+            if (s.gP[mid] - 1 < j0) g = mid + 1; else hi = mid;
+        }
+        int Pn = (g < ng) ? s.gP[g] : 0;
+        const int jend = (qt == PT - 1 || j1 >= nrow) ? nrow + 1 : j1;   // the last part also serves P = Pmax (after the last row point)
         double jd = (double)j0;
         for (int j = j0; j < jend; ++j, jd += 1.0) {
             const double mx = fma(jd, vx, x0), my = fma(jd, vy, y0);   // obstacle when the ego reaches path point j
             while (g < ng && Pn == j + 1) {
                 // horizon P = j + 1: its points are q_0 .. q_{P-2} (state bd, bj) and its own last point b_{P-1} + off n_{P-2}
                 const int P = Pn;
-                const double2 nl = s_n[P - 2], bl = s_b[P - 1];
+                const double2 nl = s.n[P - 2], bl = s.b[P - 1];
                 const double2 ql = make_double2(fma(off, nl.x, bl.x), fma(off, nl.y, bl.y));
                 const double dx = mx - ql.x, dy = my - ql.y;
                 const double dl = fma(dx, dx, dy * dy);
                 const int cj = (dl < bd) ? P - 1 : bj;      // strict '<': the last index only wins when strictly closer
                 const double hx = fma((double)cj, vx, x0), hy = fma((double)cj, vy, y0);   // the obstacle at step cj
                 const int k = (cj == P - 1) ? P - 2 : cj;
-                const double2 pk = s_q[k], pk1 = (k + 1 == P - 1) ? ql : s_q[k + 1];
+                const double2 pk = s.q[k], pk1 = (k + 1 == P - 1) ? ql : s.q[k + 1];
                 double dd;
-                const unsigned key = dp_owner_key(pk, pk1, cj, P, o, hx, hy, lat_min, lat_max, &dd);
-                if (key != 0xffffffffu) atomicMin(&s_key[g], key);
+                unsigned key = dp_owner_key(pk, pk1, cj, P, o, hx, hy, lat_min, lat_max, &dd);
+                const unsigned am = __activemask();         // (the lanes that arrive together, normally all active ones: one atomic for them)
+                key = __reduce_min_sync(am, key);
+                if (key != 0xffffffffu && lane == __ffs(am) - 1) atomicMin(&rkey[g], key);
                 ++g;
-                Pn = (g < ng) ? s_gP[g] : 0;
+                Pn = (g < ng) ? s.gP[g] : 0;
             }
             if (j < j1) {                                   // row point j enters the running argmin (it is point j of every longer horizon)
-                const double2 q = s_q[j];
+                const double2 q = s.q[j];
                 const double dx = mx - q.x, dy = my - q.y;
                 const double d = fma(dx, dx, dy * dy);
                 if (d < bd) { bd = d; bj = j; }
             }
         }
     }
+    cg::this_cluster().sync();                              // every CTA's keys have landed in the owner's shared memory
+}
+
+// arclength of horizon group g of the row to its selected point = the row prefix (+ one term when the selected point is the
+// horizon's own last point b_{P-1} + off n_{P-2}: q_{P-2} takes the normal of segment P-2 too)
+__device__ __forceinline__ double sweep_group_dis(const SweepSmem& s, int g, double off, const double* __restrict__ cum) {
+    const unsigned k = s.key[g];
+    if (k == 0xffffffffu) return DP_NOT_FOUND;              // nothing in the corridor
+    const int P = s.gP[g], jstar = (int)(k >> 16);
+    if (jstar <= P - 2) return cum[jstar];
+    const double2 nl = s.n[P - 2], b1 = s.b[P - 1], b2 = s.b[P - 2];
+    const double2 ql = make_double2(fma(off, nl.x, b1.x), fma(off, nl.y, b1.y));
+    const double2 qp = make_double2(fma(off, nl.x, b2.x), fma(off, nl.y, b2.y));
+    return cum[P - 2] + sqrt(dp_sq2(ql.x - qp.x, ql.y - qp.y));
+}
+
+struct SweepOut {                                           // FUSED: where the winner goes and the state the last CTA re-arms
+    unsigned long long* row_res;                            // device: {packed key, dis_lng bits} of every row's best group
+    unsigned* done;                                         // device: rows finished (0 between calls)
+    const int32_t* group_first;                             // lowest candidate index of each group
+    int first_nogroup;                                      // lowest candidate with fewer than 2 points (-1: none): dis_lng = DP_NOT_FOUND
+    volatile unsigned long long* host;                      // page-locked: {packed key, dis_lng bits, sequence number}
+    unsigned long long seq;
+    long long* dbg;                                         // diagnostic (DP_SWEEP_DBG=1): globaltimer stamps [row][8] of the row owners
+};
+#define SWEEP_STAMP(k) if (FUSED && out.dbg && threadIdx.x == 0 && ob == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); out.dbg[(size_t)(blockIdx.x / NB) * 8 + (k)] = (long long)t_; }
+
+// grid = max(n_rows, 1) clusters of NB CTAs (cluster dimension set by the launcher): CTA = (row blockIdx.x / NB, obstacle block blockIdx.x % NB)
+template <bool FUSED>
+__global__ void __launch_bounds__(1024)
+sweep_rows_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, int n_rows, const double* __restrict__ row_off,
+                  const int4* __restrict__ row_info, const int32_t* __restrict__ group_P, const double* __restrict__ ox,
+                  const double* __restrict__ oy, const double* __restrict__ dvx, const double* __restrict__ dvy,
+                  const __grid_constant__ SweepObs po, int n_obs, int NB, int PT, double lat_min, double lat_max, double clear_dis,
+                  unsigned* __restrict__ group_key, const double* __restrict__ row_cum, SweepOut out) {
+    namespace cg = cooperative_groups;
+    __shared__ SweepSmem s;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int ob = (int)cluster.block_rank(), row = blockIdx.x / NB, tid = threadIdx.x, nthr = blockDim.x;
+    unsigned long long mykey = ~0ull;
+    double mydis = DP_NOT_FOUND;
+    SWEEP_STAMP(0);
+    if (row < n_rows) {                                     // (uniform over the cluster)
+        // the base line does not depend on the row: its loads fly together with the row header {first group, groups, longest horizon}
+        const int4 ri = row_info[row];
+        const double off = row_off[row];
+        for (int j = tid; j < n_base; j += nthr) s.b[j] = make_double2(base_x[j], base_y[j]);
+        const int g0 = ri.x, ng = ri.y, Pmax = ri.z;
+        unsigned* rkey = cluster.map_shared_rank(s.key, 0);
+        if (FUSED)
+            sweep_row_pass(s, rkey, base_x, base_y, off, group_P + g0, ng, Pmax, n_obs, ob * 32, PT, lat_min, lat_max,
+                           [&](int k, int o) { return po.v[k][o]; });
+        else
+            sweep_row_pass(s, rkey, base_x, base_y, off, group_P + g0, ng, Pmax, n_obs, ob * 32, PT, lat_min, lat_max,
+                           [&](int k, int o) { return k == 0 ? ox[o] : k == 1 ? oy[o] : k == 2 ? (dvx ? dvx[o] : 0.0) : (dvy ? dvy[o] : 0.0); });
+        SWEEP_STAMP(1);
+        if (ob != 0) return;                                // the row's first CTA carries on with the merged keys
+        if (!FUSED) {
+            for (int g = tid; g < ng; g += nthr) group_key[g0 + g] = s.key[g];
+            return;
+        }
+        const double* cum = row_cum + (size_t)row * SWEEP_MAX_BASE;
+        for (int g = tid; g < ng; g += nthr) {
+            const double dis = sweep_group_dis(s, g, off, cum);
+            const float cost = (dis > clear_dis) ? 0.0f : __int_as_float(0x7f800000);
+            const unsigned long long k = ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)out.group_first[g0 + g];
+            if (k < mykey) { mykey = k; mydis = dis; }
+        }
+    }
+    if (!FUSED || ob != 0) return;
+    SWEEP_STAMP(2);
+    if (blockIdx.x == 0 && tid == 0 && out.first_nogroup >= 0) {
+        const float cost = (DP_NOT_FOUND > clear_dis) ? 0.0f : __int_as_float(0x7f800000);
+        const unsigned long long k = ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)out.first_nogroup;
+        if (k < mykey) { mykey = k; mydis = DP_NOT_FOUND; }
+    }
+    // keys are distinct (they end in a candidate index) unless both are ~0: the dis_lng travels with the smaller key
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(DP_FULL, mykey, o);
+        const double od = __shfl_xor_sync(DP_FULL, mydis, o);
+        if (ok < mykey) { mykey = ok; mydis = od; }
+    }
+    if ((tid & 31) == 0) { s.red[tid >> 5] = mykey; s.redd[tid >> 5] = mydis; }
+    if (tid == 0) s.last = 0;
     __syncthreads();
-    for (int g = tid; g < ng; g += nthr) if (s_key[g] != 0xffffffffu) atomicMin(&group_key[g0 + g], s_key[g]);
+    if (tid >= 32) return;
+    mykey = (tid < (nthr >> 5)) ? s.red[tid] : ~0ull;
+    mydis = (tid < (nthr >> 5)) ? s.redd[tid] : DP_NOT_FOUND;
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(DP_FULL, mykey, o);
+        const double od = __shfl_xor_sync(DP_FULL, mydis, o);
+        if (ok < mykey) { mykey = ok; mydis = od; }
+    }
+    SWEEP_STAMP(3);
+    const int rows = n_rows > 0 ? n_rows : 1;
+    int last = 0;
+    if (tid == 0) {
+        const int r = row < rows ? row : 0;
+        out.row_res[2 * r] = mykey; out.row_res[2 * r + 1] = (unsigned long long)__double_as_longlong(mydis);
+        __threadfence();
+        last = atomicAdd(out.done, 1u) == (unsigned)rows - 1u;
+        if (last) { *out.done = 0; __threadfence(); }       // re-armed for the next call (stream order)
+    }
+    last = __shfl_sync(DP_FULL, last, 0);
+    SWEEP_STAMP(4);
+    if (!last) return;
+    // the last row: first warp reduces the rows' results and publishes the winner
+    mykey = ~0ull; mydis = DP_NOT_FOUND;
+    for (int r = tid; r < rows; r += 32) {
+        const unsigned long long k = __ldcg(out.row_res + 2 * r);
+        const unsigned long long d = __ldcg(out.row_res + 2 * r + 1);
+        if (k < mykey) { mykey = k; mydis = __longlong_as_double((long long)d); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ok = __shfl_xor_sync(DP_FULL, mykey, o);
+        const double od = __shfl_xor_sync(DP_FULL, mydis, o);
+        if (ok < mykey) { mykey = ok; mydis = od; }
+    }
+    if (tid == 0) {
+        SWEEP_STAMP(5);
+        out.host[0] = mykey; out.host[1] = (unsigned long long)__double_as_longlong(mydis);
+        __threadfence_system();
+        SWEEP_STAMP(6);
+        out.host[2] = out.seq;
+    }
 }
 
 // the row's sequential prefix of segment lengths (all horizons start at q_0, so the prefix IS the reference's arclength sum):
@@ -324,24 +469,58 @@ cudaError_t dp_launch_sweep_prefix(const double* base_x, const double* base_y, i
     sweep_prefix_kernel<<<n_rows, 256, 0, st>>>(base_x, base_y, row_off, row_gbeg, group_P, row_cum);
     return cudaGetLastError();
 }
+// shape of the row clusters: NB CTAs (obstacle blocks of 32) x PT warps (parts of the row)
+static void sweep_shape(int n_obs, int* NB, int* PT) {
+    *NB = n_obs > 0 ? (n_obs + 31) / 32 : 1;
+    int pt = 16;
+    if (const char* e = getenv("DP_SWEEP_PARTS")) pt = atoi(e);
+    *PT = pt < 1 ? 1 : (pt > SWEEP_MAXW ? SWEEP_MAXW : pt);
+}
+template <bool FUSED, class... Args>
+static cudaError_t sweep_launch(int n_rows, int NB, int PT, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((n_rows > 0 ? n_rows : 1) * NB)); cfg.blockDim = dim3((unsigned)(PT * 32)); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)NB; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sweep_rows_kernel<FUSED>, args...);
+}
 cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, int n_rows, int n_groups, const double* row_off,
-                            const int32_t* row_gbeg, const int32_t* group_P, const int32_t* group_row, const int32_t* cand_group, int n_cand,
+                            const int4* row_info, const int32_t* group_P, const int32_t* group_row, const int32_t* cand_group, int n_cand,
                             const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min, double lat_max,
                             double clear_dis, unsigned* group_key, const double* row_cum, double* cand_dis_lng, unsigned long long* best_key,
                             cudaStream_t st) {
+    (void)n_groups;
     if (n_cand <= 0) return cudaSuccess;
     if (n_rows > 0) {
-        cudaError_t e = cudaMemsetAsync(group_key, 0xff, (size_t)n_groups * sizeof(unsigned), st);
+        int NB, PT;
+        sweep_shape(n_obs, &NB, &PT);
+        static const SweepObs none = {};
+        const cudaError_t e = sweep_launch<false>(n_rows, NB, PT, st, base_x, base_y, n_base, n_rows, row_off, row_info, group_P, ox, oy, dvx, dvy, none, n_obs, NB,
+                                                  PT, lat_min, lat_max, clear_dis, group_key, row_cum, SweepOut{});
         if (e != cudaSuccess) return e;
-        if (n_obs > 0) {
-            const dim3 grid(n_rows, (n_obs + SWEEP_OB - 1) / SWEEP_OB);   // a CTA = one row x 32 obstacles x 8 parts of the row
-            sweep_rows_kernel<<<grid, SWEEP_Q * SWEEP_OB, 0, st>>>(base_x, base_y, n_base, row_off, row_gbeg, group_P, ox, oy, dvx, dvy, n_obs, 0,
-                                                                  lat_min, lat_max, group_key);
-        }
     }
     sweep_select_kernel<<<(n_cand + 255) / 256, 256, 0, st>>>(cand_group, n_cand, group_row, group_P, group_key, row_cum, row_off, base_x, base_y,
                                                               clear_dis, cand_dis_lng, best_key);
     return cudaGetLastError();
+}
+// latency session: ONE launch; the winner lands in host[0..2] (page-locked), host[2] = seq last
+cudaError_t dp_launch_sweep_fused(const double* base_x, const double* base_y, int n_base, int n_rows, const double* row_off, const int4* row_info,
+                                  const int32_t* group_P, const int32_t* group_first, int first_nogroup, const double* obs4, int obs_stride,
+                                  int n_obs, double lat_min, double lat_max, double clear_dis, const double* row_cum,
+                                  unsigned long long* row_res, unsigned* done, unsigned long long* host, unsigned long long seq, long long* dbg,
+                                  cudaStream_t st) {
+    SweepObs po;                                            // (copied into the launch: no lifetime beyond the call)
+    for (int k = 0; k < 4; ++k) memcpy(po.v[k], obs4 + (size_t)k * obs_stride, (size_t)n_obs * sizeof(double));
+    int NB, PT;
+    sweep_shape(n_obs, &NB, &PT);
+    SweepOut out;
+    out.row_res = row_res; out.done = done; out.group_first = group_first; out.first_nogroup = first_nogroup; out.host = host; out.seq = seq;
+    out.dbg = dbg;
+    const double* nul = nullptr; unsigned* nkey = nullptr;
+    return sweep_launch<true>(n_rows, NB, PT, st, base_x, base_y, n_base, n_rows, row_off, row_info, group_P, nul, nul, nul, nul, po, n_obs, NB, PT,
+                              lat_min, lat_max, clear_dis, nkey, row_cum, out);
 }
 cudaError_t dp_launch_fma_peak(int which, float* sink, int iters, int blocks, cudaStream_t st) {
     if (which == 0) fma_peak_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<double*>(sink), iters);

@@ -20,7 +20,7 @@ SYMBOLS = [
     "dp_carry_download", "dp_carry_upload", "dp_cycle_batch_dev", "dp_cycle_batch", "dp_host_alloc",
     "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
-    "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy",
+    "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy", "dp_sweep_debug",
     "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev", "dp_debug_timeline",
     "dp_set_tracks", "dp_set_tracks_dev", "dp_clear_tracks",
     "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_chain", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
@@ -318,8 +318,8 @@ class Gather:
 
 
 class SweepSession:
-    """latency-mode dense candidate sweep (BASELINE config 3): candidate set resident on the device, one CUDA-graph
-    replay per call"""
+    """latency-mode dense candidate sweep (BASELINE config 3): candidate set resident on the device, one kernel launch per call
+    (obstacles in the kernel parameters, winner written to page-locked memory by the grid's last CTA)"""
 
     def __init__(self, planner, base_x, base_y, offset, n_pts, max_obs):
         self.lib = planner.lib
@@ -332,13 +332,13 @@ class SweepSession:
         self._best = C.c_int32(-1)
         self._dis = C.c_double(0)
 
-    def score(self, ox, oy, dvx=None, dvy=None, lat_min=-0.9, lat_max=0.9, clear_dis=25.0, want_dis=True):
+    def score(self, ox, oy, dvx=None, dvy=None, lat_min=-0.9, lat_max=0.9, clear_dis=25.0, want_dis=True, want_ms=True):
         ox, oy = np.ascontiguousarray(ox, np.float64), np.ascontiguousarray(oy, np.float64)
         dvx = None if dvx is None else np.ascontiguousarray(dvx, np.float64)
         dvy = None if dvy is None else np.ascontiguousarray(dvy, np.float64)
         _ck(self.lib.dp_sweep_score(self.h, abi.ptr(ox), abi.ptr(oy), abi.ptr(dvx), abi.ptr(dvy), C.c_int(ox.size), C.c_double(lat_min),
                                     C.c_double(lat_max), C.c_double(clear_dis), C.byref(self._best),
-                                    C.byref(self._dis) if want_dis else None, C.byref(self._ms)), "dp_sweep_score")
+                                    C.byref(self._dis) if want_dis else None, C.byref(self._ms) if want_ms else None), "dp_sweep_score")
         return self._best.value, self._dis.value, self._ms.value
 
     def close(self):

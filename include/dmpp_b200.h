@@ -260,8 +260,10 @@ int dp_score_candidates(dp_ctx* ctx, const double* base_x, const double* base_y,
                         double* out_dis_lng);
 
 /* Latency-mode session of (5): the candidate set (base line, offsets, point counts) is uploaded once; each
- * dp_sweep_score call stages the obstacle tracks, replays ONE captured CUDA graph (H2D of the obstacles, key reset,
- * sweep kernel, D2H of the winner) and returns when the winner is on the host.  n_obs <= max_obs <= 192. */
+ * dp_sweep_score call is ONE kernel launch: the obstacle tracks travel in the kernel parameters, a thread-block cluster per
+ * lateral offset scores all horizons of that offset, the grid's last CTA writes the winner into page-locked host memory, and
+ * the call returns as soon as the host sees it (no stream synchronisation, no copies).  n_obs <= max_obs <= 192.
+ * device_ms (nullable) = CUDA-event time around the launch; asking for it adds an event synchronisation to the call. */
 typedef struct dp_sweep dp_sweep;
 int dp_sweep_create(dp_ctx* ctx, dp_sweep** out, const double* base_x, const double* base_y, int n_base,
                     const double* offset, const int32_t* n_pts, int n_cand, int max_obs);
@@ -269,6 +271,10 @@ int dp_sweep_score(dp_sweep* s, const double* obs_x, const double* obs_y, const 
                    const double* obs_dvy, int n_obs, double lat_min, double lat_max, double clear_dis,
                    int32_t* best_index, double* best_dis_lng, float* device_ms);
 int dp_sweep_destroy(dp_sweep* s);
+/* diagnostic: globaltimer stamps [n_rows][8] (ns) of the row-owner CTAs of the last dp_sweep_score: 0 start, 1 row pass done,
+ * 2 groups selected, 3 reduced, 4 counted, 5 winner known, 6 system fence done (5, 6: last row only).  Only sessions created
+ * with DP_SWEEP_DBG=1 in the environment record them (tools/sweep_probe.py). */
+int dp_sweep_debug(dp_sweep* s, long long* out, int n_rows);
 
 /* (6) operator-level batch calls, the CShare seam.  Host pointers.
  * paths are [n_paths] polylines concatenated; path_off[n_paths+1]. */

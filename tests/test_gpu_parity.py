@@ -216,6 +216,35 @@ def test_dense_sweep_session_full_grid(planner, oracle, the_map):
     sess.close()
 
 
+@pytest.mark.parametrize("n_obs", [0, 1, 31, 33, 64])
+def test_dense_sweep_session_shapes(planner, oracle, the_map, n_obs):
+    """the one-launch session against the oracle over obstacle counts around the 32-lane blocks, ragged candidate sets (a
+    candidate with fewer than 2 points is never found: dis_lng = 999 > clear_dis makes it feasible, Decision.cpp:944), changing
+    corridor / clearance arguments and obstacles that move between calls"""
+    rng = np.random.default_rng(100 + n_obs)
+    gl = the_map.lane_index(3, 2)
+    o = the_map.lane_pt_off[gl] + 500
+    bx, by = the_map.x[o:o + 200], the_map.y[o:o + 200]
+    offset = rng.choice(-2.0 + 0.25 * np.arange(17), 600)
+    n_pts = rng.integers(2, 201, 600).astype(np.int32)
+    n_pts[rng.integers(0, 600, 5)] = 200
+    sess = planner.sweep_session(bx, by, offset, n_pts, 64)
+    n_pts1 = n_pts.copy(); n_pts1[[400, 17]] = [1, 0]        # two candidates without a path, behind many ordinary ones
+    sess1 = planner.sweep_session(bx, by, offset, n_pts1, 64)
+    for it in range(6):
+        idx = rng.integers(5, 195, n_obs)
+        ox, oy = bx[idx] + rng.normal(0, 1.2, n_obs), by[idx] + rng.normal(0, 1.2, n_obs)
+        dvx, dvy = rng.normal(0, 0.05, n_obs), rng.normal(0, 0.05, n_obs)
+        lo, hi, clear = (-0.9, 0.9, 25.0) if it % 2 == 0 else (-1.4, 0.6, 60.0 + it)
+        for s_, npt in ((sess, n_pts), (sess1, n_pts1)):
+            wbest, wall = oracle.score_candidates(bx, by, offset, npt, ox, oy, dvx, dvy, lat_min=lo, lat_max=hi, clear_dis=clear)
+            best, dis, _ = s_.score(ox, oy, dvx, dvy, lat_min=lo, lat_max=hi, clear_dis=clear)
+            assert best == wbest, (it, best, wbest)
+            assert best < 0 or dis == wall[best]
+            assert s_.score(ox, oy, dvx, dvy, lat_min=lo, lat_max=hi, clear_dis=clear, want_ms=False)[:2] == (best, dis)
+    sess.close(); sess1.close()
+
+
 def test_reset_and_carry_roundtrip(planner, oracle, the_map):
     """checkpoint/resume: episodes split in two halves with the carry downloaded and re-uploaded in
     between give the same result as one uninterrupted run (idempotent state hand-off)."""

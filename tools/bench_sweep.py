@@ -1,5 +1,5 @@
 """BASELINE config 3, latency mode: 65 536 candidates (64 lateral offsets x 32 aim distances x 32 horizons) x 50
-obstacle tracks, ONE scene, scored by one CUDA-graph replay per call.  Prints a JSON line with p50/p99 latency."""
+obstacle tracks, ONE scene, scored by one kernel launch per call.  Prints a JSON line with p50/p99 latency."""
 import json
 import os
 import sys
@@ -38,9 +38,10 @@ for i in range(50):
 for i in range(calls):
     ox = ox0 + 0.01 * (i % 97)                      # obstacles move between calls
     t0 = time.perf_counter()
-    best, _, ms = sess.score(ox, oy0, dvx, dvy, want_dis=False)
+    best, _, _ = sess.score(ox, oy0, dvx, dvy, want_ms=False)
     wall[i] = time.perf_counter() - t0
-    dev[i] = ms
+for i in range(calls):                              # device time from its own loop: the event synchronisation is not in the wall figure
+    dev[i] = sess.score(ox0 + 0.01 * (i % 97), oy0, dvx, dvy, want_dis=False)[2]
 # algorithmic work of the row-sharing formulation (csrc/dp_ops.cu): per distinct offset (row) ONE rollout + arclength prefix of
 # its longest horizon and ONE nearest-point pass per obstacle, plus the gate / lateral / corridor step per (horizon group, obstacle)
 pts = 0.0; groups = 0
@@ -52,7 +53,7 @@ pts_naive = float(n_pts.astype(np.int64).sum())
 flops_naive = 18.0 * pts_naive + N * (5.0 * pts_naive + 12.0 * offset.size)
 fp64, fp32 = p.measure_fma_peak()
 print(json.dumps({
-    "workload": "config3: 1 scene, 65536 candidates, 50 obstacle tracks, graph-replayed", "calls": calls,
+    "workload": "config3: 1 scene, 65536 candidates, 50 obstacle tracks, one launch per call", "calls": calls,
     "latency_ms_wall": {"p50": float(np.percentile(wall, 50) * 1e3), "p99": float(np.percentile(wall, 99) * 1e3), "max": float(wall.max() * 1e3)},
     "latency_ms_device": {"p50": float(np.percentile(dev, 50)), "p99": float(np.percentile(dev, 99))},
     "candidates_per_s": offset.size / float(np.median(wall)),

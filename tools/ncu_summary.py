@@ -27,6 +27,7 @@ for f,l,s,sm,ins,st in res:
 ts=sum(a[1] for a in agg.values()); ti=sum(a[2] for a in agg.values())
 print("samples",ts,"inst",ti)
 print({k:round(100*v/sum(tot.values()),1) for k,v in tot.most_common()})
-for k,a in sorted(agg.items(), key=lambda kv:-kv[1][1])[:int(sys.argv[2]) if len(sys.argv)>2 else 40]:
+BY = 2 if "--by-inst" in sys.argv else 1
+for k,a in sorted(agg.items(), key=lambda kv:-kv[1][BY])[:int(sys.argv[2]) if len(sys.argv)>2 else 40]:
     top=a[3].most_common(2)
     print("%-13s %4d smp %4.1f%% inst %4.1f%% %-28s| %s"%(k[0][:13],k[1],100*a[1]/ts,100*a[2]/ti,",".join("%s:%d"%(n[6:],v) for n,v in top),a[0]))

@@ -20,7 +20,7 @@ for c in range(K):
     o = p.cycle(np.ascontiguousarray(H[c]), OX[c], OY[c])
 T2 = np.zeros((2, 65536, 2, 8), np.int64)
 lib = load()
-assert lib.dp_debug_timeline(T2.ctypes.data_as(C.c_void_p), C.c_int(n)) == 0
+assert lib.dp_debug_scene_timeline(T2.ctypes.data_as(C.c_void_p), C.c_int(n)) == 0
 last = int(np.argmax(T2[:, :n, 1, 1].max(axis=1)))          # parity of the last cycle
 t = T2[last, :n]
 t0 = t[:, 0, 0].min()
