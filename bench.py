@@ -483,6 +483,7 @@ def run_ours(args, rank, world, local_rank):
         try:
             if world == 1:
                 extras["config3"] = config3_line(P_, m)
+                extras["config3_distinct_geometry"] = config3_bezier_line(P_, m)
                 extras["config4_shard"] = config4_line(torch, dist, P_, m, dev, rank, world, local_rank, 131072)
             else:
                 extras["config4"] = config4_line(torch, dist, P_, m, dev, rank, world, local_rank, 1048576)
@@ -669,6 +670,70 @@ def config3_line(planner_cls, m, calls=10000):
                          "note": "row-sharing formulation: candidates of one lateral offset share one pass per obstacle (3136 distinct (offset, "
                                  "horizon) groups, 64 rows); latency mode is bound by the dependent chain of one (row, obstacle) pass and the "
                                  "launch latency, not by the FMA roofline"}}
+
+
+def config3_bezier_line(planner_cls, m, calls=2000):
+    """config 3 with a longitudinal axis that changes GEOMETRY: 64 lateral offsets x 32 aim distances = 2048 distinct Bezier local
+    paths (Planning.cpp:596-611: ego pose -> aim pose on the laterally shifted lane), each with 32 horizons (prefixes of ITS line)
+    = 65 536 candidates, 50 obstacle tracks.  Per planning cycle: dp_sweep_set_bezier (all lines drawn on the device, arclength
+    prefixes) once, then dp_sweep_score; both timed, each over `calls` calls."""
+    rng = np.random.default_rng(77)
+    gl = m.lane_index(3, 2)
+    o = m.lane_pt_off[gl] + 700
+    lx, ly, ld = m.x[o:o + 400], m.y[o:o + 400], m.dir[o:o + 400]
+    n_lat, n_aim, n_hor = 64, 32, 32
+    lat = np.linspace(-3.15, 3.15, n_lat)
+    aim_id = np.linspace(40, 200, n_aim).astype(int)          # aim point 20 .. 100 m ahead
+    poses = np.zeros((n_lat * n_aim, 6))
+    for i, d in enumerate(lat):
+        for k, a in enumerate(aim_id):
+            h = np.deg2rad(ld[a])
+            poses[i * n_aim + k] = (lx[0], ly[0], ld[0], lx[a] + d * np.sin(h), ly[a] - d * np.cos(h), ld[a])
+    hor = np.linspace(8, 200, n_hor).astype(np.int32)
+    cand_line = np.repeat(np.arange(n_lat * n_aim), n_hor).astype(np.int32)
+    n_pts = np.tile(hor, n_lat * n_aim).astype(np.int32)
+    off = np.zeros(cand_line.size)
+    N = 50
+    idx = rng.integers(10, 200, N)
+    ox0, oy0 = lx[idx] + rng.normal(0, 2.0, N), ly[idx] + rng.normal(0, 2.0, N)
+    dvx, dvy = rng.normal(0, 0.03, N), rng.normal(0, 0.03, N)
+    p = planner_cls(16, 64)
+    p.upload_map(m)
+    sess = p.sweep_session(None, None, off, n_pts, 64, cand_line=cand_line, bezier_lines=n_lat * n_aim)
+    sess.set_bezier(poses)
+    for i in range(30):
+        sess.score(ox0, oy0, dvx, dvy)
+    wall, dev, setw, setd = np.zeros(calls), np.zeros(calls), np.zeros(calls), np.zeros(calls)
+    l0 = p.launch_count()
+    for i in range(calls):
+        ps = poses.copy(); ps[:, 0] += 0.01 * (i % 50)          # the ego moves: new lines every cycle
+        t0 = time.perf_counter()
+        sess.set_bezier(ps)
+        t1 = time.perf_counter()
+        sess.score(ox0 + 0.01 * (i % 97), oy0, dvx, dvy, want_ms=False)
+        t2 = time.perf_counter()
+        setw[i], wall[i] = t1 - t0, t2 - t1                    # (set_bezier only enqueues; its device time is inside the score wall time)
+    launches = p.launch_count() - l0
+    for i in range(calls):
+        setd[i] = sess.set_bezier(poses, want_ms=True)
+        dev[i] = sess.score(ox0 + 0.01 * (i % 97), oy0, dvx, dvy, want_dis=False)[2]
+    rows_pts = float(n_lat * n_aim * 200)
+    groups = float(n_lat * n_aim * n_hor)
+    flops = 18.0 * rows_pts + N * (5.0 * rows_pts + 12.0 * groups)
+    fp64, _ = p.measure_fma_peak()
+    sess.close(); p.close()
+    pc = lambda a, q: float(np.percentile(a, q))              # noqa: E731
+    return {"workload": "config3, distinct geometry: 2048 Bezier local paths (64 lateral x 32 aim distances) x 32 horizons = 65536 candidates, "
+                        "50 obstacle tracks; lines re-drawn on the device every cycle",
+            "calls": calls, "gpu_launches": int(launches),
+            "cycle_latency_ms": {"p50": pc(setw + wall, 50) * 1e3, "p99": pc(setw + wall, 99) * 1e3,
+                                 "what": "wall clock of dp_sweep_set_bezier + dp_sweep_score: poses and obstacles in, winner on the host"},
+            "score_latency_ms_device": {"p50": pc(dev, 50), "p99": pc(dev, 99)},
+            "set_bezier_ms_device": {"p50": pc(setd, 50), "p99": pc(setd, 99)},
+            "candidates_per_s": cand_line.size / float(np.median(setw + wall)),
+            "roofline": {"bound": "fp64", "kernel": "sweep_rows_kernel", "unit": "TFLOP/s", "achieved": flops / (np.median(dev) * 1e-3) / 1e12,
+                         "peak": fp64, "frac": flops / (np.median(dev) * 1e-3) / 1e12 / fp64, "algorithmic_flops_per_call": flops,
+                         "note": "2048 rows x 2 obstacle blocks x 4 parts of a row per warp (throughput shape of the same kernel)"}}
 
 
 def config3_grid(m):

@@ -181,28 +181,33 @@ struct SweepGroups {
     std::vector<double> row_off;
     std::vector<int32_t> row_gbeg, group_P, group_row, cand_group, group_first;   // group_first: lowest candidate index of the group
     int32_t first_nogroup = -1;                             // lowest candidate with fewer than 2 points
-    std::vector<int32_t> row_info;                          // per row {first group, groups, longest horizon, 0}
+    std::vector<int32_t> row_info;                          // per row {first group, groups, longest horizon, base line}
 };
-SweepGroups build_sweep_groups(const double* offset, const int32_t* n_pts, int n_cand, int n_base) {
+SweepGroups build_sweep_groups(const int32_t* cand_line, const double* offset, const int32_t* n_pts, int n_cand, int n_base) {
     SweepGroups g;
-    std::vector<std::pair<uint64_t, int32_t>> keyed((size_t)n_cand);   // (offset bits, P)
+    struct Key { int32_t line; uint64_t bits; int32_t P; };
+    std::vector<Key> keyed((size_t)n_cand);                 // (base line, offset bits, P)
     for (int c = 0; c < n_cand; ++c) {
         uint64_t b; memcpy(&b, &offset[c], 8);
-        keyed[c] = {b, n_pts[c] < n_base ? n_pts[c] : n_base};
+        keyed[c] = {cand_line ? cand_line[c] : 0, b, n_pts[c] < n_base ? n_pts[c] : n_base};
     }
     std::vector<int32_t> order((size_t)n_cand);
     for (int c = 0; c < n_cand; ++c) order[c] = c;
-    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return keyed[a] < keyed[b]; });
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        const Key &x = keyed[a], &y = keyed[b];
+        return x.line != y.line ? x.line < y.line : x.bits != y.bits ? x.bits < y.bits : x.P != y.P ? x.P < y.P : a < b;
+    });
     g.cand_group.assign((size_t)n_cand, -1);
     g.row_gbeg.push_back(0);
-    bool have_row = false; uint64_t cur_bits = 0; int32_t cur_P = -1;
+    std::vector<int32_t> row_line;
+    bool have_row = false; uint64_t cur_bits = 0; int32_t cur_P = -1, cur_line = -1;
     for (int32_t c : order) {
-        const uint64_t b = keyed[c].first; const int32_t P = keyed[c].second;
+        const uint64_t b = keyed[c].bits; const int32_t P = keyed[c].P, line = keyed[c].line;
         if (P < 2) continue;
-        if (!have_row || b != cur_bits) {
+        if (!have_row || b != cur_bits || line != cur_line) {
             if (have_row) g.row_gbeg.push_back((int32_t)g.group_P.size());
             double off; memcpy(&off, &b, 8);
-            g.row_off.push_back(off); have_row = true; cur_bits = b; cur_P = -1;
+            g.row_off.push_back(off); row_line.push_back(line); have_row = true; cur_bits = b; cur_line = line; cur_P = -1;
         }
         if (P != cur_P) { g.group_P.push_back(P); g.group_row.push_back((int32_t)g.row_off.size() - 1); g.group_first.push_back(c); cur_P = P; }
         g.cand_group[c] = (int32_t)g.group_P.size() - 1;
@@ -212,7 +217,7 @@ SweepGroups build_sweep_groups(const double* offset, const int32_t* n_pts, int n
     if (have_row) g.row_gbeg.push_back((int32_t)g.group_P.size());
     for (size_t r = 0; r + 1 < g.row_gbeg.size(); ++r) {
         const int32_t g0 = g.row_gbeg[r], ng = g.row_gbeg[r + 1] - g0;
-        g.row_info.insert(g.row_info.end(), {g0, ng, ng > 0 ? g.group_P[(size_t)g0 + ng - 1] : 0, 0});   // (horizons ascend within a row)
+        g.row_info.insert(g.row_info.end(), {g0, ng, ng > 0 ? g.group_P[(size_t)g0 + ng - 1] : 0, row_line[r]});   // (horizons ascend within a row)
     }
     return g;
 }
@@ -857,10 +862,12 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
         return fail(DP_ERR_ARG, "dp_score_candidates: bad argument (n_base in [2,256], n_obs <= 192)");
     CK(cudaSetDevice(c->device));
     Tmp tmp; cudaError_t e;
-    const SweepGroups sg = build_sweep_groups(offset, n_pts, n_cand, n_base);
+    const SweepGroups sg = build_sweep_groups(nullptr, offset, n_pts, n_cand, n_base);
     const int n_rows = (int)sg.row_off.size();
-    PUT(d_bx, double, base_x, (size_t)n_base); PUT(d_by, double, base_y, (size_t)n_base);
-    PUT(d_roff, double, sg.row_off.data(), sg.row_off.size()); PUT(d_gbeg, int32_t, sg.row_gbeg.data(), sg.row_gbeg.size());
+    std::vector<double> line((size_t)2 * n_base);           // lines[1][2][n_base]
+    memcpy(line.data(), base_x, (size_t)n_base * 8); memcpy(line.data() + n_base, base_y, (size_t)n_base * 8);
+    PUT(d_lines, double, line.data(), line.size());
+    PUT(d_roff, double, sg.row_off.data(), sg.row_off.size());
     PUT(d_gP, int32_t, sg.group_P.data(), sg.group_P.size()); PUT(d_cg, int32_t, sg.cand_group.data(), (size_t)n_cand);
     PUT(d_rinfo, int32_t, sg.row_info.data(), sg.row_info.size());
     PUT(d_grow, int32_t, sg.group_row.data(), sg.group_row.size());
@@ -873,9 +880,10 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
     PUT(d_dis, double, (const double*)nullptr, (size_t)n_cand);
     PUT(d_key, unsigned long long, (const unsigned long long*)nullptr, 1);
     CK(cudaMemsetAsync(d_key, 0xff, 8, c->st[0]));
-    CK(dp_launch_sweep_prefix(d_bx, d_by, n_rows, d_roff, d_gbeg, d_gP, d_rcum, c->st[0]));
-    CK(dp_launch_sweep(d_bx, d_by, n_base, n_rows, (int)sg.group_P.size(), d_roff, reinterpret_cast<const int4*>(d_rinfo), d_gP, d_grow, d_cg, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs,
-                       lat_min, lat_max, clear_dis, d_gkey, d_rcum, d_dis, d_key, c->st[0]));
+    const int4* d_ri = reinterpret_cast<const int4*>(d_rinfo);
+    CK(dp_launch_sweep_prefix(d_lines, n_base, n_rows, d_roff, d_ri, d_rcum, c->st[0]));
+    CK(dp_launch_sweep(d_lines, n_base, 1, n_rows, d_roff, d_ri, d_gP, d_grow, d_cg, n_cand, d_ox, d_oy, d_vx, d_vy, n_obs, lat_min, lat_max,
+                       clear_dis, d_gkey, d_rcum, d_dis, d_key, c->st[0]));
     c->launches += 3;
     ++c->launches;
     unsigned long long key = ~0ull;
@@ -895,14 +903,15 @@ int dp_score_candidates(dp_ctx* c, const double* base_x, const double* base_y, i
 // ---- latency-mode sweep session: device-resident candidate set + one captured CUDA graph per scoring call ----
 struct dp_sweep {
     dp_ctx* c = nullptr;
-    int n_base = 0, n_cand = 0, max_obs = 0;
-    double *d_bx = nullptr, *d_by = nullptr, *d_roff = nullptr, *d_rcum = nullptr;
-    int32_t *d_gbeg = nullptr, *d_gP = nullptr, *d_rinfo = nullptr;   // rows / horizon groups of the candidate set (build_sweep_groups)
+    int n_base = 0, n_lines = 1, n_cand = 0, max_obs = 0;
+    double *d_lines = nullptr, *d_roff = nullptr, *d_rcum = nullptr;   // d_lines: [n_lines][2][n_base] base lines
+    double* d_poses = nullptr;                              // Bezier sessions: [n_lines][6] end poses of the lines
+    int32_t *d_gP = nullptr, *d_rinfo = nullptr;            // rows / horizon groups of the candidate set (build_sweep_groups)
     int32_t* d_gfirst = nullptr;                            // lowest candidate index per group
     unsigned* d_done = nullptr;                             // row counter of the fused launch (0 between calls)
     int n_rows = 0, n_groups = 0, first_nogroup = -1;
     unsigned long long* d_res = nullptr;                    // {packed key, dis_lng bits} per row of the call in flight
-    double* h_obs = nullptr;                                // [4][max_obs] staging of the caller's obstacle arrays
+    double* h_obs = nullptr;                                // [4][192] staging of the caller's obstacle arrays
     unsigned long long* h_out = nullptr;                    // page-locked {packed key, dis_lng bits, sequence}: written by the grid's last CTA
     unsigned long long* h_out_dev = nullptr;                // ... as the device addresses it
     unsigned long long seq = 0;
@@ -910,17 +919,18 @@ struct dp_sweep {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 };
 
-int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const double* base_y, int n_base, const double* offset,
-                    const int32_t* n_pts, int n_cand, int max_obs) {
-    if (!c || !out || !base_x || !base_y || n_base < 2 || n_base > 256 || !offset || !n_pts || n_cand <= 0 || max_obs <= 0 || max_obs > 192)
-        return fail(DP_ERR_ARG, "dp_sweep_create: bad argument (n_base in [2,256], max_obs <= 192)");
+// lines_xy: host [n_lines][2][n_base] or null (Bezier sessions fill the lines on the device, dp_sweep_set_bezier)
+static int sweep_create(dp_ctx* c, dp_sweep** out, const double* lines_xy, int n_lines, int n_base, const int32_t* cand_line, const double* offset,
+                        const int32_t* n_pts, int n_cand, int max_obs) {
     CK(cudaSetDevice(c->device));
     dp_sweep* s = new dp_sweep();
-    s->c = c; s->n_base = n_base; s->n_cand = n_cand; s->max_obs = max_obs;
-    CK(cudaMalloc((void**)&s->d_bx, n_base * 8)); CK(cudaMalloc((void**)&s->d_by, n_base * 8));
-    const SweepGroups sg = build_sweep_groups(offset, n_pts, n_cand, n_base);
+    s->c = c; s->n_base = n_base; s->n_lines = n_lines; s->n_cand = n_cand; s->max_obs = max_obs;
+    const SweepGroups sg = build_sweep_groups(cand_line, offset, n_pts, n_cand, n_base);
     s->n_rows = (int)sg.row_off.size(); s->n_groups = (int)sg.group_P.size();
-    CK(cudaMalloc((void**)&s->d_roff, (sg.row_off.size() + 1) * 8)); CK(cudaMalloc((void**)&s->d_gbeg, sg.row_gbeg.size() * 4));
+    const size_t line_bytes = (size_t)n_lines * 2 * n_base * 8;
+    CK(cudaMalloc((void**)&s->d_lines, line_bytes)); CK(cudaMemset(s->d_lines, 0, line_bytes));
+    CK(cudaMalloc((void**)&s->d_poses, (size_t)n_lines * 6 * 8));
+    CK(cudaMalloc((void**)&s->d_roff, (sg.row_off.size() + 1) * 8));
     CK(cudaMalloc((void**)&s->d_gP, (sg.group_P.size() + 1) * 4)); CK(cudaMalloc((void**)&s->d_rinfo, (sg.row_info.size() + 4) * 4));
     CK(cudaMalloc((void**)&s->d_rcum, (sg.row_off.size() + 1) * 256 * 8));
     CK(cudaMalloc((void**)&s->d_gfirst, (sg.group_P.size() + 1) * 4)); CK(cudaMalloc((void**)&s->d_res, (sg.row_off.size() + 1) * 16));
@@ -932,18 +942,67 @@ int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const doubl
     CK(cudaHostGetDevicePointer((void**)&s->h_out_dev, s->h_out, 0));
     s->first_nogroup = sg.first_nogroup;
     if (getenv("DP_SWEEP_DBG")) { CK(cudaMalloc((void**)&s->d_dbg, (size_t)(s->n_rows + 1) * 64)); CK(cudaMemset(s->d_dbg, 0, (size_t)(s->n_rows + 1) * 64)); }
-    CK(cudaMemcpy(s->d_bx, base_x, n_base * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(s->d_by, base_y, n_base * 8, cudaMemcpyHostToDevice));
+    if (lines_xy) CK(cudaMemcpy(s->d_lines, lines_xy, line_bytes, cudaMemcpyHostToDevice));
     if (s->n_rows) CK(cudaMemcpy(s->d_roff, sg.row_off.data(), sg.row_off.size() * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(s->d_gbeg, sg.row_gbeg.data(), sg.row_gbeg.size() * 4, cudaMemcpyHostToDevice));
     if (s->n_groups) CK(cudaMemcpy(s->d_gP, sg.group_P.data(), sg.group_P.size() * 4, cudaMemcpyHostToDevice));
     if (s->n_rows) CK(cudaMemcpy(s->d_rinfo, sg.row_info.data(), sg.row_info.size() * 4, cudaMemcpyHostToDevice));
     if (s->n_groups) CK(cudaMemcpy(s->d_gfirst, sg.group_first.data(), sg.group_first.size() * 4, cudaMemcpyHostToDevice));
-    // the arclength prefix of every row does not depend on the obstacles: once, here
-    CK(dp_launch_sweep_prefix(s->d_bx, s->d_by, s->n_rows, s->d_roff, s->d_gbeg, s->d_gP, s->d_rcum, c->st[0]));
-    ++c->launches;
+    // the arclength prefix of every row does not depend on the obstacles: once, here (Bezier sessions: with every set of poses)
+    if (lines_xy) {
+        CK(dp_launch_sweep_prefix(s->d_lines, n_base, s->n_rows, s->d_roff, reinterpret_cast<const int4*>(s->d_rinfo), s->d_rcum, c->st[0]));
+        ++c->launches;
+    }
     CK(cudaStreamSynchronize(c->st[0]));
     CK(cudaEventCreate(&s->e0)); CK(cudaEventCreate(&s->e1));
     *out = s;
+    return DP_OK;
+}
+
+int dp_sweep_create(dp_ctx* c, dp_sweep** out, const double* base_x, const double* base_y, int n_base, const double* offset,
+                    const int32_t* n_pts, int n_cand, int max_obs) {
+    if (!c || !out || !base_x || !base_y || n_base < 2 || n_base > 256 || !offset || !n_pts || n_cand <= 0 || max_obs <= 0 || max_obs > 192)
+        return fail(DP_ERR_ARG, "dp_sweep_create: bad argument (n_base in [2,256], max_obs <= 192)");
+    std::vector<double> line((size_t)2 * n_base);
+    memcpy(line.data(), base_x, (size_t)n_base * 8); memcpy(line.data() + n_base, base_y, (size_t)n_base * 8);
+    return sweep_create(c, out, line.data(), 1, n_base, nullptr, offset, n_pts, n_cand, max_obs);
+}
+
+int dp_sweep_create_lines(dp_ctx* c, dp_sweep** out, const double* lines_xy, int n_lines, int n_base, const int32_t* cand_line,
+                          const double* offset, const int32_t* n_pts, int n_cand, int max_obs) {
+    if (!c || !out || !lines_xy || n_lines <= 0 || n_base < 2 || n_base > 256 || !cand_line || !offset || !n_pts || n_cand <= 0 || max_obs <= 0 ||
+        max_obs > 192)
+        return fail(DP_ERR_ARG, "dp_sweep_create_lines: bad argument (n_base in [2,256], max_obs <= 192)");
+    for (int i = 0; i < n_cand; ++i) if (cand_line[i] < 0 || cand_line[i] >= n_lines) return fail(DP_ERR_ARG, "dp_sweep_create_lines: cand_line out of range");
+    return sweep_create(c, out, lines_xy, n_lines, n_base, cand_line, offset, n_pts, n_cand, max_obs);
+}
+
+int dp_sweep_create_bezier(dp_ctx* c, dp_sweep** out, int n_lines, const int32_t* cand_line, const double* offset, const int32_t* n_pts, int n_cand,
+                           int max_obs) {
+    if (!c || !out || n_lines <= 0 || !cand_line || !offset || !n_pts || n_cand <= 0 || max_obs <= 0 || max_obs > 192)
+        return fail(DP_ERR_ARG, "dp_sweep_create_bezier: bad argument (max_obs <= 192)");
+    for (int i = 0; i < n_cand; ++i) if (cand_line[i] < 0 || cand_line[i] >= n_lines) return fail(DP_ERR_ARG, "dp_sweep_create_bezier: cand_line out of range");
+    return sweep_create(c, out, nullptr, n_lines, DP_PATH_POINTS, cand_line, offset, n_pts, n_cand, max_obs);
+}
+
+int dp_sweep_set_bezier(dp_sweep* s, const double* poses, float* device_ms) {
+    if (!s || !poses || s->n_base != DP_PATH_POINTS) return fail(DP_ERR_ARG, "dp_sweep_set_bezier: not a Bezier session");
+    dp_ctx* c = s->c;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->st[0];
+    CK(cudaMemcpyAsync(s->d_poses, poses, (size_t)s->n_lines * 6 * 8, cudaMemcpyHostToDevice, st));
+    if (device_ms) CK(cudaEventRecord(s->e0, st));
+    CK(dp_launch_bezier(s->n_lines, s->d_poses, s->d_lines, st));   // out[n][2][200] IS the lines layout
+    CK(dp_launch_sweep_prefix(s->d_lines, s->n_base, s->n_rows, s->d_roff, reinterpret_cast<const int4*>(s->d_rinfo), s->d_rcum, st));
+    c->launches += 2;
+    if (device_ms) { CK(cudaEventRecord(s->e1, st)); CK(cudaEventSynchronize(s->e1)); CK(cudaEventElapsedTime(device_ms, s->e0, s->e1)); }
+    return DP_OK;                                           // (stream order: the next dp_sweep_score sees the new lines)
+}
+
+int dp_sweep_lines(dp_sweep* s, double* lines_xy_out) {
+    if (!s || !lines_xy_out) return fail(DP_ERR_ARG, "dp_sweep_lines: null");
+    CK(cudaSetDevice(s->c->device));
+    CK(cudaMemcpyAsync(lines_xy_out, s->d_lines, (size_t)s->n_lines * 2 * s->n_base * 8, cudaMemcpyDeviceToHost, s->c->st[0]));
+    CK(cudaStreamSynchronize(s->c->st[0]));
     return DP_OK;
 }
 
@@ -962,7 +1021,7 @@ int dp_sweep_score(dp_sweep* s, const double* ox, const double* oy, const double
     // memory and re-arms the device state; the host watches the sequence word instead of synchronising the stream
     const unsigned long long seq = ++s->seq;
     if (device_ms) CK(cudaEventRecord(s->e0, st));
-    CK(dp_launch_sweep_fused(s->d_bx, s->d_by, s->n_base, s->n_rows, s->d_roff, reinterpret_cast<const int4*>(s->d_rinfo), s->d_gP, s->d_gfirst,
+    CK(dp_launch_sweep_fused(s->d_lines, s->n_base, s->n_lines, s->n_rows, s->d_roff, reinterpret_cast<const int4*>(s->d_rinfo), s->d_gP, s->d_gfirst,
                              s->first_nogroup, s->h_obs, mo, n_obs, lat_min, lat_max, clear_dis, s->d_rcum, s->d_res, s->d_done, s->h_out_dev, seq,
                              s->d_dbg, st));
     ++c->launches;
@@ -999,7 +1058,7 @@ int dp_sweep_destroy(dp_sweep* s) {
     if (!s) return DP_OK;
     cudaSetDevice(s->c->device);
     cudaStreamSynchronize(s->c->st[0]);
-    cudaFree(s->d_bx); cudaFree(s->d_by); cudaFree(s->d_roff); cudaFree(s->d_gbeg); cudaFree(s->d_gP); cudaFree(s->d_rinfo); cudaFree(s->d_rcum);
+    cudaFree(s->d_lines); cudaFree(s->d_poses); cudaFree(s->d_roff); cudaFree(s->d_gP); cudaFree(s->d_rinfo); cudaFree(s->d_rcum);
     cudaFree(s->d_dbg); cudaFree(s->d_gfirst); cudaFree(s->d_res); cudaFree(s->d_done);
     cudaFreeHost(s->h_obs); cudaFreeHost(s->h_out);
     if (s->e0) cudaEventDestroy(s->e0);

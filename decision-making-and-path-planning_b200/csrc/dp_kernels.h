@@ -64,14 +64,13 @@ cudaError_t dp_launch_mean(int n_paths, const int32_t* path_off, const double2* 
 cudaError_t dp_launch_nearest(int n_paths, const int32_t* path_off, const double2* pxy, const double* qx, const double* qy, int32_t* out_id,
                               cudaStream_t st);
 // dense candidate sweep (dp_ops.cu): candidates grouped on the host by (offset = row, point count = horizon group)
-cudaError_t dp_launch_sweep_prefix(const double* base_x, const double* base_y, int n_rows, const double* row_off, const int32_t* row_gbeg,
-                                   const int32_t* group_P, double* row_cum, cudaStream_t st);   // row_cum[n_rows][256], once per candidate set
-cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, int n_rows, int n_groups, const double* row_off,
-                            const int4* row_info, const int32_t* group_P, const int32_t* group_row, const int32_t* cand_group, int n_cand,
-                            const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min, double lat_max,
-                            double clear_dis, unsigned* group_key, const double* row_cum, double* cand_dis_lng, unsigned long long* best_key,
-                            cudaStream_t st);
-cudaError_t dp_launch_sweep_fused(const double* base_x, const double* base_y, int n_base, int n_rows, const double* row_off, const int4* row_info,
+cudaError_t dp_launch_sweep_prefix(const double* lines, int n_base, int n_rows, const double* row_off, const int4* row_info, double* row_cum,
+                                   cudaStream_t st);
+cudaError_t dp_launch_sweep(const double* lines, int n_base, int n_lines, int n_rows, const double* row_off, const int4* row_info,
+                            const int32_t* group_P, const int32_t* group_row, const int32_t* cand_group, int n_cand, const double* ox,
+                            const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min, double lat_max, double clear_dis,
+                            unsigned* group_key, const double* row_cum, double* cand_dis_lng, unsigned long long* best_key, cudaStream_t st);
+cudaError_t dp_launch_sweep_fused(const double* lines, int n_base, int n_lines, int n_rows, const double* row_off, const int4* row_info,
                                   const int32_t* group_P, const int32_t* group_first, int first_nogroup, const double* obs4, int obs_stride,
                                   int n_obs, double lat_min, double lat_max, double clear_dis, const double* row_cum,
                                   unsigned long long* row_res, unsigned* done, unsigned long long* host, unsigned long long seq, long long* dbg,

@@ -128,24 +128,26 @@ struct SweepSmem {
     double2 q[SWEEP_MAX_BASE];                              // row points b_j + off n_j
     unsigned key[SWEEP_MAX_BASE];                           // per horizon group of the row (first CTA of the cluster: the row's)
     int gP[SWEEP_MAX_BASE];                                 // the row's horizons (point counts), ascending
-    double pd[SWEEP_MAXW][32];                              // running-argmin state at the end of each part of the row, per obstacle
-    int pj[SWEEP_MAXW][32];
     double obs[4][32];                                      // this CTA's obstacle block
     unsigned long long red[SWEEP_MAXW];
     double redd[SWEEP_MAXW];
     int last;
+    // followed (dynamic shared memory) by the running-argmin state at the end of each part of the row, per obstacle:
+    // double pd[PT][32]; int pj[PT][32]
 };
+static size_t sweep_smem_bytes(int PT) { return sizeof(SweepSmem) + (size_t)PT * 32 * (sizeof(double) + sizeof(int)); }
 
 // one row against this CTA's 32 obstacles (o0 ..): min-reduces the packed selection key of every horizon group of the row into
 // rkey[0..ng) (the row owner's shared memory).  warp = part of the row; obs(k, o) = component k of obstacle track o
 template <class ObsFn>
-__device__ __forceinline__ void sweep_row_pass(SweepSmem& s, unsigned* rkey, const double* __restrict__ base_x, const double* __restrict__ base_y,
-                                               double off, const int32_t* __restrict__ gP, int ng, int Pmax, int n_obs, int o0, int PT,
-                                               double lat_min, double lat_max, ObsFn obs) {
+__device__ __forceinline__ void sweep_row_pass(SweepSmem& s, unsigned* rkey, double off, const int32_t* __restrict__ gP, int ng, int Pmax,
+                                               int n_obs, int o0, int PT, double lat_min, double lat_max, ObsFn obs) {
     namespace cg = cooperative_groups;
     const int tid = threadIdx.x, nthr = blockDim.x, qt = tid >> 5, lane = tid & 31;
+    double* s_pd = reinterpret_cast<double*>(&s + 1);
+    int* s_pj = reinterpret_cast<int*>(s_pd + PT * 32);
     for (int g = tid; g < ng; g += nthr) { s.key[g] = 0xffffffffu; s.gP[g] = gP[g]; }
-    if (tid < 128) { const int k = tid >> 5, o = o0 + lane; s.obs[k][lane] = (o < n_obs) ? obs(k, o) : 0.0; }
+    for (int t = tid; t < 128; t += nthr) { const int k = t >> 5, o = o0 + (t & 31); s.obs[k][t & 31] = (o < n_obs) ? obs(k, o) : 0.0; }
     cg::this_cluster().sync();                              // (the owner's keys are armed before any CTA of the row reduces into them)
     for (int j = tid; j + 1 < Pmax; j += nthr) {
         const double2 n = dp_normal(s.b[j], s.b[j + 1]);
@@ -159,7 +161,7 @@ __device__ __forceinline__ void sweep_row_pass(SweepSmem& s, unsigned* rkey, con
     const int qlen = (nrow + PT - 1) / PT, j0 = qt * qlen, j1 = min(nrow, j0 + qlen);
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const double x0 = s.obs[0][lane], y0 = s.obs[1][lane], vx = s.obs[2][lane], vy = s.obs[3][lane];
-    if (qt < PT) {   // pass A: argmin of the own part
+    if (qt < PT && PT > 1) {   // pass A: argmin of the own part (one part: pass B alone is the whole scan)
         double bd = INF; int bj = 0;
         if (act) {
             double jd = (double)j0;
@@ -170,16 +172,16 @@ __device__ __forceinline__ void sweep_row_pass(SweepSmem& s, unsigned* rkey, con
                 if (d < bd) { bd = d; bj = j; }
             }
         }
-        s.pd[qt][lane] = bd; s.pj[qt][lane] = bj;
+        s_pd[qt * 32 + lane] = bd; s_pj[qt * 32 + lane] = bj;
     }
-    __syncthreads();
+    if (PT > 1) __syncthreads();
     if (act) {
         // pass B: start from the state at the end of the parts before mine (index order, strict '<': lowest index on ties),
         // walk my part again and serve the horizons whose last row point falls into it
         double bd = INF; int bj = 0;
         for (int q = 0; q < qt; ++q) {
-            const double od = s.pd[q][lane];
-            if (od < bd) { bd = od; bj = s.pj[q][lane]; }
+            const double od = s_pd[q * 32 + lane];
+            if (od < bd) { bd = od; bj = s_pj[q * 32 + lane]; }
         }
         // horizon P needs the state over q_0 .. q_{P-2}: it is served by the part that holds row point P-2 ... i.e. when the
         // walk is about to add row point j = P-1 (or, for the last horizon, at the end of the last part)
@@ -250,30 +252,33 @@ struct SweepOut {                                           // FUSED: where the 
 // grid = max(n_rows, 1) clusters of NB CTAs (cluster dimension set by the launcher): CTA = (row blockIdx.x / NB, obstacle block blockIdx.x % NB)
 template <bool FUSED>
 __global__ void __launch_bounds__(1024)
-sweep_rows_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, int n_base, int n_rows, const double* __restrict__ row_off,
+sweep_rows_kernel(const double* __restrict__ lines, int n_base, int n_lines, int n_rows, const double* __restrict__ row_off,
                   const int4* __restrict__ row_info, const int32_t* __restrict__ group_P, const double* __restrict__ ox,
                   const double* __restrict__ oy, const double* __restrict__ dvx, const double* __restrict__ dvy,
                   const __grid_constant__ SweepObs po, int n_obs, int NB, int PT, double lat_min, double lat_max, double clear_dis,
                   unsigned* __restrict__ group_key, const double* __restrict__ row_cum, SweepOut out) {
     namespace cg = cooperative_groups;
-    __shared__ SweepSmem s;
+    extern __shared__ __align__(16) unsigned char sweep_raw[];
+    SweepSmem& s = *reinterpret_cast<SweepSmem*>(sweep_raw);
     cg::cluster_group cluster = cg::this_cluster();
     const int ob = (int)cluster.block_rank(), row = blockIdx.x / NB, tid = threadIdx.x, nthr = blockDim.x;
     unsigned long long mykey = ~0ull;
     double mydis = DP_NOT_FOUND;
     SWEEP_STAMP(0);
     if (row < n_rows) {                                     // (uniform over the cluster)
-        // the base line does not depend on the row: its loads fly together with the row header {first group, groups, longest horizon}
+        // row header {first group, groups, longest horizon, base line}.  With ONE base line its loads do not depend on the header
+        // and fly together with it
         const int4 ri = row_info[row];
         const double off = row_off[row];
-        for (int j = tid; j < n_base; j += nthr) s.b[j] = make_double2(base_x[j], base_y[j]);
+        const double* bx = lines + (n_lines > 1 ? (size_t)ri.w * 2 * n_base : 0);
+        for (int j = tid; j < n_base; j += nthr) s.b[j] = make_double2(bx[j], bx[n_base + j]);
         const int g0 = ri.x, ng = ri.y, Pmax = ri.z;
         unsigned* rkey = cluster.map_shared_rank(s.key, 0);
         if (FUSED)
-            sweep_row_pass(s, rkey, base_x, base_y, off, group_P + g0, ng, Pmax, n_obs, ob * 32, PT, lat_min, lat_max,
+            sweep_row_pass(s, rkey, off, group_P + g0, ng, Pmax, n_obs, ob * 32, PT, lat_min, lat_max,
                            [&](int k, int o) { return po.v[k][o]; });
         else
-            sweep_row_pass(s, rkey, base_x, base_y, off, group_P + g0, ng, Pmax, n_obs, ob * 32, PT, lat_min, lat_max,
+            sweep_row_pass(s, rkey, off, group_P + g0, ng, Pmax, n_obs, ob * 32, PT, lat_min, lat_max,
                            [&](int k, int o) { return k == 0 ? ox[o] : k == 1 ? oy[o] : k == 2 ? (dvx ? dvx[o] : 0.0) : (dvy ? dvy[o] : 0.0); });
         SWEEP_STAMP(1);
         if (ob != 0) return;                                // the row's first CTA carries on with the merged keys
@@ -350,16 +355,17 @@ sweep_rows_kernel(const double* __restrict__ base_x, const double* __restrict__ 
 // the row's sequential prefix of segment lengths (all horizons start at q_0, so the prefix IS the reference's arclength sum):
 // row_cum[row][j] = |q_1 - q_0| + ... + |q_j - q_{j-1}|, j <= Pmax - 2.  Independent of the obstacles: once per candidate set.
 __global__ void __launch_bounds__(256)
-sweep_prefix_kernel(const double* __restrict__ base_x, const double* __restrict__ base_y, const double* __restrict__ row_off,
-                    const int32_t* __restrict__ row_gbeg, const int32_t* __restrict__ group_P, double* __restrict__ row_cum) {
+sweep_prefix_kernel(const double* __restrict__ lines, int n_base, const double* __restrict__ row_off, const int4* __restrict__ row_info,
+                    double* __restrict__ row_cum) {
     __shared__ double2 s_b[SWEEP_MAX_BASE];
     __shared__ double2 s_q[SWEEP_MAX_BASE];
     __shared__ double s_cum[SWEEP_MAX_BASE];
     const int row = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
-    const int g0 = row_gbeg[row], ng = row_gbeg[row + 1] - g0;
+    const int4 ri = row_info[row];
     const double off = row_off[row];
-    const int Pmax = ng > 0 ? group_P[g0 + ng - 1] : 0;
-    for (int j = tid; j < Pmax; j += nthr) s_b[j] = make_double2(base_x[j], base_y[j]);
+    const int Pmax = ri.z;
+    const double* bx = lines + (size_t)ri.w * 2 * n_base;
+    for (int j = tid; j < Pmax; j += nthr) s_b[j] = make_double2(bx[j], bx[n_base + j]);
     __syncthreads();
     for (int j = tid; j + 1 < Pmax; j += nthr) {
         const double2 n = dp_normal(s_b[j], s_b[j + 1]);
@@ -381,8 +387,9 @@ sweep_prefix_kernel(const double* __restrict__ base_x, const double* __restrict_
 // selected point is the horizon's own last point), cost, lowest feasible index by a packed (cost bits << 32 | index) atomicMin
 __global__ void sweep_select_kernel(const int32_t* __restrict__ cand_group, int n_cand, const int32_t* __restrict__ group_row,
                                     const int32_t* __restrict__ group_P, const unsigned* __restrict__ group_key, const double* __restrict__ row_cum,
-                                    const double* __restrict__ row_off, const double* __restrict__ base_x, const double* __restrict__ base_y,
-                                    double clear_dis, double* __restrict__ cand_dis_lng, unsigned long long* __restrict__ best_key) {
+                                    const double* __restrict__ row_off, const double* __restrict__ lines, int n_base,
+                                    const int4* __restrict__ row_info, double clear_dis, double* __restrict__ cand_dis_lng,
+                                    unsigned long long* __restrict__ best_key) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long key = ~0ull;
     if (c < n_cand) {
@@ -395,7 +402,8 @@ __global__ void sweep_select_kernel(const int32_t* __restrict__ cand_group, int 
             if (jstar <= P - 2) dis = cum[jstar];
             else {                                          // the horizon's own last point b_{P-1} + off n_{P-2}: one more term after q_{P-2}
                 const double off = row_off[row];
-                const double2 b2 = make_double2(base_x[P - 2], base_y[P - 2]), b1 = make_double2(base_x[P - 1], base_y[P - 1]);
+                const double* bx = lines + (size_t)row_info[row].w * 2 * n_base;
+                const double2 b2 = make_double2(bx[P - 2], bx[n_base + P - 2]), b1 = make_double2(bx[P - 1], bx[n_base + P - 1]);
                 const double2 nl = dp_normal(b2, b1);
                 const double2 ql = make_double2(fma(off, nl.x, b1.x), fma(off, nl.y, b1.y));
                 const double2 qp = make_double2(fma(off, nl.x, b2.x), fma(off, nl.y, b2.y));   // q_{P-2} uses the normal of segment P-2 too
@@ -463,16 +471,19 @@ cudaError_t dp_launch_nearest(int n_paths, const int32_t* path_off, const double
     return cudaGetLastError();
 }
 // the obstacle-independent part of a sweep: once per candidate set
-cudaError_t dp_launch_sweep_prefix(const double* base_x, const double* base_y, int n_rows, const double* row_off, const int32_t* row_gbeg,
-                                   const int32_t* group_P, double* row_cum, cudaStream_t st) {
+cudaError_t dp_launch_sweep_prefix(const double* lines, int n_base, int n_rows, const double* row_off, const int4* row_info, double* row_cum,
+                                   cudaStream_t st) {
     if (n_rows <= 0) return cudaSuccess;
-    sweep_prefix_kernel<<<n_rows, 256, 0, st>>>(base_x, base_y, row_off, row_gbeg, group_P, row_cum);
+    sweep_prefix_kernel<<<n_rows, 256, 0, st>>>(lines, n_base, row_off, row_info, row_cum);
     return cudaGetLastError();
 }
-// shape of the row clusters: NB CTAs (obstacle blocks of 32) x PT warps (parts of the row)
-static void sweep_shape(int n_obs, int* NB, int* PT) {
+// shape of the row clusters: NB CTAs (obstacle blocks of 32) x PT warps (parts of the row).  Few rows (latency mode, the machine
+// is mostly idle): 16 parts shorten the dependent chain of a row; many rows (more than two per SM): 4 parts -- measured on the
+// 2048-row Bezier grid of bench.py: 197 / 144 / 103 / 117 / 158 us for 1 / 2 / 4 / 8 / 16 parts (fewer parts leave the SM short of
+// warps because every CTA carries the row's 14 KB of points, more parts repeat the per-part overhead)
+static void sweep_shape(int n_rows, int n_obs, int* NB, int* PT) {
     *NB = n_obs > 0 ? (n_obs + 31) / 32 : 1;
-    int pt = 16;
+    int pt = n_rows > 296 ? 4 : 16;
     if (const char* e = getenv("DP_SWEEP_PARTS")) pt = atoi(e);
     *PT = pt < 1 ? 1 : (pt > SWEEP_MAXW ? SWEEP_MAXW : pt);
 }
@@ -480,33 +491,32 @@ template <bool FUSED, class... Args>
 static cudaError_t sweep_launch(int n_rows, int NB, int PT, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((n_rows > 0 ? n_rows : 1) * NB)); cfg.blockDim = dim3((unsigned)(PT * 32)); cfg.stream = st;
+    cfg.dynamicSmemBytes = sweep_smem_bytes(PT);
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)NB; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, sweep_rows_kernel<FUSED>, args...);
 }
-cudaError_t dp_launch_sweep(const double* base_x, const double* base_y, int n_base, int n_rows, int n_groups, const double* row_off,
-                            const int4* row_info, const int32_t* group_P, const int32_t* group_row, const int32_t* cand_group, int n_cand,
-                            const double* ox, const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min, double lat_max,
-                            double clear_dis, unsigned* group_key, const double* row_cum, double* cand_dis_lng, unsigned long long* best_key,
-                            cudaStream_t st) {
-    (void)n_groups;
+cudaError_t dp_launch_sweep(const double* lines, int n_base, int n_lines, int n_rows, const double* row_off, const int4* row_info,
+                            const int32_t* group_P, const int32_t* group_row, const int32_t* cand_group, int n_cand, const double* ox,
+                            const double* oy, const double* dvx, const double* dvy, int n_obs, double lat_min, double lat_max, double clear_dis,
+                            unsigned* group_key, const double* row_cum, double* cand_dis_lng, unsigned long long* best_key, cudaStream_t st) {
     if (n_cand <= 0) return cudaSuccess;
     if (n_rows > 0) {
         int NB, PT;
-        sweep_shape(n_obs, &NB, &PT);
+        sweep_shape(n_rows, n_obs, &NB, &PT);
         static const SweepObs none = {};
-        const cudaError_t e = sweep_launch<false>(n_rows, NB, PT, st, base_x, base_y, n_base, n_rows, row_off, row_info, group_P, ox, oy, dvx, dvy, none, n_obs, NB,
-                                                  PT, lat_min, lat_max, clear_dis, group_key, row_cum, SweepOut{});
+        const cudaError_t e = sweep_launch<false>(n_rows, NB, PT, st, lines, n_base, n_lines, n_rows, row_off, row_info, group_P, ox, oy, dvx, dvy, none,
+                                                  n_obs, NB, PT, lat_min, lat_max, clear_dis, group_key, row_cum, SweepOut{});
         if (e != cudaSuccess) return e;
     }
-    sweep_select_kernel<<<(n_cand + 255) / 256, 256, 0, st>>>(cand_group, n_cand, group_row, group_P, group_key, row_cum, row_off, base_x, base_y,
-                                                              clear_dis, cand_dis_lng, best_key);
+    sweep_select_kernel<<<(n_cand + 255) / 256, 256, 0, st>>>(cand_group, n_cand, group_row, group_P, group_key, row_cum, row_off, lines, n_base,
+                                                              row_info, clear_dis, cand_dis_lng, best_key);
     return cudaGetLastError();
 }
 // latency session: ONE launch; the winner lands in host[0..2] (page-locked), host[2] = seq last
-cudaError_t dp_launch_sweep_fused(const double* base_x, const double* base_y, int n_base, int n_rows, const double* row_off, const int4* row_info,
+cudaError_t dp_launch_sweep_fused(const double* lines, int n_base, int n_lines, int n_rows, const double* row_off, const int4* row_info,
                                   const int32_t* group_P, const int32_t* group_first, int first_nogroup, const double* obs4, int obs_stride,
                                   int n_obs, double lat_min, double lat_max, double clear_dis, const double* row_cum,
                                   unsigned long long* row_res, unsigned* done, unsigned long long* host, unsigned long long seq, long long* dbg,
@@ -514,12 +524,12 @@ cudaError_t dp_launch_sweep_fused(const double* base_x, const double* base_y, in
     SweepObs po;                                            // (copied into the launch: no lifetime beyond the call)
     for (int k = 0; k < 4; ++k) memcpy(po.v[k], obs4 + (size_t)k * obs_stride, (size_t)n_obs * sizeof(double));
     int NB, PT;
-    sweep_shape(n_obs, &NB, &PT);
+    sweep_shape(n_rows, n_obs, &NB, &PT);
     SweepOut out;
     out.row_res = row_res; out.done = done; out.group_first = group_first; out.first_nogroup = first_nogroup; out.host = host; out.seq = seq;
     out.dbg = dbg;
     const double* nul = nullptr; unsigned* nkey = nullptr;
-    return sweep_launch<true>(n_rows, NB, PT, st, base_x, base_y, n_base, n_rows, row_off, row_info, group_P, nul, nul, nul, nul, po, n_obs, NB, PT,
+    return sweep_launch<true>(n_rows, NB, PT, st, lines, n_base, n_lines, n_rows, row_off, row_info, group_P, nul, nul, nul, nul, po, n_obs, NB, PT,
                               lat_min, lat_max, clear_dis, nkey, row_cum, out);
 }
 cudaError_t dp_launch_fma_peak(int which, float* sink, int iters, int blocks, cudaStream_t st) {

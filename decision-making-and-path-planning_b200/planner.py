@@ -20,7 +20,8 @@ SYMBOLS = [
     "dp_carry_download", "dp_carry_upload", "dp_cycle_batch_dev", "dp_cycle_batch", "dp_host_alloc",
     "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
-    "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy", "dp_sweep_debug",
+    "dp_memcpy_h2d", "dp_memcpy_d2h", "dp_stream_sync", "dp_sweep_create", "dp_sweep_score", "dp_sweep_destroy", "dp_sweep_debug", "dp_sweep_create_lines", "dp_sweep_create_bezier",
+    "dp_sweep_set_bezier", "dp_sweep_lines",
     "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev", "dp_debug_timeline",
     "dp_set_tracks", "dp_set_tracks_dev", "dp_clear_tracks",
     "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_chain", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
@@ -266,8 +267,8 @@ class Planner:
                                          C.byref(best_d), abi.ptr(allv)), "dp_score_candidates")
         return best.value, best_d.value, allv
 
-    def sweep_session(self, base_x, base_y, offset, n_pts, max_obs):
-        return SweepSession(self, base_x, base_y, offset, n_pts, max_obs)
+    def sweep_session(self, base_x, base_y, offset, n_pts, max_obs, **kw):
+        return SweepSession(self, base_x, base_y, offset, n_pts, max_obs, **kw)
 
     def measure_fma_peak(self):
         a, b = C.c_double(0), C.c_double(0)
@@ -319,18 +320,45 @@ class Gather:
 
 class SweepSession:
     """latency-mode dense candidate sweep (BASELINE config 3): candidate set resident on the device, one kernel launch per call
-    (obstacles in the kernel parameters, winner written to page-locked memory by the grid's last CTA)"""
+    (obstacles in the kernel parameters, winner written to page-locked memory by the grid's last CTA).
+    base_x/base_y: ONE base line; or lines=[n_lines][2][n_base] + cand_line; or bezier_lines=n (lines drawn on the device by
+    set_bezier(poses[n][6]))"""
 
-    def __init__(self, planner, base_x, base_y, offset, n_pts, max_obs):
+    def __init__(self, planner, base_x, base_y, offset, n_pts, max_obs, lines=None, cand_line=None, bezier_lines=0):
         self.lib = planner.lib
-        bx, by = np.ascontiguousarray(base_x, np.float64), np.ascontiguousarray(base_y, np.float64)
         off, npt = np.ascontiguousarray(offset, np.float64), np.ascontiguousarray(n_pts, np.int32)
         self.h = C.c_void_p()
-        _ck(self.lib.dp_sweep_create(planner.ctx, C.byref(self.h), abi.ptr(bx), abi.ptr(by), C.c_int(bx.size), abi.ptr(off), abi.ptr(npt),
-                                     C.c_int(off.size), C.c_int(max_obs)), "dp_sweep_create")
+        self.n_lines, self.n_base = 1, 0
+        if bezier_lines:
+            cl = np.ascontiguousarray(cand_line, np.int32)
+            self.n_lines, self.n_base = int(bezier_lines), 200
+            _ck(self.lib.dp_sweep_create_bezier(planner.ctx, C.byref(self.h), C.c_int(self.n_lines), abi.ptr(cl), abi.ptr(off), abi.ptr(npt),
+                                                C.c_int(off.size), C.c_int(max_obs)), "dp_sweep_create_bezier")
+        elif lines is not None:
+            ln, cl = np.ascontiguousarray(lines, np.float64), np.ascontiguousarray(cand_line, np.int32)
+            self.n_lines, self.n_base = ln.shape[0], ln.shape[2]
+            _ck(self.lib.dp_sweep_create_lines(planner.ctx, C.byref(self.h), abi.ptr(ln), C.c_int(ln.shape[0]), C.c_int(ln.shape[2]), abi.ptr(cl),
+                                               abi.ptr(off), abi.ptr(npt), C.c_int(off.size), C.c_int(max_obs)), "dp_sweep_create_lines")
+        else:
+            bx, by = np.ascontiguousarray(base_x, np.float64), np.ascontiguousarray(base_y, np.float64)
+            self.n_base = bx.size
+            _ck(self.lib.dp_sweep_create(planner.ctx, C.byref(self.h), abi.ptr(bx), abi.ptr(by), C.c_int(bx.size), abi.ptr(off), abi.ptr(npt),
+                                         C.c_int(off.size), C.c_int(max_obs)), "dp_sweep_create")
         self._ms = C.c_float(0)
         self._best = C.c_int32(-1)
         self._dis = C.c_double(0)
+
+    def set_bezier(self, poses, want_ms=False):
+        """poses[n_lines][6] = start x, y, dir, aim x, y, dir: the lines are rolled out on the device; returns device ms if asked"""
+        ps = np.ascontiguousarray(poses, np.float64)
+        assert ps.shape == (self.n_lines, 6)
+        _ck(self.lib.dp_sweep_set_bezier(self.h, abi.ptr(ps), C.byref(self._ms) if want_ms else None), "dp_sweep_set_bezier")
+        return self._ms.value if want_ms else None
+
+    def lines(self):
+        out = np.zeros((self.n_lines, 2, self.n_base))
+        _ck(self.lib.dp_sweep_lines(self.h, abi.ptr(out)), "dp_sweep_lines")
+        return out
 
     def score(self, ox, oy, dvx=None, dvy=None, lat_min=-0.9, lat_max=0.9, clear_dis=25.0, want_dis=True, want_ms=True):
         ox, oy = np.ascontiguousarray(ox, np.float64), np.ascontiguousarray(oy, np.float64)

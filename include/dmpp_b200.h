@@ -271,6 +271,21 @@ int dp_sweep_score(dp_sweep* s, const double* obs_x, const double* obs_y, const 
                    const double* obs_dvy, int n_obs, double lat_min, double lat_max, double clear_dis,
                    int32_t* best_index, double* best_dis_lng, float* device_ms);
 int dp_sweep_destroy(dp_sweep* s);
+/* The same session over SEVERAL base lines (distinct geometries): candidate c is the offset copy (offset[c]) of the first
+ * n_pts[c] points of line cand_line[c]; lines_xy = [n_lines][2][n_base] (x row, y row per line).  Candidates that share
+ * (line, offset) share one scan per obstacle, as in dp_sweep_create.  A row is cut into 16 parts (one warp each) when there are few rows, to shorten
+ * the dependent chain, and into 4 when there are many (> 296) and the rows fill the machine. */
+int dp_sweep_create_lines(dp_ctx* ctx, dp_sweep** out, const double* lines_xy, int n_lines, int n_base,
+                          const int32_t* cand_line, const double* offset, const int32_t* n_pts, int n_cand, int max_obs);
+/* ... whose lines are the 200-point local paths CShare::BezierPlanning draws (Planning.cpp:596-611, 863) from a start pose
+ * to an aim pose: dp_sweep_set_bezier(poses[n_lines][6] = start x,y,dir, aim x,y,dir) rolls all lines out ON THE DEVICE
+ * (two launches: the Bezier operator of dp_bezier_planning into the session's line buffer, then the rows' arclength
+ * prefixes); the dp_sweep_score calls that follow score them.  A lateral x aim-distance grid of local paths, each with
+ * its horizons, is this session with offset = 0.  dp_sweep_lines reads the lines back ([n_lines][2][200]). */
+int dp_sweep_create_bezier(dp_ctx* ctx, dp_sweep** out, int n_lines, const int32_t* cand_line, const double* offset,
+                           const int32_t* n_pts, int n_cand, int max_obs);
+int dp_sweep_set_bezier(dp_sweep* s, const double* poses, float* device_ms);
+int dp_sweep_lines(dp_sweep* s, double* lines_xy_out);
 /* diagnostic: globaltimer stamps [n_rows][8] (ns) of the row-owner CTAs of the last dp_sweep_score: 0 start, 1 row pass done,
  * 2 groups selected, 3 reduced, 4 counted, 5 winner known, 6 system fence done (5, 6: last row only).  Only sessions created
  * with DP_SWEEP_DBG=1 in the environment record them (tools/sweep_probe.py). */

@@ -245,6 +245,63 @@ def test_dense_sweep_session_shapes(planner, oracle, the_map, n_obs):
     sess.close(); sess1.close()
 
 
+def bezier_grid(the_map, n_lat, n_aim, n_hor, seed=7):
+    """lateral x aim-distance grid of local paths (Planning.cpp:596-611): ego pose on a lane, aim poses at arclength a on the
+    laterally shifted lane; every (lateral, aim) pair is its own Bezier line, its horizons are prefixes of that line"""
+    gl = the_map.lane_index(3, 2)
+    o = the_map.lane_pt_off[gl] + 700
+    lx, ly, ld = the_map.x[o:o + 400], the_map.y[o:o + 400], the_map.dir[o:o + 400]
+    lat = np.linspace(-3.0, 3.0, n_lat)
+    aim_id = np.linspace(40, 200, n_aim).astype(int)        # 20 .. 100 m ahead at 0.5 m spacing
+    poses = np.zeros((n_lat * n_aim, 6))
+    for i, d in enumerate(lat):
+        for k, a in enumerate(aim_id):
+            h = np.deg2rad(ld[a])
+            # map headings are degrees from +x, counter-clockwise (scenes.Map.add_lane): (sin h, -cos h) is the right normal
+            poses[i * n_aim + k] = (lx[0], ly[0], ld[0], lx[a] + d * np.sin(h), ly[a] - d * np.cos(h), ld[a])
+    hor = np.linspace(8, 200, n_hor).astype(np.int32)
+    cand_line = np.repeat(np.arange(n_lat * n_aim), n_hor).astype(np.int32)
+    n_pts = np.tile(hor, n_lat * n_aim).astype(np.int32)
+    return poses, cand_line, n_pts, (lx, ly)
+
+
+def test_dense_sweep_bezier_lines(planner, oracle, the_map):
+    """distinct-geometry grid: every (lateral, aim distance) pair is its own Bezier local path drawn ON THE DEVICE
+    (dp_sweep_set_bezier), every horizon a prefix of it.  Lines == the BezierPlanning operator bit for bit; winner and its
+    dis_lng == the oracle scoring each line's horizons alone (lowest candidate index over all lines), for the latency shape
+    (few rows, 16 parts per row) and the throughput shape (> 296 rows, 4 parts per row)."""
+    rng = np.random.default_rng(5)
+    for n_lat, n_aim, n_hor in ((6, 5, 7), (20, 16, 4)):
+        poses, cand_line, n_pts, (lx, ly) = bezier_grid(the_map, n_lat, n_aim, n_hor)
+        n_lines = n_lat * n_aim
+        off = np.zeros(cand_line.size)
+        sess = planner.sweep_session(None, None, off, n_pts, 64, cand_line=cand_line, bezier_lines=n_lines)
+        sess.set_bezier(poses)
+        lines = sess.lines()
+        want_lines = planner.bezier_planning(poses)
+        assert np.array_equal(lines.reshape(n_lines, 400), np.asarray(want_lines).reshape(n_lines, 400))
+        for it in range(3):
+            N = 50
+            idx = rng.integers(10, 200, N)
+            ox, oy = lx[idx] + rng.normal(0, 2.0, N), ly[idx] + rng.normal(0, 2.0, N)
+            dvx, dvy = rng.normal(0, 0.03, N), rng.normal(0, 0.03, N)
+            clear = (25.0, 60.0, 5.0)[it]
+            wbest, wdis = -1, None
+            for ln in range(n_lines):                       # candidates of a line are contiguous, lines ascend: first feasible overall
+                sel = np.nonzero(cand_line == ln)[0]
+                b, dall = oracle.score_candidates(lines[ln, 0], lines[ln, 1], off[sel], n_pts[sel], ox, oy, dvx, dvy, clear_dis=clear)
+                if b >= 0:
+                    wbest, wdis = int(sel[b]), dall[b]
+                    break
+            best, dis, _ = sess.score(ox, oy, dvx, dvy, clear_dis=clear)
+            assert best == wbest, (n_lat, it, best, wbest)
+            assert best < 0 or dis == wdis
+        # the same lines uploaded from the host (dp_sweep_create_lines) score identically
+        sess2 = planner.sweep_session(None, None, off, n_pts, 64, lines=lines, cand_line=cand_line)
+        assert sess2.score(ox, oy, dvx, dvy, clear_dis=clear)[:2] == (best, dis)
+        sess.close(); sess2.close()
+
+
 def test_reset_and_carry_roundtrip(planner, oracle, the_map):
     """checkpoint/resume: episodes split in two halves with the carry downloaded and re-uploaded in
     between give the same result as one uninterrupted run (idempotent state hand-off)."""
