@@ -39,8 +39,8 @@ def workload_desc(world):
                         "ego + %d vehicles, %d-cycle scripted episodes" % (SCENES, N_OBS, EPISODE),
             "scenes_per_gpu": SCENES, "obstacles": N_OBS, "episode_cycles": EPISODE,
             "parallelism": "scenes sharded %d-way, no data-path collective in the compute phase; when N>1 every rank's plan records are "
-                           "gathered on every rank each step: GATHER_KIND; the gather of step i is finished beside the kernels of "
-                           "step i+1 (triple-buffered), the last one is exposed and counted" % world,
+                           "gathered on every rank each step: GATHER_KIND; step i+1 is complete when its kernels AND the gather of step i are, "
+                           "the last step's gather (dp_gather_flush) is exposed and counted" % world,
             "l2": "256 MiB buffer written between timed steps (L2 flush); inputs resident in HBM for `value`"}
 
 
@@ -225,8 +225,8 @@ def run_ours(args, rank, world, local_rank):
             hs = [None] * world
             dist.all_gather_object(hs, gat.my_handle())
             gat.attach(hs)
-            gather_kind = ("dp_gather_* (C ABI): peer stores + completion flags from the cycle kernel over NVLink (CUDA IPC mapping), "
-                           "a one-thread wait kernel one step behind the launches")
+            gather_kind = ("dp_gather_* (C ABI, CUDA IPC mapping), deferred: the cycle kernel of step i+1 forwards step i's records to every "
+                           "rank over NVLink as its warps start, raises the completion flags and waits for every rank's in its last warp")
         except Exception as e:  # noqa: BLE001
             print("dp_gather unavailable (%s): falling back to torch symmetric memory" % e, file=sys.stderr)
             gat = None
@@ -276,10 +276,10 @@ def run_ours(args, rank, world, local_rank):
             flush.zero_()
             rec_i = d_recs[i % 3]
             if gat is not None:
-                # step i+1 of the fused gather: the kernel stores records and flags on every rank; the wait for the PREVIOUS
-                # step's flags follows the launch on the same stream (depth 4: nobody overwrites a slice a peer still waits for)
-                gat.arm(i + 1)
-                gat.chain(pending[0] + 1 if pending is not None else 0)   # the wait for step i rides in the launch of step i+1
+                # step i+1 of the fused gather, deferred: this launch forwards the records of the launch before to every rank as its
+                # warps start, raises that step's flags when its Decision half retires and waits for every rank's flag in its
+                # last warp (depth 4: nobody overwrites a slice a peer still reads)
+                gat.arm_deferred(i + 1)
                 ev[i][0].record(stream)
                 planner.cycle_dev(SCENES, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), rec_i.data_ptr(),
                                   stream=stream.cuda_stream)
@@ -306,7 +306,7 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             tail_ev[0].record(stream)
             if gat is not None:
-                gat.wait(pending[0] + 1, stream=stream.cuda_stream)
+                gat.flush(stream=stream.cuda_stream)         # the last step's records: forwarded, flagged and awaited
             else:
                 finish_gather(*pending)
             tail_ev[1].record(stream)
@@ -397,11 +397,13 @@ def run_ours(args, rank, world, local_rank):
         planner.set_record_mirrors([p + rank * SCENES * 128 for p in hdl[0].buffer_ptrs])
     gstep = [W + K + 1]                                      # fused-gather step numbers continue after the device loops
 
-    def arm_gather(chain=False):
+    def arm_gather(deferred=False):
         if gat is not None:
             gstep[0] += 1
-            gat.arm(gstep[0])
-            gat.chain(gstep[0] - 1 if chain else 0)          # pipelined: the wait for the step before rides in this launch
+            if deferred:
+                gat.arm_deferred(gstep[0])                   # pipelined: this launch forwards / flags / awaits the step before
+            else:
+                gat.arm(gstep[0]); gat.chain(0)
 
     def step_gather():
         if world > 1:
@@ -450,12 +452,16 @@ def run_ours(args, rank, world, local_rank):
                 s1 = min(SCENES, s0 + CH)
                 if len(pend) == 2:
                     planner.wait(); got += int(pend.pop(0)["n_traj"].sum(dtype=np.int64))
-                arm_gather(chain=True)
+                arm_gather(deferred=True)
                 planner.submit(Hh[c, s0:s1], OXh[c, s0:s1], OYh[c, s0:s1], recs2[i & 1][s0:s1], first=s0)
                 pend.append(recs2[i & 1][s0:s1])
         while pend:
             planner.wait(); got += int(pend.pop(0)["n_traj"].sum(dtype=np.int64))
-        step_gather()                                        # pipelined: the gathered records become readable once, after the last wait
+        if gat is not None:
+            gat.flush(stream=stream.cuda_stream)             # the last step's records; every earlier step was complete when its successor was
+            torch.cuda.current_stream().synchronize()
+        else:
+            step_gather()
         return got
 
     barrier()

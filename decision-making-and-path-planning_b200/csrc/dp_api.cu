@@ -87,7 +87,11 @@ struct dp_ctx {
     unsigned* peer_flag[DP_MAX_MIRRORS] = {};
     int n_peer_flag = 0; unsigned flag_value = 0;
     const unsigned* wait_flag = nullptr; int n_wait = 0; unsigned wait_value = 0;
-    unsigned* d_tally_g = nullptr;
+    // deferred gather (dp_gather_arm_deferred): the next launch forwards the records of the last one; one-shot
+    dp_plan_record* fwd_dst[DP_MAX_MIRRORS] = {};
+    int n_fwd = 0; bool deferred = false;
+    dp_plan_record* last_rec = nullptr; int last_first = -1, last_n = 0;   // record array (device) and slot range of the last cycle launch
+    unsigned* d_tally_g = nullptr;                          // [2]: launch tally, Decision-half tally of the deferred gather
 };
 
 namespace {
@@ -102,12 +106,45 @@ DpIo make_io(dp_ctx* c, int first, dp_plan_record* host_rec) {
     for (int k = 0; k < c->n_peer_flag; ++k) io.peer_flag[k] = c->peer_flag[k];
     io.n_peer_flag = c->n_peer_flag; io.flag_value = c->flag_value;
     io.wait_flag = c->wait_flag; io.n_wait = c->n_wait; io.wait_value = c->wait_value;
+    if (c->n_fwd && c->last_rec) {
+        io.fwd_src = c->last_rec; io.n_fwd = c->n_fwd;
+        for (int k = 0; k < c->n_fwd; ++k) io.fwd_dst[k] = c->fwd_dst[k] + first;
+        io.tally2 = c->d_tally_g + 1;
+    }
     return io;
+}
+// one cycle of n scenes (carry slots first ..) on stream st
+// bookkeeping of every cycle launch: remember its record array (the deferred gather of the NEXT launch forwards it) and drop the
+// one-shot deferred state
+struct LaunchDone {
+    dp_ctx* c; dp_plan_record* rec; int first, n;
+    ~LaunchDone() {
+        c->last_rec = rec; c->last_first = first; c->last_n = n;
+        if (c->deferred) { c->n_fwd = 0; c->n_peer_flag = 0; c->n_wait = 0; c->wait_flag = nullptr; c->deferred = false; }
+    }
+};
+// the warp-per-scene kernel pair (dp_cycle.cu) for slots first .. first + n
+cudaError_t launch_warp(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec,
+                        dp_trace_record* trace, double* path_xy, double* path_ll, cudaStream_t st, const DpIo& io) {
+    if (io.n_fwd && (first != c->last_first || n != c->last_n)) return cudaErrorInvalidValue;   // deferred gather: same slot range as the launch before
+    LaunchDone done_{c, rec, first, n};
+    c->launches += c->split ? 2 : 1;
+    DpIo iow = io;
+    if (!iow.tally) {
+        // deferred gather with split launches: the Decision half forwards, flags and waits by itself (tally2): the Planning half ends as
+        // it does without a gather; otherwise the launch's last warp does it and needs the tally
+        if (iow.n_fwd && iow.tally2 && c->split) iow.tally_n = (unsigned)n;
+        else if (iow.n_peer_flag || iow.n_wait) { iow.tally = c->d_tally_g; iow.tally_n = (unsigned)n; }
+    }
+    return dp_launch_cycle(c->gmap, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace,
+                           path_xy, path_ll, st, c->split, iow, c->lc);
 }
 // one cycle of n scenes (carry slots first ..) on stream st
 cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec,
                       dp_trace_record* trace, double* path_xy, double* path_ll, cudaStream_t st, const DpIo& io) {
     if (c->kernel == 1 || c->tracks_T > 0) {                // (track tiles are only read by the group kernel)
+        if (io.n_fwd && (first != c->last_first || n != c->last_n)) return cudaErrorInvalidValue;
+        LaunchDone done_{c, rec, first, n};
         DgIo g = {};
         if (c->tracks_T > 0) {
             const size_t tb = (size_t)first * c->max_obs;
@@ -118,6 +155,8 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
         for (int k = 0; k < io.n_peer_flag; ++k) g.peer_flag[k] = io.peer_flag[k];
         g.n_peer_flag = io.n_peer_flag; g.flag_value = io.flag_value;
         g.wait_flag = io.wait_flag; g.n_wait = io.n_wait; g.wait_value = io.wait_value;
+        g.fwd_src = io.fwd_src; g.n_fwd = io.n_fwd;
+        for (int k = 0; k < io.n_fwd; ++k) g.fwd_dst[k] = io.fwd_dst[k];
         if ((g.n_peer_flag || g.n_wait) && !g.tally) { g.tally = c->d_tally_g; g.tally_n = (unsigned)n; }
         g.timeline = (n <= 8192) ? c->d_timeline : nullptr;
         if (g.timeline) cudaMemsetAsync(c->d_timeline, 0, (size_t)8192 * 32 * 8, st);
@@ -125,11 +164,7 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
         return dp_launch_group(c->gmap, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec,
                                trace, path_xy, path_ll, st, g, c->lc);
     }
-    c->launches += c->split ? 2 : 1;
-    DpIo iow = io;
-    if ((iow.n_peer_flag || iow.n_wait) && !iow.tally) { iow.tally = c->d_tally_g; iow.tally_n = (unsigned)n; }
-    return dp_launch_cycle(c->gmap, c->p, n, hdr, ox, oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS, rec, trace,
-                           path_xy, path_ll, st, c->split, iow, c->lc);
+    return launch_warp(c, first, n, hdr, ox, oy, rec, trace, path_xy, path_ll, st, io);
 }
 }  // namespace
 
@@ -272,8 +307,8 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     if ((r = dev_alloc(&c->d_last, (size_t)max_scenes * DP_PATH_POINTS))) { delete c; return r; }
     if ((r = dev_alloc(&c->d_done, (size_t)max_scenes))) { delete c; return r; }
     if ((r = dev_alloc(&c->d_pdone, (size_t)max_scenes)) || (r = dev_alloc(&c->d_inflag, 2)) || (r = dev_alloc(&c->d_tally, 2)) ||
-        (r = dev_alloc(&c->d_tally_g, 1))) { delete c; return r; }
-    CK(cudaMemset(c->d_tally_g, 0, sizeof(unsigned)));
+        (r = dev_alloc(&c->d_tally_g, 2))) { delete c; return r; }
+    CK(cudaMemset(c->d_tally_g, 0, 2 * sizeof(unsigned)));
     CK(cudaMemset(c->d_pdone, 0, (size_t)max_scenes * sizeof(unsigned)));
     CK(cudaMemset(c->d_inflag, 0, 2 * sizeof(unsigned))); CK(cudaMemset(c->d_tally, 0, 2 * sizeof(unsigned)));
     CK(cudaHostAlloc((void**)&c->h_done, 4 * sizeof(unsigned), cudaHostAllocMapped));
@@ -478,9 +513,7 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
         cudaStream_t st = c->st[0];
         DpIo io = make_io(c, first, (dp_plan_record*)dv_rec);
         io.hdr_stage = c->d_hdr[0]; io.ox_stage = c->d_ox[0]; io.oy_stage = c->d_oy[0];
-        CK(dp_launch_cycle(c->gmap, c->p, n, (const dp_scene_hdr*)dv_hdr, (const double*)dv_ox, (const double*)dv_oy, c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
-                           c->d_rec[0], nullptr, nullptr, nullptr, st, c->split, io, c->lc));
-        c->launches += 2;
+        CK(launch_warp(c, first, n, (const dp_scene_hdr*)dv_hdr, (const double*)dv_ox, (const double*)dv_oy, c->d_rec[0], nullptr, nullptr, nullptr, st, io));
         CK(cudaStreamSynchronize(st));
         return DP_OK;
     }
@@ -572,8 +605,7 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
         io.pdone = c->d_pdone + first; io.prev_epoch = prev;
         io.tally = c->d_tally + s; io.tally_n = (unsigned)n; io.host_done = (unsigned*)dv_done + s;
         c->wait_epoch[s] = n > 0 ? io.epoch : 0u;
-        CK(dp_launch_cycle(c->gmap, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
-                           c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, io, c->lc));
+        CK(launch_warp(c, first, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->d_rec[s], nullptr, nullptr, nullptr, st, io));
         c->chain_prev_epoch = io.epoch; c->chain_first = first; c->chain_n = n;
     } else {
         CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
@@ -583,12 +615,11 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
             CK(cudaEventRecord(c->in_ready[s][k], c->cp[k]));
             CK(cudaStreamWaitEvent(st, c->in_ready[s][k], 0));
         }
-        CK(dp_launch_cycle(c->gmap, c->p, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->max_obs, c->d_carry + first, c->d_last + (size_t)first * DP_PATH_POINTS,
-                           c->d_rec[s], nullptr, nullptr, nullptr, st, c->split, make_io(c, first, (dp_plan_record*)dv_rec), c->lc));
+        CK(launch_warp(c, first, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->d_rec[s], nullptr, nullptr, nullptr, st,
+                       make_io(c, first, (dp_plan_record*)dv_rec)));
         CK(cudaEventRecord(c->done[s], st));
         c->wait_epoch[s] = 0;
     }
-    c->launches += c->split ? 2 : 1;
     ++c->submitted;
     return DP_OK;
 }
@@ -671,7 +702,19 @@ struct dp_gather {
     unsigned char* base[DP_MAX_MIRRORS] = {};               // every rank's allocation as seen from here (own: the local pointer)
     bool opened[DP_MAX_MIRRORS] = {};
     size_t rec_bytes = 0;                                   // records come first ([depth][world][slots]), the flags ([depth][world] u32) follow
+    unsigned pending = 0;                                   // deferred mode: step whose records have been computed but not forwarded yet
 };
+namespace {
+// deferred gather: point the context (or a flush launch) at the buffers / flags of step `step`
+void gather_route(dp_gather* g, unsigned step, dp_plan_record** dst, unsigned** flag, const unsigned** wait) {
+    const size_t b = step % (unsigned)g->depth;
+    for (int r = 0; r < g->world; ++r) {
+        dst[r] = reinterpret_cast<dp_plan_record*>(g->base[r]) + (b * g->world + g->rank) * g->slots;
+        flag[r] = reinterpret_cast<unsigned*>(g->base[r] + g->rec_bytes) + b * g->world + g->rank;
+    }
+    *wait = reinterpret_cast<const unsigned*>(g->base[g->rank] + g->rec_bytes) + b * g->world;
+}
+}  // namespace
 static_assert(DP_IPC_BYTES >= sizeof(cudaIpcMemHandle_t), "DP_IPC_BYTES");
 
 int dp_gather_create(dp_ctx* c, int world, int rank, int slots, int depth, dp_gather** out, void* handle_out) {
@@ -717,6 +760,35 @@ int dp_gather_arm(dp_gather* g, unsigned step) {
     c->flag_value = step;
     return DP_OK;
 }
+int dp_gather_arm_deferred(dp_gather* g, unsigned step) {
+    if (!g || step == 0) return fail(DP_ERR_ARG, "dp_gather_arm_deferred: bad argument (steps count from 1)");
+    dp_ctx* c = g->c;
+    for (int r = 0; r < g->world; ++r) if (!g->base[r]) return fail(DP_ERR_STATE, "dp_gather_arm_deferred: dp_gather_attach first");
+    c->n_mirror = 0; c->n_fwd = 0; c->n_peer_flag = 0; c->n_wait = 0; c->wait_flag = nullptr;
+    if (g->pending && c->last_rec) {                        // the launch that follows forwards, flags and awaits the step before
+        gather_route(g, g->pending, c->fwd_dst, c->peer_flag, &c->wait_flag);
+        c->n_fwd = c->n_peer_flag = c->n_wait = g->world;
+        c->flag_value = c->wait_value = g->pending;
+    }
+    c->deferred = true;
+    g->pending = step;
+    return DP_OK;
+}
+int dp_gather_flush(dp_gather* g, void* stream) {
+    if (!g) return fail(DP_ERR_ARG, "dp_gather_flush: null");
+    dp_ctx* c = g->c;
+    if (!g->pending || !c->last_rec) return DP_OK;
+    CK(cudaSetDevice(c->device));
+    DpIo io = dp_io_none();
+    gather_route(g, g->pending, io.fwd_dst, io.peer_flag, &io.wait_flag);
+    for (int r = 0; r < g->world; ++r) io.fwd_dst[r] += c->last_first;
+    io.n_fwd = io.n_peer_flag = io.n_wait = g->world;
+    io.flag_value = io.wait_value = g->pending;
+    CK(dp_launch_gather_flush(c->last_rec, c->last_n, io, (cudaStream_t)stream));
+    c->launches += 2;
+    g->pending = 0;
+    return DP_OK;
+}
 int dp_gather_chain(dp_gather* g, unsigned prev_step) {
     if (!g) return fail(DP_ERR_ARG, "dp_gather_chain: null");
     dp_ctx* c = g->c;
@@ -730,6 +802,7 @@ int dp_gather_disarm(dp_gather* g) {
     if (!g) return fail(DP_ERR_ARG, "dp_gather_disarm: null");
     g->c->n_mirror = 0; g->c->n_peer_flag = 0;
     g->c->wait_flag = nullptr; g->c->n_wait = 0; g->c->wait_value = 0;
+    g->c->n_fwd = 0; g->c->deferred = false; g->pending = 0;
     return DP_OK;
 }
 int dp_gather_wait(dp_gather* g, unsigned step, void* stream) {

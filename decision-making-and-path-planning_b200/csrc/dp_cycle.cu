@@ -269,11 +269,20 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     // chained submit: the previous cycle's Planning warp of THIS scene may still be running (it reads the hand-off in the
     // carry this warp is about to overwrite): wait for it, scene by scene
     if (PHASE == 1 && io.prev_epoch) dp_await(io.pdone + scene, io.prev_epoch);
+    // deferred gather: last cycle's record of this scene goes out first (DgIo); the load is issued here, the stores follow
+    // once the obstacle loads below have been issued too (one L2 round trip for all of them)
+    uint32_t fwd_w = 0;
+    if (PHASE != 2 && io.n_fwd) fwd_w = __ldcg(reinterpret_cast<const uint32_t*>(io.fwd_src + scene) + lane);
     const LaneMap lm = dp_lane_map(N, lane);
     // this lane's obstacle stays in registers for the whole cycle when N < 32
     const bool lm_act = (lm.nchunk > 1) && (lane < N * lm.nchunk);
     const bool via_l2 = PHASE == 2 || io.in_flag != nullptr;
     const double mx = lm_act ? (via_l2 ? dp_l2(ox + lm.o) : ox[lm.o]) : 0.0, my = lm_act ? (via_l2 ? dp_l2(oy + lm.o) : oy[lm.o]) : 0.0;
+    if (PHASE != 2 && io.n_fwd) {
+#pragma unroll
+        for (int k = 0; k < DP_MAX_MIRRORS; ++k)
+            if (k < io.n_fwd) reinterpret_cast<uint32_t*>(io.fwd_dst[k] + scene)[lane] = fwd_w;
+    }
     dp_trace_record* tr = trace ? trace + scene : nullptr;
     if (tr && PHASE != 2) {                                 // zero the trace record cooperatively
         uint32_t* w = reinterpret_cast<uint32_t*>(tr);
@@ -646,6 +655,19 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         }
         DBG_END(0, n_traj);
         if (io.done) dp_publish(io.done + scene, io.epoch, lane);
+        if (io.flag_mode == 1 && io.tally2) {               // deferred gather: every forwarded record is out when the last Decision warp retires
+            if (!io.done) { __threadfence(); __syncwarp(); }
+            if (lane == 0 && atomicAdd(io.tally2, 1u) == io.tally_n - 1u) {
+                *io.tally2 = 0;
+                __threadfence_system();
+#pragma unroll
+                for (int k = 0; k < DP_MAX_MIRRORS; ++k)
+                    if (k < io.n_peer_flag) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+                // ... and this warp stays until every rank's flag of that step is here: the pair of launches is complete only
+                // when the gathered buffer of the step before is (the Planning half needs no tally for it)
+                dg_wait_flags(io.wait_flag, io.n_wait, io.wait_value);
+            }
+        }
         return;
     }
 
@@ -947,7 +969,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             __threadfence_system();                         // cumulative: everything the other warps fenced before their tally increment
 #pragma unroll
             for (int k = 0; k < DP_MAX_MIRRORS; ++k)
-                if (k < io.n_peer_flag) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+                if (k < io.n_peer_flag && io.flag_mode == 0) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
             dg_wait_flags(io.wait_flag, io.n_wait, io.wait_value);
             if (io.host_done) *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
         }
@@ -962,7 +984,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                 __threadfence_system();                     // cumulative: everything the other warps fenced before their tally increment
 #pragma unroll
                 for (int k = 0; k < DP_MAX_MIRRORS; ++k)     // fused gather: this rank's slice of the step is complete on every rank
-                    if (k < io.n_peer_flag) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+                    if (k < io.n_peer_flag && io.flag_mode == 0) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
                 dg_wait_flags(io.wait_flag, io.n_wait, io.wait_value);
                 *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
             }
@@ -1077,7 +1099,7 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
     }
     const int sm_count = lc.sm_count;
     if (!split) {
-        DpIo io0 = io; io0.done = nullptr; io0.in_flag = nullptr; io0.pdone = nullptr; io0.prev_epoch = 0;
+        DpIo io0 = io; io0.done = nullptr; io0.in_flag = nullptr; io0.pdone = nullptr; io0.prev_epoch = 0; io0.flag_mode = 0;
         const int blocks = (n + 3) / 4;
         dp_cycle_kernel<0, 4><<<blocks, 128, 0, st>>>(m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io0);
     } else {
@@ -1090,6 +1112,7 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
         DpIo io1 = io; io1.n_mirror = 0;
         DpIo io2 = io; io2.hdr_stage = nullptr; io2.ox_stage = nullptr; io2.oy_stage = nullptr;
         if (split != 2) { io1.done = io2.done = nullptr; io1.in_flag = io2.in_flag = nullptr; io1.pdone = io2.pdone = nullptr; io1.prev_epoch = 0; }
+        io1.flag_mode = io2.flag_mode = (io.n_fwd && io.tally2) ? 1 : 0;   // deferred gather: the Decision half forwards and raises the flags
         {
             // chained submit: the Decision half is a programmatic dependent of the previous cycle's Planning half (which triggers
             // at entry); its warps wait per scene for that cycle's Planning warp (io.prev_epoch) and for the staged inputs
@@ -1121,6 +1144,25 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
 }
 cudaError_t dp_launch_gather_wait(const unsigned* flags, int world, unsigned step, cudaStream_t st) {
     dp_gather_wait_kernel<<<1, 1, 0, st>>>(flags, world, step);
+    return cudaGetLastError();
+}
+// deferred gather, last step of a sequence: nobody launches another cycle to forward its records
+__global__ void dp_gather_forward_kernel(const dp_plan_record* __restrict__ src, int n, DpIo io) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;    // one 16-byte piece per thread
+    if (i >= n * 8) return;
+    const uint4 w = __ldcg(reinterpret_cast<const uint4*>(src) + i);
+#pragma unroll
+    for (int k = 0; k < DP_MAX_MIRRORS; ++k)
+        if (k < io.n_fwd) reinterpret_cast<uint4*>(io.fwd_dst[k])[i] = w;
+}
+__global__ void dp_gather_raise_kernel(DpIo io) {           // (after the forward kernel in stream order: its stores are complete)
+    __threadfence_system();
+    for (int k = 0; k < io.n_peer_flag; ++k) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
+    dg_wait_flags(io.wait_flag, io.n_wait, io.wait_value);
+}
+cudaError_t dp_launch_gather_flush(const dp_plan_record* src, int n, const DpIo& io, cudaStream_t st) {
+    dp_gather_forward_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(src, n, io);
+    dp_gather_raise_kernel<<<1, 1, 0, st>>>(io);
     return cudaGetLastError();
 }
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st) {

@@ -101,6 +101,11 @@ struct DgIo {
     // until wait_flag[0..n_wait) (this rank's flag words of that step, one per rank) all hold wait_value, and only then tells the
     // host -- "this launch is complete" implies "every rank's records of the step before are in my gathered buffer"
     const unsigned* wait_flag; int n_wait; unsigned wait_value;
+    // deferred gather (dp_gather_arm_deferred): the records of the PREVIOUS launch (fwd_src, indexed like rec) are copied to
+    // fwd_dst[0..n_fwd) by the warps / CTAs as they START -- the NVLink round trips hide under the cycle -- and the flags above
+    // then stand for THAT step: nothing of the gather is left at the end of the launch but one fence, the flags and the wait
+    const dp_plan_record* fwd_src; dp_plan_record* fwd_dst[DG_MAX_MIRRORS]; int n_fwd;
+    unsigned* tally2; int flag_mode;                        // warp kernel, split launches: flags raised at the end of the Decision half (mode 1)
     long long* timeline;                           // instrumented runs only (tools/group_timeline.py): [block][32] globaltimer stamps
     // predicted agent tracks (BASELINE config 5, dp_set_tracks): constant-turn-rate parameters [scene][max_obs] -- displacement of
     // step 0 (vx, vy) and heading change per step (deg) -- and the horizon T; null = static obstacles (the reference's semantics)
@@ -799,6 +804,17 @@ DG_BODY dg_group_cycle(const DgMap& m, const dp_params& p, const int first, cons
         uint4* sh = reinterpret_cast<uint4*>(sm.hdr);
         uint4* sc = reinterpret_cast<uint4*>(sm.carry);
         for (int i = tid; i < S * 8; i += TPB) { sh[i] = gh[i]; sc[i] = gc[i]; }
+#if !defined(DP_EMU)
+        if (io.n_fwd) {                                     // deferred gather: last cycle's records of these scenes go out first
+            const uint4* fs = reinterpret_cast<const uint4*>(io.fwd_src + first);
+            for (int i = tid; i < S * 8; i += TPB) {
+                const uint4 w = __ldcg(fs + i);
+#pragma unroll
+                for (int q = 0; q < DG_MAX_MIRRORS; ++q)
+                    if (q < io.n_fwd) reinterpret_cast<uint4*>(io.fwd_dst[q] + first)[i] = w;
+            }
+        }
+#endif
         if (trace) {
             uint32_t* w = reinterpret_cast<uint32_t*>(trace + first);
             for (int i = tid; i < S * (int)(sizeof(dp_trace_record) / 4); i += TPB) w[i] = 0;

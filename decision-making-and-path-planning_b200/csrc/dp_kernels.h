@@ -25,6 +25,8 @@ struct DpIo {
     unsigned* host_done;                       // (page-locked host memory)
     unsigned* peer_flag[DP_MAX_MIRRORS]; int n_peer_flag; unsigned flag_value;   // fused gather (dp_gather_*), see DgIo
     const unsigned* wait_flag; int n_wait; unsigned wait_value;                  // the previous step's barrier, folded in (DgIo)
+    const dp_plan_record* fwd_src; dp_plan_record* fwd_dst[DP_MAX_MIRRORS]; int n_fwd;   // deferred gather (DgIo)
+    unsigned* tally2; int flag_mode;
 };
 inline DpIo dp_io_none() { DpIo io = {}; return io; }
 
@@ -42,6 +44,7 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
                             double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io, DpLaunchCfg& lc);   // split: 0 fused, 1 two launches, 2 overlapped
 // (io.prev_epoch != 0 additionally launches the Decision half as a programmatic dependent of the previous cycle's Planning half)
+cudaError_t dp_launch_gather_flush(const dp_plan_record* src, int n, const DpIo& io, cudaStream_t st);
 cudaError_t dp_launch_gather_wait(const unsigned* flags, int world, unsigned step, cudaStream_t st);
 cudaError_t dp_launch_reset(dp_carry* carry, double2* last_path, int first, int count, cudaStream_t st);
 cudaError_t dp_launch_map_prep(const double* x, const double* y, const uint16_t* attr, const int32_t* lane_pt_off, int n_lanes, double2* xy,

@@ -239,6 +239,15 @@ int dp_gather_create(dp_ctx* ctx, int world, int rank, int slots_per_rank, int d
 int dp_gather_attach(dp_gather* g, const void* handles);
 int dp_gather_arm(dp_gather* g, unsigned step);
 int dp_gather_chain(dp_gather* g, unsigned prev_step);
+/* Deferred variant -- the one a pipelined loop should use.  dp_gather_arm_deferred(g, s) before the launch of step s: that
+ * launch keeps its own records local; instead its warps, AS THEY START, copy the records of the launch before (step s-1, armed
+ * the same way, same slot range) into every rank's buffer, so the NVLink round trips hide under the cycle; the flags of s-1
+ * go up when the last Decision warp retires and the launch's last warp waits for every rank's flag of s-1:
+ *     launch of step s complete  =>  dp_gather_buffer(s-1) holds every rank's records of step s-1
+ * (the contract of arm + chain, at about 1 us per step instead of 8).  One-shot: arm before every launch.
+ * dp_gather_flush(g, stream) forwards, flags and awaits the LAST armed step (two small launches), at the end of a sequence. */
+int dp_gather_arm_deferred(dp_gather* g, unsigned step);
+int dp_gather_flush(dp_gather* g, void* stream);
 int dp_gather_disarm(dp_gather* g);
 int dp_gather_wait(dp_gather* g, unsigned step, void* stream);
 const void* dp_gather_buffer(dp_gather* g, unsigned step);

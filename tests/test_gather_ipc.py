@@ -56,6 +56,7 @@ def worker(rank, world, conn, n, n_obs, cycles, q):
         got.append((host.copy(), rec_h.view(np.uint8).reshape(n, 128).copy()))
     # chained: no wait launches -- the launch of step s carries the wait for step s-1 (dp_gather_chain); the gathered buffer of
     # s-1 is read right behind the kernel of s, the last one after an explicit wait
+    g_step = [3 * cycles]
     p.reset(0, n)
     own = []
     for c in range(cycles + 1):
@@ -72,6 +73,48 @@ def worker(rank, world, conn, n, n_obs, cycles, q):
             assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step - 1)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
             assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
             got.append((host.copy(), own[c - 1]))
+    # deferred: the launch of step s forwards / flags / awaits step s-1 as its warps start (dp_gather_arm_deferred); records go
+    # to alternating buffers and, in a second round, to ONE buffer (a warp forwards its scene's old record before overwriting it);
+    # the last step is pushed by dp_gather_flush
+    for bufs in (2, 1):
+        p.reset(0, n)
+        d_r = [torch.empty((n, 128), dtype=torch.uint8, device=dev) for _ in range(bufs)]
+        own = []
+        base = g_step[0]
+        for c in range(cycles + 1):
+            step = base + c + 1
+            if c < cycles:
+                g.arm_deferred(step)
+                p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_r[c % bufs].data_ptr(), stream=st.cuda_stream)
+                own.append(d_r[c % bufs].cpu().numpy().copy())
+            else:
+                g.flush(stream=st.cuda_stream)
+            if c:
+                host = np.zeros((world * n, 128), np.uint8)
+                assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step - 1)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
+                assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
+                got.append((host.copy(), own[c - 1]))
+        g_step[0] = base + cycles
+    # ... and through the pipelined host-pointer calls (dp_cycle_submit / dp_cycle_wait, two in flight)
+    p.reset(0, n)
+    recs = [torch.empty((n, 128), dtype=torch.uint8).pin_memory().numpy().view(abi.plan_record).reshape(n) for _ in range(2)]
+    base = g_step[0]
+    own, pend = {}, []
+    for c in range(cycles):
+        if len(pend) == 2:
+            p.wait(); k = pend.pop(0); own[k] = recs[k & 1].view(np.uint8).reshape(n, 128).copy()
+        g.arm_deferred(base + c + 1)
+        p.submit(Hh[c], OXh[c], OYh[c], recs[c & 1])
+        pend.append(c)
+    while pend:
+        p.wait(); k = pend.pop(0); own[k] = recs[k & 1].view(np.uint8).reshape(n, 128).copy()
+    g.flush(stream=st.cuda_stream)
+    assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
+    for c in range(cycles - 4, cycles):                      # depth 4: the last four steps are still in the buffers
+        host = np.zeros((world * n, 128), np.uint8)
+        assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(base + c + 1)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
+        assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
+        got.append((host.copy(), own[c]))
     q.put((rank, got))
     conn.recv()                                              # keep the mapping alive until the peer has finished too
     g.close(); p.close()
@@ -95,10 +138,13 @@ def test_two_processes_gather_through_cuda_ipc(n_obs):
     for pr in procs:
         pr.join(timeout=120)
         assert pr.exitcode == 0
-    for c in range(3 * cycles):
+    bad = []
+    for c in range(len(res[0])):
         own = [res[r][c][1] for r in range(world)]           # what each rank computed this step
         assert own[0].any()
         for r in range(world):
             gathered = res[r][c][0].reshape(world, n, 128)
             for k in range(world):
-                assert np.array_equal(gathered[k], own[k]), "step %d: rank %d does not hold rank %d's records" % (c, r, k)
+                if not np.array_equal(gathered[k], own[k]):
+                    bad.append((c, r, k, int((gathered[k] != own[k]).any(axis=1).sum())))
+    assert not bad, "(entry, rank, slice of rank, differing records): %s" % bad

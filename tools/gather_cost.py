@@ -3,6 +3,8 @@
   local    records mirrored into this rank's OWN gathered buffer + flags (no NVLink traffic)
   peers    records + flags stored on every rank        (dp_gather_arm)
   chained  ... and the wait for the previous step folded into the launch (dp_gather_chain)
+  deferred the launch forwards the records of the launch BEFORE as its warps start, raises that step's flags when its Decision
+           half retires and waits for them in its last warp (dp_gather_arm_deferred)
 Each leg: 200 cycles, 256 MiB L2 flush before each, CUDA events around the launch; prints p50 / mean per rank."""
 import os
 import sys
@@ -52,6 +54,9 @@ def main():
             elif name == "local":
                 g.disarm()
                 p.set_record_mirrors([g.buffer(1)])
+            elif name == "deferred":
+                step[0] += 1
+                g.arm_deferred(step[0])
             else:
                 step[0] += 1
                 g.arm(step[0])
@@ -61,12 +66,14 @@ def main():
             ev[i][1].record(st)
         if name in ("peers", "chained"):
             g.wait(step[0], stream=st.cuda_stream)
+        if name == "deferred":
+            g.flush(stream=st.cuda_stream)
         torch.cuda.synchronize(); dist.barrier()
         p.set_record_mirrors([])
         ms = np.array([a.elapsed_time(b) for a, b in ev])[5:]
         print("rank %d %-8s p50 %.2f us  mean %.2f us  p90 %.2f us" % (rank, name, np.percentile(ms, 50) * 1e3, ms.mean() * 1e3, np.percentile(ms, 90) * 1e3), flush=True)
 
-    for name in os.environ.get("LEGS", "plain,local,peers,chained,plain").split(","):
+    for name in os.environ.get("LEGS", "plain,local,peers,chained,deferred,plain").split(","):
         leg(name)
     g.close(); p.close()
     dist.destroy_process_group()
