@@ -39,8 +39,8 @@ def workload_desc(world):
                         "ego + %d vehicles, %d-cycle scripted episodes" % (SCENES, N_OBS, EPISODE),
             "scenes_per_gpu": SCENES, "obstacles": N_OBS, "episode_cycles": EPISODE,
             "parallelism": "scenes sharded %d-way, no data-path collective in the compute phase; when N>1 every rank's plan records are "
-                           "gathered on every rank each step: GATHER_KIND; step i+1 is complete when its kernels AND the gather of step i are, "
-                           "the last step's gather (dp_gather_flush) is exposed and counted" % world,
+                           "gathered on every rank each step: GATHER_KIND; step i+1 is complete when its kernels AND the gather of step i-1 are, "
+                           "the gathers of the last two steps (dp_gather_flush) are exposed and counted" % world,
             "l2": "256 MiB buffer written between timed steps (L2 flush); inputs resident in HBM for `value`"}
 
 
@@ -222,11 +222,12 @@ def run_ours(args, rank, world, local_rank):
         try:   # the C ABI's own fused gather: CUDA IPC peer mapping, records + completion flags stored by the cycle kernel
             from dmpp_b200.planner import Gather
             gat = Gather(planner, world, rank, SCENES, depth=4)
+            gat.set_lag(int(os.environ.get("DP_GATHER_LAG", "2")))   # a launch awaits the gather two steps back: a whole step of slack between ranks
             hs = [None] * world
             dist.all_gather_object(hs, gat.my_handle())
             gat.attach(hs)
             gather_kind = ("dp_gather_* (C ABI, CUDA IPC mapping), deferred: the cycle kernel of step i+1 forwards step i's records to every "
-                           "rank over NVLink as its warps start, raises the completion flags and waits for every rank's in its last warp")
+                           "rank over NVLink as its warps start, raises that step's completion flags and waits for every rank's flags of step i-1 (lag 2)")
         except Exception as e:  # noqa: BLE001
             print("dp_gather unavailable (%s): falling back to torch symmetric memory" % e, file=sys.stderr)
             gat = None

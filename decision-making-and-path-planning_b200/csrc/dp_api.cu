@@ -703,6 +703,8 @@ struct dp_gather {
     bool opened[DP_MAX_MIRRORS] = {};
     size_t rec_bytes = 0;                                   // records come first ([depth][world][slots]), the flags ([depth][world] u32) follow
     unsigned pending = 0;                                   // deferred mode: step whose records have been computed but not forwarded yet
+    unsigned forwarded = 0;                                 // ... and the newest step that has been forwarded (flags raised by this rank)
+    int lag = 1;                                            // a launch awaits the flags of the step `lag` launches back (dp_gather_set_lag)
 };
 namespace {
 // deferred gather: point the context (or a flush launch) at the buffers / flags of step `step`
@@ -765,13 +767,27 @@ int dp_gather_arm_deferred(dp_gather* g, unsigned step) {
     dp_ctx* c = g->c;
     for (int r = 0; r < g->world; ++r) if (!g->base[r]) return fail(DP_ERR_STATE, "dp_gather_arm_deferred: dp_gather_attach first");
     c->n_mirror = 0; c->n_fwd = 0; c->n_peer_flag = 0; c->n_wait = 0; c->wait_flag = nullptr;
-    if (g->pending && c->last_rec) {                        // the launch that follows forwards, flags and awaits the step before
+    if (g->pending && c->last_rec) {                        // the launch that follows forwards and flags the step before ...
         gather_route(g, g->pending, c->fwd_dst, c->peer_flag, &c->wait_flag);
-        c->n_fwd = c->n_peer_flag = c->n_wait = g->world;
-        c->flag_value = c->wait_value = g->pending;
+        c->n_fwd = c->n_peer_flag = g->world;
+        c->flag_value = g->pending;
+        // ... and awaits every rank's flags of that step (lag 1) or of the one before it (lag 2: a full step of slack between the
+        // ranks; that step was forwarded by the launch before, so only launches that have one to wait for do)
+        const unsigned w = (g->lag == 1) ? g->pending : g->forwarded;
+        if (w) {
+            dp_plan_record* d_[DP_MAX_MIRRORS]; unsigned* f_[DP_MAX_MIRRORS];
+            gather_route(g, w, d_, f_, &c->wait_flag);
+            c->n_wait = g->world; c->wait_value = w;
+        } else c->wait_flag = nullptr;
+        g->forwarded = g->pending;
     }
     c->deferred = true;
     g->pending = step;
+    return DP_OK;
+}
+int dp_gather_set_lag(dp_gather* g, int lag) {
+    if (!g || lag < 1 || lag > 2 || g->depth < lag + 2) return fail(DP_ERR_ARG, "dp_gather_set_lag: lag 1 or 2, depth >= lag + 2");
+    g->lag = lag;
     return DP_OK;
 }
 int dp_gather_flush(dp_gather* g, void* stream) {
@@ -784,9 +800,14 @@ int dp_gather_flush(dp_gather* g, void* stream) {
     for (int r = 0; r < g->world; ++r) io.fwd_dst[r] += c->last_first;
     io.n_fwd = io.n_peer_flag = io.n_wait = g->world;
     io.flag_value = io.wait_value = g->pending;
+    if (g->lag == 2 && g->forwarded) {                      // the step before may not have been awaited by any launch yet
+        CK(dp_launch_gather_wait(reinterpret_cast<const unsigned*>(g->base[g->rank] + g->rec_bytes) + (size_t)(g->forwarded % (unsigned)g->depth) * g->world,
+                                 g->world, g->forwarded, (cudaStream_t)stream));
+        ++c->launches;
+    }
     CK(dp_launch_gather_flush(c->last_rec, c->last_n, io, (cudaStream_t)stream));
     c->launches += 2;
-    g->pending = 0;
+    g->pending = 0; g->forwarded = 0;
     return DP_OK;
 }
 int dp_gather_chain(dp_gather* g, unsigned prev_step) {
@@ -802,7 +823,7 @@ int dp_gather_disarm(dp_gather* g) {
     if (!g) return fail(DP_ERR_ARG, "dp_gather_disarm: null");
     g->c->n_mirror = 0; g->c->n_peer_flag = 0;
     g->c->wait_flag = nullptr; g->c->n_wait = 0; g->c->wait_value = 0;
-    g->c->n_fwd = 0; g->c->deferred = false; g->pending = 0;
+    g->c->n_fwd = 0; g->c->deferred = false; g->pending = 0; g->forwarded = 0;
     return DP_OK;
 }
 int dp_gather_wait(dp_gather* g, unsigned step, void* stream) {

@@ -269,8 +269,10 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     // chained submit: the previous cycle's Planning warp of THIS scene may still be running (it reads the hand-off in the
     // carry this warp is about to overwrite): wait for it, scene by scene
     if (PHASE == 1 && io.prev_epoch) dp_await(io.pdone + scene, io.prev_epoch);
-    // deferred gather: last cycle's record of this scene goes out first (DgIo); the load is issued here, the stores follow
-    // once the obstacle loads below have been issued too (one L2 round trip for all of them)
+    // deferred gather: last cycle's record of this scene (DgIo) is picked up here, before this cycle overwrites it, and sent
+    // when the Decision half of the scene is done: the warps of a launch START together (28 per SM x 148 SMs x world stores at
+    // once is a 4 us NVLink burst that every warp then sits behind: +3.9 us per step at 8 GPUs), but they FINISH spread over
+    // 15-50 us
     uint32_t fwd_w = 0;
     if (PHASE != 2 && io.n_fwd) fwd_w = __ldcg(reinterpret_cast<const uint32_t*>(io.fwd_src + scene) + lane);
     const LaneMap lm = dp_lane_map(N, lane);
@@ -278,11 +280,6 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     const bool lm_act = (lm.nchunk > 1) && (lane < N * lm.nchunk);
     const bool via_l2 = PHASE == 2 || io.in_flag != nullptr;
     const double mx = lm_act ? (via_l2 ? dp_l2(ox + lm.o) : ox[lm.o]) : 0.0, my = lm_act ? (via_l2 ? dp_l2(oy + lm.o) : oy[lm.o]) : 0.0;
-    if (PHASE != 2 && io.n_fwd) {
-#pragma unroll
-        for (int k = 0; k < DP_MAX_MIRRORS; ++k)
-            if (k < io.n_fwd) reinterpret_cast<uint32_t*>(io.fwd_dst[k] + scene)[lane] = fwd_w;
-    }
     dp_trace_record* tr = trace ? trace + scene : nullptr;
     if (tr && PHASE != 2) {                                 // zero the trace record cooperatively
         uint32_t* w = reinterpret_cast<uint32_t*>(tr);
@@ -654,9 +651,14 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             if (tr) { tr->ub_hits = (uint16_t)ub; tr->pts_scored = (uint32_t)pts; }
         }
         DBG_END(0, n_traj);
-        if (io.done) dp_publish(io.done + scene, io.epoch, lane);
+        if (io.done) dp_publish(io.done + scene, io.epoch, lane);   // (the scene's Planning warp goes on; what follows is off its path)
+        if (io.n_fwd) {
+#pragma unroll
+            for (int k = 0; k < DP_MAX_MIRRORS; ++k)
+                if (k < io.n_fwd) reinterpret_cast<uint32_t*>(io.fwd_dst[k] + scene)[lane] = fwd_w;
+        }
         if (io.flag_mode == 1 && io.tally2) {               // deferred gather: every forwarded record is out when the last Decision warp retires
-            if (!io.done) { __threadfence(); __syncwarp(); }
+            __threadfence(); __syncwarp();                  // (every lane: its forwarded words before the tally)
             if (lane == 0 && atomicAdd(io.tally2, 1u) == io.tally_n - 1u) {
                 *io.tally2 = 0;
                 __threadfence_system();
@@ -671,6 +673,11 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         return;
     }
 
+    if (PHASE == 0 && io.n_fwd) {                           // one launch for both halves: the forward goes here, the end-of-launch tally covers it
+#pragma unroll
+        for (int k = 0; k < DP_MAX_MIRRORS; ++k)
+            if (k < io.n_fwd) reinterpret_cast<uint32_t*>(io.fwd_dst[k] + scene)[lane] = fwd_w;
+    }
     // ================================ Planning thread iteration ================================
     // last_Bpoints (Planning.cpp:6) -> sm.plan by one TMA bulk copy; the staging area of the decision half is free now and
     // the copy lands while the aim point is searched

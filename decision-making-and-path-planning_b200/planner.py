@@ -24,7 +24,7 @@ SYMBOLS = [
     "dp_sweep_set_bezier", "dp_sweep_lines",
     "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev", "dp_debug_timeline",
     "dp_set_tracks", "dp_set_tracks_dev", "dp_clear_tracks",
-    "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_chain", "dp_gather_arm_deferred", "dp_gather_flush", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
+    "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_chain", "dp_gather_arm_deferred", "dp_gather_set_lag", "dp_gather_flush", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
 ]
 
 _lib = None
@@ -306,6 +306,10 @@ class Gather:
     def arm_deferred(self, step):
         """the next cycle launch keeps its records local and forwards / flags / awaits the step armed before it"""
         _ck(self.lib.dp_gather_arm_deferred(self.h, C.c_uint(step)), "dp_gather_arm_deferred")
+
+    def set_lag(self, lag):
+        """deferred mode: a launch awaits the flags of the step `lag` launches back (1, or 2 with depth >= 4)"""
+        _ck(self.lib.dp_gather_set_lag(self.h, C.c_int(lag)), "dp_gather_set_lag")
 
     def flush(self, stream=0):
         """forward, flag and await the last deferred step (end of a sequence)"""

@@ -245,8 +245,13 @@ int dp_gather_chain(dp_gather* g, unsigned prev_step);
  * go up when the last Decision warp retires and the launch's last warp waits for every rank's flag of s-1:
  *     launch of step s complete  =>  dp_gather_buffer(s-1) holds every rank's records of step s-1
  * (the contract of arm + chain, at about 1 us per step instead of 8).  One-shot: arm before every launch.
- * dp_gather_flush(g, stream) forwards, flags and awaits the LAST armed step (two small launches), at the end of a sequence. */
+ * dp_gather_flush(g, stream) forwards, flags and awaits the LAST armed step (two small launches), at the end of a sequence.
+ * dp_gather_set_lag(g, 2) (depth >= 4) relaxes the contract by one step -- launch of step s complete => buffer(s-2) complete --
+ * which leaves a whole step of slack between the ranks instead of the ~20 us between the end of a Decision half and the end
+ * of its launch: ranks whose steps differ by a few microseconds (different scenes) no longer wait for the slowest one at
+ * every step.  dp_gather_flush then awaits the last two steps. */
 int dp_gather_arm_deferred(dp_gather* g, unsigned step);
+int dp_gather_set_lag(dp_gather* g, int lag);
 int dp_gather_flush(dp_gather* g, void* stream);
 int dp_gather_disarm(dp_gather* g);
 int dp_gather_wait(dp_gather* g, unsigned step, void* stream);

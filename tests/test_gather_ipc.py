@@ -76,25 +76,30 @@ def worker(rank, world, conn, n, n_obs, cycles, q):
     # deferred: the launch of step s forwards / flags / awaits step s-1 as its warps start (dp_gather_arm_deferred); records go
     # to alternating buffers and, in a second round, to ONE buffer (a warp forwards its scene's old record before overwriting it);
     # the last step is pushed by dp_gather_flush
-    for bufs in (2, 1):
+    for bufs, lag in ((2, 1), (1, 1), (2, 2)):
+        g.set_lag(lag)                                       # lag 2: the launch of step s awaits step s-2 (a whole step of slack)
         p.reset(0, n)
         d_r = [torch.empty((n, 128), dtype=torch.uint8, device=dev) for _ in range(bufs)]
         own = []
         base = g_step[0]
-        for c in range(cycles + 1):
-            step = base + c + 1
-            if c < cycles:
-                g.arm_deferred(step)
-                p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_r[c % bufs].data_ptr(), stream=st.cuda_stream)
-                own.append(d_r[c % bufs].cpu().numpy().copy())
-            else:
-                g.flush(stream=st.cuda_stream)
-            if c:
-                host = np.zeros((world * n, 128), np.uint8)
-                assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step - 1)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
-                assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
-                got.append((host.copy(), own[c - 1]))
+
+        def read(step):
+            host = np.zeros((world * n, 128), np.uint8)
+            assert p.lib.dp_memcpy_d2h(p.ctx, abi.ptr(host), C.c_void_p(g.buffer(step)), C.c_size_t(host.nbytes), C.c_void_p(st.cuda_stream)) == 0
+            assert p.lib.dp_stream_sync(p.ctx, C.c_void_p(st.cuda_stream)) == 0
+            got.append((host.copy(), own[step - base - 1]))
+
+        for c in range(cycles):
+            g.arm_deferred(base + c + 1)
+            p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_r[c % bufs].data_ptr(), stream=st.cuda_stream)
+            own.append(d_r[c % bufs].cpu().numpy().copy())
+            if c >= lag:
+                read(base + c + 1 - lag)                     # complete as soon as this launch is
+        g.flush(stream=st.cuda_stream)
+        for k in range(lag):
+            read(base + cycles - lag + 1 + k)
         g_step[0] = base + cycles
+    g.set_lag(1)
     # ... and through the pipelined host-pointer calls (dp_cycle_submit / dp_cycle_wait, two in flight)
     p.reset(0, n)
     recs = [torch.empty((n, 128), dtype=torch.uint8).pin_memory().numpy().view(abi.plan_record).reshape(n) for _ in range(2)]
