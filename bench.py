@@ -811,18 +811,29 @@ def config4_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, tota
     if world > 1 and not os.environ.get("DP_BENCH_NO_IPC"):
         try:
             from dmpp_b200.planner import Gather
-            gat = Gather(p, world, rank, n, depth=2)
+            gat = Gather(p, world, rank, n, depth=4)
+            gat.set_lag(2)
             hs = [None] * world
             dist.all_gather_object(hs, gat.my_handle())
             gat.attach(hs)
             st_ = torch.cuda.current_stream()
             cnt = [0]
 
+            # many waves per launch: the eager variant (records stored on every rank as each Planning warp ends) measured cheaper than
+            # the deferred one (131072 scenes per GPU, 2 GPUs: 1.95 ms without a gather, 2.04 eager, 2.14 deferred; tools/config4_probe.py)
+            mode4 = os.environ.get("DP_CFG4_GATHER", "eager")
+
             def before(i):
                 cnt[0] += 1
-                gat.arm(cnt[0])
-            after = lambda i: gat.wait(cnt[0], stream=st_.cuda_stream)   # noqa: E731
-            gather = "dp_gather_* (C ABI, CUDA IPC): peer stores + flags from the kernel, wait for every rank's flag inside the timed step"
+                if mode4 == "deferred":
+                    gat.arm_deferred(cnt[0])
+                elif mode4 == "eager":
+                    gat.arm(cnt[0])
+            after = (lambda i: gat.wait(cnt[0], stream=st_.cuda_stream)) if mode4 == "eager" else None
+            gather = {"deferred": "dp_gather_* (C ABI, CUDA IPC), deferred: the launch of step i+1 forwards step i's records to every rank, raises the "
+                                  "flags and awaits every rank's flags of step i-1; the last two steps' gathers (dp_gather_flush) are timed and added",
+                      "eager": "dp_gather_* (C ABI, CUDA IPC), eager: peer stores + flags from the kernel as it ends, wait for every rank's flag inside the timed step",
+                      "none": "NO gather (experiment)"}[mode4]
         except Exception as e:  # noqa: BLE001
             gat = None
             gather = "dp_gather failed (%s)" % type(e).__name__
@@ -840,8 +851,15 @@ def config4_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, tota
             gather = "all_gather_into_tensor inside the timed step (%s)" % type(e).__name__
     l0 = p.launch_count()
     ms, traj = device_cycles(torch, p, n, d_hdr, d_ox, d_oy, d_rec, episode, warmup, steps, after=after, before=before if gat is not None else None)
+    tail = 0.0
+    if gat is not None:                                      # the gathers still in flight belong to the timed work
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st_ = torch.cuda.current_stream()
+        e0.record(st_); gat.flush(stream=st_.cuda_stream); e1.record(st_)
+        torch.cuda.synchronize()
+        tail = e0.elapsed_time(e1)
     launches = p.launch_count() - l0
-    t = torch.tensor([ms.sum()], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms.sum() + tail], dtype=torch.float64, device=dev)
     tr = torch.tensor([float(traj)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.barrier()
