@@ -364,7 +364,7 @@ def run_ours(args, rank, world, local_rank):
         for i in range(LAT_N):
             c = i % EPISODE
             if c == 0:
-                planner.reset(0, SCENES)
+                planner.reset_dev(0, SCENES, stream=stream.cuda_stream)   # ON the launching stream: dp_reset runs on the context's own
             flush.zero_()
             lev[i][0].record(stream)
             planner.cycle_dev(SCENES, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_recs[0].data_ptr(), stream=stream.cuda_stream)

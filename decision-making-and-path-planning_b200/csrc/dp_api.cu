@@ -420,6 +420,16 @@ int dp_reset(dp_ctx* c, int first, int count) {
     return DP_OK;
 }
 
+int dp_reset_dev(dp_ctx* c, int first, int count, void* stream) {
+    if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_reset_dev: range");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_reset_dev: submitted cycles in flight, call dp_cycle_wait first");
+    c->chain_prev_epoch = 0;
+    CK(cudaSetDevice(c->device));
+    CK(dp_launch_reset(c->d_carry, c->d_last, first, count, (cudaStream_t)stream));
+    ++c->launches;
+    return DP_OK;
+}
+
 int dp_carry_download(dp_ctx* c, int first, int count, dp_carry* hc, double* hl) {
     if (!c || first < 0 || count < 0 || first + count > c->max_scenes) return fail(DP_ERR_ARG, "dp_carry_download: range");
     if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_carry_download: submitted cycles in flight, call dp_cycle_wait first");

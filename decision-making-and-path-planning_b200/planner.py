@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_here, "libdmpp_b200.so")
 
 # every symbol include/dmpp_b200.h declares (tests/test_abi.py checks the export table against the header)
 SYMBOLS = [
-    "dp_last_error", "dp_default_params", "dp_create", "dp_destroy", "dp_map_upload", "dp_reset",
+    "dp_last_error", "dp_default_params", "dp_create", "dp_destroy", "dp_map_upload", "dp_reset", "dp_reset_dev",
     "dp_carry_download", "dp_carry_upload", "dp_cycle_batch_dev", "dp_cycle_batch", "dp_host_alloc",
     "dp_host_free", "dp_score_candidates", "dp_search_obstacle", "dp_create_new_path", "dp_bezier_planning",
     "dp_mean_points", "dp_measure_fma_peak", "dp_launch_count", "dp_dev_alloc", "dp_dev_free",
@@ -91,6 +91,11 @@ class Planner:
     def reset(self, first=0, count=None):
         count = self.max_scenes - first if count is None else count
         _ck(self.lib.dp_reset(self.ctx, C.c_int(first), C.c_int(count)), "dp_reset")
+
+    def reset_dev(self, first=0, count=None, stream=0):
+        """stream-ordered reset for loops that launch cycle_dev on their own stream"""
+        count = self.max_scenes - first if count is None else count
+        _ck(self.lib.dp_reset_dev(self.ctx, C.c_int(first), C.c_int(count), C.c_void_p(stream)), "dp_reset_dev")
 
     def launch_count(self):
         return int(self.lib.dp_launch_count(self.ctx))

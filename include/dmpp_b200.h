@@ -165,8 +165,11 @@ int dp_destroy(dp_ctx* ctx);
 int dp_map_upload(dp_ctx* ctx, const dp_map_desc* map);
 
 /* reset the carry of scenes [first, first+count) to the constructor state
- * (Decision.cpp:8-29, Planning.cpp:8-11,62). */
+ * (Decision.cpp:8-29, Planning.cpp:8-11,62).  dp_reset runs on the context's own stream and returns when done: it is ordered
+ * with the host-pointer calls; cycles launched with dp_cycle_batch_dev on the CALLER's stream are not ordered with it -- use
+ * dp_reset_dev(stream) there (enqueued on that stream, asynchronous) or synchronise the stream first. */
 int dp_reset(dp_ctx* ctx, int first, int count);
+int dp_reset_dev(dp_ctx* ctx, int first, int count, void* stream);
 int dp_carry_download(dp_ctx* ctx, int first, int count, dp_carry* host_out, double* host_last_path);
 int dp_carry_upload(dp_ctx* ctx, int first, int count, const dp_carry* host_in, const double* host_last_path);
 

@@ -47,7 +47,7 @@ def main():
         for i in range(reps):
             c = i % ep_len
             if c == 0:
-                p.reset(0, n)
+                p.reset_dev(0, n, stream=st.cuda_stream)     # (ordered with the launches of this loop)
             flush.zero_()
             if name == "plain":
                 g.disarm()
