@@ -521,7 +521,7 @@ def run_ours(args, rank, world, local_rank):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
     try:   # DRAM bytes per launch of dp_cycle_kernel from the committed `ncu --set full` capture of tools/profile_cycle.py
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_r1.json")))["dp_cycle_kernel"]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_r2.json")))["dp_cycle_kernel"]["dram_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
     line = {

@@ -321,6 +321,35 @@ def test_reset_and_carry_roundtrip(planner, oracle, the_map):
         assert (o["rec"].tobytes() == full["rec"][c].tobytes())
 
 
+def test_reset_dev_is_ordered_with_the_callers_stream(planner, oracle, the_map):
+    """dp_reset_dev enqueues the reset on the caller's stream: back-to-back episodes launched without any host synchronisation
+    (the loop shape of bench.py's latency histogram) repeat the first episode bit for bit"""
+    import torch
+    from dmpp_b200 import scenes
+    n, cycles = 256, 8
+    ep = scenes.Episodes(the_map, np.arange(7000, 7000 + n), cycles=cycles, n_obs=10)
+    H, OX, OY = ep.all_cycles()
+    PX, PY = pad_obs(OX, OY, planner.max_obs)
+    dev = torch.device("cuda", 0)
+    d_hdr = torch.from_numpy(H.view(np.uint8).reshape(cycles, n, 128)).to(dev)
+    d_ox, d_oy = torch.from_numpy(PX).to(dev), torch.from_numpy(PY).to(dev)
+    d_rec = torch.empty((3, cycles, n, 128), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    torch.cuda.synchronize()
+    for e in range(3):
+        planner.reset_dev(0, n, stream=st.cuda_stream)
+        for c in range(cycles):
+            planner.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec[e, c].data_ptr(), stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    r = d_rec.cpu().numpy()
+    want = oracle.run(H, OX, OY, exhaustive=False, threads=4, paths=False, calls=False, trace=False)["rec"]
+    for e in range(3):
+        assert r[e].tobytes() == r[0].tobytes(), e
+    got = r[0].view(want.dtype).reshape(cycles, n)
+    for f in ("behavior", "n_traj", "sweep_index", "path_near_id", "afresh_planning"):
+        assert np.array_equal(got[f], want[f]), f
+
+
 def test_library_is_the_cuda_path(planner):
     """the calls above really launched kernels from libdmpp_b200.so"""
     assert planner.launch_count() > 100
