@@ -601,7 +601,6 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
         // Planning warp; the last Planning warp of the batch stores the epoch to page-locked host memory (dp_cycle_wait).
         const unsigned prev = (c->chain >= 2 && c->chain_prev_epoch && c->chain_first == first && c->chain_n == n) ? c->chain_prev_epoch : 0u;
         DpIo io = make_io(c, first, (dp_plan_record*)dv_rec);
-        CK(cudaMemsetAsync(c->d_tally + s, 0, sizeof(unsigned), c->cp[0]));
         CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
         CK(cudaMemcpyAsync(c->d_ox[s], ox, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[0]));
         CK(cudaMemcpyAsync(c->d_oy[s], oy, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[0]));

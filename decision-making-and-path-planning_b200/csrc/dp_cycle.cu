@@ -682,6 +682,9 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     // last_Bpoints (Planning.cpp:6) -> sm.plan by one TMA bulk copy; the staging area of the decision half is free now and
     // the copy lands while the aim point is searched
     __syncwarp();
+    // chained submits: the previous cycle's Planning warp of this scene wrote last_path with generic stores and may belong to a launch
+    // that is still running: order those writes (seen through the pdone acquire) before the async-proxy read of the bulk copy
+    if (PHASE == 2 && io.pdone) asm volatile("fence.proxy.async.global;" ::: "memory");
     dp_bulk_prefetch(sm.plan, lastp, DP_PATH_POINTS * (uint32_t)sizeof(double2), &sm.mbar, lane);
     const int plan_his_behavior = dp_l2(&cg->plan_his_behavior), carried_near_id = dp_l2(&cg->path_near_id), plan_count = dp_l2(&cg->plan_count);
     double aim_x = dp_l2(&cg->aim_x), aim_y = dp_l2(&cg->aim_y), aim_dir = dp_l2(&cg->aim_dir);
@@ -988,6 +991,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         if (lane == 0) {
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(io.pdone + scene), "r"(io.epoch) : "memory");
             if (io.host_done && atomicAdd(io.tally, 1u) == io.tally_n - 1u) {
+                *io.tally = 0;                              // re-armed here: a memset on the copy stream could run as a kernel and find no SM slot
                 __threadfence_system();                     // cumulative: everything the other warps fenced before their tally increment
 #pragma unroll
                 for (int k = 0; k < DP_MAX_MIRRORS; ++k)     // fused gather: this rank's slice of the step is complete on every rank

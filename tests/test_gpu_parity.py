@@ -432,6 +432,38 @@ def test_pipelined_submit_wait(planner, oracle, the_map):
         assert o["rec"].tobytes() == got[c].tobytes(), "cycle %d" % c
 
 
+@pytest.mark.parametrize("chain", ["0", "2"])
+def test_pipelined_submit_wait_chain_levels(oracle, the_map, monkeypatch, chain):
+    """the pipelined pair under the other DP_CHAIN levels (read by dp_create): 0 = stream events, 2 = the next cycle's Decision
+    launch as a programmatic dependent of the previous Planning launch with per-scene flags.  Same records as the oracle; level 2
+    also with 4096 scenes (one full wave: early Decision CTAs and the Planning launch compete for the slots)."""
+    import torch
+    from dmpp_b200 import abi, scenes
+    from dmpp_b200.planner import Planner
+    monkeypatch.setenv("DP_CHAIN", chain)
+    for n, cycles in ((512, 10), (4096, 6)) if chain == "2" else ((512, 10),):
+        p = Planner(n, 10)
+        p.upload_map(the_map)
+        ep = scenes.Episodes(the_map, np.arange(31000, 31000 + n), cycles=cycles, n_obs=10)
+        H, OX, OY = ep.all_cycles()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+        Hp = pin(H.view(np.uint8).reshape(cycles, n, 128)).view(abi.scene_hdr).reshape(cycles, n)
+        PXp, PYp = pin(OX), pin(OY)
+        recs = [torch.empty((n, 128), dtype=torch.uint8).pin_memory().numpy().view(abi.plan_record).reshape(n) for _ in range(2)]
+        p.reset(0, n)
+        got, pend = [], []
+        for c in range(cycles):
+            if len(pend) == 2:
+                p.wait(); got.append(recs[pend.pop(0) & 1].copy())
+            p.submit(Hp[c], PXp[c], PYp[c], recs[c & 1])
+            pend.append(c)
+        while pend:
+            p.wait(); got.append(recs[pend.pop(0) & 1].copy())
+        want = oracle.run(H, OX, OY, paths=False, calls=False, trace=False, exhaustive=False)
+        assert_records_equal(np.stack(got), want["rec"], REC_EXACT, close=DIR_ERR_TOL, what="pipelined, DP_CHAIN=%s, %d scenes" % (chain, n))
+        p.close()
+
+
 def test_record_mirrors(planner, the_map):
     """dp_set_record_mirrors: every finished record is also stored at base[k] + slot (the hook the multi-GPU gather uses
     with peer-mapped buffers); here two device buffers on the same GPU and a non-zero first slot."""
