@@ -64,6 +64,10 @@ struct dp_ctx {
     int zero_copy = 0;                                      // DP_ZERO_COPY=1: the kernels read pinned host inputs directly over PCIe (slower than the DMA route)
     // pipelined submit / wait: inputs of cycle k+1 cross PCIe on the copy stream while cycle k computes
     cudaStream_t cp[3] = {nullptr, nullptr, nullptr};       // one copy stream per input array: the three DMAs overlap
+    cudaStream_t cp_out = nullptr;                          // records device -> host by DMA behind the kernels of a pipelined submit
+    cudaEvent_t kdone[2] = {nullptr, nullptr};
+    int rec_dma = 0;                                        // DP_REC_DMA=1: records of dp_cycle_submit return by DMA behind the kernels instead of
+                                                            // stores from the Planning warps (measured slower with two cycles in flight: see profiles/README.md)
     cudaEvent_t in_ready[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}, done[2] = {nullptr, nullptr};
     unsigned long long submitted = 0, waited = 0;
     // overlapped split launch (split == 2): per-scene hand-off flags and the epoch of the next cycle
@@ -169,6 +173,7 @@ cudaError_t run_cycle(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, cons
 }  // namespace
 
 namespace {
+int cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec, bool dma);
 bool is_pinned(const void* p, void** dev = nullptr) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -329,6 +334,9 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
         CK(cudaEventCreateWithFlags(&c->done[s], cudaEventDisableTiming));
     }
     for (int k = 0; k < 3; ++k) CK(cudaStreamCreateWithFlags(&c->cp[k], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->cp_out, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) CK(cudaEventCreateWithFlags(&c->kdone[s], cudaEventDisableTiming));
+    if (const char* e = getenv("DP_REC_DMA")) c->rec_dma = atoi(e);
     *out = c;
     return dp_reset(c, 0, max_scenes);
 }
@@ -350,6 +358,8 @@ int dp_destroy(dp_ctx* c) {
         if (c->done[s]) cudaEventDestroy(c->done[s]);
     }
     for (int k = 0; k < 3; ++k) if (c->cp[k]) cudaStreamDestroy(c->cp[k]);
+    if (c->cp_out) cudaStreamDestroy(c->cp_out);
+    for (int s = 0; s < 2; ++s) if (c->kdone[s]) cudaEventDestroy(c->kdone[s]);
     delete c;
     return DP_OK;
 }
@@ -511,7 +521,7 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
     if (plain && pin_in && pin_rec && !c->zero_copy) {
         // Page-locked buffers: the pipelined machinery with one cycle in flight -- three overlapping input DMAs, the two
         // launches, and the Planning launch storing each finished 128-byte record straight into the caller's buffer.
-        int rs = dp_cycle_submit(c, first, n, hdr, ox, oy, rec);
+        int rs = cycle_submit(c, first, n, hdr, ox, oy, rec, false);   // one call in flight: the kernel stores the records itself
         if (rs != DP_OK) return rs;
         return dp_cycle_wait(c);
     }
@@ -562,7 +572,11 @@ int dp_cycle_batch(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const d
     return DP_OK;
 }
 
-int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec) {
+}  // extern "C"
+namespace {
+// dma: the records reach the caller's buffer by a device->host copy behind the kernels (pipelined use: it overlaps the next cycle);
+// otherwise the Planning warps store them there themselves (one call in flight: no copy in the tail of the call)
+int cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec, bool dma) {
     if (!c || !hdr || !ox || !oy || !rec || n < 0 || first < 0 || first + n > c->max_scenes || n > c->chunk)
         return fail(DP_ERR_ARG, "dp_cycle_submit: bad argument");
     if (!c->have_map) return fail(DP_ERR_STATE, "dp_cycle_submit: map not uploaded");
@@ -600,7 +614,7 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
         // four-byte copy that raises in_flag; the Decision warps wait for that flag, and per scene for the previous cycle's
         // Planning warp; the last Planning warp of the batch stores the epoch to page-locked host memory (dp_cycle_wait).
         const unsigned prev = (c->chain >= 2 && c->chain_prev_epoch && c->chain_first == first && c->chain_n == n) ? c->chain_prev_epoch : 0u;
-        DpIo io = make_io(c, first, (dp_plan_record*)dv_rec);
+        DpIo io = make_io(c, first, dma ? nullptr : (dp_plan_record*)dv_rec);
         CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
         CK(cudaMemcpyAsync(c->d_ox[s], ox, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[0]));
         CK(cudaMemcpyAsync(c->d_oy[s], oy, (size_t)n * mo * 8, cudaMemcpyHostToDevice, c->cp[0]));
@@ -612,9 +626,17 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
         CK(cudaHostGetDevicePointer(&dv_done, c->h_done, 0));
         io.in_flag = c->d_inflag + s;
         io.pdone = c->d_pdone + first; io.prev_epoch = prev;
-        io.tally = c->d_tally + s; io.tally_n = (unsigned)n; io.host_done = (unsigned*)dv_done + s;
+        if (!dma) { io.tally = c->d_tally + s; io.tally_n = (unsigned)n; io.host_done = (unsigned*)dv_done + s; }
         c->wait_epoch[s] = n > 0 ? io.epoch : 0u;
         CK(launch_warp(c, first, n, c->d_hdr[s], c->d_ox[s], c->d_oy[s], c->d_rec[s], nullptr, nullptr, nullptr, st, io));
+        if (dma) {
+            // behind the kernels, on its own stream: the records, then the completion word (the epoch the input copies left in
+            // d_inflag[s]) -- two DMAs that run beside the next cycle's kernels; dp_cycle_wait polls the same page-locked word
+            CK(cudaEventRecord(c->kdone[s], st));
+            CK(cudaStreamWaitEvent(c->cp_out, c->kdone[s], 0));
+            CK(cudaMemcpyAsync(rec, c->d_rec[s], (size_t)n * sizeof(dp_plan_record), cudaMemcpyDeviceToHost, c->cp_out));
+            CK(cudaMemcpyAsync(c->h_done + s, c->d_inflag + s, sizeof(unsigned), cudaMemcpyDeviceToHost, c->cp_out));
+        }
         c->chain_prev_epoch = io.epoch; c->chain_first = first; c->chain_n = n;
     } else {
         CK(cudaMemcpyAsync(c->d_hdr[s], hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyHostToDevice, c->cp[0]));
@@ -632,6 +654,11 @@ int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const 
     ++c->submitted;
     return DP_OK;
 }
+}  // namespace
+extern "C" {
+int dp_cycle_submit(dp_ctx* c, int first, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy, dp_plan_record* rec) {
+    return cycle_submit(c, first, n, hdr, ox, oy, rec, c && c->rec_dma != 0);
+}
 int dp_cycle_wait(dp_ctx* c) {
     if (!c) return fail(DP_ERR_ARG, "dp_cycle_wait: null context");
     if (c->submitted == c->waited) return fail(DP_ERR_STATE, "dp_cycle_wait: nothing in flight");
@@ -646,7 +673,11 @@ int dp_cycle_wait(dp_ctx* c) {
                 if ((spin & 0xfff) == 0xfff) {              // a kernel that trapped never raises the flag: ask the stream now and then
                     const cudaError_t q = cudaStreamQuery(c->st[0]);
                     if (q != cudaSuccess && q != cudaErrorNotReady) return fail(DP_ERR_CUDA, "dp_cycle_wait", q);
-                    if (q == cudaSuccess && *flag != want) return fail(DP_ERR_CUDA, "dp_cycle_wait: the stream drained without the completion flag");
+                    if (q == cudaSuccess) {                  // (the flag may still be on its way behind the record copy, on the output stream)
+                        const cudaError_t q2 = cudaStreamQuery(c->cp_out);
+                        if (q2 != cudaSuccess && q2 != cudaErrorNotReady) return fail(DP_ERR_CUDA, "dp_cycle_wait", q2);
+                        if (q2 == cudaSuccess && *flag != want) return fail(DP_ERR_CUDA, "dp_cycle_wait: the streams drained without the completion flag");
+                    }
                     if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) return fail(DP_ERR_CUDA, "dp_cycle_wait: timed out");
                 }
             }

@@ -990,14 +990,14 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         __syncwarp();
         if (lane == 0) {
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(io.pdone + scene), "r"(io.epoch) : "memory");
-            if (io.host_done && atomicAdd(io.tally, 1u) == io.tally_n - 1u) {
+            if (io.tally && atomicAdd(io.tally, 1u) == io.tally_n - 1u) {
                 *io.tally = 0;                              // re-armed here: a memset on the copy stream could run as a kernel and find no SM slot
                 __threadfence_system();                     // cumulative: everything the other warps fenced before their tally increment
 #pragma unroll
                 for (int k = 0; k < DP_MAX_MIRRORS; ++k)     // fused gather: this rank's slice of the step is complete on every rank
                     if (k < io.n_peer_flag && io.flag_mode == 0) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(io.peer_flag[k]), "r"(io.flag_value) : "memory");
                 dg_wait_flags(io.wait_flag, io.n_wait, io.wait_value);
-                *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
+                if (io.host_done) *reinterpret_cast<volatile unsigned*>(io.host_done) = io.epoch;
             }
         }
     }

@@ -212,7 +212,8 @@ int dp_cycle_batch(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scene_hd
  * path).  DP_CHAIN=2 additionally chains the launches: when two consecutive submits cover the same scene slots, the second
  * cycle's Decision launch becomes a programmatic dependent of the first one's Planning launch and waits scene by scene (it
  * starts while the other is still draining): measured 77.5 vs 78.5 us per step, not the default (tests/test_gpu_parity.py
- * runs the pipelined test under both).
+ * runs the pipelined test under both).  DP_REC_DMA=1 returns the records by a device->host copy behind the kernels instead of
+ * stores from the Planning warps (measured slower with two cycles in flight; under test as well).
  * dp_cycle_batch / dp_reset / dp_carry_* return DP_ERR_STATE while cycles are in flight. */
 int dp_cycle_submit(dp_ctx* ctx, int first_scene, int n_scenes, const dp_scene_hdr* hdr,
                     const double* obs_x, const double* obs_y, dp_plan_record* rec);

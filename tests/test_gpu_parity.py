@@ -432,7 +432,7 @@ def test_pipelined_submit_wait(planner, oracle, the_map):
         assert o["rec"].tobytes() == got[c].tobytes(), "cycle %d" % c
 
 
-@pytest.mark.parametrize("chain", ["0", "2"])
+@pytest.mark.parametrize("chain", ["0", "2", "dma"])
 def test_pipelined_submit_wait_chain_levels(oracle, the_map, monkeypatch, chain):
     """the pipelined pair under the other DP_CHAIN levels (read by dp_create): 0 = stream events, 2 = the next cycle's Decision
     launch as a programmatic dependent of the previous Planning launch with per-scene flags.  Same records as the oracle; level 2
@@ -440,8 +440,11 @@ def test_pipelined_submit_wait_chain_levels(oracle, the_map, monkeypatch, chain)
     import torch
     from dmpp_b200 import abi, scenes
     from dmpp_b200.planner import Planner
-    monkeypatch.setenv("DP_CHAIN", chain)
-    for n, cycles in ((512, 10), (4096, 6)) if chain == "2" else ((512, 10),):
+    if chain == "dma":                                       # default flags, records returned by a device->host copy behind the kernels
+        monkeypatch.setenv("DP_REC_DMA", "1")
+    else:
+        monkeypatch.setenv("DP_CHAIN", chain)
+    for n, cycles in ((512, 10), (4096, 6)) if chain != "0" else ((512, 10),):
         p = Planner(n, 10)
         p.upload_map(the_map)
         ep = scenes.Episodes(the_map, np.arange(31000, 31000 + n), cycles=cycles, n_obs=10)
