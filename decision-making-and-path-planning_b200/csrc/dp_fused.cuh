@@ -170,17 +170,31 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int u0, int cn
             r.dis_lat = __shfl_sync(DP_FULL, dlat, ci * N + ostar);
             const int gc = dp_sweep_g(u0 + ci, K);
             const double dcc = dp_sweep_offset(gc, K);
-            __syncwarp();
-            for (int j = lane; j < jstar; j += 32) {
-                const double2 a = dp_sweep_point(sm, j, dcc), b = dp_sweep_point(sm, j + 1, dcc);
-                sm.scr[j] = sqrt(dp_sq2(b.x - a.x, b.y - a.y));
+            // Only the `dis_lng > clear` decision is consumed unless a trace is kept.  The jstar segments of the shifted line
+            // are each between tl = hmin - |d| dn and th = hmax + |d| dn long (hmin / hmax carry a 1e-4 relative margin, far above
+            // the rounding of jstar <= 120 sequential additions), so jstar tl > clear or jstar th <= clear settles it without a sum;
+            // on a 0.5 m map with clear = 25 that leaves jstar = 50 for the exact evaluation
+            int decided = 0;                                // 1: passes, 2: fails
+            if (!need_all && hmax >= 0.f) {
+                const float adc = (float)fabs(dcc) * 1.0001f;
+                const float tl = hmin - adc * dn, th = hmax + adc * dn;
+                if (tl > 0.f && (double)jstar * (double)tl > clear) decided = 1;
+                else if ((double)jstar * (double)th <= clear) decided = 2;
             }
-            dp_pad_scr(sm, jstar, lane);
-            __syncwarp();
-            if (need_all) r.dis_lng = dp_seq_sum(sm, jstar, 0.0);
-            else {                                          // only the `dis_lng > clear` decision is needed: monotone partial sums
-                const SeqHit hq = dp_seq_first(sm, jstar, 0.0, 0.0, clear);
-                r.dis_lng = (hq.k >= 0) ? DP_NOT_FOUND : hq.acc;   // (value beyond the threshold is not consumed)
+            if (decided) r.dis_lng = (decided == 1) ? DP_NOT_FOUND : 0.0;   // (the value itself is not consumed)
+            else {
+                __syncwarp();
+                for (int j = lane; j < jstar; j += 32) {
+                    const double2 a = dp_sweep_point(sm, j, dcc), b = dp_sweep_point(sm, j + 1, dcc);
+                    sm.scr[j] = sqrt(dp_sq2(b.x - a.x, b.y - a.y));
+                }
+                dp_pad_scr(sm, jstar, lane);
+                __syncwarp();
+                if (need_all) r.dis_lng = dp_seq_sum(sm, jstar, 0.0);
+                else {                                      // monotone partial sums, stop at the first one beyond the threshold
+                    const SeqHit hq = dp_seq_first(sm, jstar, 0.0, 0.0, clear);
+                    r.dis_lng = (hq.k >= 0) ? DP_NOT_FOUND : hq.acc;   // (value beyond the threshold is not consumed)
+                }
             }
         }
         sink(dp_sweep_g(u0 + ci, K), r, first < 0);          // (candidate, result, scored by the reference too?)
