@@ -166,6 +166,10 @@ class Planner:
         _ck(self.lib.dp_cycle_submit(self.ctx, C.c_int(first), C.c_int(n), abi.ptr(hdr), abi.ptr(ox), abi.ptr(oy), abi.ptr(rec)),
             "dp_cycle_submit")
 
+    def submit_raw(self, first, n, hdr_ptr, ox_ptr, oy_ptr, rec_ptr):
+        """dp_cycle_submit with addresses the caller has resolved once (a replay loop re-submits the same pinned buffers)"""
+        _ck(self.lib.dp_cycle_submit(self.ctx, first, n, hdr_ptr, ox_ptr, oy_ptr, rec_ptr), "dp_cycle_submit")
+
     def wait(self):
         _ck(self.lib.dp_cycle_wait(self.ctx), "dp_cycle_wait")
 
