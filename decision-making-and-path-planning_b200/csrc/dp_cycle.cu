@@ -360,6 +360,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
         // ---- AroundObstacle (Decision.cpp:759-881): the four trajectories in ONE fused pass ----
         const int nslot = (side == 2) ? 4 : 2;
         double gF = 0.0, gNF = 0.0, gNR = 0.0;              // gaps stay 0 (memset state) for paths that are not evaluated
+        double bdF = 0.0;                                   // lane o < N: squared distance of obstacle o to its nearest point of F (avoid sweep)
         {
             const int rb[4] = {F.base, R.base, NF.base, NR.base}, rs[4] = {F.stride, R.stride, NF.stride, NR.stride};
             const int rP[4] = {F.P, R.P, NF.P, NR.P};
@@ -372,6 +373,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
             dg_bounds(m, gl, 0.0, -0.5 * Vw, 0.5 * Vw, &hbF, &dmF);
             dg_bounds(m, gn, NF.d, nlo, nhi, &hbN, &dmN);
             int qoff = 0;
+            bdF = __longlong_as_double(0x7ff0000000000000LL);
 #pragma unroll 1
             for (int r = 0; r < 4; ++r) {                   // one copy of the search code, four staged trajectories
                 const int Pr = (r == 0) ? F.P : (r == 1) ? R.P : (r == 2) ? NF.P : NR.P;
@@ -379,7 +381,7 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                     Src sp = dp_src_run(m.xy, 1, Pr);
                     sp.q_off = qoff;
                     const SearchRes sr = dp_search(sp, mx, my, ox, oy, N, lm, r < 2 ? -0.5 * Vw : nlo, r < 2 ? 0.5 * Vw : nhi, sm, lane,
-                                                   DP_PRUNE_REGION ? (r < 2 ? hbF : hbN) : 0.f, r < 2 ? dmF : dmN);
+                                                   DP_PRUNE_REGION ? (r < 2 ? hbF : hbN) : 0.f, r < 2 ? dmF : dmN, r == 0 ? &bdF : nullptr);
                     ++n_traj; pts += Pr;
                     put_slot(tr ? &tr->region[r < 2 ? r : nslot + r - 2] : nullptr, sr, 1, lane);
                     if (r == 0) gF = sr.dis_lng; else if (r == 2) gNF = sr.dis_lng; else if (r == 3) gNR = sr.dis_lng;
@@ -427,16 +429,34 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
                     if (shifted > 0 && N > 0 && N <= 16) {
                         dp_sweep_stage(m, sm, F.base, F.P, lane);
                         const float hmaxF = m.lane_hmax[gl], hminF = m.lane_hmin[gl], dnF = m.lane_dnmax[gl];
-                        const int per = min(8, 32 / N);
+                        // Which obstacles can matter to ANY candidate?  A point of a candidate is its point of F moved by |d| <= 0.3 (K-1),
+                        // so an obstacle is at least (its distance to F) - |d| away from every candidate, and it can only pass a corridor
+                        // test from within that candidate's reach (dg_dmax, growing with |d|).  The F region search has just measured the
+                        // distance of every obstacle to F: the few that remain are dealt out as (candidate, obstacle) lanes -- normally
+                        // all 2(K-1) candidates in ONE pass instead of 32 / N per pass.
+                        unsigned relmask = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+                        {
+                            const float adm = 0.3f * (float)(K - 1) * 1.0001f;
+                            const float hbm = hmaxF + adm * dnF + 1e-4f;
+                            const float dlt = (hminF > 1e-6f) ? dnF * (1.0f + 4.0f * adm / hminF) * 1.0001f + 1e-6f : 2.0f;
+                            const float dmm = dg_dmax(-0.5 * Vw, 0.5 * Vw, hbm, dlt, hminF - adm * dnF);
+                            const bool rel = lane < N && !(sqrt(bdF) - (double)adm > (double)dmm * 1.000001 + 1e-6);
+                            relmask &= __ballot_sync(DP_FULL, rel);
+                            if (relmask == 0u) relmask = 1u;        // nobody within reach: one obstacle stands in (it cannot produce a key either)
+                        }
+                        const int M = __popc(relmask);
+                        const int per = min(8, 32 / M);
+                        const int oid = (int)__fns(relmask, 0, lane % M + 1);   // this lane's obstacle: the (lane mod M)-th relevant one
+                        const double smx = __shfl_sync(DP_FULL, mx, oid), smy = __shfl_sync(DP_FULL, my, oid);
                         for (int u0 = 0; u0 < shifted && (sweep_pick < 0 || tr); u0 += per) {
                             const int cnt = min(per, shifted - u0);
                             const bool none_yet = sweep_pick < 0;
                             int first_g = -1;
-                            const int first = dp_sweep_pass(sm, F.P, u0, cnt, K, mx, my, N, lm, -0.5 * Vw, 0.5 * Vw, 25.0, tr != nullptr, lane,
+                            const int first = dp_sweep_pass(sm, F.P, u0, cnt, K, smx, smy, M, lm, -0.5 * Vw, 0.5 * Vw, 25.0, tr != nullptr, lane,
                                 [&](int g, const SearchRes& r, bool before_first) {
                                     if (before_first && r.dis_lng > 25) first_g = g;
                                     if (tr) put_slot(&tr->sweep[(g / K) * DP_MAX_SWEEP + (g % K)], r, (none_yet && before_first) ? 1 : 2, lane);
-                                }, DP_PRUNE_SWEEP ? hmaxF : -1.f, hminF, dnF);
+                                }, DP_PRUNE_SWEEP ? hmaxF : -1.f, hminF, dnF, oid, relmask);
                             if (sweep_pick < 0 && first >= 0) sweep_pick = first_g;
                         }
                     } else {

@@ -214,7 +214,10 @@ __device__ __forceinline__ void dp_bulk_wait(unsigned long long* mbar) {
 // min(best sample, dmax); an obstacle whose best point is farther than dmax cannot be in the corridor and is dropped.
 __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my, const double* __restrict__ ox,
                                                    const double* __restrict__ oy, int N, const LaneMap lm, double lo, double hi,
-                                                   WarpSmem& sm, int lane, const float hb = 0.f, const float dmax = 0.f) {
+                                                   WarpSmem& sm, int lane, const float hb = 0.f, const float dmax = 0.f,
+                                                   double* bd_out = nullptr) {
+    // bd_out (N < 32 only): lane o < N receives the squared distance from obstacle o to its nearest path point (+inf: none)
+    if (bd_out) *bd_out = __longlong_as_double(0x7ff0000000000000LL);
     SearchRes r;
     r.found = false; r.dis_lat = DP_NOT_FOUND; r.dis_lng = DP_NOT_FOUND; r.ob = -1; r.pathid = 0;
     const int P = s.n0 + s.n1;
@@ -295,6 +298,7 @@ __device__ __forceinline__ SearchRes dp_search(const Src s, double mx, double my
             const int oj = __shfl_sync(DP_FULL, bj, src);
             if (lane < N && od < bd) { bd = od; bj = oj; }
         }
+        if (bd_out && nchunk > 1) *bd_out = bd;
         const bool owner = ((nchunk == 1) ? active : (lane < N)) && (!prune || (bd < INF && dg_within_reach(bd, dmax)));
         if (owner) {
             const int k = (bj == P - 1) ? P - 2 : bj;

@@ -129,10 +129,13 @@ __device__ __forceinline__ double dp_sweep_offset(int g, int K) { return (g < K)
 template <class Sink>
 // hmax / hmin / dn: pruning bounds of F's lane (longest / shortest segment, largest change of normal); each lane derives the
 // bounds of ITS shifted candidate from them (dg_bounds) and runs the exactly pruned scan of dp_group.cuh.
+// relmask: the obstacles that can reach the corridor of ANY candidate (bit o), N = their number; lane (ci, r) scores candidate
+// u0 + ci against the r-th of them, whose position the caller has put into (mx, my) and whose index into oid -- an obstacle
+// left out can only produce the empty key, so the result is the one over all obstacles.
 __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int u0, int cnt, int K, double mx, double my, int N, const LaneMap lm,
                                              double lo, double hi, double clear, bool need_all, int lane, Sink sink,
-                                             const float hmax, const float hmin, const float dn) {
-    const int ci_me = lane / N, o = lane - ci_me * N;       // N <= 16 here
+                                             const float hmax, const float hmin, const float dn, const int oid, const unsigned relmask) {
+    const int ci_me = lane / N, o = oid;                    // N <= 16 here
     const bool active = ci_me < cnt;
     const int g_me = dp_sweep_g(u0 + ci_me, K);
     const double dc = dp_sweep_offset(g_me, K);
@@ -167,7 +170,7 @@ __device__ __forceinline__ int dp_sweep_pass(WarpSmem& sm, int P, int u0, int cn
         if (P >= 2 && gmin != 0xffffffffu) {
             const int jstar = (int)(gmin >> 16), ostar = (int)(gmin & 0xffffu);
             r.found = true; r.pathid = jstar; r.ob = ostar;
-            r.dis_lat = __shfl_sync(DP_FULL, dlat, ci * N + ostar);
+            r.dis_lat = __shfl_sync(DP_FULL, dlat, ci * N + __popc(relmask & ((1u << ostar) - 1u)));
             const int gc = dp_sweep_g(u0 + ci, K);
             const double dcc = dp_sweep_offset(gc, K);
             // Only the `dis_lng > clear` decision is consumed unless a trace is kept.  The jstar segments of the shifted line
