@@ -16,8 +16,19 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 K = 12
 m = scenes.Map(); ep = scenes.Episodes(m, np.arange(n), cycles=K, n_obs=10); H, OX, OY = ep.all_cycles()
 p = Planner(n, 10); p.upload_map(m)
-for c in range(K):
-    o = p.cycle(np.ascontiguousarray(H[c]), OX[c], OY[c])
+if os.environ.get("TL_DEV"):                                  # the bench's `value` path: device pointers, L2 flushed before every cycle
+    import torch
+    dev = torch.device("cuda", 0)
+    d_hdr = torch.from_numpy(H.view(np.uint8).reshape(K, n, 128)).to(dev); d_ox = torch.from_numpy(OX).to(dev); d_oy = torch.from_numpy(OY).to(dev)
+    d_rec = torch.empty((n, 128), dtype=torch.uint8, device=dev); flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    for c in range(K):
+        flush.fill_(c)
+        p.cycle_dev(n, d_hdr[c].data_ptr(), d_ox[c].data_ptr(), d_oy[c].data_ptr(), d_rec.data_ptr(), stream=st.cuda_stream)
+        torch.cuda.synchronize()
+else:
+    for c in range(K):
+        o = p.cycle(np.ascontiguousarray(H[c]), OX[c], OY[c])
 T2 = np.zeros((2, 65536, 2, 8), np.int64)
 lib = load()
 assert lib.dp_debug_scene_timeline(T2.ctypes.data_as(C.c_void_p), C.c_int(n)) == 0
