@@ -80,6 +80,22 @@ ref_call = np.dtype(
 )
 assert ref_call.itemsize == 48
 
+ctrl_frame = np.dtype(
+    [("cnt", "u1"), ("apa", "u1"), ("desacc_vd", "u1"), ("desstr_vd", "u1"), ("road_type", "u1"), ("sstop", "u1"), ("light", "<u2"),
+     ("brakedis", "<f8"), ("brake_speed", "<f8"), ("desacc", "<f8"), ("desspd", "<f8"), ("desstr", "<f8"), ("radius", "<f8"),
+     ("pnts", "<f8", (OUT_POINTS, 2))]
+)
+assert ctrl_frame.itemsize == 1656
+
+status_frame = np.dtype(
+    [("afresh_cause", "<i4"), ("trafficlight", "<u2"), ("reserved", "<u2"), ("near_ob_dist", "<f8"), ("planspeed", "<f8"),
+     ("planacc", "<f8"), ("path_points", "<f8", (OUT_POINTS, 2))]
+)
+assert status_frame.itemsize == 1632
+
+agent = np.dtype([("u", "<f8"), ("v", "<f8"), ("lat", "<f8"), ("lane", "<i4"), ("i", "<i4")])
+assert agent.itemsize == 32
+
 connector = np.dtype(
     [("last_road", "<u2"), ("next_road", "<u2"), ("last_lane", "<u2"), ("next_lane", "<u2"), ("lane", "<i4")]
 )
@@ -95,6 +111,11 @@ class Params(C.Structure):
         ("lat0", C.c_double), ("lng0", C.c_double), ("k_lat", C.c_double), ("k_lng", C.c_double),
         ("id_more", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class WorldParams(C.Structure):
+    _fields_ = [("a_max", C.c_double), ("loc_back", C.c_int32), ("loc_fwd", C.c_int32), ("end_margin", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class MapDesc(C.Structure):

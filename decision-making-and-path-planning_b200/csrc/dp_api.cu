@@ -60,6 +60,14 @@ struct dp_ctx {
     double* d_pxy[2] = {nullptr, nullptr};
     double* d_pll[2] = {nullptr, nullptr};
     long long launches = 0;
+    // closed-loop episodes (dp_run_closed_loop_dev): world-step parameters, the capture stream, the cached episode graph and its key
+    dp_world_params wp;
+    cudaStream_t ep_stream = nullptr;
+    cudaGraphExec_t ep_exec = nullptr;
+    const void* ep_key[8] = {}; int ep_dims[3] = {-1, -1, -1};
+    long long ep_launches = 0;
+    int ep_graph = 1;                                       // DP_EPISODE_GRAPH=0: enqueue the launches directly
+    int ep_last_graph = 0;
     int split = 1;                                          // Decision / Planning halves as two launches (DP_SPLIT=0: one fused launch)
     int zero_copy = 0;                                      // DP_ZERO_COPY=1: the kernels read pinned host inputs directly over PCIe (slower than the DMA route)
     // pipelined submit / wait: inputs of cycle k+1 cross PCIe on the copy stream while cycle k computes
@@ -294,6 +302,8 @@ int dp_create(dp_ctx** out, int device, const dp_params* params, int max_scenes,
     c->split = 2;
     if (const char* e = getenv("DP_SPLIT")) c->split = atoi(e);   // 0: one fused launch, 1: two launches back to back, 2: overlapped
     if (const char* e = getenv("DP_ZERO_COPY")) c->zero_copy = atoi(e) != 0;
+    if (const char* e = getenv("DP_EPISODE_GRAPH")) c->ep_graph = atoi(e) != 0;
+    dp_world_default_params(&c->wp);
     // Kernel choice, from the measurements in profiles/README.md (round 2): the warp-per-scene kernel wins while a scene's
     // obstacles fit one warp pass (N < 32: 71 vs 96 us per 4096-scene cycle at N = 10); the group kernel, whose scans are flat
     // (trajectory, obstacle) lists with exact pruning, wins for crowded scenes (N = 200: 135 vs 212 us per 1024 junction scenes).
@@ -346,6 +356,8 @@ int dp_destroy(dp_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void* p : c->map_allocs) cudaFree(p);
+    if (c->ep_exec) cudaGraphExecDestroy(c->ep_exec);
+    if (c->ep_stream) cudaStreamDestroy(c->ep_stream);
     cudaFree(c->d_timeline); cudaFree(c->d_trk);
     cudaFree(c->d_carry); cudaFree(c->d_last); cudaFree(c->d_done); cudaFree(c->d_pdone); cudaFree(c->d_inflag); cudaFree(c->d_tally); cudaFree(c->d_tally_g);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -1233,6 +1245,130 @@ int dp_measure_fma_peak(dp_ctx* c, double* fp64_tflops, double* fp32_tflops) {
     if (fp32_tflops) *fp32_tflops = out[1];
     return DP_OK;
 }
+
+// ---- (8) output stage ----
+int dp_pack_frames_dev(dp_ctx* c, int first, int n, const dp_plan_record* rec, dp_ctrl_frame* ctrl, dp_status_frame* status, void* stream) {
+    if (!c || !rec || n < 0 || first < 0 || first + n > c->max_scenes) return fail(DP_ERR_ARG, "dp_pack_frames_dev: bad argument");
+    CK(cudaSetDevice(c->device));
+    if (!ctrl && !status) return DP_OK;
+    c->launches += n > 0 ? 1 : 0;
+    CK(dp_launch_frames(c->p, n, rec, c->d_last + (size_t)first * DP_PATH_POINTS, ctrl, status, (cudaStream_t)stream));
+    return DP_OK;
+}
+int dp_pack_frames(dp_ctx* c, int first, int n, const dp_plan_record* rec, dp_ctrl_frame* ctrl, dp_status_frame* status) {
+    if (!c || !rec || n < 0 || first < 0 || first + n > c->max_scenes) return fail(DP_ERR_ARG, "dp_pack_frames: bad argument");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_pack_frames: submitted cycles in flight, call dp_cycle_wait first");
+    CK(cudaSetDevice(c->device));
+    if (n == 0 || (!ctrl && !status)) return DP_OK;
+    Tmp t;
+    cudaError_t e = cudaSuccess;
+    dp_plan_record* d_rec = t.put(rec, (size_t)n, e);
+    if (e != cudaSuccess) return fail(DP_ERR_CUDA, "dp_pack_frames: staging", e);
+    dp_ctrl_frame* d_c = ctrl ? t.put((const dp_ctrl_frame*)nullptr, (size_t)n, e) : nullptr;
+    if (e != cudaSuccess) return fail(DP_ERR_NOMEM, "dp_pack_frames: staging", e);
+    dp_status_frame* d_s = status ? t.put((const dp_status_frame*)nullptr, (size_t)n, e) : nullptr;
+    if (e != cudaSuccess) return fail(DP_ERR_NOMEM, "dp_pack_frames: staging", e);
+    cudaStream_t st = c->st[0];
+    c->launches += 1;
+    CK(dp_launch_frames(c->p, n, d_rec, c->d_last + (size_t)first * DP_PATH_POINTS, d_c, d_s, st));
+    if (ctrl) CK(cudaMemcpyAsync(ctrl, d_c, (size_t)n * sizeof(dp_ctrl_frame), cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, d_s, (size_t)n * sizeof(dp_status_frame), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DP_OK;
+}
+
+// ---- (9) closed-loop episodes ----
+void dp_world_default_params(dp_world_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->a_max = 3.0; p->loc_back = 8; p->loc_fwd = 56; p->end_margin = 160;
+}
+int dp_world_set_params(dp_ctx* c, const dp_world_params* p) {
+    if (!c || !p || !(p->a_max >= 0) || p->loc_back < 0 || p->loc_fwd < 0) return fail(DP_ERR_ARG, "dp_world_set_params: bad argument");
+    c->wp = *p;
+    if (c->ep_exec) { cudaGraphExecDestroy(c->ep_exec); c->ep_exec = nullptr; }   // (the parameters are baked into the graph's launches)
+    return DP_OK;
+}
+int dp_world_step_dev(dp_ctx* c, int first, int n, dp_scene_hdr* hdr, dp_agent* agents, double* ox, double* oy, const dp_plan_record* rec,
+                      void* stream) {
+    if (!c || !hdr || !agents || !ox || !oy || n < 0 || first < 0 || first + n > c->max_scenes)
+        return fail(DP_ERR_ARG, "dp_world_step_dev: bad argument");
+    if (!c->have_map) return fail(DP_ERR_STATE, "dp_world_step_dev: map not uploaded");
+    CK(cudaSetDevice(c->device));
+    c->launches += n > 0 ? 1 : 0;
+    CK(dp_launch_world(c->gmap, c->p, c->wp, n, c->max_obs, hdr, agents, ox, oy, rec, c->d_last + (size_t)first * DP_PATH_POINTS,
+                       (cudaStream_t)stream));
+    return DP_OK;
+}
+namespace {
+// the launches of one closed-loop episode, in order, on st (a capturing stream, or the caller's)
+cudaError_t enqueue_closed_loop(dp_ctx* c, int first, int n, int cycles, dp_scene_hdr* hdr, dp_agent* agents, double* ox, double* oy,
+                                dp_plan_record* rec, dp_scene_hdr* hdr_log, double* olx, double* oly, cudaStream_t st, bool rearm) {
+    const size_t mo = (size_t)c->max_obs;
+    const double2* last = c->d_last + (size_t)first * DP_PATH_POINTS;
+    cudaError_t e;
+    // a replayed graph re-uses its hand-off epochs: the per-scene Decision -> Planning flags start every replay from 0
+    if (rearm && (e = cudaMemsetAsync(c->d_done + first, 0, (size_t)n * sizeof(unsigned), st)) != cudaSuccess) return e;
+    c->launches += 1;
+    if ((e = dp_launch_world(c->gmap, c->p, c->wp, n, c->max_obs, hdr, agents, ox, oy, nullptr, last, st)) != cudaSuccess) return e;
+    for (int k = 0; k < cycles; ++k) {
+        if (hdr_log && (e = cudaMemcpyAsync(hdr_log + (size_t)k * n, hdr, (size_t)n * sizeof(dp_scene_hdr), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+        if (olx && (e = cudaMemcpyAsync(olx + (size_t)k * n * mo, ox, (size_t)n * mo * sizeof(double), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+        if (oly && (e = cudaMemcpyAsync(oly + (size_t)k * n * mo, oy, (size_t)n * mo * sizeof(double), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+        const DpIo io = make_io(c, first, nullptr);
+        if ((e = run_cycle(c, first, n, hdr, ox, oy, rec + (size_t)k * n, nullptr, nullptr, nullptr, st, io)) != cudaSuccess) return e;
+        c->launches += 1;
+        if ((e = dp_launch_world(c->gmap, c->p, c->wp, n, c->max_obs, hdr, agents, ox, oy, rec + (size_t)k * n, last, st)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+}  // namespace
+int dp_run_closed_loop_dev(dp_ctx* c, int first, int n, int cycles, dp_scene_hdr* hdr, dp_agent* agents, double* ox, double* oy,
+                           dp_plan_record* rec, dp_scene_hdr* hdr_log, double* olx, double* oly, void* stream) {
+    if (!c || !hdr || !agents || !ox || !oy || !rec || n < 0 || cycles < 0 || first < 0 || first + n > c->max_scenes)
+        return fail(DP_ERR_ARG, "dp_run_closed_loop_dev: bad argument");
+    if (!c->have_map) return fail(DP_ERR_STATE, "dp_run_closed_loop_dev: map not uploaded");
+    if (c->submitted != c->waited) return fail(DP_ERR_STATE, "dp_run_closed_loop_dev: submitted cycles in flight, call dp_cycle_wait first");
+    CK(cudaSetDevice(c->device));
+    c->ep_last_graph = 0;
+    if (n == 0) return DP_OK;
+    // the graph holds the warp-kernel launches of a plain context (no gather armed, no record mirrors, no predicted tracks)
+    const bool plain = c->kernel == 0 && c->tracks_T == 0 && !c->n_mirror && !c->n_peer_flag && !c->n_wait && !c->n_fwd;
+    if (c->ep_graph && plain) {
+        const void* key[8] = {hdr, agents, ox, oy, rec, hdr_log, olx, oly};
+        const int dims[3] = {first, n, cycles};
+        if (!c->ep_exec || memcmp(key, c->ep_key, sizeof(key)) != 0 || memcmp(dims, c->ep_dims, sizeof(dims)) != 0) {
+            if (c->ep_exec) { cudaGraphExecDestroy(c->ep_exec); c->ep_exec = nullptr; }
+            if (!c->ep_stream) CK(cudaStreamCreateWithFlags(&c->ep_stream, cudaStreamNonBlocking));
+            dp_launch_prepare(c->lc);                       // function attributes are set outside the capture
+            const long long before = c->launches;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(c->ep_stream, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                const cudaError_t e1 = enqueue_closed_loop(c, first, n, cycles, hdr, agents, ox, oy, rec, hdr_log, olx, oly, c->ep_stream, true);
+                e = cudaStreamEndCapture(c->ep_stream, &g);
+                if (e1 != cudaSuccess) e = e1;
+            }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&c->ep_exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            c->ep_launches = c->launches - before;
+            c->launches = before;
+            if (e != cudaSuccess) {                         // no graph on this driver / for these launches: enqueue them directly from now on
+                cudaGetLastError();
+                c->ep_exec = nullptr; c->ep_graph = 0;
+            } else { memcpy(c->ep_key, key, sizeof(key)); memcpy(c->ep_dims, dims, sizeof(dims)); }
+        }
+        if (c->ep_exec) {
+            CK(cudaGraphLaunch(c->ep_exec, (cudaStream_t)stream));
+            c->launches += c->ep_launches;
+            c->ep_last_graph = 1;
+            return DP_OK;
+        }
+    }
+    CK(enqueue_closed_loop(c, first, n, cycles, hdr, agents, ox, oy, rec, hdr_log, olx, oly, (cudaStream_t)stream, false));
+    return DP_OK;
+}
+int dp_closed_loop_is_graph(dp_ctx* c) { return c ? c->ep_last_graph : 0; }
 
 int64_t dp_launch_count(dp_ctx* c) { return c ? c->launches : 0; }
 

@@ -1116,18 +1116,20 @@ dp_group_kernel(DgMap m, dp_params p, int n_scenes, int g, const dp_scene_hdr* _
 }
 
 // ---- launchers (called from dp_api.cu) ----
+void dp_launch_prepare(DpLaunchCfg& lc) {
+    if (lc.attr_warp) return;                               // 196 of 256 KB as shared memory, the rest stays L1 (per context: no process-wide state)
+    cudaFuncSetAttribute(dp_cycle_kernel<0, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+    cudaFuncSetAttribute(dp_cycle_kernel<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+    cudaFuncSetAttribute(dp_cycle_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+    cudaFuncSetAttribute(dp_cycle_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+    cudaFuncSetAttribute(dp_cycle_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
+    lc.attr_warp = true;
+}
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
                             int max_obs, dp_carry* carry, double2* last_path, dp_plan_record* rec, dp_trace_record* trace,
                             double* path_xy, double* path_ll, cudaStream_t st, int split, const DpIo& io, DpLaunchCfg& lc) {
     if (n <= 0) return cudaSuccess;
-    if (!lc.attr_warp) {                                    // 196 of 256 KB as shared memory, the rest stays L1 (per context: no process-wide state)
-        cudaFuncSetAttribute(dp_cycle_kernel<0, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
-        cudaFuncSetAttribute(dp_cycle_kernel<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
-        cudaFuncSetAttribute(dp_cycle_kernel<2, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
-        cudaFuncSetAttribute(dp_cycle_kernel<1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
-        cudaFuncSetAttribute(dp_cycle_kernel<2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
-        lc.attr_warp = true;
-    }
+    dp_launch_prepare(lc);
     const int sm_count = lc.sm_count;
     if (!split) {
         DpIo io0 = io; io0.done = nullptr; io0.in_flag = nullptr; io0.pdone = nullptr; io0.prev_epoch = 0; io0.flag_mode = 0;

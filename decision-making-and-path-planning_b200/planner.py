@@ -24,6 +24,8 @@ SYMBOLS = [
     "dp_sweep_set_bezier", "dp_sweep_lines",
     "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev", "dp_debug_timeline",
     "dp_set_tracks", "dp_set_tracks_dev", "dp_clear_tracks",
+    "dp_pack_frames_dev", "dp_pack_frames", "dp_world_default_params", "dp_world_set_params", "dp_world_step_dev",
+    "dp_run_closed_loop_dev", "dp_closed_loop_is_graph",
     "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_chain", "dp_gather_arm_deferred", "dp_gather_set_lag", "dp_gather_flush", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
 ]
 
@@ -158,6 +160,80 @@ class Planner:
         """`cycles` chained cycles of n scenes, all buffers device pointers: hdr[cycles][n], obs[cycles][n][max_obs], rec[cycles][n]"""
         _ck(self.lib.dp_run_episode_dev(self.ctx, C.c_int(first), C.c_int(n), C.c_int(cycles), C.c_void_p(d_hdr), C.c_void_p(d_ox),
                                         C.c_void_p(d_oy), C.c_void_p(d_rec), C.c_void_p(stream)), "dp_run_episode_dev")
+
+    # ---- output stage: controller / status frames (include/dmpp_b200.h section 8) ----
+    def pack_frames(self, rec, first=0, ctrl=True, status=True):
+        """frames of the cycle that just ran for carry slots first ..: host records in, host frames out"""
+        rec = np.ascontiguousarray(rec)
+        n = rec.shape[0]
+        cf = np.zeros(n, abi.ctrl_frame) if ctrl else None
+        sf = np.zeros(n, abi.status_frame) if status else None
+        _ck(self.lib.dp_pack_frames(self.ctx, C.c_int(first), C.c_int(n), abi.ptr(rec), abi.ptr(cf), abi.ptr(sf)), "dp_pack_frames")
+        return cf, sf
+
+    def pack_frames_dev(self, n, d_rec, d_ctrl, d_status, first=0, stream=0):
+        _ck(self.lib.dp_pack_frames_dev(self.ctx, C.c_int(first), C.c_int(n), C.c_void_p(d_rec), C.c_void_p(d_ctrl or 0),
+                                        C.c_void_p(d_status or 0), C.c_void_p(stream)), "dp_pack_frames_dev")
+
+    # ---- closed-loop episodes (include/dmpp_b200.h section 9) ----
+    def world_params(self):
+        wp = abi.WorldParams()
+        self.lib.dp_world_default_params(C.byref(wp))
+        return wp
+
+    def set_world_params(self, wp):
+        _ck(self.lib.dp_world_set_params(self.ctx, C.byref(wp)), "dp_world_set_params")
+
+    def world_step_dev(self, n, d_hdr, d_agents, d_ox, d_oy, d_rec=None, first=0, stream=0):
+        _ck(self.lib.dp_world_step_dev(self.ctx, C.c_int(first), C.c_int(n), C.c_void_p(d_hdr), C.c_void_p(d_agents), C.c_void_p(d_ox),
+                                       C.c_void_p(d_oy), C.c_void_p(d_rec or 0), C.c_void_p(stream)), "dp_world_step_dev")
+
+    def run_closed_loop_dev(self, n, cycles, d_hdr, d_agents, d_ox, d_oy, d_rec, d_hdr_log=None, d_obs_log_x=None, d_obs_log_y=None,
+                            first=0, stream=0):
+        _ck(self.lib.dp_run_closed_loop_dev(self.ctx, C.c_int(first), C.c_int(n), C.c_int(cycles), C.c_void_p(d_hdr), C.c_void_p(d_agents),
+                                            C.c_void_p(d_ox), C.c_void_p(d_oy), C.c_void_p(d_rec), C.c_void_p(d_hdr_log or 0),
+                                            C.c_void_p(d_obs_log_x or 0), C.c_void_p(d_obs_log_y or 0), C.c_void_p(stream)),
+            "dp_run_closed_loop_dev")
+
+    def closed_loop_is_graph(self):
+        return bool(self.lib.dp_closed_loop_is_graph(self.ctx))
+
+    def run_closed_loop(self, hdr, agents, cycles, log=True, repeat=1):
+        """host arrays in, host arrays out (the same dictionary as oracle.binding's run_closed_loop); `repeat` > 1 replays the
+        episode from the same initial world (same device buffers, i.e. the cached graph) and returns the last run"""
+        n, mo = agents.shape
+        assert mo == self.max_obs and hdr.shape == (n,)
+        sizes = {"hdr": n * 128, "agents": n * mo * 32, "ox": n * mo * 8, "oy": n * mo * 8, "rec": cycles * n * 128,
+                 "hdr_log": cycles * n * 128, "obs_log_x": cycles * n * mo * 8, "obs_log_y": cycles * n * mo * 8}
+        d = {}
+        try:
+            for k, b in sizes.items():
+                if log or not k.endswith(("_log", "_log_x", "_log_y")):
+                    p = C.c_void_p()
+                    _ck(self.lib.dp_dev_alloc(self.ctx, C.byref(p), C.c_size_t(b)), "dp_dev_alloc")
+                    d[k] = p.value
+            h0, a0 = np.ascontiguousarray(hdr), np.ascontiguousarray(agents)
+            for _ in range(repeat):
+                self.reset(0, n)
+                _ck(self.lib.dp_memcpy_h2d(self.ctx, C.c_void_p(d["hdr"]), abi.ptr(h0), C.c_size_t(sizes["hdr"]), None), "h2d")
+                _ck(self.lib.dp_memcpy_h2d(self.ctx, C.c_void_p(d["agents"]), abi.ptr(a0), C.c_size_t(sizes["agents"]), None), "h2d")
+                _ck(self.lib.dp_stream_sync(self.ctx, None), "sync")
+                self.run_closed_loop_dev(n, cycles, d["hdr"], d["agents"], d["ox"], d["oy"], d["rec"], d.get("hdr_log"),
+                                         d.get("obs_log_x"), d.get("obs_log_y"))
+                _ck(self.lib.dp_stream_sync(self.ctx, None), "sync")
+            o = {"hdr": np.zeros(n, abi.scene_hdr), "agents": np.zeros((n, mo), abi.agent), "ox": np.zeros((n, mo)), "oy": np.zeros((n, mo)),
+                 "rec": np.zeros((cycles, n), abi.plan_record)}
+            if log:
+                o.update(hdr_log=np.zeros((cycles, n), abi.scene_hdr), obs_log_x=np.zeros((cycles, n, mo)), obs_log_y=np.zeros((cycles, n, mo)))
+            for k in o:
+                _ck(self.lib.dp_memcpy_d2h(self.ctx, abi.ptr(o[k]), C.c_void_p(d[k]), C.c_size_t(sizes[k]), None), "d2h")
+            _ck(self.lib.dp_stream_sync(self.ctx, None), "sync")
+            o["carry"], o["last_path"] = self.download_carry(0, n)
+            o["graph"] = self.closed_loop_is_graph()
+            return o
+        finally:
+            for p in d.values():
+                self.lib.dp_dev_free(self.ctx, C.c_void_p(p))
 
     # ---- pipelined form: at most two cycles in flight, buffers page-locked (see include/dmpp_b200.h) ----
     def submit(self, hdr, ox, oy, rec, first=0):

@@ -407,6 +407,30 @@ class Episodes:
         return H, OX, OY, VX, VY, DTH
 
 
+class World:
+    """Initial worlds for the closed-loop episode runner (include/dmpp_b200.h section 9): the scene drawn by
+    `Episodes(kind='highway')` at cycle 0 -- ego pose, speed, navigation slice -- plus one `dp_agent` per obstacle (lane, map
+    index, offset into the segment, speed, lateral offset).  From there on nothing is scripted: the library advances ego,
+    agents and localisation itself.  The cycle period is a whole number of milliseconds per scene, fixed over the episode."""
+
+    def __init__(self, m: Map, seeds, n_obs=10, roads=None):
+        ep = Episodes(m, seeds, n_obs=n_obs, kind="highway", cycles=1, roads=roads)
+        self.m, self.n, self.n_obs = m, ep.n, int(n_obs)
+        self.hdr = ep.hdr(0)
+        self.hdr["period_ms"] = ep.period_ticks(0).astype(np.float64)
+        a = np.zeros((self.n, self.n_obs), abi.agent)
+        gl = m.road_lane_base[ep.road - 1].astype(np.int64)[:, None] + ep.ob_lane - 1
+        cnt = (m.lane_pt_off[gl + 1] - m.lane_pt_off[gl]).astype(np.int64)
+        f = np.clip(ep.ob_s0 / SPACING, 0.0, cnt - 2.0)
+        i = np.floor(f).astype(np.int64)
+        a["lane"] = gl
+        a["i"] = i
+        a["u"] = (f - i) * SPACING
+        a["v"] = ep.ob_v
+        a["lat"] = ep.ob_lat
+        self.agents = np.ascontiguousarray(a)
+
+
 # streams of the directed families
 (D_FAM, D_LANE, D_ID, D_GAP, D_LAT, D_SPEED, D_NAV, D_STALL, D_YAW, D_PERIOD, D_OTHER_S, D_OTHER_L, D_MOVE, D_WOB) = range(100, 114)
 

@@ -351,6 +351,88 @@ int dp_set_tracks(dp_ctx* ctx, int first_scene, int n_scenes, int T, const doubl
 int dp_set_tracks_dev(dp_ctx* ctx, int T, const double* vx, const double* vy, const double* dtheta_deg);
 int dp_clear_tracks(dp_ctx* ctx);
 
+/* (8) Output stage: the two frames CPlanningThread publishes at the end of every cycle, packed on the
+ * device in a fixed little-endian layout (the reference's struct definitions are not in the reference; the field order
+ * follows its assignments, every reserved byte is zero).  The path samples come from the carried local path of the carry
+ * slot (= road_points of the cycle that just ran, Planning.cpp:217), so the call follows a cycle call in stream order and
+ * needs none of that call's optional path outputs. */
+typedef struct dp_ctrl_frame {       /* PlanningOut -> app->SetUdpSendCtrl (Planning.cpp:189-214) */
+    uint8_t cnt;                     /* count % 100                 :189 */
+    uint8_t apa;                     /* 0                           :190 */
+    uint8_t desacc_vd;               /* acc_flag                    :193 */
+    uint8_t desstr_vd;               /* false                       :197 */
+    uint8_t road_type;               /* 0                           :200 */
+    uint8_t sstop;                   /* TRUE                        :201 */
+    uint16_t light;                  /* DecisionOut.light           :198 */
+    double brakedis;                 /* mindist_lon                 :191 */
+    double brake_speed;              /* 0                           :192 */
+    double desacc;                   /* des_acc                     :194 */
+    double desspd;                   /* brakespeed                  :195 */
+    double desstr;                   /* 0                           :196 */
+    double radius;                   /* CalculateRadius()           :199 */
+    double pnts[DP_OUT_POINTS][2];   /* GlobalToWGS84(road_points[2 i]) as (lat, lng)  :203-212 */
+} dp_ctrl_frame;                     /* 1656 bytes */
+typedef struct dp_status_frame {     /* PlanningStatus -> app->SetPlanningStatus (Planning.cpp:173-186) */
+    int32_t afresh_cause;            /* :174 */
+    uint16_t trafficlight;           /* DecisionOut.light  :178 */
+    uint16_t reserved;
+    double near_ob_dist;             /* mindist_lon        :175 */
+    double planspeed;                /* brakespeed         :176 */
+    double planacc;                  /* des_acc            :177 */
+    double path_points[DP_OUT_POINTS][2];   /* road_points[2 i] as (x, y)  :180-183 */
+} dp_status_frame;                   /* 1632 bytes */
+/* rec[n_scenes] = the records of the cycle that just ran for carry slots first_scene ..; ctrl / status nullable.
+ * _dev: device pointers, asynchronous on `stream`; the other form takes host pointers and returns when the frames are valid. */
+int dp_pack_frames_dev(dp_ctx* ctx, int first_scene, int n_scenes, const dp_plan_record* rec, dp_ctrl_frame* ctrl,
+                       dp_status_frame* status, void* stream);
+int dp_pack_frames(dp_ctx* ctx, int first_scene, int n_scenes, const dp_plan_record* rec, dp_ctrl_frame* ctrl,
+                   dp_status_frame* status);
+
+/* (9) Closed-loop episodes: ego and agents advanced ON THE DEVICE between cycles, the carry (hysteresis
+ * counters Decision.cpp:915-917, carried path Planning.cpp:6, his_behavior / count Planning.cpp:216-223) never leaves HBM, and
+ * a whole episode is ONE CUDA graph launch.  The reference has no vehicle or traffic model (localisation, perception and
+ * control are other modules of its application); the world step below is this library's, its arithmetic is frozen in
+ * oracle/world_spec.h and the parity of this part is oracle-only by construction.  Segment driving (pos 0) only.
+ *
+ * world step of one scene, given the record of the cycle that just ran (rec == NULL: place the agents and localise only):
+ *   ego    target speed = rec.brakespeed [m/s, the unit of the planner's constants 3 / 10, Planning.cpp:888-990] * 3.6 km/h,
+ *          approached with |dv| <= a_max * dt; distance = mean speed * dt, walked along the carried local path from
+ *          rec.path_near_id (perfect tracking); heading = CalcGlobalDir of the segment it lands on; an ego whose lane index
+ *          is within end_margin points of the lane end stops;
+ *   agents agent k moves v[k] * dt along its lane (index i, offset u into segment i -> i+1), keeps its lateral offset `lat`
+ *          (LEFT positive) and stops at the lane end; its obstacle point is written to obs_x / obs_y;
+ *   localisation  hdr.id[l] = nearest point of lane l of the ego's road within [id[l] - loc_back, id[l] + loc_fwd]
+ *          (squared distance, strict '<'), hdr.lane_num = the lane with the smallest such distance (lowest lane on ties),
+ *          hdr.x / y / dir / velocity = the new ego state; everything else in the header is left as it is. */
+typedef struct dp_agent {
+    double u;                        /* metres into segment i -> i+1 */
+    double v;                        /* m/s along the lane */
+    double lat;                      /* lateral offset from the lane centre line, LEFT positive, metres */
+    int32_t lane;                    /* global lane index (road_lane_base[road - 1] + lane - 1) */
+    int32_t i;                       /* map point index within the lane */
+} dp_agent;                          /* 32 bytes; agents[n_scenes][max_obs], the first hdr.n_obs of a scene are used */
+typedef struct dp_world_params {
+    double a_max;                    /* m/s^2, default 3.0 (the planner's own braking command, Planning.cpp des_acc = -3) */
+    int32_t loc_back, loc_fwd;       /* localisation window in map points, default 8 / 56 */
+    int32_t end_margin;              /* default 160: the front region (120 points + ID_MORE) stays inside the lane */
+    int32_t reserved;
+} dp_world_params;
+void dp_world_default_params(dp_world_params* p);
+int dp_world_set_params(dp_ctx* ctx, const dp_world_params* p);
+/* one world step for carry slots first_scene ..: hdr, agents, obs_x, obs_y are updated in place (device pointers) */
+int dp_world_step_dev(dp_ctx* ctx, int first_scene, int n_scenes, dp_scene_hdr* hdr, dp_agent* agents, double* obs_x,
+                      double* obs_y, const dp_plan_record* rec, void* stream);
+/* `cycles` x (Decision + Planning cycle, world step) from the world in hdr / agents (placed and localised first), everything in
+ * HBM, enqueued on `stream` as one graph launch (the graph is built on the first call and reused while the arguments stay the
+ * same; DP_EPISODE_GRAPH=0 or a failed capture enqueues the same launches directly).  rec[cycles][n_scenes]; hdr_log
+ * (nullable) [cycles][n_scenes] and obs_log_x / obs_log_y (nullable) [cycles][n_scenes][max_obs] receive the inputs every
+ * cycle ran on -- replaying them through dp_run_episode_dev gives the same records.  hdr / agents / obs hold the final world. */
+int dp_run_closed_loop_dev(dp_ctx* ctx, int first_scene, int n_scenes, int cycles, dp_scene_hdr* hdr, dp_agent* agents,
+                           double* obs_x, double* obs_y, dp_plan_record* rec, dp_scene_hdr* hdr_log, double* obs_log_x,
+                           double* obs_log_y, void* stream);
+/* 1 when the last dp_run_closed_loop_dev call of this context was a graph launch, 0 when it enqueued the launches directly */
+int dp_closed_loop_is_graph(dp_ctx* ctx);
+
 /* diagnostic: phase time stamps (globaltimer, ns) of the most recent cycle launch, one row of 32 per CTA (row b = scenes
  * [b*g, (b+1)*g) of the batch; stamp 0 = CTA start, stamp i = end of phase i of csrc/dp_group.cuh).  Only contexts created
  * with DP_TIMELINE=1 in the environment record them; used by tools/group_timeline.py, never by the product path. */

@@ -46,6 +46,28 @@ class _Runner:
         return out
 
 
+def _closed_loop(lib, fn, params, wp, hdr, agents, cycles, paths, threads):
+    n, max_obs = agents.shape
+    o = {"hdr": hdr.copy(), "agents": agents.copy(), "ox": np.zeros((n, max_obs)), "oy": np.zeros((n, max_obs)),
+         "rec": np.zeros((cycles, n), abi.plan_record), "hdr_log": np.zeros((cycles, n), abi.scene_hdr),
+         "obs_log_x": np.zeros((cycles, n, max_obs)), "obs_log_y": np.zeros((cycles, n, max_obs)),
+         "path_xy": np.zeros((cycles, n, 2, abi.PATH_POINTS)) if paths else None,
+         "carry": np.zeros(n, abi.carry), "last_path": np.zeros((n, 2, abi.PATH_POINTS))}
+    args = [C.byref(params), C.byref(wp), C.c_int(n), C.c_int(cycles), C.c_int(max_obs), abi.ptr(o["hdr"]), abi.ptr(o["agents"]),
+            abi.ptr(o["ox"]), abi.ptr(o["oy"]), abi.ptr(o["rec"]), abi.ptr(o["hdr_log"]), abi.ptr(o["obs_log_x"]), abi.ptr(o["obs_log_y"]),
+            abi.ptr(o["path_xy"]), abi.ptr(o["carry"]), abi.ptr(o["last_path"])]
+    if threads is not None:
+        o["ub_scene"] = np.zeros(n, np.int32)
+        args += [C.c_int(threads), abi.ptr(o["ub_scene"])]
+    f = getattr(lib, fn)
+    f.restype = C.c_longlong if threads is not None else C.c_int
+    rc = f(*args)
+    if rc < 0:
+        raise RuntimeError("%s failed: %d" % (fn, rc))
+    o["status"] = rc
+    return o
+
+
 class Oracle(_Runner):
     """the restated oracle (liboracle.so): re-entrant, multi-threaded."""
 
@@ -105,6 +127,30 @@ class Oracle(_Runner):
         o["ub_hits"] = ub
         o["seconds"] = sec.value
         return o
+
+    # ---- closed-loop episodes and output frames (oracle/world_spec.h) ----
+    def world_params(self):
+        wp = abi.WorldParams()
+        self.lib.oracle_world_default_params(C.byref(wp))
+        return wp
+
+    def world_step(self, hdr, agents, ox, oy, rec=None, last_path=None, wp=None):
+        """in place; rec None: place the agents and localise only"""
+        wp = wp or self.world_params()
+        n, max_obs = ox.shape
+        assert self.lib.oracle_world_step(C.byref(self.params), C.byref(wp), C.c_int(n), C.c_int(max_obs), abi.ptr(hdr), abi.ptr(agents),
+                                          abi.ptr(ox), abi.ptr(oy), abi.ptr(rec), abi.ptr(last_path)) == 0
+
+    def run_closed_loop(self, hdr, agents, cycles, wp=None, paths=False, threads=1):
+        """hdr[n], agents[n][max_obs] (copied; the final world is returned)"""
+        return _closed_loop(self.lib, "oracle_run_closed_loop", self.params, wp or self.world_params(), hdr, agents, cycles, paths, threads)
+
+    def pack_frames(self, rec, path_xy):
+        n = rec.shape[0]
+        ctrl, status = np.zeros(n, abi.ctrl_frame), np.zeros(n, abi.status_frame)
+        self.lib.oracle_pack_frames(C.byref(self.params), C.c_int(n), abi.ptr(np.ascontiguousarray(rec)),
+                                    abi.ptr(np.ascontiguousarray(path_xy)), abi.ptr(ctrl), abi.ptr(status))
+        return ctrl, status
 
     def rollout_ctr(self, x0, y0, vx, vy, dth, T):
         ox, oy = np.zeros(T), np.zeros(T)
@@ -210,3 +256,19 @@ class Reference(_Runner):
         o["seconds"] = sec.value
         o["traj"] = traj.value
         return o
+
+    def run_with_frames(self, H, OX, OY):
+        """run() that also captures what the Planning thread hands to SetUdpSendCtrl / SetPlanningStatus every cycle"""
+        cycles, n = H.shape
+        ctrl, status = np.zeros((cycles, n), abi.ctrl_frame), np.zeros((cycles, n), abi.status_frame)
+        self.lib.ref_capture_frames(abi.ptr(ctrl), abi.ptr(status))
+        try:
+            o = self.run(H, OX, OY, paths=True, calls=False)
+        finally:
+            self.lib.ref_capture_frames(None, None)
+        o["ctrl"], o["status"] = ctrl, status
+        return o
+
+    def run_closed_loop(self, params, wp, hdr, agents, cycles, paths=False):
+        """closed-loop episodes of the unmodified reference with the world step of oracle/world_spec.cpp between its cycles"""
+        return _closed_loop(self.lib, "ref_run_closed_loop", params, wp, hdr, agents, cycles, paths, None)

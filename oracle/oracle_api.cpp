@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 #include "planner_oracle.h"
+#include "world_spec.h"
 
 namespace { oracle::MapView g_map; bool g_have_map = false; }
 
@@ -208,6 +209,76 @@ double oracle_lat_dis(double qx, double qy, double ax, double ay, double bx, dou
     return spec::lat_dis({qx, qy}, {ax, ay}, {bx, by}, 1e-6);
 }
 double oracle_calc_distance(double ax, double ay, double bx, double by) { return spec::calc_distance({ax, ay}, {bx, by}); }
+
+// ---- closed-loop episodes and output frames (world_spec.h) ----
+void oracle_world_default_params(dp_world_params* p) { oracle::world_default_params(p); }
+
+// one world step for n scenes from host arrays; rec nullable (place + localise only); last_path[n][2][200] (ignored when rec is null)
+int oracle_world_step(const dp_params* p, const dp_world_params* wp, int n, int max_obs, dp_scene_hdr* hdr, dp_agent* agents, double* ox,
+                      double* oy, const dp_plan_record* rec, const double* last_path) {
+    if (!g_have_map) return -1;
+    for (int s = 0; s < n; ++s)
+        oracle::world_step(g_map, *p, *wp, hdr[s], agents + (size_t)s * max_obs, ox + (size_t)s * max_obs, oy + (size_t)s * max_obs,
+                           rec ? rec + s : nullptr, last_path ? last_path + (size_t)s * 400 : nullptr,
+                           last_path ? last_path + (size_t)s * 400 + 200 : nullptr);
+    return 0;
+}
+
+// `cycles` x (cycle, world step) per scene from the world in hdr[n] / agents[n][max_obs] (updated in place, like ox / oy[n][max_obs]).
+// rec[cycles][n]; hdr_log[cycles][n], obs_log_[xy][cycles][n][max_obs], path_xy[cycles][n][2][200] nullable.
+long long oracle_run_closed_loop(const dp_params* p, const dp_world_params* wp, int n, int cycles, int max_obs, dp_scene_hdr* hdr,
+                                 dp_agent* agents, double* ox, double* oy, dp_plan_record* rec, dp_scene_hdr* hdr_log, double* obs_log_x,
+                                 double* obs_log_y, double* path_xy, dp_carry* carry_out, double* last_path_out, int threads,
+                                 int32_t* ub_scene /* nullable [n]: reference-UB sites hit by each scene */) {
+    if (!g_have_map) return -1;
+    if (threads < 1) threads = 1;
+    std::atomic<long long> ub(0);
+    auto work = [&](int s0, int s1) {
+        long long lub = 0;
+        for (int s = s0; s < s1; ++s) {
+            const long long lub0 = lub;
+            oracle::SceneState st;
+            oracle::reset_state(st);
+            dp_agent* ag = agents + (size_t)s * max_obs;
+            double* sx = ox + (size_t)s * max_obs; double* sy = oy + (size_t)s * max_obs;
+            oracle::world_step(g_map, *p, *wp, hdr[s], ag, sx, sy, nullptr, nullptr, nullptr);
+            for (int c = 0; c < cycles; ++c) {
+                const size_t e = (size_t)c * n + s;
+                if (hdr_log) hdr_log[e] = hdr[s];
+                if (obs_log_x) std::memcpy(obs_log_x + e * max_obs, sx, sizeof(double) * max_obs);
+                if (obs_log_y) std::memcpy(obs_log_y + e * max_obs, sy, sizeof(double) * max_obs);
+                oracle::CycleOut o{};
+                o.rec = rec + e;
+                o.path_xy = path_xy ? path_xy + e * 400 : nullptr;
+                oracle::cycle(g_map, *p, hdr[s], sx, sy, st, o, false);
+                lub += o.ub_hits;
+                oracle::world_step(g_map, *p, *wp, hdr[s], ag, sx, sy, rec + e, st.last_x, st.last_y);
+            }
+            if (ub_scene) ub_scene[s] = (int32_t)(lub - lub0);
+            if (carry_out) carry_out[s] = st.c;
+            if (last_path_out) {
+                std::memcpy(last_path_out + (size_t)s * 400, st.last_x, sizeof(st.last_x));
+                std::memcpy(last_path_out + (size_t)s * 400 + 200, st.last_y, sizeof(st.last_y));
+            }
+        }
+        ub += lub;
+    };
+    if (threads == 1) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; ++t) th.emplace_back(work, (int)((long long)n * t / threads), (int)((long long)n * (t + 1) / threads));
+        for (auto& t : th) t.join();
+    }
+    return ub.load();
+}
+
+// frames of n scenes: rec[n], path_xy[n][2][200] = road_points of the cycle; ctrl / status nullable
+void oracle_pack_frames(const dp_params* p, int n, const dp_plan_record* rec, const double* path_xy, dp_ctrl_frame* ctrl,
+                        dp_status_frame* status) {
+    for (int s = 0; s < n; ++s)
+        oracle::pack_frames(*p, rec[s], path_xy + (size_t)s * 400, path_xy + (size_t)s * 400 + 200, ctrl ? ctrl + s : nullptr,
+                            status ? status + s : nullptr);
+}
 int oracle_sizeof(int which) {
     switch (which) {
         case 0: return (int)sizeof(dp_scene_hdr);
@@ -217,6 +288,10 @@ int oracle_sizeof(int which) {
         case 4: return (int)sizeof(dp_trace_record);
         case 5: return (int)sizeof(dp_params);
         case 6: return (int)sizeof(dp_map_desc);
+        case 7: return (int)sizeof(dp_ctrl_frame);
+        case 8: return (int)sizeof(dp_status_frame);
+        case 9: return (int)sizeof(dp_agent);
+        case 10: return (int)sizeof(dp_world_params);
     }
     return -1;
 }

@@ -106,7 +106,40 @@ extern "C" long long g_search_calls;
 #endif
 
 // ---- map ------------------------------------------------------------------------------------------
+static dp_map_desc g_desc;
+extern "C" const dp_map_desc* ref_map_desc() { return &g_desc; }   // (the caller keeps the arrays alive)
+// capture of the frames the Planning thread publishes (ref_capture_frames), and a per-cycle hook (closed loop, ref_closed_loop.cpp)
+static dp_ctrl_frame* g_cap_ctrl = nullptr;
+static dp_status_frame* g_cap_status = nullptr;
+static dp_ctrl_frame* g_cap_ctrl_base = nullptr;
+static dp_status_frame* g_cap_status_base = nullptr;
+static long g_cap_stride = 0;
+static void (*g_hook)(int, void*) = nullptr;
+static void* g_hook_user = nullptr;
+extern "C" void ref_capture_frames(dp_ctrl_frame* ctrl, dp_status_frame* status) { g_cap_ctrl_base = ctrl; g_cap_status_base = status; }
+extern "C" void ref_set_cycle_hook(void (*fn)(int, void*), void* user) { g_hook = fn; g_hook_user = user; }
+extern "C" void ref_last_path(double* x, double* y) {
+    for (int i = 0; i < 200; ++i) { x[i] = CPlanning::last_Bpoints[i].x; y[i] = CPlanning::last_Bpoints[i].y; }
+}
+// the reference's own output objects, field by field, into the frame layout of include/dmpp_b200.h
+static void fill_frames(const PlanningOut& po, const PlanningStatus& ps, dp_ctrl_frame* cf, dp_status_frame* sf) {
+    if (cf) {
+        memset(cf, 0, sizeof(*cf));
+        cf->cnt = po.cnt; cf->apa = po.APA; cf->desacc_vd = po.desaccVd; cf->desstr_vd = po.desstrVd; cf->road_type = po.road_type;
+        cf->sstop = (uint8_t)po.sstop; cf->light = po.light; cf->brakedis = po.brakedis; cf->brake_speed = po.brake_speed;
+        cf->desacc = po.desacc; cf->desspd = po.desspd; cf->desstr = po.desstr; cf->radius = po.radius;
+        for (int i = 0; i < 100; ++i) { cf->pnts[i][0] = po.pnts[i].x; cf->pnts[i][1] = po.pnts[i].y; }
+    }
+    if (sf) {
+        memset(sf, 0, sizeof(*sf));
+        sf->afresh_cause = ps.afresh_cause; sf->trafficlight = ps.trafficlight; sf->near_ob_dist = ps.near_ob_dist;
+        sf->planspeed = ps.planspeed; sf->planacc = ps.planacc;
+        for (int i = 0; i < 100; ++i) { sf->path_points[i][0] = ps.path_points[i].x; sf->path_points[i][1] = ps.path_points[i].y; }
+    }
+}
+
 extern "C" int ref_set_map(const dp_map_desc* m) {
+    g_desc = *m;
     g_app.decision_MapData.clear();
     g_app.decision_MapData.resize(m->n_roads);
     for (int r = 0; r < m->n_roads; ++r) {
@@ -266,6 +299,9 @@ extern "C" int ref_run_episode(int cycles, const dp_scene_hdr* hdr, long hdr_str
             double* o = path_ll + c * path_ll_stride;
             for (int i = 0; i < 100; ++i) { o[i] = po.pnts[i].x; o[100 + i] = po.pnts[i].y; }
         }
+        fill_frames(po, g_app.out_status, g_cap_ctrl ? g_cap_ctrl + c * g_cap_stride : nullptr,
+                    g_cap_status ? g_cap_status + c * g_cap_stride : nullptr);
+        if (g_hook) g_hook(c, g_hook_user);   // may rewrite the inputs of the cycles that follow
     }
     if (carry_out) {
         CDecision& d = CDecision::Instance();
@@ -302,12 +338,16 @@ extern "C" long long ref_run_batch(int n, int cycles, int max_obs, const dp_scen
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int s = 0; s < n; ++s) {
+        g_cap_ctrl = g_cap_ctrl_base ? g_cap_ctrl_base + s : nullptr;
+        g_cap_status = g_cap_status_base ? g_cap_status_base + s : nullptr;
+        g_cap_stride = n;
         int rc = ref_run_episode(cycles, hdr + s, n, ox + (size_t)s * max_obs, oy + (size_t)s * max_obs, (long)n * max_obs,
                                  rec + s, n, path_xy ? path_xy + (size_t)s * 400 : nullptr, (long)n * 400,
                                  path_ll ? path_ll + (size_t)s * 200 : nullptr, (long)n * 200,
                                  calls ? calls + (size_t)s * calls_cap : nullptr, n_calls ? n_calls + s : nullptr, n,
                                  (long)n * calls_cap, calls_cap, carry_out ? carry_out + s : nullptr,
                                  last_path_out ? last_path_out + (size_t)s * 400 : nullptr);
+        g_cap_ctrl = nullptr; g_cap_status = nullptr;
         if (rc < 0) return rc;
         if (rc > worst) worst = rc;
     }
