@@ -506,6 +506,9 @@ def run_ours(args, rank, world, local_rank):
                 extras["config4"] = config4_line(torch, dist, P_, m, dev, rank, world, local_rank, 1048576)
                 extras["config3_split"] = config3_split_line(torch, dist, P_, m, dev, rank, world, local_rank)
             extras["config5"] = config5_line(torch, dist, P_, m, dev, rank, world, local_rank)
+            extras["closed_loop"] = closed_loop_line(torch, dist, P_, m, dev, rank, world, local_rank)
+            if world == 1:
+                extras["output_frames"] = frames_line(torch, P_, m, dev, local_rank)
         except Exception as e:  # noqa: BLE001
             extras["extras_error"] = repr(e)
     sampler.stop = True
@@ -950,6 +953,100 @@ def config5_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, n=10
                          "(SURVEY.md 8d), per GPU; the pruned search evaluates a fraction of the P x N pairs, so this is work done per second, "
                          "not FMA-pipe utilisation"},
             "tracks": "constant-turn-rate rollout fused into the search: T x N positions per scene exist only in registers"}
+
+
+def measured_hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback 6650 GB/s"
+
+
+def closed_loop_line(torch, dist, planner_cls, m, dev, rank, world, local_rank, n=4096, cycles=25, reps=10):
+    """closed-loop episodes.  Ego, agents and localisation are advanced on the device between cycles
+    (dp_world_kernel), the carry never leaves HBM, and a whole episode of `cycles` x (Decision + Planning launch pair, world step)
+    is ONE CUDA graph launch (dp_run_closed_loop_dev).  Weak scaling: n worlds per GPU, no exchange between ranks.  Warm L2 (the
+    episode is one launch: nothing can be flushed in between), CUDA events around the whole episode."""
+    w = scenes.World(m, np.arange(9_000_000 + rank * n, 9_000_000 + (rank + 1) * n), 10)
+    p = planner_cls(max_scenes=n, max_obs=10, device=local_rank)
+    p.upload_map(m)
+    h0 = torch.from_numpy(w.hdr.view(np.uint8).reshape(n, 128)).to(dev)
+    a0 = torch.from_numpy(w.agents.view(np.uint8).reshape(n, 320)).to(dev)
+    d_h, d_a = torch.empty_like(h0), torch.empty_like(a0)
+    d_x = torch.zeros((n, 10), dtype=torch.float64, device=dev); d_y = torch.zeros_like(d_x)
+    d_r = torch.zeros((cycles, n, 128), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    ms, traj = [], 0
+    l0 = p.launch_count()
+    for r in range(reps):
+        d_h.copy_(h0); d_a.copy_(a0)
+        p.reset_dev(0, n, stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        p.run_closed_loop_dev(n, cycles, d_h.data_ptr(), d_a.data_ptr(), d_x.data_ptr(), d_y.data_ptr(), d_r.data_ptr(), stream=st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        if r >= 3:
+            ms.append(e0.elapsed_time(e1))
+            traj += traj_of(torch, d_r.reshape(cycles * n, 128))
+    launches = p.launch_count() - l0
+    graph = p.closed_loop_is_graph()
+    p.close()
+    ms = np.array(ms)
+    t = torch.tensor([ms.sum()], dtype=torch.float64, device=dev)
+    tr = torch.tensor([float(traj)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+    secs = float(t.item()) * 1e-3
+    eps = len(ms)
+    return {"workload": "closed loop: %d worlds/GPU (the config-2 scene draw at cycle 0, then nothing scripted) x %d cycles; ego walked "
+                        "along its own plan, agents along their lanes, windowed re-localisation, all on the device" % (n, cycles),
+            "worlds_per_gpu": n, "cycles": cycles, "episodes_timed": eps, "one_graph_launch_per_episode": bool(graph),
+            "value": float(tr[0].item()) / secs, "unit": UNIT, "plan_cycles_per_s": n * world * cycles * eps / secs,
+            "ms_per_episode": secs / eps * 1e3, "us_per_cycle": secs / eps / cycles * 1e6, "p50_ms_per_episode": float(np.percentile(ms, 50)),
+            "gpu_launches": int(launches), "kernels_per_episode": 3 * cycles + 1, "scaling": "weak", "l2": "warm (one launch per episode)"}
+
+
+def frames_line(torch, planner_cls, m, dev, local_rank, n=131072, reps=20):
+    """the output stage.  dp_frames_kernel packs PlanningOut (1656 B) and PlanningStatus (1632 B) per scene
+    from the 128-byte plan record and the carried 3200-byte local path: byte work bound by HBM, measured against the copy peak
+    of MEASURED_PEAKS.json with a cold L2."""
+    ep = scenes.Episodes(m, np.arange(n), cycles=1, n_obs=10)
+    H, OX, OY = ep.all_cycles()
+    p = planner_cls(max_scenes=n, max_obs=10, device=local_rank)
+    p.upload_map(m)
+    d_h = torch.from_numpy(H[0].view(np.uint8).reshape(n, 128)).to(dev)
+    d_x, d_y = torch.from_numpy(OX[0]).to(dev), torch.from_numpy(OY[0]).to(dev)
+    d_r = torch.zeros((n, 128), dtype=torch.uint8, device=dev)
+    d_c = torch.zeros((n, abi.ctrl_frame.itemsize), dtype=torch.uint8, device=dev)
+    d_s = torch.zeros((n, abi.status_frame.itemsize), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    p.reset_dev(0, n, stream=st.cuda_stream)
+    p.cycle_dev(n, d_h.data_ptr(), d_x.data_ptr(), d_y.data_ptr(), d_r.data_ptr(), stream=st.cuda_stream)
+    ms = []
+    for r in range(reps):
+        flush.fill_(r & 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        p.pack_frames_dev(n, d_r.data_ptr(), d_c.data_ptr(), d_s.data_ptr(), stream=st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        if r >= 3:
+            ms.append(e0.elapsed_time(e1))
+    p.close()
+    peak, src = measured_hbm_peak()
+    t = float(np.median(ms)) * 1e-3
+    by = n * (128 + 3200 + abi.ctrl_frame.itemsize + abi.status_frame.itemsize)
+    return {"workload": "PlanningOut + PlanningStatus frames of %d scenes, one launch" % n, "scenes": n, "ms": t * 1e3,
+            "frames_per_s": 2 * n / t, "gpu_launches": reps,
+            "roofline": {"bound": "hbm", "kernel": "dp_frames_kernel", "unit": "GB/s", "achieved": by / t / 1e9, "peak": peak,
+                         "frac": by / t / 1e9 / peak, "algorithmic_bytes_per_launch": by, "peak_source": src,
+                         "note": "bytes = scenes x (128 record + 3200 carried path in, 1656 + 1632 frames out)"},
+            "l2": "256 MiB buffer written before every launch"}
 
 
 _OUT_FD = None
