@@ -96,6 +96,19 @@ assert status_frame.itemsize == 1632
 agent = np.dtype([("u", "<f8"), ("v", "<f8"), ("lat", "<f8"), ("lane", "<i4"), ("i", "<i4")])
 assert agent.itemsize == 32
 
+v2x_data = np.dtype(
+    [("ped_distance", "<f8"), ("ped_lat", "<f8"), ("ped_lng", "<f8"), ("rsi_lat", "<f8"), ("rsi_lng", "<f8"), ("ego_lat", "<f8"),
+     ("ego_lng", "<f8"), ("ped_direction", "<i4"), ("spat_lane_occupied", "<i4"), ("spat_state", "<i4"), ("warn_status", "<i4"),
+     ("wp_first", "<i4"), ("wp_count", "<i4")]
+)
+assert v2x_data.itemsize == 80
+
+v2x_flags = np.dtype(
+    [("light_flag", "<u2"), ("construction_flag", "u1"), ("pedestrian_flag", "u1"), ("ub", "u1"), ("pad", "u1", (3,)),
+     ("lng_distance", "<f8"), ("lat_distance", "<f8")]
+)
+assert v2x_flags.itemsize == 24
+
 connector = np.dtype(
     [("last_road", "<u2"), ("next_road", "<u2"), ("last_lane", "<u2"), ("next_lane", "<u2"), ("lane", "<i4")]
 )

@@ -1277,6 +1277,46 @@ int dp_pack_frames(dp_ctx* c, int first, int n, const dp_plan_record* rec, dp_ct
     return DP_OK;
 }
 
+// ---- (10) V2X event handlers ----
+int dp_v2x_event_batch_dev(dp_ctx* c, int n, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat, const double* wp_lng, int mode,
+                           dp_v2x_flags* out, void* stream) {
+    if (!c || !hdr || !v2x || !out || n < 0 || (mode != 0 && mode != 1)) return fail(DP_ERR_ARG, "dp_v2x_event_batch_dev: bad argument");
+    if (!c->have_map) return fail(DP_ERR_STATE, "dp_v2x_event_batch_dev: map not uploaded");
+    CK(cudaSetDevice(c->device));
+    c->launches += n > 0 ? 1 : 0;
+    CK(dp_launch_v2x(c->gmap, c->p, n, hdr, v2x, wp_lat, wp_lng, mode, out, (cudaStream_t)stream));
+    return DP_OK;
+}
+int dp_v2x_event_batch(dp_ctx* c, int n, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat, const double* wp_lng, int n_wp,
+                       int mode, dp_v2x_flags* out) {
+    if (!c || !hdr || !v2x || !out || n < 0 || n_wp < 0 || (n_wp > 0 && (!wp_lat || !wp_lng)) || (mode != 0 && mode != 1))
+        return fail(DP_ERR_ARG, "dp_v2x_event_batch: bad argument");
+    if (!c->have_map) return fail(DP_ERR_STATE, "dp_v2x_event_batch: map not uploaded");
+    for (int s = 0; s < n; ++s)                             // the slices must lie inside the list, and the ego inside the map tables
+        if (v2x[s].wp_count < 0 || (v2x[s].wp_count > 0 && (v2x[s].wp_first < 0 || v2x[s].wp_first + v2x[s].wp_count > n_wp)) ||
+            hdr[s].road_num < 1 || hdr[s].road_num > c->gmap.n_roads || hdr[s].lane_num < 1 || hdr[s].lane_num > DP_LANESUM)
+            return fail(DP_ERR_ARG, "dp_v2x_event_batch: scene header or warning-point slice out of range");
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return DP_OK;
+    Tmp t;
+    cudaError_t e = cudaSuccess;
+    dp_scene_hdr* d_h = t.put(hdr, (size_t)n, e);
+    if (e != cudaSuccess) return fail(DP_ERR_CUDA, "dp_v2x_event_batch: staging", e);
+    dp_v2x_data* d_v = t.put(v2x, (size_t)n, e);
+    if (e != cudaSuccess) return fail(DP_ERR_CUDA, "dp_v2x_event_batch: staging", e);
+    double* d_la = t.put(wp_lat, (size_t)n_wp, e);
+    if (e != cudaSuccess) return fail(DP_ERR_CUDA, "dp_v2x_event_batch: staging", e);
+    double* d_lo = t.put(wp_lng, (size_t)n_wp, e);
+    if (e != cudaSuccess) return fail(DP_ERR_CUDA, "dp_v2x_event_batch: staging", e);
+    dp_v2x_flags* d_o = t.put((const dp_v2x_flags*)nullptr, (size_t)n, e);
+    if (e != cudaSuccess) return fail(DP_ERR_NOMEM, "dp_v2x_event_batch: staging", e);
+    c->launches += 1;
+    CK(dp_launch_v2x(c->gmap, c->p, n, d_h, d_v, d_la, d_lo, mode, d_o, c->st[0]));
+    CK(cudaMemcpyAsync(out, d_o, (size_t)n * sizeof(dp_v2x_flags), cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+
 // ---- (9) closed-loop episodes ----
 void dp_world_default_params(dp_world_params* p) {
     if (!p) return;

@@ -431,6 +431,53 @@ class World:
         self.agents = np.ascontiguousarray(a)
 
 
+def v2x_events(m: Map, hdr, seed=0, p_far=0.12):
+    """Seeded V2X inputs for the scenes of `hdr` (highway headers): a pedestrian, a signal phase, a road-works event point and a
+    list of warning points per scene, placed relative to the ego's lane so that every branch of the handlers
+    (Decision.cpp:1824-2434) is reached: ahead of / behind the ego, left / right of / on its path, on the neighbour lanes,
+    beyond 100 m.  Returns (v2x[n] as abi.v2x_data, wp_lat, wp_lng); positions go through the equirectangular datum of the
+    default parameters."""
+    n = hdr.shape[0]
+    sd = np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(1000003)
+    lat0, lng0, k_lat, k_lng = 23.0, 113.0, 1.0 / 110574.0, 1.0 / 102470.0
+    lane = hdr["lane_num"].astype(np.int64)
+    gl = m.road_lane_base[hdr["road_num"].astype(np.int64) - 1].astype(np.int64) + lane - 1
+    off = m.lane_pt_off[gl].astype(np.int64)
+    cnt = (m.lane_pt_off[gl + 1] - m.lane_pt_off[gl]).astype(np.int64)
+    eid = np.take_along_axis(hdr["id"].astype(np.int64), (lane - 1)[:, None], axis=1)[:, 0]
+
+    def place(k, stream, lat_span):
+        """a point `ahead` map points in front of the ego (sometimes behind / far), `d` metres to the LEFT of its lane"""
+        ahead = (rnd(sd, stream, k) * 180.0).astype(np.int64) + 2
+        far = rnd(sd, stream + 1, k) < p_far
+        ahead = np.where(far, np.where(rnd(sd, stream + 2, k) < 0.5, -30, 260), ahead)
+        i = np.clip(eid + ahead, 0, cnt - 2)
+        d = (rnd(sd, stream + 3, k) - 0.45) * lat_span
+        x0, y0 = m.x[off + i], m.y[off + i]
+        hr = np.radians(m.dir[off + i])
+        x, y = x0 - d * np.sin(hr), y0 + d * np.cos(hr)
+        return lat0 + y * k_lat, lng0 + x * k_lng
+
+    v = np.zeros(n, abi.v2x_data)
+    v["warn_status"] = np.array([3, 4, 5, 4, 5, 0, 4, 5])[(rnd(sd, 200) * 8).astype(np.int64)]
+    v["ped_lat"], v["ped_lng"] = place(0, 210, 14.0)
+    v["ped_distance"] = -10.0 + rnd(sd, 201) * 125.0
+    v["ped_direction"] = (rnd(sd, 202) < 0.3).astype(np.int32)
+    v["spat_lane_occupied"] = (rnd(sd, 203) < 0.7).astype(np.int32)
+    v["spat_state"] = np.array([3, 6, 7, 1, 0])[(rnd(sd, 204) * 5).astype(np.int64)]
+    v["rsi_lat"], v["rsi_lng"] = place(1, 220, 9.0)
+    none = rnd(sd, 205) < 0.1
+    v["rsi_lat"] = np.where(none, 0.0, v["rsi_lat"])
+    v["ego_lat"], v["ego_lng"] = lat0 + hdr["y"] * k_lat, lng0 + hdr["x"] * k_lng
+    cntw = (rnd(sd, 206) * 6).astype(np.int64)
+    v["wp_count"] = cntw
+    v["wp_first"] = np.concatenate([[0], np.cumsum(cntw)[:-1]])
+    cols = [place(10 + k, 230, 5.0) for k in range(6)]         # entry k of every scene's list; kept where k < its count
+    la, lo = np.stack([c[0] for c in cols], axis=1), np.stack([c[1] for c in cols], axis=1)
+    keep = np.arange(6)[None, :] < cntw[:, None]
+    return v, np.ascontiguousarray(la[keep]), np.ascontiguousarray(lo[keep])
+
+
 # streams of the directed families
 (D_FAM, D_LANE, D_ID, D_GAP, D_LAT, D_SPEED, D_NAV, D_STALL, D_YAW, D_PERIOD, D_OTHER_S, D_OTHER_L, D_MOVE, D_WOB) = range(100, 114)
 

@@ -433,6 +433,37 @@ int dp_run_closed_loop_dev(dp_ctx* ctx, int first_scene, int n_scenes, int cycle
 /* 1 when the last dp_run_closed_loop_dev call of this context was a graph launch, 0 when it enqueued the launches directly */
 int dp_closed_loop_is_graph(dp_ctx* ctx);
 
+/* (10) V2X event handlers (Decision.cpp:1824-2434).  The reference evaluates them every segment cycle
+ * (V2XEventDecision, Decision.cpp:283) and then discards the three flags; here they are a batch operator next to the cycle, one
+ * warp per scene, with every quirk of the handlers kept (see oracle/v2x_oracle.cpp, which is pinned to the unmodified
+ * reference's own private methods).  What a caller does with the flags is its business, as in the reference. */
+typedef struct dp_v2x_data {         /* V2X_Data as the handlers read it + LocationOut.gpspoint + this scene's slice of the warning list */
+    double ped_distance, ped_lat, ped_lng;     /* PedesDistance / PedesLatitude / PedesLongitude  Decision.cpp:1859-1861 */
+    double rsi_lat, rsi_lng;                   /* RSILatitude / RSILongitude                       :2038, :2262 */
+    double ego_lat, ego_lng;                   /* LocationOut.gpspoint                             :2257-2258 */
+    int32_t ped_direction;                     /* PedesDirection    :1862 */
+    int32_t spat_lane_occupied, spat_state;    /* SPATLaneOccupied / SPATState  :1979-1980 */
+    int32_t warn_status;                       /* V2XWarnStatus: 3 signal, 4 road works, 5 pedestrian  :2149-2161 */
+    int32_t wp_first, wp_count;                /* z_RSIWarningPointList = wp_lat / wp_lng[wp_first .. wp_first + wp_count) */
+} dp_v2x_data;                       /* 80 bytes */
+typedef struct dp_v2x_flags {
+    uint16_t light_flag;             /* V2XLight_flag: 0 none, 1 red / yellow, 2 green   Decision.cpp:1984-1995 */
+    uint8_t construction_flag;       /* :2124-2137, :2407-2425 */
+    uint8_t pedestrian_flag;         /* :1935-1961 */
+    uint8_t ub;                      /* the handler would have read its path vector out of bounds (empty path, nearest point = last point):
+                                        the flags are then all 0 */
+    uint8_t pad[3];
+    double lng_distance;             /* pedestrian: lng_distance; road works: min_distance_construction (9999 when not computed) */
+    double lat_distance;             /* pedestrian: lat_distance; road works: near_lat_distance         (9999 when not computed) */
+} dp_v2x_flags;                      /* 24 bytes */
+/* mode 0: V2XEventDecision as the reference calls it (status 4 -> V2XConstructionEvent); mode 1: status 4 ->
+ * V2XConstructionEventTemporal (the alternative commented out at Decision.cpp:2156).  hdr[n] is the cycle's scene header
+ * (road, lane, per-lane ids); wp_lat / wp_lng[n_wp] may be NULL when n_wp is 0.  Host pointers; _dev: device pointers, asynchronous. */
+int dp_v2x_event_batch(dp_ctx* ctx, int n_scenes, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat,
+                       const double* wp_lng, int n_wp, int mode, dp_v2x_flags* out);
+int dp_v2x_event_batch_dev(dp_ctx* ctx, int n_scenes, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat,
+                           const double* wp_lng, int mode, dp_v2x_flags* out, void* stream);
+
 /* diagnostic: phase time stamps (globaltimer, ns) of the most recent cycle launch, one row of 32 per CTA (row b = scenes
  * [b*g, (b+1)*g) of the batch; stamp 0 = CTA start, stamp i = end of phase i of csrc/dp_group.cuh).  Only contexts created
  * with DP_TIMELINE=1 in the environment record them; used by tools/group_timeline.py, never by the product path. */

@@ -68,6 +68,17 @@ def _closed_loop(lib, fn, params, wp, hdr, agents, cycles, paths, threads):
     return o
 
 
+def _v2x(fn, head, hdr, v2x, wp_lat, wp_lng, mode):
+    n = hdr.shape[0]
+    out = np.zeros(n, abi.v2x_flags)
+    wl, wg = np.ascontiguousarray(wp_lat, np.float64), np.ascontiguousarray(wp_lng, np.float64)
+    rc = fn(*head, C.c_int(n), abi.ptr(np.ascontiguousarray(hdr)), abi.ptr(np.ascontiguousarray(v2x)), abi.ptr(wl), abi.ptr(wg),
+            C.c_int(mode), abi.ptr(out))
+    if rc != 0:
+        raise RuntimeError("v2x_event failed: %d" % rc)
+    return out
+
+
 class Oracle(_Runner):
     """the restated oracle (liboracle.so): re-entrant, multi-threaded."""
 
@@ -151,6 +162,9 @@ class Oracle(_Runner):
         self.lib.oracle_pack_frames(C.byref(self.params), C.c_int(n), abi.ptr(np.ascontiguousarray(rec)),
                                     abi.ptr(np.ascontiguousarray(path_xy)), abi.ptr(ctrl), abi.ptr(status))
         return ctrl, status
+
+    def v2x_event(self, hdr, v2x, wp_lat, wp_lng, mode=0):
+        return _v2x(self.lib.oracle_v2x_event, [C.byref(self.params)], hdr, v2x, wp_lat, wp_lng, mode)
 
     def rollout_ctr(self, x0, y0, vx, vy, dth, T):
         ox, oy = np.zeros(T), np.zeros(T)
@@ -268,6 +282,10 @@ class Reference(_Runner):
             self.lib.ref_capture_frames(None, None)
         o["ctrl"], o["status"] = ctrl, status
         return o
+
+    def v2x_event(self, hdr, v2x, wp_lat, wp_lng, mode=0):
+        """the reference's own V2XEventDecision / V2XConstructionEventTemporal, one call per scene (only the flags are observable)"""
+        return _v2x(self.lib.ref_v2x_event, [], hdr, v2x, wp_lat, wp_lng, mode)
 
     def run_closed_loop(self, params, wp, hdr, agents, cycles, paths=False):
         """closed-loop episodes of the unmodified reference with the world step of oracle/world_spec.cpp between its cycles"""

@@ -9,6 +9,7 @@
 #include <vector>
 #include "planner_oracle.h"
 #include "world_spec.h"
+#include "v2x_oracle.h"
 
 namespace { oracle::MapView g_map; bool g_have_map = false; }
 
@@ -279,6 +280,13 @@ void oracle_pack_frames(const dp_params* p, int n, const dp_plan_record* rec, co
         oracle::pack_frames(*p, rec[s], path_xy + (size_t)s * 400, path_xy + (size_t)s * 400 + 200, ctrl ? ctrl + s : nullptr,
                             status ? status + s : nullptr);
 }
+// V2X event handlers of n scenes (v2x_oracle.h)
+int oracle_v2x_event(const dp_params* p, int n, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat, const double* wp_lng,
+                     int mode, dp_v2x_flags* out) {
+    if (!g_have_map) return -1;
+    for (int s = 0; s < n; ++s) oracle::v2x_event(g_map, *p, hdr[s], v2x[s], wp_lat, wp_lng, mode, out + s);
+    return 0;
+}
 int oracle_sizeof(int which) {
     switch (which) {
         case 0: return (int)sizeof(dp_scene_hdr);
@@ -292,6 +300,8 @@ int oracle_sizeof(int which) {
         case 8: return (int)sizeof(dp_status_frame);
         case 9: return (int)sizeof(dp_agent);
         case 10: return (int)sizeof(dp_world_params);
+        case 11: return (int)sizeof(dp_v2x_data);
+        case 12: return (int)sizeof(dp_v2x_flags);
     }
     return -1;
 }

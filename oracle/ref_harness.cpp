@@ -326,6 +326,39 @@ extern "C" int ref_run_episode(int cycles, const dp_scene_hdr* hdr, long hdr_str
     return g_msgbox ? 1 : 0;
 }
 
+// ---- the V2X handlers of the unmodified reference, called as SegmentDecision calls them (Decision.cpp:251-283): fresh flags,
+// empty path vectors; mode 1 routes status 4 to V2XConstructionEventTemporal (the alternative commented out at :2156) ----
+extern "C" int ref_v2x_event(int n, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat, const double* wp_lng, int mode,
+                             dp_v2x_flags* out) {
+    CDecision& d = CDecision::Instance();
+    for (int s = 0; s < n; ++s) {
+        const dp_scene_hdr& h = hdr[s];
+        const dp_v2x_data& v = v2x[s];
+        LocationOut lo;
+        memset(&lo, 0, sizeof(lo));
+        lo.globalpoint.x = h.x; lo.globalpoint.y = h.y; lo.globalpoint.dir = h.dir;
+        lo.gpspoint.lat = v.ego_lat; lo.gpspoint.lng = v.ego_lng;
+        for (int i = 0; i < LANESUM; ++i) lo.id[i] = h.id[i];
+        lo.lane_num = h.lane_num; lo.road_num = h.road_num; lo.pos = (BYTE)h.pos;
+        V2X_Data x;
+        memset(&x, 0, sizeof(x));
+        x.PedesDistance = v.ped_distance; x.PedesLatitude = v.ped_lat; x.PedesLongitude = v.ped_lng; x.PedesDirection = v.ped_direction;
+        x.SPATLaneOccupied = v.spat_lane_occupied; x.SPATState = v.spat_state; x.RSILatitude = v.rsi_lat; x.RSILongitude = v.rsi_lng;
+        x.V2XWarnStatus = v.warn_status;
+        vector<WarningPoint> list;
+        for (int k = 0; k < v.wp_count; ++k) { WarningPoint w; w.latitude = wp_lat[v.wp_first + k]; w.longitude = wp_lng[v.wp_first + k]; list.push_back(w); }
+        bool pedestrian_flag = false, construction_flag = false;
+        WORD light = 0;
+        vector<GlobalPoint2D> f, lf, rf;
+        if (mode == 1 && v.warn_status == 4) d.V2XConstructionEventTemporal(lo, x, list, f, lf, rf, construction_flag);
+        else d.V2XEventDecision(lo, x, list, f, lf, rf, pedestrian_flag, light, construction_flag);
+        memset(&out[s], 0, sizeof(out[s]));
+        out[s].light_flag = light; out[s].construction_flag = construction_flag; out[s].pedestrian_flag = pedestrian_flag;
+        out[s].lng_distance = 9999; out[s].lat_distance = 9999;   // (locals of the handlers: not observable)
+    }
+    return 0;
+}
+
 // Batch form with the [cycle][scene] layout shared with liboracle.so and the CUDA path.
 // Scenes run sequentially on ONE thread: the reference is not re-entrant (function statics
 // Decision.cpp:915-917, static last_Bpoints Planning.cpp:6).  *seconds covers the whole loop.
