@@ -920,8 +920,8 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     rem.q_off = s0;
     // pruning bounds of the local path (FP32, rounded outwards): longest / shortest segment, largest difference of consecutive
     // segment vectors (|u/|u| - w/|w|| <= |u - w| / hmin bounds the change of direction)
-    float hbL, dmL;
-    {
+    float hbL = 0.f, dmL = 0.f;
+    if (DP_PRUNE_LOCAL) {                                   // (the warp reductions below are never dead code to the compiler: keep them out when unused)
         float hmx = 0.f, hmn = __int_as_float(0x7f800000), dmx = 0.f;
         for (int j = s0 + lane; j < DP_PATH_POINTS - 1; j += 32) {
             const double2 a = sm.plan[j], b = sm.plan[j + 1];

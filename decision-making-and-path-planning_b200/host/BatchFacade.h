@@ -38,6 +38,20 @@ public:
         if (!decision_started_ || !planning_started_) throw std::runtime_error("CBatchApp::Cycle: start both threads first");
         batch_->Cycle(0, n, hdr, obs_x, obs_y, rec_.data());
         n_ = n;
+        if (publish_frames_) {                               // app->SetPlanningStatus / app->SetUdpSendCtrl (Planning.cpp:186, :214)
+            ctrl_.resize((size_t)n); status_.resize((size_t)n);
+            batch_->PackFrames(0, n, rec_.data(), ctrl_.data(), status_.data());
+        }
+    }
+    // what the reference hands to the controller link and to the debug UI at the end of every Planning cycle
+    void PublishFrames(bool on) { publish_frames_ = on; }
+    const dp_ctrl_frame& UdpSendCtrl(int scene) const {
+        if (!publish_frames_ || scene < 0 || scene >= n_) throw std::out_of_range("frame");
+        return ctrl_[(size_t)scene];
+    }
+    const dp_status_frame& PlanningStatus(int scene) const {
+        if (!publish_frames_ || scene < 0 || scene >= n_) throw std::out_of_range("frame");
+        return status_[(size_t)scene];
     }
     const dp_plan_record& Record(int scene) const {
         if (scene < 0 || scene >= n_) throw std::out_of_range("scene index");
@@ -50,6 +64,9 @@ private:
     CBatchApp() {}
     std::unique_ptr<CPlannerBatch> batch_;
     std::vector<dp_plan_record> rec_;
+    std::vector<dp_ctrl_frame> ctrl_;
+    std::vector<dp_status_frame> status_;
+    bool publish_frames_ = false;
     int n_ = 0;
 };
 

@@ -34,6 +34,15 @@ public:
                      void* stream, dp_trace_record* trace = nullptr, double* road_points = nullptr, double* latlng = nullptr) {
         check(dp_cycle_batch_dev(ctx_, first, n, hdr, obs_x, obs_y, rec, trace, road_points, latlng, stream), "dp_cycle_batch_dev");
     }
+    // the two frames CPlanningThread publishes at the end of a cycle (Planning.cpp:173-214), for the cycle that just ran
+    void PackFrames(int first, int n, const dp_plan_record* rec, dp_ctrl_frame* ctrl, dp_status_frame* status) {
+        check(dp_pack_frames(ctx_, first, n, rec, ctrl, status), "dp_pack_frames");
+    }
+    // V2XEventDecision (Decision.cpp:283) for n scenes; the flags are the caller's to use, as in the reference
+    void V2XEvents(int n, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat, const double* wp_lng, int n_wp,
+                   dp_v2x_flags* out, int mode = 0) {
+        check(dp_v2x_event_batch(ctx_, n, hdr, v2x, wp_lat, wp_lng, n_wp, mode, out), "dp_v2x_event_batch");
+    }
     dp_ctx* ctx() const { return ctx_; }
     int max_scenes() const { return max_scenes_; }
     int max_obs() const { return max_obs_; }

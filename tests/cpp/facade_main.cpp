@@ -26,6 +26,7 @@ int main(int argc, char** argv) {
     auto width = rd<uint16_t>(f, n_points); auto attr = rd<uint16_t>(f, n_points);
     auto H = rd<dp_scene_hdr>(f, (size_t)cycles * n); auto OX = rd<double>(f, (size_t)cycles * n * max_obs);
     auto OY = rd<double>(f, (size_t)cycles * n * max_obs); auto want = rd<dp_plan_record>(f, (size_t)cycles * n);
+    auto want_ctrl = rd<dp_ctrl_frame>(f, (size_t)cycles * n); auto want_status = rd<dp_status_frame>(f, (size_t)cycles * n);
     fclose(f);
     dp_map_desc md;
     md.n_roads = n_roads; md.road_lane_base = rlb.data(); md.n_lanes = n_lanes; md.lane_pt_off = lpo.data(); md.n_conn = n_conn;
@@ -36,6 +37,7 @@ int main(int argc, char** argv) {
     if (CDecision::Instance().startCDecisionThread() != 0) { fprintf(stderr, "thread started without an application\n"); return 1; }
     CBatchApp::Instance().Open(n, max_obs, md);
     if (CDecision::Instance().startCDecisionThread() != 1 || CPlanning::Instance().startCPlanningThread() != 1) return 1;
+    CBatchApp::Instance().PublishFrames(true);
     CDecision& D = CDecision::Instance();
     CPlanning& P = CPlanning::Instance();
     long bad = 0, b3 = 0;
@@ -50,6 +52,8 @@ int main(int argc, char** argv) {
                       P.path_front_near_id(s) == w.path_front_near_id && same(P.brakespeed(s), w.brakespeed) &&
                       P.acc_flag(s) == (w.acc_flag != 0) && same(P.des_acc(s), w.des_acc) && same(P.brakedis(s), w.mindist_lon) &&
                       same(P.radius(s), w.radius) && !(P.path_dir_err(s) - w.path_dir_err > 1e-9) && !(w.path_dir_err - P.path_dir_err(s) > 1e-9);
+            ok = ok && memcmp(&CBatchApp::Instance().UdpSendCtrl(s), &want_ctrl[(size_t)c * n + s], sizeof(dp_ctrl_frame)) == 0 &&
+                 memcmp(&CBatchApp::Instance().PlanningStatus(s), &want_status[(size_t)c * n + s], sizeof(dp_status_frame)) == 0;
             if (!ok && bad++ < 5) fprintf(stderr, "mismatch cycle %d scene %d: behavior %d vs %d\n", c, s, (int)D.behavior(s), (int)w.behavior);
             b3 += D.behavior(s) != 1;
         }

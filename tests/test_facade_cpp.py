@@ -18,6 +18,7 @@ def test_cpp_facade_matches_oracle(oracle, the_map):
     ep = scenes.Episodes(the_map, np.arange(60_000, 60_000 + n), cycles=cycles, n_obs=n_obs)
     H, OX, OY = ep.all_cycles()
     want = oracle.run(H, OX, OY, exhaustive=False, threads=4)
+    ctrl, status = oracle.pack_frames(want["rec"].reshape(-1), want["path_xy"].reshape(-1, 2, 200))
     m = the_map
     exe = os.path.join(tempfile.gettempdir(), "dmpp_facade_main")
     pkg = os.path.join(ROOT, "decision-making-and-path-planning_b200")
@@ -25,7 +26,7 @@ def test_cpp_facade_matches_oracle(oracle, the_map):
                            "-L" + pkg, "-ldmpp_b200", "-Wl,-rpath," + pkg])
     with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
         np.array([m.n_roads, m.n_lanes, len(m.conn), m.x.size, n, cycles, n_obs, 0], np.int32).tofile(f)
-        for a in (m.road_lane_base, m.lane_pt_off, m.conn, m.x, m.y, m.dir, m.lane_width, m.lanechg_attr, H, OX, OY, want["rec"]):
+        for a in (m.road_lane_base, m.lane_pt_off, m.conn, m.x, m.y, m.dir, m.lane_width, m.lanechg_attr, H, OX, OY, want["rec"], ctrl, status):
             np.ascontiguousarray(a).tofile(f)
         dump = f.name
     try:
