@@ -381,14 +381,27 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
     CK(cudaSetDevice(c->device));
     for (void* p : c->map_allocs) cudaFree(p);
     c->map_allocs.clear();
-    auto up = [&](const void* src, size_t bytes, void** dst) -> int {
-        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 8);
+    c->have_map = false; c->lc.l2_base = nullptr; c->lc.l2_bytes = 0;   // (until the new tables are complete)
+    if (c->ep_exec) { cudaGraphExecDestroy(c->ep_exec); c->ep_exec = nullptr; }   // (a cached episode graph points into the old map)
+    // every map table lives in ONE arena (256-byte aligned pieces), so that a single L2 access-policy window covers the map
+    const size_t np = (size_t)m->n_points;
+    const size_t arena_bytes = 16 * 256 + np * (8 * 3 + 16 * 2 + 8 * 2 + 8 + 4 * 2 + 2 * 2) + (size_t)m->n_lanes * (4 * 3 + 8 + 4) +
+                               (size_t)(m->n_roads + m->n_lanes + 2) * 4 + (size_t)m->n_conn * sizeof(dp_connector) + 32 * 256;
+    char* arena = nullptr;
+    {
+        cudaError_t e = cudaMalloc((void**)&arena, arena_bytes);
         if (e != cudaSuccess) return fail(DP_ERR_NOMEM, "cudaMalloc(map)", e);
-        c->map_allocs.push_back(*dst);
-        if (src && bytes) { e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "cudaMemcpy(map)", e); }
+        c->map_allocs.push_back(arena);
+    }
+    size_t arena_used = 0;
+    auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+        const size_t need = (bytes ? bytes : 8);
+        if (arena_used + need > arena_bytes) return fail(DP_ERR_NOMEM, "dp_map_upload: arena");
+        *dst = arena + arena_used;
+        arena_used = (arena_used + need + 255) & ~(size_t)255;
+        if (src && bytes) { cudaError_t e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(DP_ERR_CUDA, "cudaMemcpy(map)", e); }
         return DP_OK;
     };
-    const size_t np = (size_t)m->n_points;
     // the avoid sweep enumerates i < (W - Vw) / 0.6 candidates per side with no cap (Decision.cpp:940); this library holds
     // DP_MAX_SWEEP of them: a lane wide enough to need more is rejected here instead of diverging silently
     for (size_t i = 0; i < np; ++i)
@@ -428,6 +441,24 @@ int dp_map_upload(dp_ctx* c, const dp_map_desc* m) {
     d.cump = d_cump; d.lane_cerr = d_cerr; d.run_end0 = d_re0; d.run_end1 = d_re1;
     c->gmap = d;
     c->have_map = true;
+    // L2 persistence (DP_L2_PERSIST=0 switches it off): reserve a set-aside as large as the arena (if the device allows) and let
+    // the cycle launches mark their map accesses persisting -- constant tables every scene gathers from should not be evicted
+    // by what streams through the cache between two cycles
+    c->lc.l2_base = nullptr; c->lc.l2_bytes = 0;
+    int want = 1;
+    if (const char* e = getenv("DP_L2_PERSIST")) want = atoi(e);
+    if (want) {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+        size_t cur = 0;
+        cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+        const size_t bytes = arena_used;
+        if (max_persist > 0 && bytes <= (size_t)max_persist && bytes <= (size_t)max_window) {
+            bool ok = cur >= bytes || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes + (1u << 20)) == cudaSuccess;
+            if (ok) { c->lc.l2_base = arena; c->lc.l2_bytes = bytes; } else cudaGetLastError();
+        }
+    }
     return DP_OK;
 }
 

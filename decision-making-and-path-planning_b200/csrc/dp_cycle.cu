@@ -1116,6 +1116,15 @@ dp_group_kernel(DgMap m, dp_params p, int n_scenes, int g, const dp_scene_hdr* _
 }
 
 // ---- launchers (called from dp_api.cu) ----
+// access-policy window over the map arena: every access inside it is "persisting" (kept in the L2 set-aside)
+static void dp_l2_window(cudaLaunchAttribute& a, const DpLaunchCfg& lc) {
+    a.id = cudaLaunchAttributeAccessPolicyWindow;
+    a.val.accessPolicyWindow.base_ptr = lc.l2_base;
+    a.val.accessPolicyWindow.num_bytes = lc.l2_bytes;
+    a.val.accessPolicyWindow.hitRatio = 1.0f;
+    a.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+}
 void dp_launch_prepare(DpLaunchCfg& lc) {
     if (lc.attr_warp) return;                               // 196 of 256 KB as shared memory, the rest stays L1 (per context: no process-wide state)
     cudaFuncSetAttribute(dp_cycle_kernel<0, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, DP_CARVEOUT);
@@ -1151,10 +1160,15 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
             // at entry); its warps wait per scene for that cycle's Planning warp (io.prev_epoch) and for the staged inputs
             cudaLaunchConfig_t cfg1 = {};
             cfg1.gridDim = dim3(blocks); cfg1.blockDim = dim3(threads); cfg1.dynamicSmemBytes = 0; cfg1.stream = st;
-            cudaLaunchAttribute at1[1];
-            at1[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at1[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg1.attrs = at1; cfg1.numAttrs = io1.prev_epoch ? 1 : 0;
+            cudaLaunchAttribute at1[2];
+            int na1 = 0;
+            if (io1.prev_epoch) {
+                at1[na1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at1[na1].val.programmaticStreamSerializationAllowed = 1;
+                ++na1;
+            }
+            if (lc.l2_bytes) dp_l2_window(at1[na1++], lc);
+            cfg1.attrs = at1; cfg1.numAttrs = na1;
             cudaError_t e1 = wide ? cudaLaunchKernelEx(&cfg1, dp_cycle_kernel<1, 4>, m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1)
                                   : cudaLaunchKernelEx(&cfg1, dp_cycle_kernel<1, 1>, m, p, n, hdr, ox, oy, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io1);
             if (e1 != cudaSuccess) return e1;
@@ -1163,12 +1177,17 @@ cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp
         const double* ox2 = io.ox_stage ? io.ox_stage : ox; const double* oy2 = io.oy_stage ? io.oy_stage : oy;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
+        int na = 0;
         // programmatic dependent launch WITHOUT a grid-wide dependency wait in the kernel: scenes hand over one by one
         // (dp_publish / dp_await), so Planning CTAs run in the slots the Decision launch frees while its tail finishes
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = io2.done ? 1 : 0;
+        if (io2.done) {
+            at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (lc.l2_bytes) dp_l2_window(at[na++], lc);
+        cfg.attrs = at; cfg.numAttrs = na;
         cudaError_t e = wide ? cudaLaunchKernelEx(&cfg, dp_cycle_kernel<2, 4>, m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2)
                              : cudaLaunchKernelEx(&cfg, dp_cycle_kernel<2, 1>, m, p, n, hdr2, ox2, oy2, max_obs, carry, last_path, rec, trace, path_xy, path_ll, io2);
         if (e != cudaSuccess) return e;

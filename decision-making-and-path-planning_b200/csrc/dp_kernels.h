@@ -38,6 +38,9 @@ struct DpLaunchCfg {
     int force_wpb = 0;                         // DP_WPB = 1 | 4: CTA size of the warp kernel (0: by batch size)
     int group_cfg = 0;                         // DP_GROUP_CFG = 0 | 1 | 2: CTA shape of the group kernel (16 x 256, 8 x 128, 8 x 256)
     int group_g = 0;                           // DP_GROUP_G: scenes per CTA (0: spread one wave evenly)
+    // L2 persistence for the map arena (dp_map_upload): the warp-kernel launches carry an access-policy window over it, so the
+    // ~3 MB of map tables every scene gathers from stay resident in the L2 set-aside whatever streams through in between
+    void* l2_base = nullptr; size_t l2_bytes = 0;
 };
 
 cudaError_t dp_launch_cycle(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const double* ox, const double* oy,
