@@ -25,7 +25,7 @@ ncu --metrics gpu__time_duration.sum,sm__throughput.avg.pct_of_peak_sustained_el
 python tools/bench_closed_loop.py 25 > $O/r2_closed_loop.json || exit 1
 ncu --set full --clock-control none --import-source on -k regex:dp_frames_kernel -s 25 -c 1 -f -o $O/r2_dp_frames_kernel python tools/bench_closed_loop.py 2 > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,dram__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,dram__bytes.sum \
-    --clock-control none -k regex:'dp_world|dp_frames|dp_v2x' -c 60 --csv --log-file $O/r2_new_kernels.csv \
+    --clock-control none -k regex:'dp_world|dp_frames|dp_v2x' -c 240 --csv --log-file $O/r2_new_kernels.csv \
     python -m pytest tests/test_closed_loop.py tests/test_v2x.py -m gpu -q -k "ragged or frames_equal or v2x_equals" > /dev/null 2>&1
 python tools/group_timeline.py 4096 12 > $O/r2_group_timeline_cfg2.txt 2>&1
 DP_DEBUG_LIB=$PWD/decision-making-and-path-planning_b200/libdmpp_b200_dbg.so python tools/scene_timeline.py 4096 > $O/r2_scene_timeline.txt 2>&1
