@@ -1348,6 +1348,30 @@ int dp_v2x_event_batch(dp_ctx* c, int n, const dp_scene_hdr* hdr, const dp_v2x_d
     return DP_OK;
 }
 
+int dp_v2x_apply_dev(dp_ctx* c, int n, const dp_v2x_flags* flags, dp_plan_record* rec, void* stream) {
+    if (!c || !flags || !rec || n < 0) return fail(DP_ERR_ARG, "dp_v2x_apply_dev: bad argument");
+    CK(cudaSetDevice(c->device));
+    c->launches += n > 0 ? 1 : 0;
+    CK(dp_launch_v2x_apply(n, flags, rec, (cudaStream_t)stream));
+    return DP_OK;
+}
+int dp_v2x_apply(dp_ctx* c, int n, const dp_v2x_flags* flags, dp_plan_record* rec) {
+    if (!c || !flags || !rec || n < 0) return fail(DP_ERR_ARG, "dp_v2x_apply: bad argument");
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return DP_OK;
+    Tmp t;
+    cudaError_t e = cudaSuccess;
+    dp_v2x_flags* d_f = t.put(flags, (size_t)n, e);
+    if (e != cudaSuccess) return fail(DP_ERR_CUDA, "dp_v2x_apply: staging", e);
+    dp_plan_record* d_r = t.put((const dp_plan_record*)rec, (size_t)n, e);
+    if (e != cudaSuccess) return fail(DP_ERR_CUDA, "dp_v2x_apply: staging", e);
+    c->launches += 1;
+    CK(dp_launch_v2x_apply(n, d_f, d_r, c->st[0]));
+    CK(cudaMemcpyAsync(rec, d_r, (size_t)n * sizeof(dp_plan_record), cudaMemcpyDeviceToHost, c->st[0]));
+    CK(cudaStreamSynchronize(c->st[0]));
+    return DP_OK;
+}
+
 // ---- (9) closed-loop episodes ----
 void dp_world_default_params(dp_world_params* p) {
     if (!p) return;

@@ -313,6 +313,21 @@ __global__ void __launch_bounds__(WPB * 32) dp_v2x_kernel(DevMap m, dp_params p,
 }
 }  // namespace
 
+namespace {
+// the opt-in speed command of include/dmpp_b200.h section 10: one thread per scene, a 128-byte record each
+__global__ void dp_v2x_apply_kernel(int n, const dp_v2x_flags* __restrict__ flags, dp_plan_record* __restrict__ rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const dp_v2x_flags f = flags[i];
+    if (f.pedestrian_flag || f.light_flag == 1) { rec[i].brakespeed = 0.0; rec[i].acc_flag = 1; rec[i].des_acc = -3.0; }
+    else if (f.construction_flag && rec[i].brakespeed > 3.0) rec[i].brakespeed = 3.0;
+}
+}  // namespace
+cudaError_t dp_launch_v2x_apply(int n, const dp_v2x_flags* flags, dp_plan_record* rec, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    dp_v2x_apply_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, flags, rec);
+    return cudaGetLastError();
+}
 cudaError_t dp_launch_v2x(const DevMap& m, const dp_params& p, int n, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat,
                           const double* wp_lng, int mode, dp_v2x_flags* out, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;

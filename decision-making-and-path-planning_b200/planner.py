@@ -25,7 +25,7 @@ SYMBOLS = [
     "dp_cycle_submit", "dp_cycle_wait", "dp_set_record_mirrors", "dp_nearest_id", "dp_run_episode_dev", "dp_debug_timeline",
     "dp_set_tracks", "dp_set_tracks_dev", "dp_clear_tracks",
     "dp_pack_frames_dev", "dp_pack_frames", "dp_world_default_params", "dp_world_set_params", "dp_world_step_dev",
-    "dp_run_closed_loop_dev", "dp_closed_loop_is_graph", "dp_v2x_event_batch", "dp_v2x_event_batch_dev",
+    "dp_run_closed_loop_dev", "dp_closed_loop_is_graph", "dp_v2x_event_batch", "dp_v2x_event_batch_dev", "dp_v2x_apply", "dp_v2x_apply_dev",
     "dp_gather_create", "dp_gather_attach", "dp_gather_arm", "dp_gather_chain", "dp_gather_arm_deferred", "dp_gather_set_lag", "dp_gather_flush", "dp_gather_disarm", "dp_gather_wait", "dp_gather_buffer", "dp_gather_destroy",
 ]
 
@@ -184,6 +184,15 @@ class Planner:
         _ck(self.lib.dp_v2x_event_batch(self.ctx, C.c_int(hdr.shape[0]), abi.ptr(hdr), abi.ptr(v2x), abi.ptr(wl) if wl.size else None,
                                         abi.ptr(wg) if wg.size else None, C.c_int(wl.size), C.c_int(mode), abi.ptr(out)), "dp_v2x_event_batch")
         return out
+
+    def v2x_apply(self, flags, rec):
+        """opt-in: the flags act on the speed command of the records (returns the adjusted copy)"""
+        out = np.ascontiguousarray(rec).copy()
+        _ck(self.lib.dp_v2x_apply(self.ctx, C.c_int(out.shape[0]), abi.ptr(np.ascontiguousarray(flags)), abi.ptr(out)), "dp_v2x_apply")
+        return out
+
+    def v2x_apply_dev(self, n, d_flags, d_rec, stream=0):
+        _ck(self.lib.dp_v2x_apply_dev(self.ctx, C.c_int(n), C.c_void_p(d_flags), C.c_void_p(d_rec), C.c_void_p(stream)), "dp_v2x_apply_dev")
 
     def v2x_event_dev(self, n, d_hdr, d_v2x, d_wp_lat, d_wp_lng, d_out, mode=0, stream=0):
         _ck(self.lib.dp_v2x_event_batch_dev(self.ctx, C.c_int(n), C.c_void_p(d_hdr), C.c_void_p(d_v2x), C.c_void_p(d_wp_lat or 0),

@@ -463,6 +463,14 @@ int dp_v2x_event_batch(dp_ctx* ctx, int n_scenes, const dp_scene_hdr* hdr, const
                        const double* wp_lng, int n_wp, int mode, dp_v2x_flags* out);
 int dp_v2x_event_batch_dev(dp_ctx* ctx, int n_scenes, const dp_scene_hdr* hdr, const dp_v2x_data* v2x, const double* wp_lat,
                            const double* wp_lng, int mode, dp_v2x_flags* out, void* stream);
+/* OPT-IN extension beyond the reference (which drops the flags, Decision.cpp:283-313): let the flags act on the speed command of
+ * the records, in place, with the planner's own vocabulary (SpeedPlanning, Planning.cpp:888-990):
+ *   pedestrian_flag or light_flag == 1 (red / yellow)  ->  brakespeed = 0, acc_flag = 1, des_acc = -3   (its "obstacle closer than 5 m" command)
+ *   else construction_flag and brakespeed > 3          ->  brakespeed = 3                               (its creep speed)
+ * Everything else in the record is left alone; lane choice is NOT touched.  A closed loop that steps the world with the adjusted
+ * records (dp_world_step_dev) makes the ego actually stop.  Arithmetic-free, so parity is against oracle/v2x_oracle.cpp only. */
+int dp_v2x_apply(dp_ctx* ctx, int n_scenes, const dp_v2x_flags* flags, dp_plan_record* rec);
+int dp_v2x_apply_dev(dp_ctx* ctx, int n_scenes, const dp_v2x_flags* flags, dp_plan_record* rec, void* stream);
 
 /* diagnostic: phase time stamps (globaltimer, ns) of the most recent cycle launch, one row of 32 per CTA (row b = scenes
  * [b*g, (b+1)*g) of the batch; stamp 0 = CTA start, stamp i = end of phase i of csrc/dp_group.cuh).  Only contexts created

@@ -166,6 +166,11 @@ class Oracle(_Runner):
     def v2x_event(self, hdr, v2x, wp_lat, wp_lng, mode=0):
         return _v2x(self.lib.oracle_v2x_event, [C.byref(self.params)], hdr, v2x, wp_lat, wp_lng, mode)
 
+    def v2x_apply(self, flags, rec):
+        out = np.ascontiguousarray(rec).copy()
+        self.lib.oracle_v2x_apply(C.c_int(out.shape[0]), abi.ptr(np.ascontiguousarray(flags)), abi.ptr(out))
+        return out
+
     def rollout_ctr(self, x0, y0, vx, vy, dth, T):
         ox, oy = np.zeros(T), np.zeros(T)
         self.lib.oracle_rollout_ctr.argtypes = [C.c_double] * 5 + [C.c_int, C.c_void_p, C.c_void_p]

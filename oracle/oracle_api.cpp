@@ -287,6 +287,9 @@ int oracle_v2x_event(const dp_params* p, int n, const dp_scene_hdr* hdr, const d
     for (int s = 0; s < n; ++s) oracle::v2x_event(g_map, *p, hdr[s], v2x[s], wp_lat, wp_lng, mode, out + s);
     return 0;
 }
+void oracle_v2x_apply(int n, const dp_v2x_flags* flags, dp_plan_record* rec) {
+    for (int s = 0; s < n; ++s) oracle::v2x_apply(flags[s], rec[s]);
+}
 int oracle_sizeof(int which) {
     switch (which) {
         case 0: return (int)sizeof(dp_scene_hdr);

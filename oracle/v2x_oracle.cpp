@@ -160,4 +160,8 @@ void v2x_event(const MapView& m, const dp_params& p, const dp_scene_hdr& h, cons
     else if (v.warn_status == 5) pedestrian(m, p, h, v, o);
     if (o->ub) { o->light_flag = 0; o->construction_flag = 0; o->pedestrian_flag = 0; o->lng_distance = 9999; o->lat_distance = 9999; }
 }
+void v2x_apply(const dp_v2x_flags& f, dp_plan_record& r) {
+    if (f.pedestrian_flag || f.light_flag == 1) { r.brakespeed = 0.0; r.acc_flag = 1; r.des_acc = -3.0; }
+    else if (f.construction_flag && r.brakespeed > 3.0) r.brakespeed = 3.0;
+}
 }  // namespace oracle

@@ -117,3 +117,31 @@ def test_gpu_v2x_rejects_bad_slices(planner, the_map):
     v["wp_first"][3], v["wp_count"][3] = wl.size, 2
     with pytest.raises(DpError):
         planner.v2x_event(h, v, wl, wg)
+
+
+def test_v2x_apply_spec(oracle):
+    """the opt-in speed command: stop for a pedestrian or a red / yellow light, creep past road works, nothing else touched"""
+    from dmpp_b200 import abi
+    rec = np.zeros(5, abi.plan_record)
+    rec["brakespeed"], rec["des_acc"], rec["behavior"] = [10.0, 8.0, 7.0, 2.0, 9.0], 0.0, 2
+    f = np.zeros(5, abi.v2x_flags)
+    f["pedestrian_flag"][0] = 1; f["light_flag"][1] = 1; f["construction_flag"][2] = 1; f["construction_flag"][3] = 1; f["light_flag"][4] = 2
+    out = oracle.v2x_apply(f, rec)
+    assert out["brakespeed"].tolist() == [0.0, 0.0, 3.0, 2.0, 9.0] and out["acc_flag"].tolist() == [1, 1, 0, 0, 0]
+    assert out["des_acc"].tolist() == [-3.0, -3.0, 0.0, 0.0, 0.0] and (out["behavior"] == 2).all()
+
+
+@pytest.mark.gpu
+def test_gpu_v2x_apply_and_closed_loop_stop(planner, oracle, the_map):
+    """CUDA == oracle on the adjusted records; and a world stepped with them brakes (a_max x dt per cycle) where a flag is up"""
+    from dmpp_b200 import abi, scenes
+    h, v, wl, wg = events(the_map, 0, 64, 1)
+    flags = planner.v2x_event(h, v, wl, wg)
+    ep = scenes.Episodes(the_map, np.arange(64), cycles=1)
+    planner.reset(0, 64)
+    rec = planner.cycle(np.ascontiguousarray(ep.hdr(0)), *ep.obstacles(0))["rec"]
+    got = planner.v2x_apply(flags, rec)
+    assert got.tobytes() == oracle.v2x_apply(flags, rec).tobytes()
+    up = (flags["pedestrian_flag"] == 1) | (flags["light_flag"] == 1)
+    assert up.sum() >= 5 and (got["brakespeed"][up] == 0).all() and (got["acc_flag"][up] == 1).all()
+    assert got[~up & (flags["construction_flag"] == 0)].tobytes() == rec[~up & (flags["construction_flag"] == 0)].tobytes()
