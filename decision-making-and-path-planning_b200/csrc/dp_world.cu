@@ -31,8 +31,10 @@ __global__ void __launch_bounds__(WPB * 32) dp_world_kernel(DevMap m, dp_params 
     const double dt = h.period_ms / 1000.0;
     double x = h.x, y = h.y, dir = h.dir, vn = h.velocity;
     const bool step = rec != nullptr;
-    if (step && lane == 0) {
-        // ---- ego: bounded approach to the planned speed, then a walk along the carried local path ----
+    if (step) {
+        // ---- ego: bounded approach to the planned speed, then a walk along the carried local path (every lane computes the same
+        // scalars; the path segments come in 32 at a time, one per lane, and are walked in index order through shuffles, so the
+        // sequential `rem -= L` of the specification never waits for memory) ----
         const dp_plan_record& r = rec[scene];
         const int gl = m.road_lane_base[h.road_num - 1] + h.lane_num - 1;
         const int cnt = m.lane_pt_off[gl + 1] - m.lane_pt_off[gl];
@@ -51,21 +53,28 @@ __global__ void __launch_bounds__(WPB * 32) dp_world_kernel(DevMap m, dp_params 
             if (i < 0) i = 0;
             if (i > DP_PATH_POINTS - 2) i = DP_PATH_POINTS - 2;
             double rem = ds;
-            double2 a = lp[i];
-            for (;;) {
-                const double2 b = lp[i + 1];
+            for (int base = i;; base += 32) {
+                const int idx = min(base + lane, DP_PATH_POINTS - 2);
+                const double2 a = lp[idx], b = lp[idx + 1];
                 double ddx, ddy;
                 const double L = seg_len(a, b, &ddx, &ddy);
-                if (rem < L || i == DP_PATH_POINTS - 2) {
-                    if (L > 0) {
-                        double t = rem / L;
-                        if (t > 1) t = 1;
-                        x = a.x + t * ddx; y = a.y + t * ddy;
-                        dir = dp_heading(a.x, a.y, b.x, b.y, p.epsilon, p.pi);
-                    } else { x = a.x; y = a.y; }
-                    break;
+                int hit = -1;
+                for (int k = 0; k < 32; ++k) {
+                    const double Lk = __shfl_sync(DP_FULL, L, k);
+                    if (rem < Lk || base + k == DP_PATH_POINTS - 2) { hit = k; break; }
+                    rem -= Lk;
                 }
-                rem -= L; ++i; a = b;
+                if (hit < 0) continue;
+                const double ax = __shfl_sync(DP_FULL, a.x, hit), ay = __shfl_sync(DP_FULL, a.y, hit);
+                const double bx = __shfl_sync(DP_FULL, b.x, hit), by = __shfl_sync(DP_FULL, b.y, hit);
+                const double sdx = __shfl_sync(DP_FULL, ddx, hit), sdy = __shfl_sync(DP_FULL, ddy, hit), Lh = __shfl_sync(DP_FULL, L, hit);
+                if (Lh > 0) {
+                    double t = rem / Lh;
+                    if (t > 1) t = 1;
+                    x = ax + t * sdx; y = ay + t * sdy;
+                    dir = dp_heading(ax, ay, bx, by, p.epsilon, p.pi);
+                } else { x = ax; y = ay; }
+                break;
             }
         }
     }
