@@ -247,6 +247,14 @@ dp_cycle_kernel(DevMap m, dp_params p, int n_scenes, const dp_scene_hdr* __restr
     if (PHASE == 2 && io.pdone) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // ... and the next cycle's Decision CTAs
     if (PHASE == 1 && io.in_flag) dp_await(io.in_flag, io.epoch);                                // chained submit: inputs staged?
     if (PHASE == 2 && io.done) dp_await(io.done + scene, io.epoch);
+    // while the header is on its way: ask L2 for the lines the warp needs next and whose addresses do not depend on it -- the two
+    // obstacle rows and the carry (otherwise three DRAM round trips in a row at the start of every scene after an L2 flush)
+    if (PHASE == 1 && !io.in_flag && !io.hdr_stage && lane < 5) {
+        const size_t row = (size_t)scene * max_obs, last = (size_t)(max_obs > 0 ? max_obs - 1 : 0);
+        const void* a = lane == 0 ? (const void*)(obs_x + row) : lane == 1 ? (const void*)(obs_x + row + last)
+                      : lane == 2 ? (const void*)(obs_y + row) : lane == 3 ? (const void*)(obs_y + row + last) : (const void*)(carry + scene);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
     // the 128-byte scene header comes in with one coalesced warp load (from HBM, or straight from pinned host memory
     // over PCIe in the zero-copy mode of dp_cycle_batch) and is read from shared memory afterwards
     sm.hdr[lane] = (PHASE == 2 || io.in_flag) ? dp_l2(reinterpret_cast<const uint32_t*>(hdr + scene) + lane)   // (staged by a concurrent launch / copy)
