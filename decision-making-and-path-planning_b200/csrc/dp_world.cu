@@ -27,7 +27,10 @@ __global__ void __launch_bounds__(WPB * 32) dp_world_kernel(DevMap m, dp_params 
     sh[wib][lane] = reinterpret_cast<const uint32_t*>(hdr + scene)[lane];   // one coalesced 128-byte load
     __syncwarp();
     const dp_scene_hdr& h = *reinterpret_cast<const dp_scene_hdr*>(sh[wib]);
-    const int n_obs = h.n_obs;
+    // a header that does not name a lane of the map (device-pointer callers are not validated on the host) leaves its world untouched
+    if (h.road_num < 1 || h.road_num > m.n_roads || h.lane_num < 1 ||
+        h.lane_num > m.road_lane_base[h.road_num] - m.road_lane_base[h.road_num - 1] || h.lane_num > DP_LANESUM) return;
+    const int n_obs = min((int)h.n_obs, max_obs);
     const double dt = h.period_ms / 1000.0;
     double x = h.x, y = h.y, dir = h.dir, vn = h.velocity;
     const bool step = rec != nullptr;

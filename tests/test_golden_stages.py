@@ -30,9 +30,9 @@ def golden(name, *inputs):
     return g
 
 
-def check_closed_loop(a, g, extra=()):
+def check_closed_loop(a, g, close=None):
     clean = g["ub_scene"] == 0
-    assert_records_equal(a["rec"][:, clean], g["rec"][:, clean], REC + list(extra), what="record")
+    assert_records_equal(a["rec"][:, clean], g["rec"][:, clean], REC, close=close, what="record")
     assert_records_equal(a["hdr_log"][:, clean], g["hdr_log"][:, clean], HDR, what="logged header")
     assert same(a["obs_log_x"][:, clean], g["obs_log_x"][:, clean]).all() and same(a["obs_log_y"][:, clean], g["obs_log_y"][:, clean]).all()
     assert_records_equal(a["hdr"][clean], g["hdr"][clean], HDR, what="final header")
@@ -73,7 +73,8 @@ def test_cuda_matches_stage_goldens(the_map):
     w, cycles = G.closed_loop_inputs(the_map)
     p = Planner(max_scenes=2048, max_obs=10)
     p.upload_map(the_map)
-    check_closed_loop(p.run_closed_loop(w.hdr, w.agents, cycles), golden("closed_loop_24", w.hdr, w.agents))
+    # (path_dir_err: the reference calls libm atan there, the device evaluates the specification's polynomial -- 1e-9 degrees, as everywhere)
+    check_closed_loop(p.run_closed_loop(w.hdr, w.agents, cycles), golden("closed_loop_24", w.hdr, w.agents), close={"path_dir_err": 1e-9})
     for name in sorted(G.FRAMES):
         H, OX, OY = G.frames_inputs(the_map, name)
         g = golden(name, H, OX, OY)
