@@ -252,8 +252,13 @@ __global__ void __launch_bounds__(WPB * 32) dp_v2x_kernel(DevMap m, dp_params p,
     const dp_v2x_data v = v2x[scene];
     unsigned light = 0, cons = 0, ped = 0, ub = 0;
     double lng = 9999, lat = 9999;
-    const int ln = h.lane_num, gl = m.road_lane_base[h.road_num - 1] + ln - 1, id = h.id[ln - 1];
-    if (v.warn_status == 3) {                               // V2XSignalLight
+    // a header that names no lane of the map (device-pointer callers are not validated on the host): no flags, `ub` set
+    const bool bad_hdr = h.road_num < 1 || h.road_num > m.n_roads || h.lane_num < 1 || h.lane_num > DP_LANESUM ||
+                         h.lane_num > m.road_lane_base[h.road_num < 1 || h.road_num > m.n_roads ? 1 : h.road_num] -
+                                          m.road_lane_base[h.road_num < 1 || h.road_num > m.n_roads ? 0 : h.road_num - 1];
+    const int ln = bad_hdr ? 1 : h.lane_num, gl = bad_hdr ? 0 : m.road_lane_base[h.road_num - 1] + ln - 1, id = bad_hdr ? 0 : h.id[ln - 1];
+    if (bad_hdr) ub = 1;
+    else if (v.warn_status == 3) {                               // V2XSignalLight
         if (v.spat_lane_occupied == 1) light = (v.spat_state == 3 || v.spat_state == 7) ? 1 : (v.spat_state == 6) ? 2 : 0;
     } else if (v.warn_status == 4 && mode != 1) {           // V2XConstructionEvent
         const V2xPath f = v2x_front(m, gl, id, p.id_more);
