@@ -497,20 +497,25 @@ def run_ours(args, rank, world, local_rank):
     extras = {}
     if not args.no_extras:
         from dmpp_b200.planner import Planner as P_
-        try:
-            if world == 1:
-                extras["config3"] = config3_line(P_, m)
-                extras["config3_distinct_geometry"] = config3_bezier_line(P_, m)
-                extras["config4_shard"] = config4_line(torch, dist, P_, m, dev, rank, world, local_rank, 131072)
-            else:
-                extras["config4"] = config4_line(torch, dist, P_, m, dev, rank, world, local_rank, 1048576)
-                extras["config3_split"] = config3_split_line(torch, dist, P_, m, dev, rank, world, local_rank)
-            extras["config5"] = config5_line(torch, dist, P_, m, dev, rank, world, local_rank)
-            extras["closed_loop"] = closed_loop_line(torch, dist, P_, m, dev, rank, world, local_rank)
-            if world == 1:
-                extras["output_frames"] = frames_line(torch, P_, m, dev, local_rank)
-        except Exception as e:  # noqa: BLE001
-            extras["extras_error"] = repr(e)
+
+        def extra(key, fn, *a):
+            """every extra key is measured on its own: one that fails reports its error and the others still run"""
+            try:
+                extras[key] = fn(*a)
+            except Exception as e:  # noqa: BLE001
+                extras[key] = {"error": repr(e)}
+
+        if world == 1:
+            extra("config3", config3_line, P_, m)
+            extra("config3_distinct_geometry", config3_bezier_line, P_, m)
+            extra("config4_shard", config4_line, torch, dist, P_, m, dev, rank, world, local_rank, 131072)
+        else:
+            extra("config4", config4_line, torch, dist, P_, m, dev, rank, world, local_rank, 1048576)
+            extra("config3_split", config3_split_line, torch, dist, P_, m, dev, rank, world, local_rank)
+        extra("config5", config5_line, torch, dist, P_, m, dev, rank, world, local_rank)
+        extra("closed_loop", closed_loop_line, torch, dist, P_, m, dev, rank, world, local_rank)
+        if world == 1:
+            extra("output_frames", frames_line, torch, P_, m, dev, local_rank)
     sampler.stop = True
     sampler.join(timeout=2)
 
