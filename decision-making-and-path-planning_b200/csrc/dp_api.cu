@@ -355,6 +355,7 @@ int dp_destroy(dp_ctx* c) {
     if (!c) return DP_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->lc.l2_bytes) { cudaCtxResetPersistingL2Cache(); cudaGetLastError(); }   // hand the map's lines in the L2 set-aside back
     for (void* p : c->map_allocs) cudaFree(p);
     if (c->ep_exec) cudaGraphExecDestroy(c->ep_exec);
     if (c->ep_stream) cudaStreamDestroy(c->ep_stream);
