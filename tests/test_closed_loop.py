@@ -95,6 +95,46 @@ def test_world_step_known_answers(oracle, the_map):
     assert h["velocity"][0] == 36.0 - 3.0 * 3.6 * 0.1
 
 
+def test_world_step_invariants(oracle, the_map):
+    """properties of the world step that do not depend on its exact arithmetic: bounded acceleration, forward motion, agents
+    that keep their lateral offset from their lane, indices inside the localisation window, a localised ego on the right lane"""
+    from dmpp_b200 import abi
+    w = world(the_map, 2024, 384)
+    cycles = 40
+    a = oracle.run_closed_loop(w.hdr, w.agents, cycles, threads=4)
+    H = a["hdr_log"]
+    wp = oracle.world_params()
+    dt = H["period_ms"][0] / 1000.0
+    ids = H["id"].astype(int)
+    lane = H["lane_num"].astype(int)
+    ego_id = np.take_along_axis(ids, (lane - 1)[..., None], axis=2)[..., 0]
+    at_end = ego_id >= 2000 - wp.end_margin                                         # (an ego at the end of its lane is stopped outright)
+    dv = np.abs(np.diff(H["velocity"], axis=0))
+    assert (dv <= wp.a_max * 3.6 * dt[None, :] * (1 + 1e-12) + 1e-12)[~at_end[:-1]].all() and (H["velocity"] >= 0).all()
+    assert (H["velocity"][1:][at_end[:-1]] == 0).all()
+    step = np.diff(ids, axis=0)
+    assert (step >= -wp.loc_back).all() and (step <= wp.loc_fwd).all()              # every new index lies in the window of the old one
+    assert (np.diff(ego_id, axis=0)[lane[1:] == lane[:-1]] >= -1).all()            # no driving backwards on a lane
+    # the ego sits within half a lane (+ tracking slack) of the centre line of the lane it is localised on
+    m = the_map
+    gl = m.road_lane_base[H["road_num"].astype(int) - 1] + lane - 1
+    k = m.lane_pt_off[gl] + ego_id
+    d = np.hypot(H["x"] - m.x[k], H["y"] - m.y[k])
+    assert np.percentile(d, 99) < 2.2 and d.max() < 4.0
+    # agents: moved by v * dt along their lane (arclength = index advance x spacing on the 0.5 m map), lateral offset kept
+    ag0, ag1 = w.agents, a["agents"]
+    T = float(cycles) * dt[:, None]
+    adv = (ag1["i"] - ag0["i"]) * 0.5 + (ag1["u"] - ag0["u"])
+    free = ag1["i"] < 1990                                                           # (not stopped at the lane end)
+    assert np.abs(adv - ag0["v"] * T)[free].max() < 0.05 * cycles                    # arc / S-curve lanes are not exactly 0.5 m apart
+    assert (ag1["lane"] == ag0["lane"]).all() and (ag1["lat"] == ag0["lat"]).all() and (ag1["v"] == ag0["v"]).all()
+    gla = ag1["lane"].astype(int)
+    ka = m.lane_pt_off[gla] + ag1["i"]
+    hr = np.radians(m.dir[ka])
+    off_left = -(a["ox"] - m.x[ka]) * np.sin(hr) + (a["oy"] - m.y[ka]) * np.cos(hr)
+    assert np.abs(off_left - ag1["lat"]).max() < 0.05                                # LEFT-positive offset from the lane centre line
+
+
 # ---------------------------------------------------------------- CPU: frames vs the reference's own output objects
 @pytest.mark.parametrize("kind,seed0,n,cycles", [("highway", 0, 256, 25), ("junction", 70000, 64, 80)])
 def test_frames_equal_what_the_reference_publishes(oracle, reference, the_map, kind, seed0, n, cycles):
