@@ -27,6 +27,10 @@ int main(int argc, char** argv) {
     auto H = rd<dp_scene_hdr>(f, (size_t)cycles * n); auto OX = rd<double>(f, (size_t)cycles * n * max_obs);
     auto OY = rd<double>(f, (size_t)cycles * n * max_obs); auto want = rd<dp_plan_record>(f, (size_t)cycles * n);
     auto want_ctrl = rd<dp_ctrl_frame>(f, (size_t)cycles * n); auto want_status = rd<dp_status_frame>(f, (size_t)cycles * n);
+    // V2X events for the scenes of cycle 0 and the oracle's flags in both modes
+    const int n_wp = hd[7];
+    auto v2x = rd<dp_v2x_data>(f, (size_t)n); auto wp_lat = rd<double>(f, (size_t)n_wp); auto wp_lng = rd<double>(f, (size_t)n_wp);
+    auto want_f0 = rd<dp_v2x_flags>(f, (size_t)n); auto want_f1 = rd<dp_v2x_flags>(f, (size_t)n);
     fclose(f);
     dp_map_desc md;
     md.n_roads = n_roads; md.road_lane_base = rlb.data(); md.n_lanes = n_lanes; md.lane_pt_off = lpo.data(); md.n_conn = n_conn;
@@ -56,6 +60,18 @@ int main(int argc, char** argv) {
                  memcmp(&CBatchApp::Instance().PlanningStatus(s), &want_status[(size_t)c * n + s], sizeof(dp_status_frame)) == 0;
             if (!ok && bad++ < 5) fprintf(stderr, "mismatch cycle %d scene %d: behavior %d vs %d\n", c, s, (int)D.behavior(s), (int)w.behavior);
             b3 += D.behavior(s) != 1;
+        }
+    }
+    {   // the V2X handlers through the same C++ wrapper (its own context: the facade keeps its batch private)
+        CPlannerBatch vb(n, max_obs);
+        vb.UploadMap(md);
+        std::vector<dp_v2x_flags> got((size_t)n);
+        for (int mode = 0; mode < 2; ++mode) {
+            vb.V2XEvents(n, H.data(), v2x.data(), wp_lat.data(), wp_lng.data(), n_wp, got.data(), mode);
+            const std::vector<dp_v2x_flags>& want_f = mode ? want_f1 : want_f0;
+            for (int s = 0; s < n; ++s)
+                if (memcmp(&got[(size_t)s], &want_f[(size_t)s], sizeof(dp_v2x_flags)) != 0 && bad++ < 5)
+                    fprintf(stderr, "V2X mismatch mode %d scene %d\n", mode, s);
         }
     }
     CBatchApp::Instance().Close();
